@@ -1,0 +1,353 @@
+"""CPU oracle for the ACC-UNet HANC/MLFC hot path.  TEST INFRASTRUCTURE ONLY.
+
+This file is the checker, never the product: only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference``
+leg may import it.  The product path (``acc-unet-unext_b200/accx``) never does
+and fails loudly when its CUDA library is missing.
+
+It restates, as pure functions over a flat ``state_dict`` (name -> tensor), the
+arithmetic of the reference's ``ACC_UNet/ACC_UNet.py`` blocks.  Tensors are
+NCHW-shaped like the reference's; everything runs on the CPU through basic
+torch ops so ``torch.autograd`` supplies the gradient oracle as well.
+
+Parity pin: the reference has no tests or golden vectors of its own for this
+path, so the oracle is pinned against outputs of the
+reference itself, imported in the build container by
+``tests/golden/make_golden.py`` and committed under ``tests/golden/*.npz``;
+``tests/test_oracle_golden.py`` re-checks the oracle against those fixtures.
+
+Reference lines each function follows (relative to /root/reference):
+  batchnorm       torch.nn.BatchNorm2d as used at ACC_UNet/ACC_UNet.py:34,74,244,...
+  se_layer        ACC_UNet/ACC_UNet.py:37-49
+  hanc_pyramid    ACC_UNet/ACC_UNet.py:83-138
+  hanc_layer      ACC_UNet/ACC_UNet.py:77-142
+  hanc_block      ACC_UNet/ACC_UNet.py:267-286
+  conv_bn_se      ACC_UNet/ACC_UNet.py:182-186   (Conv2d_batchnorm)
+  respath         ACC_UNet/ACC_UNet.py:323-328
+  mlfc            ACC_UNet/ACC_UNet.py:420-527  (W blend: ACC_UNet_w.py:497-522,
+                                                  Lite: ACC_UNet_lite.py:424-427)
+  acc_unet        ACC_UNet/ACC_UNet.py:601-659
+  dice_bce_loss   Experiments/utils.py:21-74,109-171
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+
+State = Dict[str, torch.Tensor]
+LRELU_SLOPE = 0.01
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+
+
+class Ctx:
+    """Carries the state dict, the train/eval switch and collects BN buffer updates."""
+
+    def __init__(self, state: State, training: bool = True):
+        self.sd = state
+        self.training = training
+        self.updates: State = {}
+
+    def p(self, name: str) -> torch.Tensor:
+        return self.sd[name]
+
+
+def lrelu(x):
+    return torch.where(x > 0, x, x * LRELU_SLOPE)
+
+
+def batchnorm(cx: Ctx, name: str, x: torch.Tensor) -> torch.Tensor:
+    """BatchNorm2d: batch statistics (biased var) in training, running stats in eval.
+    Running buffers: momentum 0.1, unbiased variance; recorded in cx.updates."""
+    g, b = cx.p(name + ".weight"), cx.p(name + ".bias")
+    rm, rv = cx.p(name + ".running_mean"), cx.p(name + ".running_var")
+    if cx.training:
+        n = x.numel() // x.shape[1]
+        mu = x.mean(dim=(0, 2, 3))
+        var = ((x - mu[None, :, None, None]) ** 2).mean(dim=(0, 2, 3))
+        with torch.no_grad():
+            cx.updates[name + ".running_mean"] = (1 - BN_MOMENTUM) * rm + BN_MOMENTUM * mu
+            cx.updates[name + ".running_var"] = (1 - BN_MOMENTUM) * rv + BN_MOMENTUM * var * (n / max(n - 1, 1))
+            cx.updates[name + ".num_batches_tracked"] = cx.p(name + ".num_batches_tracked") + 1
+    else:
+        mu, var = rm, rv
+    inv = torch.rsqrt(var + BN_EPS)
+    return (x - mu[None, :, None, None]) * (inv * g)[None, :, None, None] + b[None, :, None, None]
+
+
+def pointwise(cx: Ctx, name: str, x: torch.Tensor) -> torch.Tensor:
+    """1x1 convolution = per-pixel matrix product with W[out,in] plus bias."""
+    w = cx.p(name + ".weight")
+    y = torch.einsum("bchw,oc->bohw", x, w.reshape(w.shape[0], w.shape[1]))
+    return y + cx.p(name + ".bias")[None, :, None, None]
+
+
+def block_reduce(x: torch.Tensor, s: int, how: str) -> torch.Tensor:
+    """Non-overlapping s x s pooling computed directly on x."""
+    B, C, H, W = x.shape
+    v = x.reshape(B, C, H // s, s, W // s, s)
+    if how == "avg":
+        return v.mean(dim=(3, 5))
+    return v.amax(dim=(3, 5))
+
+
+def replicate(x: torch.Tensor, s: int) -> torch.Tensor:
+    """Nearest-neighbour upsampling by an integer factor."""
+    return x.repeat_interleave(s, dim=2).repeat_interleave(s, dim=3)
+
+
+def se_layer(cx: Ctx, name: str, x: torch.Tensor) -> torch.Tensor:
+    """Squeeze-excite gate followed by BN and LeakyReLU (non-standard tail)."""
+    m = x.mean(dim=(2, 3))
+    h = lrelu(m @ cx.p(name + ".fc1.weight").t() + cx.p(name + ".fc1.bias"))
+    g = torch.sigmoid(h @ cx.p(name + ".fc2.weight").t() + cx.p(name + ".fc2.bias"))
+    return lrelu(batchnorm(cx, name + ".bn", x * g[:, :, None, None]))
+
+
+def hanc_pyramid(x: torch.Tensor, k: int) -> torch.Tensor:
+    """[x, avg2, avg4, .., max2, max4, ..] interleaved so channel index = c*(2k-1)+j."""
+    if k == 1:
+        return x
+    maps = [x]
+    for j in range(1, k):
+        maps.append(replicate(block_reduce(x, 2 ** j, "avg"), 2 ** j))
+    for j in range(1, k):
+        maps.append(replicate(block_reduce(x, 2 ** j, "max"), 2 ** j))
+    B, C, H, W = x.shape
+    return torch.stack(maps, dim=2).reshape(B, C * (2 * k - 1), H, W)
+
+
+def hanc_layer(cx: Ctx, name: str, x: torch.Tensor, k: int) -> torch.Tensor:
+    return lrelu(batchnorm(cx, name + ".bn", pointwise(cx, name + ".cnv", hanc_pyramid(x, k))))
+
+
+def hanc_block(cx: Ctx, name: str, inp: torch.Tensor, k: int) -> torch.Tensor:
+    x = lrelu(batchnorm(cx, name + ".norm1", pointwise(cx, name + ".conv1", inp)))
+    w2 = cx.p(name + ".conv2.weight")
+    x = F.conv2d(x, w2, cx.p(name + ".conv2.bias"), padding=1, groups=w2.shape[0])
+    x = lrelu(batchnorm(cx, name + ".norm2", x))
+    x = hanc_layer(cx, name + ".hnc", x, k)
+    x = batchnorm(cx, name + ".norm", x + inp)
+    x = lrelu(batchnorm(cx, name + ".norm3", pointwise(cx, name + ".conv3", x)))
+    return se_layer(cx, name + ".sqe", x)
+
+
+def conv_bn_se(cx: Ctx, name: str, x: torch.Tensor) -> torch.Tensor:
+    x = lrelu(batchnorm(cx, name + ".batchnorm", pointwise(cx, name + ".conv1", x)))
+    return se_layer(cx, name + ".sqe", x)
+
+
+def respath(cx: Ctx, name: str, x: torch.Tensor, n_lvl: int) -> torch.Tensor:
+    for i in range(n_lvl):
+        y = F.conv2d(x, cx.p(f"{name}.convs.{i}.weight"), cx.p(f"{name}.convs.{i}.bias"), padding=1)
+        x = x + se_layer(cx, f"{name}.sqes.{i}", lrelu(batchnorm(cx, f"{name}.bns.{i}", y)))
+    # the module registered under the name 'sqe' is a BatchNorm2d
+    return batchnorm(cx, name + ".sqe", lrelu(batchnorm(cx, name + ".bn", x)))
+
+
+def _to_level(x: torch.Tensor, src: int, dst: int) -> torch.Tensor:
+    """Bring pyramid level `src` to the resolution of level `dst` with chained
+    avg-pool(2) / nearest(2), exactly as many times as the reference chains them."""
+    for _ in range(dst - src):
+        x = block_reduce(x, 2, "avg")
+    for _ in range(src - dst):
+        x = replicate(x, 2)
+    return x
+
+
+def mlfc(cx: Ctx, name: str, xs: List[torch.Tensor], lenn: int = 1, variant: str = "base"):
+    if variant == "lite":
+        return tuple(se_layer(cx, f"{name}.sqe{l + 1}", xs[l]) for l in range(4))
+    xc = list(xs)
+    for i in range(lenn):
+        xc = []
+        for l in range(4):
+            gathered = torch.cat([_to_level(xs[s], s, l) for s in range(4)], dim=1)
+            t = conv_bn_se(cx, f"{name}.cnv_blks{l + 1}.{i}", gathered)
+            xc.append(lrelu(batchnorm(cx, f"{name}.bns{l + 1}.{i}", t)))
+        for l in range(4):
+            B, C, H, W = xs[l].shape
+            merged = torch.stack([xc[l], xs[l]], dim=2).reshape(B, 2 * C, H, W)
+            t = conv_bn_se(cx, f"{name}.cnv_mrg{l + 1}.{i}", merged)
+            if variant == "w":
+                wmix = cx.p(name + ".W")
+                t = t * wmix + xs[l] * (1 - wmix)
+            else:
+                t = t + xs[l]
+            xc[l] = lrelu(batchnorm(cx, f"{name}.bns_mrg{l + 1}.{i}", t))
+    return tuple(se_layer(cx, f"{name}.sqe{l + 1}", xc[l]) for l in range(4))
+
+
+# (name, k) of the 18 HANC blocks in execution order, ACC_UNet.py:554-592
+ENC = [("cnv11", 3), ("cnv12", 3), ("cnv21", 3), ("cnv22", 3), ("cnv31", 3), ("cnv32", 3),
+       ("cnv41", 2), ("cnv42", 2), ("cnv51", 1), ("cnv52", 1)]
+DEC = [("up6", "cnv61", "cnv62", 2), ("up7", "cnv71", "cnv72", 3),
+       ("up8", "cnv81", "cnv82", 3), ("up9", "cnv91", "cnv92", 3)]
+
+
+def acc_unet(cx: Ctx, x: torch.Tensor, variant: str = "base", logits: bool = False) -> torch.Tensor:
+    """Whole ACC-UNet forward (variant in base|w|lite).  With logits=True the
+    final sigmoid is skipped (reference: last_activation=None, ACC_UNet.py:653-657)."""
+    skips = []
+    for idx, (nm, k) in enumerate(ENC):
+        x = hanc_block(cx, nm, x, k)
+        if idx % 2 == 1 and idx < 9:
+            skips.append(x)
+            x = F.max_pool2d(x, 2)
+    for l, n_lvl in enumerate((4, 3, 2, 1)):
+        skips[l] = respath(cx, f"rspth{l + 1}", skips[l], n_lvl)
+    for m in ("mlfc1", "mlfc2", "mlfc3"):
+        skips = list(mlfc(cx, m, skips, 1, variant))
+    for (up, a, b, k), skip in zip(DEC, reversed(skips)):
+        x = F.conv_transpose2d(x, cx.p(up + ".weight"), cx.p(up + ".bias"), stride=2)
+        x = hanc_block(cx, a, torch.cat([x, skip], dim=1), k)
+        x = hanc_block(cx, b, x, k)
+    y = pointwise(cx, "out", x)
+    if not logits and cx.p("out.weight").shape[0] == 1:
+        y = torch.sigmoid(y)
+    return y
+
+
+def dice_bce_loss(logit: torch.Tensor, truth: torch.Tensor, dice_weight=0.5, bce_weight=0.5) -> torch.Tensor:
+    """WeightedDiceBCE(dice_weight, BCE_weight) on logits with class weights [0.5, 0.5]."""
+    B = logit.shape[0]
+    lg, tr = logit.reshape(B, -1).float(), truth.reshape(B, -1).float()
+    # dice part: both weights 0.5 -> every pixel scaled by 0.5
+    p = torch.sigmoid(lg) * 0.5
+    t = tr * 0.5
+    inter = (p * t).sum(-1)
+    union = (p * p).sum(-1) + (t * t).sum(-1)
+    dice = (1 - (2 * inter + 1e-5) / (union + 1e-5)).mean()
+    # BCE-with-logits, normalised separately over positives and negatives
+    l = torch.clamp(lg, min=0) - lg * tr + torch.log1p(torch.exp(-lg.abs()))
+    pos = (tr > 0.5).float()
+    neg = 1 - pos
+    bce = (0.5 * pos * l / pos.sum().clamp(min=1.0) + 0.5 * neg * l / neg.sum().clamp(min=1.0)).sum()
+    return dice_weight * dice + bce_weight * bce
+
+
+# ---------------------------------------------------------------------------------
+# Parameter construction with the torch default initialisers, in the same RNG order
+# the reference's constructors draw them, so torch.manual_seed(s) reproduces its
+# weights.  Used when /root/reference is not there (GPU box, cpu_baseline timing).
+# ---------------------------------------------------------------------------------
+
+def _conv(sd: State, name: str, cout: int, cin_per_group: int, kh: int, kw: int):
+    w = torch.empty(cout, cin_per_group, kh, kw)
+    torch.nn.init.kaiming_uniform_(w, a=math.sqrt(5))
+    bound = 1 / math.sqrt(cin_per_group * kh * kw)
+    sd[name + ".weight"] = w
+    sd[name + ".bias"] = torch.empty(cout).uniform_(-bound, bound)
+
+
+def _linear(sd: State, name: str, cin: int, cout: int):
+    w = torch.empty(cout, cin)
+    torch.nn.init.kaiming_uniform_(w, a=math.sqrt(5))
+    bound = 1 / math.sqrt(cin)
+    sd[name + ".weight"] = w
+    sd[name + ".bias"] = torch.empty(cout).uniform_(-bound, bound)
+
+
+def _bn(sd: State, name: str, c: int):
+    sd[name + ".weight"] = torch.ones(c)
+    sd[name + ".bias"] = torch.zeros(c)
+    sd[name + ".running_mean"] = torch.zeros(c)
+    sd[name + ".running_var"] = torch.ones(c)
+    sd[name + ".num_batches_tracked"] = torch.zeros((), dtype=torch.long)
+
+
+def init_se(sd: State, name: str, c: int):
+    _linear(sd, name + ".fc1", c, c // 8)
+    _linear(sd, name + ".fc2", c // 8, c)
+    _bn(sd, name + ".bn", c)
+
+
+def init_hanc_block(sd: State, name: str, c: int, cout: int, k: int, f: int):
+    e = c * f
+    _conv(sd, name + ".conv1", e, c, 1, 1)
+    _bn(sd, name + ".norm1", e)
+    _conv(sd, name + ".conv2", e, 1, 3, 3)
+    _bn(sd, name + ".norm2", e)
+    _conv(sd, name + ".hnc.cnv", c, (2 * k - 1) * e, 1, 1)
+    _bn(sd, name + ".hnc.bn", c)
+    _bn(sd, name + ".norm", c)
+    _conv(sd, name + ".conv3", cout, c, 1, 1)
+    _bn(sd, name + ".norm3", cout)
+    init_se(sd, name + ".sqe", cout)
+
+
+def init_respath(sd: State, name: str, c: int, n_lvl: int):
+    _bn(sd, name + ".bn", c)
+    _bn(sd, name + ".sqe", c)
+    for i in range(n_lvl):
+        _conv(sd, f"{name}.convs.{i}", c, c, 3, 3)
+        _bn(sd, f"{name}.bns.{i}", c)
+        init_se(sd, f"{name}.sqes.{i}", c)
+
+
+def init_mlfc(sd: State, name: str, filters, lenn: int = 1, variant: str = "base"):
+    tot = sum(filters)
+    if variant == "w":
+        sd[name + ".W"] = torch.zeros(1)
+    for i in range(lenn):
+        for l, c in enumerate(filters):
+            for kind, cin in (("cnv_blks", tot), ("cnv_mrg", 2 * c)):
+                pre = f"{name}.{kind}{l + 1}.{i}"
+                _conv(sd, pre + ".conv1", c, cin, 1, 1)
+                _bn(sd, pre + ".batchnorm", c)
+                init_se(sd, pre + ".sqe", c)
+            _bn(sd, f"{name}.bns{l + 1}.{i}", c)
+            _bn(sd, f"{name}.bns_mrg{l + 1}.{i}", c)
+    for l, c in enumerate(filters):
+        init_se(sd, f"{name}.sqe{l + 1}", c)
+
+
+def init_acc_unet(n_channels=3, n_classes=1, n_filts=32, variant="base") -> State:
+    sd: State = {}
+    f = n_filts
+    chans = [(n_channels, f), (f, f), (f, 2 * f), (2 * f, 2 * f), (2 * f, 4 * f), (4 * f, 4 * f),
+             (4 * f, 8 * f), (8 * f, 8 * f), (8 * f, 16 * f), (16 * f, 16 * f)]
+    for (nm, k), (ci, co) in zip(ENC, chans):
+        init_hanc_block(sd, nm, ci, co, k, 3)
+    for l, n_lvl in enumerate((4, 3, 2, 1)):
+        init_respath(sd, f"rspth{l + 1}", f * 2 ** l, n_lvl)
+    for m in ("mlfc1", "mlfc2", "mlfc3"):
+        init_mlfc(sd, m, (f, 2 * f, 4 * f, 8 * f), 1, variant)
+    dec = [(16 * f, 8 * f), (8 * f, 4 * f), (4 * f, 2 * f), (2 * f, f)]
+    for (up, a, b, k), (ci, co) in zip(DEC, dec):
+        w = torch.empty(ci, co, 2, 2)
+        torch.nn.init.kaiming_uniform_(w, a=math.sqrt(5))
+        bound = 1 / math.sqrt(co * 4)
+        sd[up + ".weight"] = w
+        sd[up + ".bias"] = torch.empty(co).uniform_(-bound, bound)
+        init_hanc_block(sd, a, 2 * co, co, k, 3)
+        init_hanc_block(sd, b, co, co, k, 34 if b == "cnv72" else 3)
+    _conv(sd, "out", n_classes if n_classes == 1 else n_classes + 1, f, 1, 1)
+    return sd
+
+
+def trainable(sd: State) -> List[str]:
+    return [k for k, v in sd.items() if v.is_floating_point() and "running_" not in k]
+
+
+def train_step(sd: State, x: torch.Tensor, mask: torch.Tensor, opt: Optional[torch.optim.Optimizer],
+               variant: str = "base") -> Tuple[float, Optional[torch.optim.Optimizer]]:
+    """One full training step on the CPU: forward, Dice+BCE on logits, backward, Adam(lr 1e-3).
+    (Experiments/Train_one_epoch.py:107-129, train_model.py:647,719.)"""
+    names = trainable(sd)
+    for n in names:
+        sd[n].requires_grad_(True)
+    if opt is None:
+        opt = torch.optim.Adam([sd[n] for n in names], lr=1e-3)
+    cx = Ctx(sd, training=True)
+    loss = dice_bce_loss(acc_unet(cx, x, variant, logits=True), mask)
+    opt.zero_grad(set_to_none=True)
+    loss.backward()
+    opt.step()
+    with torch.no_grad():
+        for k, v in cx.updates.items():
+            sd[k] = v
+    return float(loss), opt
