@@ -1,0 +1,379 @@
+"""Host-side launch helpers: torch tensors in, accx C-ABI calls out.
+
+torch is plumbing here (device memory, the current stream, autograd bookkeeping); every
+arithmetic pass over an activation is one accx kernel launched on torch's current stream.
+All activations are NHWC ([B, H, W, C] contiguous) in fp32 or bf16; parameters are fp32.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import List, NamedTuple, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import BF16, F32, Operand
+
+LAUNCHES = 0          # number of accx kernels launched by this process (bench.py reports it)
+
+
+def _call(name, *args):
+    global LAUNCHES
+    LAUNCHES += 1
+    _lib.call(name, *args)
+
+
+def dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise TypeError(f"accx supports float32 / bfloat16 activations, got {t.dtype}")
+
+
+def tdtype(code: int) -> torch.dtype:
+    return torch.float32 if code == F32 else torch.bfloat16
+
+
+def stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t: Optional[torch.Tensor]) -> int:
+    return 0 if t is None else t.data_ptr()
+
+
+def f32(p: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    """parameter -> contiguous fp32 device tensor (no copy in the normal case)"""
+    if p is None:
+        return None
+    p = p.detach()
+    if p.dtype != torch.float32:
+        p = p.float()
+    return p if p.is_contiguous() else p.contiguous()
+
+
+def require_cuda(x: torch.Tensor):
+    if not x.is_cuda:
+        raise _lib.AccxError("accx modules run on CUDA tensors only (sm_100a kernels; there is no CPU path)")
+    _lib.load()
+
+
+class Arena:
+    """Zero-initialised fp32 scratch carved from a few large allocations (one memset per chunk
+    instead of one per statistics buffer)."""
+
+    CHUNK = 1 << 16
+
+    def __init__(self, device):
+        self.device = device
+        self.buf = None
+        self.used = 0
+
+    def take(self, n: int) -> torch.Tensor:
+        n_al = (n + 63) // 64 * 64
+        if self.buf is None or self.used + n_al > self.buf.numel():
+            self.buf = torch.zeros(max(self.CHUNK, n_al), dtype=torch.float32, device=self.device)
+            self.used = 0
+        out = self.buf[self.used:self.used + n]
+        self.used += n_al
+        return out
+
+
+class Lazy:
+    """raw NHWC tensor + pending per-channel affine/activation (see include/accx.h)."""
+    __slots__ = ("y", "scale", "shift", "act", "mean", "rstd", "bn")
+
+    def __init__(self, y, scale=None, shift=None, act=0, mean=None, rstd=None, bn=None):
+        self.y, self.scale, self.shift, self.act = y, scale, shift, act
+        self.mean, self.rstd, self.bn = mean, rstd, bn
+
+    @property
+    def dims(self):
+        return tuple(self.y.shape[:3])
+
+    @property
+    def C(self):
+        return self.y.shape[3]
+
+
+class WV(NamedTuple):
+    """strided view into an fp32 weight tensor: element (n, k) = t.flat[off + n*ld + k*ks]"""
+    t: torch.Tensor
+    off: int
+    ld: int
+    ks: int
+
+
+class Op(NamedTuple):
+    src: Lazy
+    K: int
+    wv: WV
+    coff: int = 0      # first channel used inside src.y
+    dy: int = 0
+    dx: int = 0
+
+
+def _fill(o: Operand, op: Op, wt: Optional[torch.Tensor] = None):
+    y = op.src.y
+    esz = y.element_size()
+    o.data = y.data_ptr() + op.coff * esz
+    o.ld = y.shape[-1]
+    o.K = op.K
+    o.act = op.src.act
+    o.scale = (op.src.scale.data_ptr() + op.coff * 4) if op.src.act else 0
+    o.shift = (op.src.shift.data_ptr() + op.coff * 4) if op.src.act else 0
+    t = op.wv.t if wt is None else wt
+    o.w = t.data_ptr() + op.wv.off * 4
+    o.w_ld = op.wv.ld
+    o.w_ks = op.wv.ks
+    o.dy, o.dx = op.dy, op.dx
+
+
+def conv(ops: Sequence[Op], N: int, dims: Tuple[int, int, int], bias=None, adds: Sequence[Tuple[torch.Tensor, int]] = (),
+         stats=None, out_dtype: Optional[int] = None, out: Optional[torch.Tensor] = None, out_coff: int = 0):
+    """accx_pw_fwd.  Returns the raw [B,H,W,N] output (or writes columns [out_coff, out_coff+N) of `out`)."""
+    B, H, W = dims
+    arr = (Operand * len(ops))()
+    for i, op in enumerate(ops):
+        _fill(arr[i], op)
+    in_dt = dt(ops[0].src.y)
+    for op in ops:
+        assert dt(op.src.y) == in_dt
+    if out is None:
+        odt = in_dt if out_dtype is None else out_dtype
+        out = torch.empty((B, H, W, N), dtype=tdtype(odt), device=ops[0].src.y.device)
+    odt = dt(out)
+    ap = (ctypes.c_void_p * 4)()
+    al = (ctypes.c_int * 4)()
+    for i, (t, l) in enumerate(adds):
+        assert t.dtype == torch.float32 and t.shape[-1] == N
+        ap[i], al[i] = t.data_ptr(), l
+    _call("accx_pw_fwd", in_dt, odt, B, H, W, N, arr, len(ops), ptr(bias), ap, al, len(adds),
+          out.data_ptr() + out_coff * out.element_size(), out.shape[-1], ptr(stats), stream())
+    return out
+
+
+def wgrad(op: Op, dy: torch.Tensor, N: int, dims, gw: torch.Tensor, dy_coff: int = 0):
+    """accx_pw_wgrad: accumulate the weight gradient of one operand into gw (same layout as op.wv.t)."""
+    B, H, W = dims
+    o = Operand()
+    _fill(o, op, gw)
+    in_dt = dt(op.src.y)
+    dy_f32 = 1 if (dy.dtype == torch.float32 and in_dt != F32) else 0
+    assert dy_f32 or dt(dy) == in_dt
+    _call("accx_pw_wgrad", in_dt, B, H, W, N, ctypes.byref(o), gw.data_ptr() + op.wv.off * 4,
+          dy.data_ptr() + dy_coff * dy.element_size(),
+          dy.shape[-1], dy_f32, stream())
+
+
+def bn_affine(bn: torch.nn.BatchNorm2d, stats, count: float, arena: Arena, training: bool):
+    """statistics -> (scale, shift, mean, rstd); updates the running buffers in training."""
+    C = bn.num_features
+    buf = arena.take(4 * C)
+    scale, shift, mean, rstd = buf[:C], buf[C:2 * C], buf[2 * C:3 * C], buf[3 * C:]
+    mom = 0.1 if bn.momentum is None else bn.momentum
+    track = bn.track_running_stats and bn.running_mean is not None
+    _call("accx_bn_finalize", C, float(count), ptr(stats), ptr(f32(bn.weight)), ptr(f32(bn.bias)), float(bn.eps),
+          float(mom), 1 if training else 0, ptr(bn.running_mean) if track else 0, ptr(bn.running_var) if track else 0,
+          ptr(bn.num_batches_tracked) if track else 0, ptr(scale), ptr(shift), ptr(mean), ptr(rstd), stream())
+    return scale, shift, mean, rstd
+
+
+def bn_lazy(y: torch.Tensor, stats, bn, act: int, arena: Arena, training: bool) -> Lazy:
+    count = y.numel() // y.shape[-1]
+    scale, shift, mean, rstd = bn_affine(bn, stats, count, arena, training)
+    return Lazy(y, scale, shift, act, mean, rstd, bn)
+
+
+def materialize(L: Lazy, scale2=None, shift2=None, residual=None, stats=None, out=None, stats_only=False):
+    y = L.y
+    if out is None and not stats_only:
+        out = torch.empty_like(y)
+    _call("accx_act_apply", dt(y), y.numel() // y.shape[-1], y.shape[-1], ptr(y), ptr(L.scale), ptr(L.shift), L.act,
+          ptr(scale2), ptr(shift2), ptr(residual), ptr(out), ptr(stats), stream())
+    return out
+
+
+def add_fwd(L: Lazy, r: torch.Tensor, stats):
+    z = torch.empty_like(r)
+    _call("accx_add_fwd", dt(r), r.numel() // r.shape[-1], r.shape[-1], ptr(L.y), ptr(L.scale), ptr(L.shift), L.act,
+          ptr(r), ptr(z), ptr(stats), stream())
+    return z
+
+
+def bn_bwd(L: Lazy, da: torch.Tensor, grads: dict, arena: Arena, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """gradient w.r.t. the raw tensor L.y given the gradient w.r.t. act(BN(L.y)); accumulates
+    dgamma/dbeta into grads[bn.weight]/grads[bn.bias].  In place on `da` unless `out` is given."""
+    y = L.y
+    C = y.shape[-1]
+    P = y.numel() // C
+    sums = arena.take(2 * C)
+    dtc = dt(y)
+    assert da.dtype == y.dtype and da.is_contiguous()
+    _call("accx_bn_bwd_reduce", dtc, P, C, ptr(y), ptr(L.scale), ptr(L.shift), L.act, ptr(L.mean), ptr(L.rstd),
+          ptr(da), ptr(sums), stream())
+    dy = da if out is None else out
+    gg = grad_buf(grads, L.bn.weight)
+    gb = grad_buf(grads, L.bn.bias)
+    _call("accx_bn_bwd_apply", dtc, P, C, ptr(y), ptr(L.scale), ptr(L.shift), L.act, ptr(L.mean), ptr(L.rstd),
+          ptr(f32(L.bn.weight)), ptr(da), ptr(sums), float(P), ptr(dy), ptr(gg), ptr(gb), stream())
+    return dy
+
+
+def grad_buf(grads: dict, p: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    """zero-initialised fp32 gradient accumulator for parameter p (None if p takes no gradient)."""
+    if p is None or not p.requires_grad:
+        return None
+    g = grads.get(id(p))
+    if g is None:
+        g = torch.zeros(p.shape, dtype=torch.float32, device=p.device)
+        grads[id(p)] = g
+    return g
+
+
+def dw_fwd(L: Lazy, w, bias, stats, flip=False):
+    y = L.y
+    B, H, W, C = y.shape
+    out = torch.empty_like(y)
+    _call("accx_dw3x3_fwd", dt(y), B, H, W, C, ptr(y), ptr(L.scale), ptr(L.shift), L.act, ptr(w), ptr(bias),
+          1 if flip else 0, ptr(out), ptr(stats), stream())
+    return out
+
+
+def dw_wgrad(L: Lazy, dy: torch.Tensor, gw: torch.Tensor):
+    y = L.y
+    B, H, W, C = y.shape
+    _call("accx_dw3x3_wgrad", dt(y), B, H, W, C, ptr(y), ptr(L.scale), ptr(L.shift), L.act, ptr(dy), ptr(gw), stream())
+
+
+def hanc_pools(L: Lazy, k: int) -> List[torch.Tensor]:
+    """[B,H>>l,W>>l,2C] (avg | max) for l = 1..k-1"""
+    B, H, W, C = L.y.shape
+    outs = []
+    cur, first = L.y, 1
+    for l in range(1, k):
+        out = torch.empty((B, H >> l, W >> l, 2 * C), dtype=L.y.dtype, device=L.y.device)
+        _call("accx_hanc_pool_fwd", dt(L.y), B, H >> (l - 1), W >> (l - 1), C, first, ptr(cur), ptr(L.scale),
+              ptr(L.shift), L.act, ptr(out), stream())
+        outs.append(out)
+        cur, first = out, 0
+    return outs
+
+
+def hanc_unpool_bwd(L: Lazy, l: int, dpool: torch.Tensor, da: torch.Tensor, accumulate=True):
+    B, H, W, C = L.y.shape
+    assert dpool.dtype == torch.float32
+    _call("accx_hanc_unpool_bwd", dt(L.y), B, H, W, C, l, ptr(L.y), ptr(L.scale), ptr(L.shift), L.act, ptr(dpool),
+          ptr(da), 1 if accumulate else 0, stream())
+
+
+def pool_sum(x: torch.Tensor, l: int, mul: float, out_dtype: Optional[torch.dtype] = None):
+    B, H, W, C = x.shape
+    out = torch.empty((B, H >> l, W >> l, C), dtype=out_dtype or x.dtype, device=x.device)
+    _call("accx_pool_sum", dt(x), dt(out), B, H, W, C, l, float(mul), ptr(x), ptr(out), C, stream())
+    return out
+
+
+def upsample_add(src: torch.Tensor, dst: torch.Tensor, l: int, mul: float, accumulate: bool, src_coff=0, C=None):
+    B, H, W, Cd = dst.shape
+    C = Cd if C is None else C
+    assert C == Cd
+    _call("accx_upsample_add", dt(src), dt(dst), B, H, W, C, l, float(mul), src.data_ptr() + src_coff * src.element_size(),
+          src.shape[-1], ptr(dst), 1 if accumulate else 0, stream())
+
+
+def add_inplace(dst: torch.Tensor, other: torch.Tensor):
+    """dst += other (same shape/dtype), as one accx pass"""
+    C = dst.shape[-1]
+    _call("accx_act_apply", dt(dst), dst.numel() // C, C, ptr(dst), 0, 0, 0, 0, 0, ptr(other), ptr(dst), 0, stream())
+    return dst
+
+
+class SECtx:
+    __slots__ = ("L", "S", "gate", "hidden", "scale", "shift", "mean", "rstd", "mod", "residual", "mix", "mix_param")
+
+
+def se_fwd(L: Lazy, se, arena: Arena, training: bool, residual=None, mix=None, stats=None, mix_param=None):
+    """ChannelSELayer on a lazy input -> (materialised output, ctx)."""
+    y = L.y
+    B, H, W, C = y.shape
+    Cr = se.fc1.out_features
+    if Cr < 1:
+        raise _lib.AccxError(f"ChannelSELayer({C}): num_channels // 8 must be >= 1")
+    c = SECtx()
+    c.L, c.mod, c.residual, c.mix, c.mix_param = L, se, residual, mix, mix_param
+    c.S = arena.take(2 * B * C)
+    buf = arena.take(B * C + B * Cr + 4 * C + 1)
+    c.gate, c.hidden = buf[:B * C], buf[B * C:B * C + B * Cr]
+    o = B * C + B * Cr
+    c.scale, c.shift, c.mean, c.rstd = buf[o:o + C], buf[o + C:o + 2 * C], buf[o + 2 * C:o + 3 * C], buf[o + 3 * C:o + 4 * C]
+    counter = buf[o + 4 * C:o + 4 * C + 1]
+    d = dt(y)
+    _call("accx_se_squeeze", d, B, H * W, C, ptr(y), ptr(L.scale), ptr(L.shift), L.act, ptr(c.S), stream())
+    bn = se.bn
+    mom = 0.1 if bn.momentum is None else bn.momentum
+    _call("accx_se_gate", B, C, Cr, float(H * W), ptr(c.S), ptr(f32(se.fc1.weight)), ptr(f32(se.fc1.bias)),
+          ptr(f32(se.fc2.weight)), ptr(f32(se.fc2.bias)), ptr(f32(bn.weight)), ptr(f32(bn.bias)), float(bn.eps),
+          float(mom), 1 if training else 0, ptr(bn.running_mean), ptr(bn.running_var), ptr(bn.num_batches_tracked),
+          ptr(c.gate), ptr(c.hidden), ptr(c.scale), ptr(c.shift), ptr(c.mean), ptr(c.rstd), ptr(counter), stream())
+    out = torch.empty_like(y)
+    _call("accx_se_apply", d, B, H * W, C, ptr(y), ptr(L.scale), ptr(L.shift), L.act, ptr(c.gate), ptr(c.scale),
+          ptr(c.shift), ptr(residual), ptr(mix), ptr(out), ptr(stats), stream())
+    return out, c
+
+
+def se_bwd(c: SECtx, dout: torch.Tensor, grads: dict, arena: Arena, da: Optional[torch.Tensor] = None,
+           accumulate=False) -> torch.Tensor:
+    """gradient w.r.t. the activated SE input given d(out); parameter grads accumulate in `grads`.
+    (The residual branch, if any, simply receives dout * (1 - mix) -- handled by the caller.)"""
+    L, se = c.L, c.mod
+    y = L.y
+    B, H, W, C = y.shape
+    Cr = se.fc1.out_features
+    d = dt(y)
+    assert dout.dtype == y.dtype and dout.is_contiguous()
+    G = arena.take(2 * B * C)
+    PQR = arena.take(3 * B * C)
+    gmix = grad_buf(grads, c.mix_param) if c.mix_param is not None else None
+    _call("accx_se_bwd_reduce", d, B, H * W, C, ptr(y), ptr(L.scale), ptr(L.shift), L.act, ptr(c.gate), ptr(c.scale),
+          ptr(c.shift), ptr(dout), ptr(c.mix), ptr(c.residual) if gmix is not None else 0, ptr(gmix), ptr(G), stream())
+    _call("accx_se_bwd_gate", B, C, Cr, float(H * W), ptr(c.S), ptr(G), ptr(c.gate), ptr(c.hidden),
+          ptr(f32(se.fc1.weight)), ptr(f32(se.fc2.weight)), ptr(f32(se.bn.weight)), ptr(c.mean), ptr(c.rstd),
+          ptr(grad_buf(grads, se.fc1.weight)), ptr(grad_buf(grads, se.fc1.bias)), ptr(grad_buf(grads, se.fc2.weight)),
+          ptr(grad_buf(grads, se.fc2.bias)), ptr(grad_buf(grads, se.bn.weight)), ptr(grad_buf(grads, se.bn.bias)),
+          ptr(PQR), stream())
+    if da is None:
+        da = torch.empty_like(y)
+        accumulate = False
+    _call("accx_se_bwd_apply", d, B, H * W, C, ptr(y), ptr(L.scale), ptr(L.shift), L.act, ptr(c.gate), ptr(c.scale),
+          ptr(c.shift), ptr(dout), ptr(c.mix), ptr(PQR), ptr(da), 1 if accumulate else 0, stream())
+    return da
+
+
+def to_nhwc(x: torch.Tensor) -> torch.Tensor:
+    """NCHW-shaped tensor (any strides) -> contiguous [B,H,W,C]; free for channels_last inputs."""
+    v = x.permute(0, 2, 3, 1)
+    if v.is_contiguous():
+        return v
+    if x.is_contiguous():
+        B, C, H, W = x.shape
+        out = torch.empty((B, H, W, C), dtype=x.dtype, device=x.device)
+        _call("accx_nchw_to_nhwc", dt(x), dt(out), B, C, H * W, ptr(x), ptr(out), stream())
+        return out
+    return v.contiguous()
+
+
+def to_nchw_view(y: torch.Tensor) -> torch.Tensor:
+    """[B,H,W,C] contiguous -> NCHW-shaped channels_last view (no copy)."""
+    return y.permute(0, 3, 1, 2)
+
+
+def input_to_nhwc(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """model entry: NCHW (contiguous) -> [B,H,W,C] in the compute dtype, one accx pass"""
+    if not x.is_contiguous():
+        x = x.contiguous()
+    B, C, H, W = x.shape
+    out = torch.empty((B, H, W, C), dtype=dtype, device=x.device)
+    _call("accx_nchw_to_nhwc", dt(x), dt(out), B, C, H * W, ptr(x), ptr(out), stream())
+    return out

@@ -1,0 +1,108 @@
+"""ACC-UNet assembled from the accx drop-in blocks (caller glue of ACC_UNet.py:530-659).
+
+The five hot-path module types run the accx kernels; the glue around them that the reference
+also delegates to ATen -- MaxPool2d(2), ConvTranspose2d(2, 2, stride 2), the skip torch.cat and
+the final 1x1 conv (+ sigmoid) -- stays on torch here (SURVEY.md section 8, row a8 / f1 "next"),
+operating on channels_last tensors so no layout change happens between blocks.
+
+`compute_dtype=torch.bfloat16` stores activations in bf16 (fp32 accumulation, statistics and
+parameters); default None follows the input's dtype (fp32 = the reference's arithmetic).
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from . import engine as E
+from .modules import HANCBlock, MLFC, ResPath
+
+
+class _ACCUNetBase(nn.Module):
+    variant = "base"
+
+    def __init__(self, n_channels, n_classes, n_filts=32, compute_dtype=None):
+        super().__init__()
+        self.n_channels = n_channels
+        self.n_classes = n_classes
+        self.compute_dtype = compute_dtype
+        f = n_filts
+        self.pool = nn.MaxPool2d(2)
+        self.cnv11 = HANCBlock(n_channels, f, k=3, inv_fctr=3)
+        self.cnv12 = HANCBlock(f, f, k=3, inv_fctr=3)
+        self.cnv21 = HANCBlock(f, f * 2, k=3, inv_fctr=3)
+        self.cnv22 = HANCBlock(f * 2, f * 2, k=3, inv_fctr=3)
+        self.cnv31 = HANCBlock(f * 2, f * 4, k=3, inv_fctr=3)
+        self.cnv32 = HANCBlock(f * 4, f * 4, k=3, inv_fctr=3)
+        self.cnv41 = HANCBlock(f * 4, f * 8, k=2, inv_fctr=3)
+        self.cnv42 = HANCBlock(f * 8, f * 8, k=2, inv_fctr=3)
+        self.cnv51 = HANCBlock(f * 8, f * 16, k=1, inv_fctr=3)
+        self.cnv52 = HANCBlock(f * 16, f * 16, k=1, inv_fctr=3)
+        self.rspth1 = ResPath(f, 4)
+        self.rspth2 = ResPath(f * 2, 3)
+        self.rspth3 = ResPath(f * 4, 2)
+        self.rspth4 = ResPath(f * 8, 1)
+        self.mlfc1 = MLFC(f, f * 2, f * 4, f * 8, lenn=1, variant=self.variant)
+        self.mlfc2 = MLFC(f, f * 2, f * 4, f * 8, lenn=1, variant=self.variant)
+        self.mlfc3 = MLFC(f, f * 2, f * 4, f * 8, lenn=1, variant=self.variant)
+        self.up6 = nn.ConvTranspose2d(f * 16, f * 8, kernel_size=(2, 2), stride=2)
+        self.cnv61 = HANCBlock(f * 8 + f * 8, f * 8, k=2, inv_fctr=3)
+        self.cnv62 = HANCBlock(f * 8, f * 8, k=2, inv_fctr=3)
+        self.up7 = nn.ConvTranspose2d(f * 8, f * 4, kernel_size=(2, 2), stride=2)
+        self.cnv71 = HANCBlock(f * 4 + f * 4, f * 4, k=3, inv_fctr=3)
+        self.cnv72 = HANCBlock(f * 4, f * 4, k=3, inv_fctr=34)
+        self.up8 = nn.ConvTranspose2d(f * 4, f * 2, kernel_size=(2, 2), stride=2)
+        self.cnv81 = HANCBlock(f * 2 + f * 2, f * 2, k=3, inv_fctr=3)
+        self.cnv82 = HANCBlock(f * 2, f * 2, k=3, inv_fctr=3)
+        self.up9 = nn.ConvTranspose2d(f * 2, f, kernel_size=(2, 2), stride=2)
+        self.cnv91 = HANCBlock(f + f, f, k=3, inv_fctr=3)
+        self.cnv92 = HANCBlock(f, f, k=3, inv_fctr=3)
+        if n_classes == 1:
+            self.out = nn.Conv2d(f, n_classes, kernel_size=(1, 1))
+            self.last_activation = nn.Sigmoid()
+        else:
+            self.out = nn.Conv2d(f, n_classes + 1, kernel_size=(1, 1))
+            self.last_activation = None
+
+    def forward(self, x):
+        E.require_cuda(x)
+        cd = self.compute_dtype or x.dtype
+        if x.dtype != cd or not x.permute(0, 2, 3, 1).is_contiguous():
+            x = E.to_nchw_view(E.input_to_nhwc(x, cd)) if not x.requires_grad else \
+                x.to(cd).contiguous(memory_format=torch.channels_last)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=(cd == torch.bfloat16)):
+            x2 = self.cnv12(self.cnv11(x))
+            x3 = self.cnv22(self.cnv21(self.pool(x2)))
+            x4 = self.cnv32(self.cnv31(self.pool(x3)))
+            x5 = self.cnv42(self.cnv41(self.pool(x4)))
+            x6 = self.cnv52(self.cnv51(self.pool(x5)))
+            x2 = self.rspth1(x2)
+            x3 = self.rspth2(x3)
+            x4 = self.rspth3(x4)
+            x5 = self.rspth4(x5)
+            x2, x3, x4, x5 = self.mlfc1(x2, x3, x4, x5)
+            x2, x3, x4, x5 = self.mlfc2(x2, x3, x4, x5)
+            x2, x3, x4, x5 = self.mlfc3(x2, x3, x4, x5)
+            x7 = self.cnv62(self.cnv61(torch.cat([self.up6(x6), x5], dim=1)))
+            x8 = self.cnv72(self.cnv71(torch.cat([self.up7(x7), x4], dim=1)))
+            x9 = self.cnv82(self.cnv81(torch.cat([self.up8(x8), x3], dim=1)))
+            x10 = self.cnv92(self.cnv91(torch.cat([self.up9(x9), x2], dim=1)))
+            logits = self.out(x10)
+        logits = logits.float()
+        if self.last_activation is not None:
+            logits = self.last_activation(logits)
+        return logits
+
+
+class ACC_UNet(_ACCUNetBase):
+    """ACC_UNet/ACC_UNet.py:530-659"""
+    variant = "base"
+
+
+class ACC_UNet_W(_ACCUNetBase):
+    """ACC_UNet/ACC_UNet_w.py: MLFC merge blended by a learned scalar W"""
+    variant = "w"
+
+
+class ACC_UNet_Lite(_ACCUNetBase):
+    """ACC_UNet/ACC_UNet_lite.py: MLFC reduced to its four SE layers (its conv parameters stay unused)"""
+    variant = "lite"

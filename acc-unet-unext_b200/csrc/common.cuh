@@ -1,0 +1,212 @@
+// Shared device/host helpers for the accx kernels (sm_100a only).
+//
+// Data model used by every kernel in this library
+//   * activations: NHWC, i.e. a dense [P, C] matrix with P = B*H*W pixels, storage dtype
+//     fp32 or bf16 (ACCX_F32 / ACCX_BF16); all arithmetic and all statistics are fp32.
+//   * "lazy" operand: a raw producer output x plus a pending per-channel affine and
+//     activation, a = act(x * scale[c] + shift[c]); act: 0 = none (scale/shift ignored),
+//     1 = affine, 2 = affine + LeakyReLU(0.01).  This is how training-mode BatchNorm is fused:
+//     producers emit raw outputs + per-channel (sum, sumsq); consumers normalise on load.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/accx.h"
+
+#define ACCX_LRELU 0.01f
+
+namespace accx {
+
+void set_error(const char* fmt, ...);
+int check_launch(const char* what);
+
+#define ACCX_REQUIRE(cond, ...)          \
+  do {                                   \
+    if (!(cond)) {                       \
+      accx::set_error(__VA_ARGS__);      \
+      return ACCX_ERR_INVALID;           \
+    }                                    \
+  } while (0)
+
+typedef __nv_bfloat16 bf16;
+
+template <typename T> struct DT;
+template <> struct DT<float> { static constexpr int VEC = 4; };
+template <> struct DT<bf16> { static constexpr int VEC = 8; };
+
+__device__ __forceinline__ float to_f(float v) { return v; }
+__device__ __forceinline__ float to_f(bf16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+// ---- VEC-wide loads/stores (VEC = 1 scalar fallback, else one 16-byte access) ----
+template <typename T, int VEC>
+__device__ __forceinline__ void ldv(const T* __restrict__ p, float (&v)[VEC]) {
+  if constexpr (VEC == 1) {
+    v[0] = to_f(p[0]);
+  } else if constexpr (sizeof(T) == 4) {
+    static_assert(VEC == 4, "fp32 vectors are 4 wide");
+    float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  } else {
+    static_assert(VEC == 8, "bf16 vectors are 8 wide");
+    uint4 t = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[2 * i] = __uint_as_float(w[i] << 16);
+      v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
+}
+
+template <typename T, int VEC>
+__device__ __forceinline__ void stv(T* __restrict__ p, const float (&v)[VEC]) {
+  if constexpr (VEC == 1) {
+    p[0] = from_f<T>(v[0]);
+  } else if constexpr (sizeof(T) == 4) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  } else {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
+template <int VEC>
+__device__ __forceinline__ void ldf(const float* __restrict__ p, float (&v)[VEC]) {
+  if constexpr (VEC == 1) {
+    v[0] = p[0];
+  } else {
+#pragma unroll
+    for (int i = 0; i < VEC; i += 4) {
+      float4 t = *reinterpret_cast<const float4*>(p + i);
+      v[i] = t.x; v[i + 1] = t.y; v[i + 2] = t.z; v[i + 3] = t.w;
+    }
+  }
+}
+
+__device__ __forceinline__ float lrelu(float v) { return v > 0.f ? v : v * ACCX_LRELU; }
+
+// Per-thread channel-lane view of a lazy operand: scale/shift for this thread's VEC channels.
+template <int VEC>
+struct Lazy {
+  float s[VEC], t[VEC];
+  int act;
+  __device__ __forceinline__ void init(const float* scale, const float* shift, int act_, int c0) {
+    act = act_;
+    if (act != 0) {
+      ldf<VEC>(scale + c0, s);
+      ldf<VEC>(shift + c0, t);
+    } else {
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) { s[i] = 1.f; t[i] = 0.f; }
+    }
+  }
+  // value after the pending affine + activation
+  __device__ __forceinline__ void apply(float (&v)[VEC]) const {
+    if (act == 0) return;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      float u = fmaf(v[i], s[i], t[i]);
+      v[i] = (act == 2) ? lrelu(u) : u;
+    }
+  }
+  // d act / d (pre-activation) evaluated at raw value x
+  __device__ __forceinline__ float dact(float x, int i) const {
+    if (act != 2) return 1.f;
+    return fmaf(x, s[i], t[i]) > 0.f ? 1.f : ACCX_LRELU;
+  }
+};
+
+// ---- launch geometry for [P, C] channel-lane kernels --------------------------------
+// Threads are laid out (TX channel vectors) x (TY pixels); a thread keeps ONE channel vector
+// for its whole life, so per-channel reductions stay in registers until the end.
+struct Lanes {
+  int vec;      // elements per thread access (1 or DT<T>::VEC)
+  int cvn;      // channel vectors per pixel
+  int tx, ty;   // block shape
+  int gy;       // blocks along channel vectors
+};
+
+inline Lanes make_lanes(int C, int full_vec, bool aligned) {
+  Lanes l;
+  l.vec = (aligned && C % full_vec == 0) ? full_vec : 1;
+  l.cvn = C / l.vec;
+  if (l.cvn <= 256) {
+    l.tx = l.cvn;
+  } else {
+    l.tx = 256;
+    for (int d = 256; d >= 64; --d)
+      if (l.cvn % d == 0) { l.tx = d; break; }
+  }
+  l.ty = 256 / l.tx;
+  if (l.ty < 1) l.ty = 1;
+  l.gy = (l.cvn + l.tx - 1) / l.tx;
+  return l;
+}
+
+inline int grid_x_for(int64_t items, int per_block, int max_blocks) {
+  int64_t g = (items + per_block - 1) / per_block;
+  if (g > max_blocks) g = max_blocks;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// Block-level reduction of NS per-channel statistics held as acc[NS][VEC] by every thread
+// of a (TX, TY) block, then one atomicAdd per (stat, channel) into out[s * stride + c].
+// smem must hold blockDim.x * blockDim.y * VEC floats.
+template <int NS, int VEC>
+__device__ __forceinline__ void reduce_lanes_atomic(float (&acc)[NS][VEC], float* smem, float* out,
+                                                    int64_t stride, int c0, bool active) {
+  const int tx = threadIdx.x, ty = threadIdx.y, TX = blockDim.x, TY = blockDim.y;
+#pragma unroll
+  for (int s = 0; s < NS; ++s) {
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) smem[(ty * VEC + i) * TX + tx] = acc[s][i];
+    __syncthreads();
+    // thread (tx, ty) sums element i = ty, ty+TY, .. over all rows
+    for (int i = ty; i < VEC; i += TY) {
+      float sum = 0.f;
+      for (int r = 0; r < TY; ++r) sum += smem[(r * VEC + i) * TX + tx];
+      if (active) atomicAdd(out + s * stride + c0 + i, sum);
+    }
+  }
+}
+
+#define ACCX_DISPATCH_T(dtype, ...)                       \
+  do {                                                    \
+    if ((dtype) == ACCX_F32) {                            \
+      typedef float T;                                    \
+      __VA_ARGS__                                         \
+    } else if ((dtype) == ACCX_BF16) {                    \
+      typedef accx::bf16 T;                               \
+      __VA_ARGS__                                         \
+    } else {                                              \
+      accx::set_error("unsupported dtype %d", (int)(dtype)); \
+      return ACCX_ERR_INVALID;                            \
+    }                                                     \
+  } while (0)
+
+// instantiate BODY with a compile-time VEC (full or 1)
+#define ACCX_DISPATCH_VEC(lanes, ...)                     \
+  do {                                                    \
+    if ((lanes).vec == 1) {                               \
+      constexpr int VEC = 1;                              \
+      __VA_ARGS__                                         \
+    } else {                                              \
+      constexpr int VEC = accx::DT<T>::VEC;               \
+      __VA_ARGS__                                         \
+    }                                                     \
+  } while (0)
+
+}  // namespace accx

@@ -1,0 +1,441 @@
+// ChannelSELayer (/root/reference/ACC_UNet/ACC_UNet.py:37-49):
+//   m = mean_hw(a); g = sigmoid(W2 lrelu(W1 m + b1) + b2); z = a*g; out = lrelu(BN(z)).
+// One read pass (squeeze) yields per-(b,c) sum and sum of squares of the lazy input a; the gate
+// AND the batch statistics of z follow from them (mean_c = sum_b g*S1/n, E[z^2]_c = sum_b g^2*S2/n),
+// so the layer costs: read a (squeeze) + read a, write out (apply).  Backward mirrors it:
+// one reduce pass, a tiny per-batch kernel, one apply pass.
+#include "common.cuh"
+
+namespace accx {
+
+// grid.x = B * chunks; each block reduces a slice of one image
+template <typename T, int VEC>
+__global__ void se_squeeze_kernel(int B, int HW, int C, int chunks, const T* __restrict__ x, const float* scale,
+                                  const float* shift, int act, float* S) {
+  extern __shared__ float smem[];
+  const int cv = blockIdx.y * blockDim.x + threadIdx.x;
+  const bool active = cv * VEC < C;
+  const int c0 = active ? cv * VEC : 0;
+  const int b = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
+  Lazy<VEC> lz;
+  lz.init(scale, shift, act, c0);
+  float acc[2][VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) acc[0][i] = acc[1][i] = 0.f;
+  if (active) {
+    const T* img = x + (int64_t)b * HW * C + c0;
+    for (int p = chunk * blockDim.y + threadIdx.y; p < HW; p += chunks * blockDim.y) {
+      float v[VEC];
+      ldv<T, VEC>(img + (int64_t)p * C, v);
+      lz.apply(v);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) { acc[0][i] += v[i]; acc[1][i] += v[i] * v[i]; }
+    }
+  }
+  reduce_lanes_atomic<2, VEC>(acc, smem, S + (int64_t)b * C, (int64_t)B * C, c0, active);
+}
+
+// grid = B blocks of 256 threads; the last block to finish derives the BatchNorm affine.
+__global__ void se_gate_kernel(int B, int C, int Cr, double HW, const float* __restrict__ S,
+                               const float* __restrict__ w1, const float* __restrict__ b1,
+                               const float* __restrict__ w2, const float* __restrict__ b2,
+                               const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                               float momentum, int training, float* running_mean, float* running_var, int64_t* nbt,
+                               float* gate, float* hidden, float* scale, float* shift, float* mean_o, float* rstd_o,
+                               unsigned int* counter) {
+  extern __shared__ float sm[];
+  float* m = sm;            // [C]
+  float* h = sm + C;        // [Cr]
+  __shared__ bool is_last;
+  const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  const float inv_hw = (float)(1.0 / HW);
+  for (int c = tid; c < C; c += nt) m[c] = S[(int64_t)b * C + c] * inv_hw;
+  __syncthreads();
+  const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
+  for (int j = warp; j < Cr; j += nw) {
+    float a = 0.f;
+    for (int c = lane; c < C; c += 32) a = fmaf(w1[(int64_t)j * C + c], m[c], a);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) {
+      a += b1[j];
+      hidden[(int64_t)b * Cr + j] = a;
+      h[j] = lrelu(a);
+    }
+  }
+  __syncthreads();
+  for (int c = tid; c < C; c += nt) {
+    float a = b2[c];
+    for (int j = 0; j < Cr; ++j) a = fmaf(w2[(int64_t)c * Cr + j], h[j], a);
+    gate[(int64_t)b * C + c] = 1.f / (1.f + __expf(-a));
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    unsigned int prev = atomicAdd(counter, 1u);
+    is_last = (prev == (unsigned)(B - 1));
+    if (is_last) *counter = 0;   // re-arm for the next launch (graph replays)
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  const double n = HW * (double)B;
+  if (tid == 0 && training && nbt) *nbt += 1;
+  for (int c = tid; c < C; c += nt) {
+    float mean, var;
+    if (training) {
+      double s1 = 0, s2 = 0;
+      for (int bb = 0; bb < B; ++bb) {
+        float g = __ldcg(gate + (int64_t)bb * C + c);
+        s1 += (double)g * S[(int64_t)bb * C + c];
+        s2 += (double)g * g * S[(int64_t)B * C + (int64_t)bb * C + c];
+      }
+      double mu = s1 / n, v = s2 / n - mu * mu;
+      if (v < 0) v = 0;
+      mean = (float)mu;
+      var = (float)v;
+      if (running_mean) {
+        double unb = n > 1 ? v * n / (n - 1) : v;
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
+      }
+    } else {
+      mean = running_mean[c];
+      var = running_var[c];
+    }
+    float rstd = rsqrtf(var + eps);
+    float s = gamma[c] * rstd;
+    scale[c] = s;
+    shift[c] = beta[c] - mean * s;
+    if (mean_o) mean_o[c] = mean;
+    if (rstd_o) rstd_o[c] = rstd;
+  }
+}
+
+// out = mixf( lrelu(a*gate[b,c]*se_scale[c] + se_shift[c]) , residual )
+template <typename T, int VEC>
+__global__ void se_apply_kernel(int B, int HW, int C, const T* __restrict__ x, const float* scale, const float* shift,
+                                int act, const float* __restrict__ gate, const float* se_scale, const float* se_shift,
+                                const T* __restrict__ residual, const float* mix, T* __restrict__ out, float* stats) {
+  extern __shared__ float smem[];
+  const int cv = blockIdx.y * blockDim.x + threadIdx.x;
+  const bool active = cv * VEC < C;
+  const int c0 = active ? cv * VEC : 0;
+  Lazy<VEC> lz;
+  lz.init(scale, shift, act, c0);
+  float ss[VEC], st[VEC];
+  ldf<VEC>(se_scale + c0, ss);
+  ldf<VEC>(se_shift + c0, st);
+  const float mx = mix ? *mix : 1.f, rx = mix ? 1.f - mx : 1.f;
+  float acc[2][VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) acc[0][i] = acc[1][i] = 0.f;
+  const int64_t P = (int64_t)B * HW;
+  if (active) {
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.y + threadIdx.y; p < P; p += (int64_t)gridDim.x * blockDim.y) {
+      const int b = (int)(p / HW);
+      float v[VEC], g[VEC];
+      ldv<T, VEC>(x + p * C + c0, v);
+      ldf<VEC>(gate + (int64_t)b * C + c0, g);
+      lz.apply(v);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) v[i] = lrelu(fmaf(v[i] * g[i], ss[i], st[i]));
+      if (residual) {
+        float r[VEC];
+        ldv<T, VEC>(residual + p * C + c0, r);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) v[i] = v[i] * mx + r[i] * rx;
+      }
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) { acc[0][i] += v[i]; acc[1][i] += v[i] * v[i]; }
+      stv<T, VEC>(out + p * C + c0, v);
+    }
+  }
+  if (stats) reduce_lanes_atomic<2, VEC>(acc, smem, stats, C, c0, active);
+}
+
+// G[0,b,c] += sum_hw g', G[1,b,c] += sum_hw g'*a;  g' = dout*mix*lrelu'(v);  dmix += sum dout*(v_act - r)
+template <typename T, int VEC>
+__global__ void se_bwd_reduce_kernel(int B, int HW, int C, int chunks, const T* __restrict__ x, const float* scale,
+                                     const float* shift, int act, const float* __restrict__ gate,
+                                     const float* se_scale, const float* se_shift, const T* __restrict__ dout,
+                                     const float* mix, const T* __restrict__ residual, float* dmix, float* G) {
+  extern __shared__ float smem[];
+  const int cv = blockIdx.y * blockDim.x + threadIdx.x;
+  const bool active = cv * VEC < C;
+  const int c0 = active ? cv * VEC : 0;
+  const int b = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
+  Lazy<VEC> lz;
+  lz.init(scale, shift, act, c0);
+  float ss[VEC], st[VEC], g[VEC];
+  ldf<VEC>(se_scale + c0, ss);
+  ldf<VEC>(se_shift + c0, st);
+  ldf<VEC>(gate + (int64_t)b * C + c0, g);
+  const float mx = mix ? *mix : 1.f;
+  float acc[2][VEC];
+  float dm = 0.f;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) acc[0][i] = acc[1][i] = 0.f;
+  if (active) {
+    const int64_t off = (int64_t)b * HW * C + c0;
+    for (int p = chunk * blockDim.y + threadIdx.y; p < HW; p += chunks * blockDim.y) {
+      float v[VEC], d[VEC];
+      ldv<T, VEC>(x + off + (int64_t)p * C, v);
+      ldv<T, VEC>(dout + off + (int64_t)p * C, d);
+      lz.apply(v);
+      float r[VEC];
+      if (dmix) ldv<T, VEC>(residual + off + (int64_t)p * C, r);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        float u = fmaf(v[i] * g[i], ss[i], st[i]);
+        if (dmix) dm += d[i] * (lrelu(u) - r[i]);
+        float gp = d[i] * mx * (u > 0.f ? 1.f : ACCX_LRELU);
+        acc[0][i] += gp;
+        acc[1][i] += gp * v[i];
+      }
+    }
+  }
+  reduce_lanes_atomic<2, VEC>(acc, smem, G + (int64_t)b * C, (int64_t)B * C, c0, active);
+  if (dmix) {   // block size need not be a multiple of 32: reduce through shared memory
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x, nth = blockDim.x * blockDim.y;
+    __syncthreads();
+    smem[tid] = dm;
+    __syncthreads();
+    if (tid == 0) {
+      float s = 0.f;
+      for (int i = 0; i < nth; ++i) s += smem[i];
+      atomicAdd(dmix, s);
+    }
+  }
+}
+
+// One block per image.  Every block first derives the per-channel BN-backward constants
+// (c1 = mean g', c2 = mean g'*zhat) from G over ALL images (cheap: B*C values), then runs the
+// two tiny FC backward products for its image and emits the per-(b,c) apply coefficients.
+__global__ void se_bwd_gate_kernel(int B, int C, int Cr, double HW, const float* __restrict__ S,
+                                   const float* __restrict__ G, const float* __restrict__ gate,
+                                   const float* __restrict__ hidden, const float* __restrict__ w1,
+                                   const float* __restrict__ w2, const float* __restrict__ gamma,
+                                   const float* __restrict__ mean, const float* __restrict__ rstd, float* dw1,
+                                   float* db1, float* dw2, float* db2, float* dgamma, float* dbeta, float* PQR) {
+  extern __shared__ float sm[];
+  float* dpre2 = sm;            // [C]
+  float* m = sm + C;            // [C]
+  float* hact = sm + 2 * C;     // [Cr]
+  float* dpre1 = hact + Cr;     // [Cr]
+  const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  const double n = HW * (double)B;
+  const float inv_hw = (float)(1.0 / HW);
+  const int64_t BC = (int64_t)B * C;
+  for (int j = tid; j < Cr; j += nt) hact[j] = lrelu(hidden[(int64_t)b * Cr + j]);
+  for (int c = tid; c < C; c += nt) {
+    const float mu = mean[c], rs = rstd[c];
+    double a1 = 0, a2 = 0;
+    for (int bb = 0; bb < B; ++bb) {
+      const float g1 = G[(int64_t)bb * C + c], g2 = G[BC + (int64_t)bb * C + c];
+      a1 += g1;
+      a2 += (double)rs * ((double)gate[(int64_t)bb * C + c] * g2 - (double)mu * g1);
+    }
+    if (b == 0) {
+      if (dbeta) atomicAdd(dbeta + c, (float)a1);
+      if (dgamma) atomicAdd(dgamma + c, (float)a2);
+    }
+    const float c1 = (float)(a1 / n), c2 = (float)(a2 / n);
+    const float g = gate[(int64_t)b * C + c];
+    const float s1 = S[(int64_t)b * C + c], s2 = S[BC + (int64_t)b * C + c];
+    const float g1 = G[(int64_t)b * C + c], g2 = G[BC + (int64_t)b * C + c];
+    const float s = gamma[c] * rs;
+    // dgate = sum_hw dz * a with dz = s*(g' - c1 - zhat*c2), zhat = rs*(a*g - mu)
+    const float dgate = s * (g2 - c1 * s1 - c2 * rs * (g * s2 - mu * s1));
+    const float dp = dgate * g * (1.f - g);
+    dpre2[c] = dp;
+    m[c] = s1 * inv_hw;
+    if (db2) atomicAdd(db2 + c, dp);
+    PQR[(int64_t)b * C + c] = s * g;                                  // P
+    PQR[BC + (int64_t)b * C + c] = -s * rs * g * g * c2;              // Q
+    PQR[2 * BC + (int64_t)b * C + c] = -s * g * (c1 - c2 * rs * mu);  // R (dm/HW added below)
+  }
+  __syncthreads();
+  // dw2[c, j] += dpre2[c] * h[j];  dh[j] = sum_c w2[c, j] * dpre2[c]
+  for (int idx = tid; idx < C * Cr; idx += nt) {
+    const int c = idx / Cr, j = idx % Cr;
+    if (dw2) atomicAdd(dw2 + idx, dpre2[c] * hact[j]);
+  }
+  const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
+  for (int j = warp; j < Cr; j += nw) {
+    float a = 0.f;
+    for (int c = lane; c < C; c += 32) a = fmaf(w2[(int64_t)c * Cr + j], dpre2[c], a);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) {
+      const float d = a * (hidden[(int64_t)b * Cr + j] > 0.f ? 1.f : ACCX_LRELU);
+      dpre1[j] = d;
+      if (db1) atomicAdd(db1 + j, d);
+    }
+  }
+  __syncthreads();
+  for (int idx = tid; idx < C * Cr; idx += nt) {
+    const int j = idx / C, c = idx % C;
+    if (dw1) atomicAdd(dw1 + idx, dpre1[j] * m[c]);
+  }
+  for (int c = tid; c < C; c += nt) {
+    float dm = 0.f;
+    for (int j = 0; j < Cr; ++j) dm = fmaf(w1[(int64_t)j * C + c], dpre1[j], dm);
+    PQR[2 * BC + (int64_t)b * C + c] += dm * inv_hw;
+  }
+}
+
+// da (+)= P*g' + Q*a + R
+template <typename T, int VEC>
+__global__ void se_bwd_apply_kernel(int B, int HW, int C, const T* __restrict__ x, const float* scale,
+                                    const float* shift, int act, const float* __restrict__ gate,
+                                    const float* se_scale, const float* se_shift, const T* __restrict__ dout,
+                                    const float* mix, const float* __restrict__ PQR, T* __restrict__ da,
+                                    int accumulate) {
+  const int cv = blockIdx.y * blockDim.x + threadIdx.x;
+  if (cv * VEC >= C) return;
+  const int c0 = cv * VEC;
+  Lazy<VEC> lz;
+  lz.init(scale, shift, act, c0);
+  float ss[VEC], st[VEC];
+  ldf<VEC>(se_scale + c0, ss);
+  ldf<VEC>(se_shift + c0, st);
+  const float mx = mix ? *mix : 1.f;
+  const int64_t P = (int64_t)B * HW, BC = (int64_t)B * C;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.y + threadIdx.y; p < P; p += (int64_t)gridDim.x * blockDim.y) {
+    const int b = (int)(p / HW);
+    float v[VEC], d[VEC], g[VEC], cp[VEC], cq[VEC], cr[VEC];
+    ldv<T, VEC>(x + p * C + c0, v);
+    ldv<T, VEC>(dout + p * C + c0, d);
+    ldf<VEC>(gate + (int64_t)b * C + c0, g);
+    ldf<VEC>(PQR + (int64_t)b * C + c0, cp);
+    ldf<VEC>(PQR + BC + (int64_t)b * C + c0, cq);
+    ldf<VEC>(PQR + 2 * BC + (int64_t)b * C + c0, cr);
+    lz.apply(v);
+    float o[VEC];
+    if (accumulate) {
+      ldv<T, VEC>(da + p * C + c0, o);
+    } else {
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) o[i] = 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      float u = fmaf(v[i] * g[i], ss[i], st[i]);
+      float gp = d[i] * mx * (u > 0.f ? 1.f : ACCX_LRELU);
+      o[i] += cp[i] * gp + cq[i] * v[i] + cr[i];
+    }
+    stv<T, VEC>(da + p * C + c0, o);
+  }
+}
+
+static inline int se_chunks(int B, int HW, int ty) {
+  // enough blocks to fill the machine, but keep the number of atomics per (b,c) small
+  int per_img = (HW + ty * 8 - 1) / (ty * 8);
+  int want = (148 * 4 + B - 1) / B;
+  int c = per_img < want ? per_img : want;
+  return c < 1 ? 1 : c;
+}
+
+}  // namespace accx
+
+using namespace accx;
+
+extern "C" {
+
+int accx_se_squeeze(int dtype, int B, int HW, int C, const void* x, const float* scale, const float* shift, int act,
+                    float* S, void* stream) {
+  ACCX_REQUIRE(B > 0 && HW > 0 && C > 0 && x && S, "se_squeeze: bad arguments");
+  ACCX_DISPATCH_T(dtype, {
+    Lanes l = make_lanes(C, DT<T>::VEC, aligned16(x));
+    int chunks = se_chunks(B, HW, l.ty);
+    dim3 block(l.tx, l.ty), grid(B * chunks, l.gy);
+    size_t sm = (size_t)l.tx * l.ty * l.vec * sizeof(float);
+    ACCX_DISPATCH_VEC(l, {
+      se_squeeze_kernel<T, VEC><<<grid, block, sm, (cudaStream_t)stream>>>(B, HW, C, chunks, (const T*)x, scale, shift,
+                                                                           act, S);
+    });
+  });
+  return check_launch("se_squeeze");
+}
+
+int accx_se_gate(int B, int C, int Cr, double HW, const float* S, const float* w1, const float* b1, const float* w2,
+                 const float* b2, const float* gamma, const float* beta, float eps, float momentum, int training,
+                 float* running_mean, float* running_var, int64_t* nbt, float* gate, float* hidden, float* scale,
+                 float* shift, float* mean, float* rstd, unsigned int* counter, void* stream) {
+  ACCX_REQUIRE(B > 0 && C > 0 && Cr > 0 && S && w1 && b1 && w2 && b2 && gate && hidden && scale && shift && counter,
+               "se_gate: bad arguments (C=%d Cr=%d)", C, Cr);
+  size_t sm = (size_t)(C + Cr) * sizeof(float);
+  se_gate_kernel<<<B, 256, sm, (cudaStream_t)stream>>>(B, C, Cr, HW, S, w1, b1, w2, b2, gamma, beta, eps, momentum,
+                                                       training, running_mean, running_var, nbt, gate, hidden, scale,
+                                                       shift, mean, rstd, counter);
+  return check_launch("se_gate");
+}
+
+int accx_se_apply(int dtype, int B, int HW, int C, const void* x, const float* scale, const float* shift, int act,
+                  const float* gate, const float* se_scale, const float* se_shift, const void* residual,
+                  const float* mix, void* out, float* stats, void* stream) {
+  ACCX_REQUIRE(B > 0 && HW > 0 && C > 0 && x && gate && se_scale && se_shift && out, "se_apply: bad arguments");
+  const int64_t P = (int64_t)B * HW;
+  ACCX_DISPATCH_T(dtype, {
+    Lanes l = make_lanes(C, DT<T>::VEC, aligned16(x) && aligned16(out) && (!residual || aligned16(residual)));
+    dim3 block(l.tx, l.ty), grid(grid_x_for(P, l.ty * 8, 148 * 8), l.gy);
+    size_t sm = (size_t)l.tx * l.ty * l.vec * sizeof(float);
+    ACCX_DISPATCH_VEC(l, {
+      se_apply_kernel<T, VEC><<<grid, block, sm, (cudaStream_t)stream>>>(B, HW, C, (const T*)x, scale, shift, act, gate,
+                                                                         se_scale, se_shift, (const T*)residual, mix,
+                                                                         (T*)out, stats);
+    });
+  });
+  return check_launch("se_apply");
+}
+
+int accx_se_bwd_reduce(int dtype, int B, int HW, int C, const void* x, const float* scale, const float* shift, int act,
+                       const float* gate, const float* se_scale, const float* se_shift, const void* dout,
+                       const float* mix, const void* residual, float* dmix, float* G, void* stream) {
+  ACCX_REQUIRE(B > 0 && HW > 0 && C > 0 && x && gate && dout && G, "se_bwd_reduce: bad arguments");
+  ACCX_REQUIRE(!dmix || (mix && residual), "se_bwd_reduce: dmix needs mix and residual");
+  ACCX_DISPATCH_T(dtype, {
+    Lanes l = make_lanes(C, DT<T>::VEC, aligned16(x) && aligned16(dout) && (!residual || aligned16(residual)));
+    int chunks = se_chunks(B, HW, l.ty);
+    dim3 block(l.tx, l.ty), grid(B * chunks, l.gy);
+    size_t sm = (size_t)l.tx * l.ty * l.vec * sizeof(float);
+    ACCX_DISPATCH_VEC(l, {
+      se_bwd_reduce_kernel<T, VEC><<<grid, block, sm, (cudaStream_t)stream>>>(
+          B, HW, C, chunks, (const T*)x, scale, shift, act, gate, se_scale, se_shift, (const T*)dout, mix,
+          (const T*)residual, dmix, G);
+    });
+  });
+  return check_launch("se_bwd_reduce");
+}
+
+int accx_se_bwd_gate(int B, int C, int Cr, double HW, const float* S, const float* G, const float* gate,
+                     const float* hidden, const float* w1, const float* w2, const float* gamma, const float* mean,
+                     const float* rstd, float* dw1, float* db1, float* dw2, float* db2, float* dgamma, float* dbeta,
+                     float* PQR, void* stream) {
+  ACCX_REQUIRE(B > 0 && C > 0 && Cr > 0 && S && G && gate && hidden && w1 && w2 && gamma && mean && rstd && PQR,
+               "se_bwd_gate: bad arguments");
+  size_t sm = (size_t)(2 * C + 2 * Cr) * sizeof(float);
+  se_bwd_gate_kernel<<<B, 256, sm, (cudaStream_t)stream>>>(B, C, Cr, HW, S, G, gate, hidden, w1, w2, gamma, mean, rstd,
+                                                           dw1, db1, dw2, db2, dgamma, dbeta, PQR);
+  return check_launch("se_bwd_gate");
+}
+
+int accx_se_bwd_apply(int dtype, int B, int HW, int C, const void* x, const float* scale, const float* shift, int act,
+                      const float* gate, const float* se_scale, const float* se_shift, const void* dout,
+                      const float* mix, const float* PQR, void* da, int accumulate, void* stream) {
+  ACCX_REQUIRE(B > 0 && HW > 0 && C > 0 && x && gate && dout && PQR && da, "se_bwd_apply: bad arguments");
+  const int64_t P = (int64_t)B * HW;
+  ACCX_DISPATCH_T(dtype, {
+    Lanes l = make_lanes(C, DT<T>::VEC, aligned16(x) && aligned16(dout) && aligned16(da));
+    dim3 block(l.tx, l.ty), grid(grid_x_for(P, l.ty * 8, 148 * 8), l.gy);
+    ACCX_DISPATCH_VEC(l, {
+      se_bwd_apply_kernel<T, VEC><<<grid, block, 0, (cudaStream_t)stream>>>(B, HW, C, (const T*)x, scale, shift, act,
+                                                                            gate, se_scale, se_shift, (const T*)dout,
+                                                                            mix, PQR, (T*)da, accumulate);
+    });
+  });
+  return check_launch("se_bwd_apply");
+}
+
+}  // extern "C"

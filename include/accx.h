@@ -1,0 +1,177 @@
+/* accx -- C ABI of the B200-native (sm_100a) kernels behind ACC-UNet's HANC/MLFC blocks.
+ *
+ * This is the drop-in boundary.  The reference ( /root/reference/ACC_UNet/ACC_UNet.py ) has no
+ * native interface for this path: its five torch.nn.Module classes call ATen operators.  The
+ * entry points below are what a binding for those operators has to call; each one names the
+ * reference lines it replaces.  Plain pointers and sizes only (no torch types); the caller owns
+ * every buffer; nothing here allocates, frees or synchronises; every launch goes to the
+ * caller-supplied CUDA stream (`stream` is a cudaStream_t passed as void*), so all calls are
+ * capturable in a CUDA graph.  Return value: 0 on success, negative on error
+ * (accx_last_error() gives the message for the calling thread).
+ *
+ * Data model
+ *   activations  NHWC: a dense [P, C] matrix, P = B*H*W; storage ACCX_F32 or ACCX_BF16.
+ *   parameters   fp32, in the reference's own layouts (Conv2d weight [out, in, kh, kw], ...).
+ *   lazy operand raw tensor x + pending per-channel affine + activation:
+ *                a = act(x*scale[c] + shift[c]); act 0 none, 1 affine, 2 affine+LeakyReLU(0.01).
+ *                Training-mode BatchNorm2d + LeakyReLU never materialise: producers emit raw
+ *                outputs and per-channel (sum, sum of squares); consumers normalise on load.
+ *   stats        float[2*C]: sum then sum of squares, ACCUMULATED (atomicAdd) -- zero them first.
+ */
+#ifndef ACCX_H_
+#define ACCX_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ACCX_F32 0
+#define ACCX_BF16 1
+
+#define ACCX_OK 0
+#define ACCX_ERR_INVALID (-1)
+#define ACCX_ERR_CUDA (-2)
+
+#define ACCX_MAX_OPERANDS 9
+#define ACCX_MAX_ADDENDS 4
+
+const char* accx_last_error(void);
+int accx_version(void);
+
+/* One A-operand of a pointwise contraction together with its weight slice.
+ *   value(p, k) = act(data[p'*ld + k]*scale[k] + shift[k]),  p' = pixel p shifted by (dy, dx)
+ *                 inside its image (zero outside -- this is conv padding);
+ *   weight(n, k) = w[n*w_ld + k*w_ks]   (pointer pre-offset by the caller).
+ * The strided weight view is how the reference's interleaved concat orders are honoured with
+ * no data movement: HANCLayer K index c*(2k-1)+j (ACC_UNet.py:138), MLFC merge 2c+j (:492),
+ * MLFC gather block order (:431-485), dense 3x3 taps (ResPath, :316-318). */
+typedef struct accx_operand {
+  const void* data;
+  int64_t ld;
+  int32_t K;
+  int32_t act;
+  const float* scale;
+  const float* shift;
+  const float* w;
+  int64_t w_ld;
+  int64_t w_ks;
+  int32_t dy, dx;
+} accx_operand_t;
+
+/* Y[p, n] = sum_ops sum_k value_op(p, k) * weight_op(n, k) + bias[n]
+ *           + sum_j add_j[coarse_j(p), n]          (nearest-upsample-add, log2 factor add_log2s[j])
+ * and stats[n] += sum_p Y, stats[N+n] += sum_p Y^2 (if stats != NULL).
+ * Replaces: every 1x1 Conv2d of the path (HANCBlock.conv1/conv3 ACC_UNet.py:243,259;
+ * HANCLayer.cnv :72 in split form W.cat_j(up(p_j)) = sum_j up(W_j.p_j); Conv2d_batchnorm.conv1
+ * :171), the dense 3x3 of ResPath (:316-318, nine shifted operands), and all their input
+ * gradients (same contraction with transposed weight strides).
+ * add_j are fp32 [B, H>>l, W>>l, N] tensors.  B,H,W describe the pixel grid of Y. */
+int accx_pw_fwd(int dtype, int out_dtype, int B, int H, int W, int N,
+                const accx_operand_t* ops, int n_ops, const float* bias,
+                const float* const* add, const int* add_log2s, int n_add,
+                void* y, int64_t ldy, float* stats, void* stream);
+
+/* dW[n*w_ld + k*w_ks] += sum_p dY[p, n] * value(p, k)  for one operand (weight gradient of the
+ * contraction above; fp32 atomics).  dy is a plain [P, ldy] matrix in `dtype` storage
+ * (or fp32 when dy_f32 != 0). */
+int accx_pw_wgrad(int dtype, int B, int H, int W, int N, const accx_operand_t* op, float* dw,
+                  const void* dy, int64_t ldy, int dy_f32, void* stream);
+
+/* BatchNorm2d statistics -> affine (torch.nn.BatchNorm2d as used at ACC_UNet.py:34,74,178,
+ * 244-260,311-319,388-410).  training: mean/var from stats (biased var), running buffers
+ * updated with `momentum` and the unbiased variance, num_batches_tracked += 1.  eval: running
+ * buffers.  Outputs scale = gamma*rstd, shift = beta - mean*scale, and mean/rstd for backward. */
+int accx_bn_finalize(int C, double count, const float* stats, const float* gamma, const float* beta,
+                     float eps, float momentum, int training, float* running_mean, float* running_var,
+                     int64_t* num_batches_tracked, float* scale, float* shift, float* mean, float* rstd,
+                     void* stream);
+
+/* out = post(act(x)) with optional second affine post(u) = u*scale2 + shift2 (ResPath tail
+ * BN(lrelu(BN(x))), ACC_UNet.py:328), optional residual add, optional stats of the value
+ * written.  out == NULL: statistics only. */
+int accx_act_apply(int dtype, int64_t P, int C, const void* x, const float* scale, const float* shift, int act,
+                   const float* scale2, const float* shift2, const void* residual, void* out, float* stats,
+                   void* stream);
+
+/* BatchNorm2d backward through a lazy boundary a = act(y*scale+shift):
+ *   g = da * act'(.), sums[c] += sum g, sums[C+c] += sum g*xhat          (reduce)
+ *   dy = gamma*rstd*(g - sums[c]/n - xhat*sums[C+c]/n); dgamma += sums[C+c]; dbeta += sums[c] (apply)
+ * dy may alias da. */
+int accx_bn_bwd_reduce(int dtype, int64_t P, int C, const void* y, const float* scale, const float* shift, int act,
+                       const float* mean, const float* rstd, const void* da, float* sums, void* stream);
+int accx_bn_bwd_apply(int dtype, int64_t P, int C, const void* y, const float* scale, const float* shift, int act,
+                      const float* mean, const float* rstd, const float* gamma, const void* da, const float* sums,
+                      double count, void* dy, float* dgamma, float* dbeta, void* stream);
+
+/* Depthwise 3x3, stride 1, zero padding 1 (HANCBlock.conv2, ACC_UNet.py:246-252) on a lazy
+ * input; raw output + stats.  w is the Conv2d weight [C,1,3,3]; flip != 0 rotates the filter by
+ * 180 degrees (= input gradient).  wgrad: dw[c*9 + tap] += sum dy[p] * a[p + tap]. */
+int accx_dw3x3_fwd(int dtype, int B, int H, int W, int C, const void* x, const float* scale, const float* shift,
+                   int act, const float* w, const float* bias, int flip, void* y, float* stats, void* stream);
+int accx_dw3x3_wgrad(int dtype, int B, int H, int W, int C, const void* x, const float* scale, const float* shift,
+                     int act, const void* dy, float* dw, void* stream);
+
+/* HANC pyramid (HANCLayer.forward, ACC_UNet.py:83-136), one 2x level per call.
+ * first != 0: x is the lazy [B,H,W,C] map, else x is the previous level [B,H,W,2C] (avg | max).
+ * out [B,H/2,W/2,2C]: channels [0,C) 2x2 average, [C,2C) 2x2 maximum. */
+int accx_hanc_pool_fwd(int dtype, int B, int H, int W, int C, int first, const void* x, const float* scale,
+                       const float* shift, int act, void* out, void* stream);
+/* Gradient of the s x s (s = 1<<log2s) avg/max branches w.r.t. the activated map a:
+ * da[p] (+)= davg[blk]/s^2 + (p is the FIRST row-major maximum of its block ? dmax[blk] : 0),
+ * dpool = [B,H/s,W/s,2C] (avg | max), fp32. */
+int accx_hanc_unpool_bwd(int dtype, int B, int H, int W, int C, int log2s, const void* x, const float* scale,
+                         const float* shift, int act, const float* dpool, void* da, int accumulate, void* stream);
+
+/* out[b, h, w, coff + c] = mul * sum over the s x s block of x (MLFC's chained AvgPool2d(2),
+ * ACC_UNet.py:361,448-480 with mul = 1/s^2; block sums of gradients with mul = 1). */
+int accx_pool_sum(int in_dtype, int out_dtype, int B, int H, int W, int C, int log2s, float mul, const void* x,
+                  void* out, int64_t out_ld, void* stream);
+/* dst[b,h,w,c] (+)= mul * src[b, h>>l, w>>l, c]  (nearest Upsample, ACC_UNet.py:360, and the
+ * gradient of the average pool). */
+int accx_upsample_add(int in_dtype, int out_dtype, int B, int H, int W, int C, int log2s, float mul,
+                      const void* src, int64_t src_ld, void* dst, int accumulate, void* stream);
+
+/* ChannelSELayer (ACC_UNet.py:37-49) in three launches:
+ *   squeeze  S[0,b,c] += sum_hw a, S[1,b,c] += sum_hw a^2   (one read gives the gate input AND
+ *            the batch statistics of the gated tensor: mean_c = sum_b g*S1/n, E[z^2] = sum_b g^2*S2/n)
+ *   gate     fc1 -> LeakyReLU -> fc2 -> sigmoid, then the trailing BatchNorm's scale/shift
+ *   apply    out = lrelu(a*gate[b,c]*scale[c] + shift[c]) (+ residual) (stats of out optional)
+ * mix (device scalar, ACC_UNet_w.py:497-522): out = v*mix + residual*(1-mix). */
+int accx_se_squeeze(int dtype, int B, int HW, int C, const void* x, const float* scale, const float* shift, int act,
+                    float* S, void* stream);
+int accx_se_gate(int B, int C, int Cr, double HW, const float* S, const float* w1, const float* b1, const float* w2,
+                 const float* b2, const float* gamma, const float* beta, float eps, float momentum, int training,
+                 float* running_mean, float* running_var, int64_t* num_batches_tracked, float* gate, float* hidden,
+                 float* scale, float* shift, float* mean, float* rstd, unsigned int* counter, void* stream);
+int accx_se_apply(int dtype, int B, int HW, int C, const void* x, const float* scale, const float* shift, int act,
+                  const float* gate, const float* se_scale, const float* se_shift, const void* residual,
+                  const float* mix, void* out, float* stats, void* stream);
+/* backward: G[0,b,c] += sum_hw g', G[1,b,c] += sum_hw g'*a with g' = dout*lrelu'(v)  (reduce);
+ * the tiny gate kernel turns G into per-(b,c) coefficients PQR and all parameter gradients;
+ * apply: da (+)= P*g' + Q*a + R.  With mix: g' carries the factor mix and
+ * dmix += sum dout*(v - residual). */
+int accx_se_bwd_reduce(int dtype, int B, int HW, int C, const void* x, const float* scale, const float* shift, int act,
+                       const float* gate, const float* se_scale, const float* se_shift, const void* dout,
+                       const float* mix, const void* residual, float* dmix, float* G, void* stream);
+int accx_se_bwd_gate(int B, int C, int Cr, double HW, const float* S, const float* G, const float* gate,
+                     const float* hidden, const float* w1, const float* w2, const float* gamma, const float* mean,
+                     const float* rstd, float* dw1, float* db1, float* dw2, float* db2, float* dgamma, float* dbeta,
+                     float* PQR, void* stream);
+int accx_se_bwd_apply(int dtype, int B, int HW, int C, const void* x, const float* scale, const float* shift, int act,
+                      const float* gate, const float* se_scale, const float* se_shift, const void* dout,
+                      const float* mix, const float* PQR, void* da, int accumulate, void* stream);
+
+/* z = act(a) + r with stats (HANCBlock: norm(x + inp), ACC_UNet.py:279). */
+int accx_add_fwd(int dtype, int64_t P, int C, const void* a, const float* scale, const float* shift, int act,
+                 const void* r, void* z, float* stats, void* stream);
+
+/* NCHW <-> NHWC with optional dtype change (model entry / exit only). */
+int accx_nchw_to_nhwc(int in_dtype, int out_dtype, int B, int C, int HW, const void* src, void* dst, void* stream);
+int accx_nhwc_to_nchw(int in_dtype, int out_dtype, int B, int C, int HW, const void* src, void* dst, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ACCX_H_ */

@@ -1,0 +1,91 @@
+"""CPU: the C-ABI library loads and exports every symbol include/accx.h declares; the Python
+mirror of the reference interface keeps its constructors, state_dict layout and error behaviour.
+No compute calls here (no GPU in the build container)."""
+import ctypes
+import inspect
+import os
+
+import pytest
+import torch
+
+from helpers import load_case, module_cases
+
+
+def test_library_exports_every_declared_symbol():
+    from accx import _lib
+    protos = _lib.parse_header()
+    assert len(protos) >= 20
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in protos:
+        assert hasattr(lib, name), f"{name} declared in include/accx.h but not exported by libaccx.so"
+    _lib.load()
+    assert _lib.load().accx_version() >= 100
+    assert ctypes.sizeof(_lib.Operand) == 72          # accx_operand_t layout (8-byte aligned fields)
+
+
+def test_invalid_arguments_return_error_codes_not_crashes():
+    from accx import _lib
+    lib = _lib.load()
+    rc = lib.accx_bn_finalize(0, 1.0, None, None, None, 1e-5, 0.1, 1, None, None, None, None, None, None, None, None)
+    assert rc == -1 and b"bn_finalize" in lib.accx_last_error()
+    with pytest.raises(_lib.AccxError):
+        _lib.call("accx_pool_sum", 0, 0, 1, 3, 3, 8, 1, 1.0, 1, 1, 8, None)     # 3x3 not divisible by 2
+
+
+def test_reference_signatures_are_kept():
+    import accx
+    sig = lambda c: list(inspect.signature(c.__init__).parameters)[1:]
+    assert sig(accx.ChannelSELayer) == ["num_channels"]
+    assert sig(accx.HANCLayer) == ["in_chnl", "out_chnl", "k"]
+    assert sig(accx.HANCBlock) == ["n_filts", "out_channels", "k", "inv_fctr"]
+    assert sig(accx.ResPath) == ["in_chnls", "n_lvl"]
+    assert sig(accx.MLFC)[:5] == ["in_filters1", "in_filters2", "in_filters3", "in_filters4", "lenn"]
+    assert sig(accx.ACC_UNet)[:3] == ["n_channels", "n_classes", "n_filts"]
+    d = inspect.signature(accx.HANCBlock.__init__).parameters
+    assert d["k"].default == 3 and d["inv_fctr"].default == 3
+
+
+@pytest.mark.parametrize("name", module_cases())
+def test_state_dict_layout_matches_reference(name):
+    from test_modules_gpu import build
+    case = load_case(name)
+    mod = build(name)
+    sd = mod.state_dict()
+    assert list(sd.keys()) == list(case["sd"].keys())
+    for k, v in case["sd"].items():
+        assert tuple(sd[k].shape) == tuple(v.shape), k
+    mod.load_state_dict(case["sd"])
+
+
+def test_default_init_reproduces_reference_weights():
+    """same submodule construction order => torch.manual_seed(2) gives the reference's weights"""
+    import accx
+    z = load_case("init_seed2_f8")["raw"]
+    torch.manual_seed(2)
+    sd = accx.ACC_UNet(3, 1, 8).state_dict()
+    assert [str(n) for n in z["names"]] == list(sd.keys())
+    for n, s in zip(z["names"], z["sums"]):
+        assert abs(float(sd[str(n)].double().sum()) - s) <= 1e-9 + 1e-9 * abs(s), n
+
+
+def test_dropin_module_names_importable():
+    import ACC_UNet, ACC_UNet_lite, ACC_UNet_w   # noqa: E401
+    assert ACC_UNet.MLFC(8, 8, 8, 8).variant == "base"
+    assert ACC_UNet_w.MLFC(8, 8, 8, 8).variant == "w" and hasattr(ACC_UNet_w.MLFC(8, 8, 8, 8), "W")
+    assert ACC_UNet_lite.MLFC(8, 8, 8, 8).variant == "lite"
+    for cls in ("ChannelSELayer", "HANCLayer", "HANCBlock", "ResPath", "MLFC", "ACC_UNet"):
+        assert hasattr(ACC_UNet, cls)
+
+
+def test_no_cpu_path():
+    import accx
+    with pytest.raises(accx.AccxError):
+        accx.HANCBlock(8, 8)(torch.randn(1, 8, 4, 4))
+
+
+def test_product_never_imports_the_oracle():
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "acc-unet-unext_b200")
+    for dp, _, fs in os.walk(root):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                assert "oracle" not in open(os.path.join(dp, f)).read().lower(), f
