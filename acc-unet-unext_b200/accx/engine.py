@@ -170,8 +170,7 @@ def wgrad(op: Op, dy: torch.Tensor, N: int, dims, gw: torch.Tensor, dy_coff: int
 def bn_affine(bn: torch.nn.BatchNorm2d, stats, count: float, arena: Arena, training: bool):
     """statistics -> (scale, shift, mean, rstd); updates the running buffers in training."""
     C = bn.num_features
-    buf = arena.take(4 * C)
-    scale, shift, mean, rstd = buf[:C], buf[C:2 * C], buf[2 * C:3 * C], buf[3 * C:]
+    scale, shift, mean, rstd = arena.take(C), arena.take(C), arena.take(C), arena.take(C)
     mom = 0.1 if bn.momentum is None else bn.momentum
     track = bn.track_running_stats and bn.running_mean is not None
     _call("accx_bn_finalize", C, float(count), ptr(stats), ptr(f32(bn.weight)), ptr(f32(bn.bias)), float(bn.eps),
@@ -304,11 +303,9 @@ def se_fwd(L: Lazy, se, arena: Arena, training: bool, residual=None, mix=None, s
     c = SECtx()
     c.L, c.mod, c.residual, c.mix, c.mix_param = L, se, residual, mix, mix_param
     c.S = arena.take(2 * B * C)
-    buf = arena.take(B * C + B * Cr + 4 * C + 1)
-    c.gate, c.hidden = buf[:B * C], buf[B * C:B * C + B * Cr]
-    o = B * C + B * Cr
-    c.scale, c.shift, c.mean, c.rstd = buf[o:o + C], buf[o + C:o + 2 * C], buf[o + 2 * C:o + 3 * C], buf[o + 3 * C:o + 4 * C]
-    counter = buf[o + 4 * C:o + 4 * C + 1]
+    c.gate, c.hidden = arena.take(B * C), arena.take(B * Cr)      # every slice 256-byte aligned
+    c.scale, c.shift, c.mean, c.rstd = arena.take(C), arena.take(C), arena.take(C), arena.take(C)
+    counter = arena.take(1)
     d = dt(y)
     _call("accx_se_squeeze", d, B, H * W, C, ptr(y), ptr(L.scale), ptr(L.shift), L.act, ptr(c.S), stream())
     bn = se.bn

@@ -87,3 +87,22 @@ def whole_model_checks(name, case, y, gin, grads, updates, slack=3.0, floor=2e-3
     for k, v in case["upd"].items():
         if k in updates:
             close(updates[k].float(), v, 1e-3, 2e-3, f"{name} buffer {k}")
+
+
+def close_frac(a, b, rtol, atol_rel, what, max_frac):
+    """like close(), but lets a fraction `max_frac` of the elements miss the tolerance: gradients that
+    pass through max-pool / LeakyReLU are discontinuous in the activations, so a rounding-level
+    difference at a near-tie re-routes an isolated element (the reference on another device does too)."""
+    a = a.detach().double().cpu()
+    b = b.detach().double().cpu()
+    assert a.shape == b.shape, f"{what}: shape {tuple(a.shape)} vs {tuple(b.shape)}"
+    assert torch.isfinite(a).all(), f"{what}: non-finite values"
+    scale = float(b.abs().max()) if b.numel() else 0.0
+    bad = (a - b).abs() > atol_rel * scale + rtol * b.abs()
+    frac = float(bad.double().mean()) if bad.numel() else 0.0
+    assert frac <= max_frac, (f"{what}: {frac:.2e} of elements outside rtol {rtol} / atol {atol_rel * scale:.2e} "
+                              f"(allowed {max_frac:.1e}); rel-l2 {rel_l2(a, b):.2e}")
+
+
+def flat_cat(tensors):
+    return torch.cat([t.detach().double().cpu().reshape(-1) for t in tensors])

@@ -10,6 +10,9 @@ from helpers import close
 pytestmark = pytest.mark.gpu
 
 DEV = "cuda"
+# the torch restatement must be real fp32 (cuDNN/cuBLAS default to TF32 for convolutions)
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
 TOL = {torch.float32: (1e-3, 1e-5), torch.bfloat16: (2e-2, 1e-2)}
 
 

@@ -9,12 +9,15 @@ from oracle import acc_oracle as O
 RTOL, ATOL = 1e-4, 2e-5
 
 
-def run_oracle(name, case, training=True):
-    sd = {k: v.clone() for k, v in case["sd"].items()}
-    for k, v in sd.items():
-        if v.is_floating_point() and "running_" not in k:
-            v.requires_grad_(training)
-    xs = [x.clone().requires_grad_(training) for x in case["in"]]
+def run_oracle(name, case, training=True, prepared=False):
+    if prepared:        # caller already placed / typed / marked the tensors
+        sd, xs = case["sd"], case["in"]
+    else:
+        sd = {k: v.clone() for k, v in case["sd"].items()}
+        for k, v in sd.items():
+            if v.is_floating_point() and "running_" not in k:
+                v.requires_grad_(training)
+        xs = [x.clone().requires_grad_(training) for x in case["in"]]
     cx = O.Ctx(sd, training)
     kind = name.split("_")[0]
     if kind == "se":
