@@ -15,12 +15,26 @@ from . import _lib
 from ._lib import BF16, F32, Operand
 
 LAUNCHES = 0          # number of accx kernels launched by this process (bench.py reports it)
+PROFILE = None        # list -> every launch is bracketed by CUDA events on the launching stream and
+                      # appended as (kernel, start, end, algorithmic_bytes, flops); see bench.py
 
 
-def _call(name, *args):
+def _call(name, *args, cost=(0, 0)):
     global LAUNCHES
     LAUNCHES += 1
+    if PROFILE is None:
+        _lib.call(name, *args)
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     _lib.call(name, *args)
+    e1.record()
+    PROFILE.append((name, e0, e1, cost[0], cost[1]))
+
+
+def nb(*ts) -> int:
+    """bytes of the given tensors (algorithmic traffic accounting: each tensor once)"""
+    return sum(t.numel() * t.element_size() for t in ts if t is not None)
 
 
 def dt(t: torch.Tensor) -> int:
@@ -149,8 +163,17 @@ def conv(ops: Sequence[Op], N: int, dims: Tuple[int, int, int], bias=None, adds:
     for i, (t, l) in enumerate(adds):
         assert t.dtype == torch.float32 and t.shape[-1] == N
         ap[i], al[i] = t.data_ptr(), l
+    P = B * H * W
+    seen, rd = set(), 0
+    for op in ops:          # shifted taps of one tensor / column slices count once per distinct column range
+        key = (op.src.y.data_ptr(), op.coff)
+        if key not in seen:
+            seen.add(key)
+            rd += P * op.K * op.src.y.element_size()
+    rd += sum(t.numel() * 4 for t, _ in adds)
     _call("accx_pw_fwd", in_dt, odt, B, H, W, N, arr, len(ops), ptr(bias), ap, al, len(adds),
-          out.data_ptr() + out_coff * out.element_size(), out.shape[-1], ptr(stats), stream())
+          out.data_ptr() + out_coff * out.element_size(), out.shape[-1], ptr(stats), stream(),
+          cost=(rd + P * N * out.element_size(), 2 * P * N * sum(op.K for op in ops)))
     return out
 
 
@@ -164,7 +187,8 @@ def wgrad(op: Op, dy: torch.Tensor, N: int, dims, gw: torch.Tensor, dy_coff: int
     assert dy_f32 or dt(dy) == in_dt
     _call("accx_pw_wgrad", in_dt, B, H, W, N, ctypes.byref(o), gw.data_ptr() + op.wv.off * 4,
           dy.data_ptr() + dy_coff * dy.element_size(),
-          dy.shape[-1], dy_f32, stream())
+          dy.shape[-1], dy_f32, stream(),
+          cost=(B * H * W * (op.K * op.src.y.element_size() + N * dy.element_size()), 2 * B * H * W * N * op.K))
 
 
 def bn_affine(bn: torch.nn.BatchNorm2d, stats, count: float, arena: Arena, training: bool):
@@ -190,14 +214,14 @@ def materialize(L: Lazy, scale2=None, shift2=None, residual=None, stats=None, ou
     if out is None and not stats_only:
         out = torch.empty_like(y)
     _call("accx_act_apply", dt(y), y.numel() // y.shape[-1], y.shape[-1], ptr(y), ptr(L.scale), ptr(L.shift), L.act,
-          ptr(scale2), ptr(shift2), ptr(residual), ptr(out), ptr(stats), stream())
+          ptr(scale2), ptr(shift2), ptr(residual), ptr(out), ptr(stats), stream(), cost=(nb(y, residual, out), 0))
     return out
 
 
 def add_fwd(L: Lazy, r: torch.Tensor, stats):
     z = torch.empty_like(r)
     _call("accx_add_fwd", dt(r), r.numel() // r.shape[-1], r.shape[-1], ptr(L.y), ptr(L.scale), ptr(L.shift), L.act,
-          ptr(r), ptr(z), ptr(stats), stream())
+          ptr(r), ptr(z), ptr(stats), stream(), cost=(nb(L.y, r, z), 0))
     return z
 
 
@@ -211,12 +235,13 @@ def bn_bwd(L: Lazy, da: torch.Tensor, grads: dict, arena: Arena, out: Optional[t
     dtc = dt(y)
     assert da.dtype == y.dtype and da.is_contiguous()
     _call("accx_bn_bwd_reduce", dtc, P, C, ptr(y), ptr(L.scale), ptr(L.shift), L.act, ptr(L.mean), ptr(L.rstd),
-          ptr(da), ptr(sums), stream())
+          ptr(da), ptr(sums), stream(), cost=(nb(y, da), 0))
     dy = da if out is None else out
     gg = grad_buf(grads, L.bn.weight)
     gb = grad_buf(grads, L.bn.bias)
     _call("accx_bn_bwd_apply", dtc, P, C, ptr(y), ptr(L.scale), ptr(L.shift), L.act, ptr(L.mean), ptr(L.rstd),
-          ptr(f32(L.bn.weight)), ptr(da), ptr(sums), float(P), ptr(dy), ptr(gg), ptr(gb), stream())
+          ptr(f32(L.bn.weight)), ptr(da), ptr(sums), float(P), ptr(dy), ptr(gg), ptr(gb), stream(),
+          cost=(nb(y, da, dy), 0))
     return dy
 
 
@@ -236,14 +261,15 @@ def dw_fwd(L: Lazy, w, bias, stats, flip=False):
     B, H, W, C = y.shape
     out = torch.empty_like(y)
     _call("accx_dw3x3_fwd", dt(y), B, H, W, C, ptr(y), ptr(L.scale), ptr(L.shift), L.act, ptr(w), ptr(bias),
-          1 if flip else 0, ptr(out), ptr(stats), stream())
+          1 if flip else 0, ptr(out), ptr(stats), stream(), cost=(nb(y, out), 18 * y.numel()))
     return out
 
 
 def dw_wgrad(L: Lazy, dy: torch.Tensor, gw: torch.Tensor):
     y = L.y
     B, H, W, C = y.shape
-    _call("accx_dw3x3_wgrad", dt(y), B, H, W, C, ptr(y), ptr(L.scale), ptr(L.shift), L.act, ptr(dy), ptr(gw), stream())
+    _call("accx_dw3x3_wgrad", dt(y), B, H, W, C, ptr(y), ptr(L.scale), ptr(L.shift), L.act, ptr(dy), ptr(gw), stream(),
+          cost=(nb(y, dy), 18 * y.numel()))
 
 
 def hanc_pools(L: Lazy, k: int) -> List[torch.Tensor]:
@@ -254,7 +280,7 @@ def hanc_pools(L: Lazy, k: int) -> List[torch.Tensor]:
     for l in range(1, k):
         out = torch.empty((B, H >> l, W >> l, 2 * C), dtype=L.y.dtype, device=L.y.device)
         _call("accx_hanc_pool_fwd", dt(L.y), B, H >> (l - 1), W >> (l - 1), C, first, ptr(cur), ptr(L.scale),
-              ptr(L.shift), L.act, ptr(out), stream())
+              ptr(L.shift), L.act, ptr(out), stream(), cost=(nb(cur, out), 0))
         outs.append(out)
         cur, first = out, 0
     return outs
@@ -264,13 +290,13 @@ def hanc_unpool_bwd(L: Lazy, l: int, dpool: torch.Tensor, da: torch.Tensor, accu
     B, H, W, C = L.y.shape
     assert dpool.dtype == torch.float32
     _call("accx_hanc_unpool_bwd", dt(L.y), B, H, W, C, l, ptr(L.y), ptr(L.scale), ptr(L.shift), L.act, ptr(dpool),
-          ptr(da), 1 if accumulate else 0, stream())
+          ptr(da), 1 if accumulate else 0, stream(), cost=(nb(L.y, dpool, da) + (nb(da) if accumulate else 0), 0))
 
 
 def pool_sum(x: torch.Tensor, l: int, mul: float, out_dtype: Optional[torch.dtype] = None):
     B, H, W, C = x.shape
     out = torch.empty((B, H >> l, W >> l, C), dtype=out_dtype or x.dtype, device=x.device)
-    _call("accx_pool_sum", dt(x), dt(out), B, H, W, C, l, float(mul), ptr(x), ptr(out), C, stream())
+    _call("accx_pool_sum", dt(x), dt(out), B, H, W, C, l, float(mul), ptr(x), ptr(out), C, stream(), cost=(nb(x, out), 0))
     return out
 
 
@@ -279,13 +305,15 @@ def upsample_add(src: torch.Tensor, dst: torch.Tensor, l: int, mul: float, accum
     C = Cd if C is None else C
     assert C == Cd
     _call("accx_upsample_add", dt(src), dt(dst), B, H, W, C, l, float(mul), src.data_ptr() + src_coff * src.element_size(),
-          src.shape[-1], ptr(dst), 1 if accumulate else 0, stream())
+          src.shape[-1], ptr(dst), 1 if accumulate else 0, stream(),
+          cost=(nb(dst) * (2 if accumulate else 1) + src.numel() // src.shape[-1] * C * src.element_size(), 0))
 
 
 def add_inplace(dst: torch.Tensor, other: torch.Tensor):
     """dst += other (same shape/dtype), as one accx pass"""
     C = dst.shape[-1]
-    _call("accx_act_apply", dt(dst), dst.numel() // C, C, ptr(dst), 0, 0, 0, 0, 0, ptr(other), ptr(dst), 0, stream())
+    _call("accx_act_apply", dt(dst), dst.numel() // C, C, ptr(dst), 0, 0, 0, 0, 0, ptr(other), ptr(dst), 0, stream(),
+          cost=(3 * nb(dst), 0))
     return dst
 
 
@@ -307,7 +335,8 @@ def se_fwd(L: Lazy, se, arena: Arena, training: bool, residual=None, mix=None, s
     c.scale, c.shift, c.mean, c.rstd = arena.take(C), arena.take(C), arena.take(C), arena.take(C)
     counter = arena.take(1)
     d = dt(y)
-    _call("accx_se_squeeze", d, B, H * W, C, ptr(y), ptr(L.scale), ptr(L.shift), L.act, ptr(c.S), stream())
+    _call("accx_se_squeeze", d, B, H * W, C, ptr(y), ptr(L.scale), ptr(L.shift), L.act, ptr(c.S), stream(),
+          cost=(nb(y), 0))
     bn = se.bn
     mom = 0.1 if bn.momentum is None else bn.momentum
     _call("accx_se_gate", B, C, Cr, float(H * W), ptr(c.S), ptr(f32(se.fc1.weight)), ptr(f32(se.fc1.bias)),
@@ -316,7 +345,7 @@ def se_fwd(L: Lazy, se, arena: Arena, training: bool, residual=None, mix=None, s
           ptr(c.gate), ptr(c.hidden), ptr(c.scale), ptr(c.shift), ptr(c.mean), ptr(c.rstd), ptr(counter), stream())
     out = torch.empty_like(y)
     _call("accx_se_apply", d, B, H * W, C, ptr(y), ptr(L.scale), ptr(L.shift), L.act, ptr(c.gate), ptr(c.scale),
-          ptr(c.shift), ptr(residual), ptr(mix), ptr(out), ptr(stats), stream())
+          ptr(c.shift), ptr(residual), ptr(mix), ptr(out), ptr(stats), stream(), cost=(nb(y, residual, out), 0))
     return out, c
 
 
@@ -334,7 +363,8 @@ def se_bwd(c: SECtx, dout: torch.Tensor, grads: dict, arena: Arena, da: Optional
     PQR = arena.take(3 * B * C)
     gmix = grad_buf(grads, c.mix_param) if c.mix_param is not None else None
     _call("accx_se_bwd_reduce", d, B, H * W, C, ptr(y), ptr(L.scale), ptr(L.shift), L.act, ptr(c.gate), ptr(c.scale),
-          ptr(c.shift), ptr(dout), ptr(c.mix), ptr(c.residual) if gmix is not None else 0, ptr(gmix), ptr(G), stream())
+          ptr(c.shift), ptr(dout), ptr(c.mix), ptr(c.residual) if gmix is not None else 0, ptr(gmix), ptr(G), stream(),
+          cost=(nb(y, dout), 0))
     _call("accx_se_bwd_gate", B, C, Cr, float(H * W), ptr(c.S), ptr(G), ptr(c.gate), ptr(c.hidden),
           ptr(f32(se.fc1.weight)), ptr(f32(se.fc2.weight)), ptr(f32(se.bn.weight)), ptr(c.mean), ptr(c.rstd),
           ptr(grad_buf(grads, se.fc1.weight)), ptr(grad_buf(grads, se.fc1.bias)), ptr(grad_buf(grads, se.fc2.weight)),
@@ -344,7 +374,8 @@ def se_bwd(c: SECtx, dout: torch.Tensor, grads: dict, arena: Arena, da: Optional
         da = torch.empty_like(y)
         accumulate = False
     _call("accx_se_bwd_apply", d, B, H * W, C, ptr(y), ptr(L.scale), ptr(L.shift), L.act, ptr(c.gate), ptr(c.scale),
-          ptr(c.shift), ptr(dout), ptr(c.mix), ptr(PQR), ptr(da), 1 if accumulate else 0, stream())
+          ptr(c.shift), ptr(dout), ptr(c.mix), ptr(PQR), ptr(da), 1 if accumulate else 0, stream(),
+          cost=(nb(y, dout, da), 0))
     return da
 
 
