@@ -38,7 +38,7 @@ def parse_header(path: str = HEADER):
     src = open(path).read()
     src = re.sub(r"/\*.*?\*/", " ", src, flags=re.S)
     protos = {}
-    for m in re.finditer(r"(const char\*|int)\s+(accx_\w+)\s*\(([^)]*)\)\s*;", src):
+    for m in re.finditer(r"(const char\*|int64_t|int)\s+(accx_\w+)\s*\(([^)]*)\)\s*;", src):
         ret, name, args = m.group(1), m.group(2), m.group(3).strip()
         types, names = [], []
         if args and args != "void":
@@ -51,7 +51,8 @@ def parse_header(path: str = HEADER):
                     types.append(ctypes.POINTER(Operand) if "accx_operand_t" in ty else ctypes.c_void_p)
                 else:
                     types.append(_SCALARS[ty.replace("const ", "")])
-        protos[name] = (ctypes.c_char_p if "char" in ret else ctypes.c_int, types, names)
+        rt = ctypes.c_char_p if "char" in ret else (ctypes.c_int64 if ret == "int64_t" else ctypes.c_int)
+        protos[name] = (rt, types, names)
     return protos
 
 

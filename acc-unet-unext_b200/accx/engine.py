@@ -14,7 +14,11 @@ import torch
 from . import _lib
 from ._lib import BF16, F32, Operand
 
+import os
+
+TC = os.environ.get("ACCX_TC", "1") != "0"   # tcgen05 tensor-core contraction for bf16 activations
 LAUNCHES = 0          # number of accx kernels launched by this process (bench.py reports it)
+LAUNCHES_EXTRA = [0]  # kernels launched inside an accx call beyond the first (weight re-pack)
 PROFILE = None        # list -> every launch is bracketed by CUDA events on the launching stream and
                       # appended as (kernel, start, end, algorithmic_bytes, flops); see bench.py
 
@@ -171,9 +175,17 @@ def conv(ops: Sequence[Op], N: int, dims: Tuple[int, int, int], bias=None, adds:
             seen.add(key)
             rd += P * op.K * op.src.y.element_size()
     rd += sum(t.numel() * 4 for t, _ in adds)
-    _call("accx_pw_fwd", in_dt, odt, B, H, W, N, arr, len(ops), ptr(bias), ap, al, len(adds),
-          out.data_ptr() + out_coff * out.element_size(), out.shape[-1], ptr(stats), stream(),
-          cost=(rd + P * N * out.element_size(), 2 * P * N * sum(op.K for op in ops)))
+    cost = (rd + P * N * out.element_size(), 2 * P * N * sum(op.K for op in ops))
+    yptr = out.data_ptr() + out_coff * out.element_size()
+    if TC and in_dt == BF16 and all(o.K % 8 == 0 and o.ld % 8 == 0 and o.data % 16 == 0 for o in arr):
+        ws_bytes = _lib.load().accx_pw_tc_workspace_bytes(N, arr, len(ops))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=out.device)
+        LAUNCHES_EXTRA[0] += 1          # the weight re-pack kernel
+        _call("accx_pw_fwd_tc", in_dt, odt, B, H, W, N, arr, len(ops), ptr(bias), ap, al, len(adds),
+              yptr, out.shape[-1], ptr(stats), ptr(ws), ws_bytes, stream(), cost=cost)
+    else:
+        _call("accx_pw_fwd", in_dt, odt, B, H, W, N, arr, len(ops), ptr(bias), ap, al, len(adds),
+              yptr, out.shape[-1], ptr(stats), stream(), cost=cost)
     return out
 
 

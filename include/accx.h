@@ -73,6 +73,17 @@ int accx_pw_fwd(int dtype, int out_dtype, int B, int H, int W, int N,
                 const float* const* add, const int* add_log2s, int n_add,
                 void* y, int64_t ldy, float* stats, void* stream);
 
+/* Same contract as accx_pw_fwd on the tcgen05 tensor cores (bf16 operands, fp32 accumulation in
+ * TMEM): producer warps apply the pending BatchNorm affine + LeakyReLU while staging the
+ * 128B-swizzled A tiles, weights arrive by bulk TMA from a bf16 re-pack made in `workspace`
+ * (accx_pw_tc_workspace_bytes gives its size).  Requires every operand K and ld to be a multiple
+ * of 8 elements and 16-byte aligned bases; otherwise use accx_pw_fwd. */
+int64_t accx_pw_tc_workspace_bytes(int N, const accx_operand_t* ops, int n_ops);
+int accx_pw_fwd_tc(int dtype, int out_dtype, int B, int H, int W, int N,
+                   const accx_operand_t* ops, int n_ops, const float* bias,
+                   const float* const* add, const int* add_log2s, int n_add,
+                   void* y, int64_t ldy, float* stats, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* dW[n*w_ld + k*w_ks] += sum_p dY[p, n] * value(p, k)  for one operand (weight gradient of the
  * contraction above; fp32 atomics).  dy is a plain [P, ldy] matrix in `dtype` storage
  * (or fp32 when dy_f32 != 0). */

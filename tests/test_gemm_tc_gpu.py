@@ -1,0 +1,117 @@
+"""GPU: the tcgen05/TMEM contraction (accx_pw_fwd_tc) against a torch fp32 restatement computed
+from the same bf16 inputs.  bf16 operands, fp32 accumulation: rtol 2e-2, atol 1e-2 * max."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import close
+from test_kernels_gpu import DEV, E, mk_lazy, lrelu
+
+pytestmark = pytest.mark.gpu
+RT, AT = 2e-2, 1e-2
+
+
+def bf(x):
+    return x.to(torch.bfloat16).float()
+
+
+@pytest.fixture(autouse=True)
+def tc_on():
+    e = E()
+    old = e.TC
+    e.TC = True
+    yield
+    e.TC = old
+
+
+@pytest.mark.parametrize("P_shape", [(2, 12, 20), (1, 16, 8), (3, 7, 11)])
+@pytest.mark.parametrize("K,N,act", [(32, 96, 0), (96, 32, 2), (480, 64, 1), (128, 136, 2), (16, 256, 2), (64, 272, 2),
+                                     (8, 8, 0), (1088, 128, 2), (24, 40, 2)])
+def test_tc_single_operand(P_shape, K, N, act):
+    e = E()
+    B, H, W = P_shape
+    L, a = mk_lazy((B, H, W, K), torch.bfloat16, act, 1)
+    g = torch.Generator().manual_seed(2)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV)
+    b = torch.randn(N, generator=g).to(DEV)
+    stats = torch.zeros(2 * N, device=DEV)
+    n0 = e.LAUNCHES_EXTRA[0]
+    y = e.conv([e.Op(L, K, e.WV(w, 0, K, 1))], N, (B, H, W), bias=b, stats=stats)
+    assert e.LAUNCHES_EXTRA[0] == n0 + 1, "tensor-core path was not taken"
+    ref = bf(a) @ bf(w).t() + b
+    close(y.float(), ref, RT, AT, "tc pw_fwd")
+    close(stats[:N], ref.sum((0, 1, 2)), 2e-2, 2e-2, "tc stats sum")
+    close(stats[N:], (ref * ref).sum((0, 1, 2)), 2e-2, 2e-2, "tc stats sumsq")
+
+
+def test_tc_matches_simt_path_bitwise_inputs():
+    """same call through both paths (tensor cores vs CUDA cores)"""
+    e = E()
+    B, H, W, K, N = 2, 24, 24, 192, 64
+    L, a = mk_lazy((B, H, W, K), torch.bfloat16, 2, 3)
+    w = (torch.randn(N, K, generator=torch.Generator().manual_seed(4)) / K ** 0.5).to(DEV)
+    y_tc = e.conv([e.Op(L, K, e.WV(w, 0, K, 1))], N, (B, H, W), out_dtype=e.F32)
+    e.TC = False
+    y_simt = e.conv([e.Op(L, K, e.WV(w, 0, K, 1))], N, (B, H, W), out_dtype=e.F32)
+    close(y_tc, y_simt, 1e-2, 1e-2, "tc vs simt")
+
+
+def test_tc_multi_operand_strided_weights_adds_fp32_out():
+    e = E()
+    B, H, W, C, N = 2, 8, 16, 24, 40
+    L0, a0 = mk_lazy((B, H, W, C), torch.bfloat16, 2, 3)
+    L1, a1 = mk_lazy((B, H, W, C), torch.bfloat16, 0, 4)
+    g = torch.Generator().manual_seed(5)
+    w = (torch.randn(N, 2 * C, generator=g) / C ** 0.5).to(DEV)
+    add1 = torch.randn(B, H // 2, W // 2, N, generator=g).to(DEV)
+    add2 = torch.randn(B, H // 4, W // 4, N, generator=g).to(DEV)
+    y = e.conv([e.Op(L0, C, e.WV(w, 0, 2 * C, 2)), e.Op(L1, C, e.WV(w, 1, 2 * C, 2))], N, (B, H, W),
+               adds=[(add1, 1), (add2, 2)], out_dtype=e.F32)
+    ref = bf(a0) @ bf(w[:, 0::2]).t() + bf(a1) @ bf(w[:, 1::2]).t()
+    ref = ref + add1.repeat_interleave(2, 1).repeat_interleave(2, 2) + add2.repeat_interleave(4, 1).repeat_interleave(4, 2)
+    assert y.dtype == torch.float32
+    close(y, ref, RT, AT, "tc multi")
+
+
+def test_tc_column_slices_and_sliced_output():
+    e = E()
+    B, H, W, C, N = 1, 4, 8, 16, 8
+    L, a = mk_lazy((B, H, W, 2 * C), torch.bfloat16, 0, 6)
+    w = torch.randn(N, 5 * C, generator=torch.Generator().manual_seed(7)).to(DEV) / 4
+    out = torch.zeros(B, H, W, 3 * N, device=DEV, dtype=torch.float32)
+    e.conv([e.Op(L, C, e.WV(w, 1, 5 * C, 5), 0), e.Op(L, C, e.WV(w, 3, 5 * C, 5), C)], N, (B, H, W), out=out, out_coff=N)
+    ref = bf(a[..., :C]) @ bf(w[:, 1::5]).t() + bf(a[..., C:]) @ bf(w[:, 3::5]).t()
+    close(out[..., N:2 * N], ref, RT, AT, "tc sliced out")
+    assert float(out[..., :N].abs().max()) == 0 and float(out[..., 2 * N:].abs().max()) == 0
+
+
+@pytest.mark.parametrize("C", [8, 32, 72])
+def test_tc_dense3x3_nine_shifted_operands(C):
+    e = E()
+    B, H, W = 2, 9, 12
+    L, a = mk_lazy((B, H, W, C), torch.bfloat16, 0, 8)
+    g = torch.Generator().manual_seed(9)
+    w = (torch.randn(C, C, 3, 3, generator=g) / (3 * C ** 0.5)).to(DEV)
+    b = torch.randn(C, generator=g).to(DEV)
+    ops = [e.Op(L, C, e.WV(w, ky * 3 + kx, C * 9, 9), 0, ky - 1, kx - 1) for ky in range(3) for kx in range(3)]
+    y = e.conv(ops, C, (B, H, W), bias=b)
+    torch.backends.cudnn.allow_tf32 = False
+    ref = F.conv2d(bf(a).permute(0, 3, 1, 2), bf(w), b, padding=1).permute(0, 2, 3, 1)
+    close(y.float(), ref, RT, AT, "tc conv3x3")
+
+
+def test_tc_large_tile_count_and_k_pipeline():
+    """many M tiles, 17 N tiles (N=4352, the cnv72.conv1 shape) and a deep K loop (cnv72.hnc main: K=4352)"""
+    e = E()
+    B, H, W = 2, 28, 28
+    L, a = mk_lazy((B, H, W, 128), torch.bfloat16, 0, 11)
+    w = (torch.randn(4352, 128, generator=torch.Generator().manual_seed(12)) / 11.3).to(DEV)
+    y = e.conv([e.Op(L, 128, e.WV(w, 0, 128, 1))], 4352, (B, H, W))
+    close(y.float(), bf(a) @ bf(w).t(), RT, AT, "tc N=4352")
+    L2, a2 = mk_lazy((B, H, W, 4352), torch.bfloat16, 2, 13)
+    w2 = (torch.randn(128, 4352, generator=torch.Generator().manual_seed(14)) / 66.0).to(DEV)
+    stats = torch.zeros(256, device=DEV)
+    y2 = e.conv([e.Op(L2, 4352, e.WV(w2, 0, 4352, 1))], 128, (B, H, W), stats=stats)
+    ref2 = bf(a2) @ bf(w2).t()
+    close(y2.float(), ref2, RT, AT, "tc K=4352")
+    close(stats[:128], ref2.sum((0, 1, 2)), 2e-2, 2e-2, "tc K=4352 stats")
