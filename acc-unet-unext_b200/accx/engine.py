@@ -23,7 +23,7 @@ PROFILE = None        # list -> every launch is bracketed by CUDA events on the 
                       # appended as (kernel, start, end, algorithmic_bytes, flops); see bench.py
 
 
-def _call(name, *args, cost=(0, 0)):
+def _call(name, *args, cost=(0, 0), tag=""):
     global LAUNCHES
     LAUNCHES += 1
     if PROFILE is None:
@@ -33,7 +33,7 @@ def _call(name, *args, cost=(0, 0)):
     e0.record()
     _lib.call(name, *args)
     e1.record()
-    PROFILE.append((name, e0, e1, cost[0], cost[1]))
+    PROFILE.append((name, e0, e1, cost[0], cost[1], tag))
 
 
 def nb(*ts) -> int:
@@ -182,10 +182,12 @@ def conv(ops: Sequence[Op], N: int, dims: Tuple[int, int, int], bias=None, adds:
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=out.device)
         LAUNCHES_EXTRA[0] += 1          # the weight re-pack kernel
         _call("accx_pw_fwd_tc", in_dt, odt, B, H, W, N, arr, len(ops), ptr(bias), ap, al, len(adds),
-              yptr, out.shape[-1], ptr(stats), ptr(ws), ws_bytes, stream(), cost=cost)
+              yptr, out.shape[-1], ptr(stats), ptr(ws), ws_bytes, stream(), cost=cost,
+              tag=f"P={P} N={N} K={[o.K for o in ops]} shift={any(o.dy or o.dx for o in ops)} adds={len(adds)}")
     else:
         _call("accx_pw_fwd", in_dt, odt, B, H, W, N, arr, len(ops), ptr(bias), ap, al, len(adds),
-              yptr, out.shape[-1], ptr(stats), stream(), cost=cost)
+              yptr, out.shape[-1], ptr(stats), stream(), cost=cost,
+              tag=f"P={P} N={N} K={[o.K for o in ops]} in={in_dt} out={odt}")
     return out
 
 
@@ -200,7 +202,8 @@ def wgrad(op: Op, dy: torch.Tensor, N: int, dims, gw: torch.Tensor, dy_coff: int
     _call("accx_pw_wgrad", in_dt, B, H, W, N, ctypes.byref(o), gw.data_ptr() + op.wv.off * 4,
           dy.data_ptr() + dy_coff * dy.element_size(),
           dy.shape[-1], dy_f32, stream(),
-          cost=(B * H * W * (op.K * op.src.y.element_size() + N * dy.element_size()), 2 * B * H * W * N * op.K))
+          cost=(B * H * W * (op.K * op.src.y.element_size() + N * dy.element_size()), 2 * B * H * W * N * op.K),
+          tag=f"P={B * H * W} N={N} K={op.K} shift={bool(op.dy or op.dx)}")
 
 
 def bn_affine(bn: torch.nn.BatchNorm2d, stats, count: float, arena: Arena, training: bool):

@@ -118,7 +118,7 @@ def run_reference(args, rank):
 def kernel_table(profile):
     torch.cuda.synchronize()
     agg = {}
-    for name, e0, e1, nbytes, flops in profile:
+    for name, e0, e1, nbytes, flops, _tag in profile:
         a = agg.setdefault(name, [0, 0.0, 0, 0])
         a[0] += 1
         a[1] += e0.elapsed_time(e1)
@@ -234,6 +234,7 @@ def main():
         eager(x_dev, m_dev)
         t_e1.record()
         agg = kernel_table(E.PROFILE)
+        calls = sorted(((e0.elapsed_time(e1), n_, tg, nb_, fl_) for n_, e0, e1, nb_, fl_, tg in E.PROFILE), reverse=True)[:40]
         E.PROFILE = None
         step_ms = t_e0.elapsed_time(t_e1)
         tot = sum(a[1] for a in agg.values())
@@ -252,7 +253,10 @@ def main():
                      "gb_per_s": a[2] / max(a[1], 1e-9) / 1e6, "tflop_per_s": a[3] / max(a[1], 1e-9) / 1e9}
                  for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1])}
         if args.kernel_table:
-            json.dump({"step_ms_eager": step_ms, "accx_ms": tot, "kernels": table}, open(args.kernel_table, "w"), indent=1)
+            json.dump({"step_ms_eager": step_ms, "accx_ms": tot, "kernels": table,
+                       "slowest_calls": [{"ms": c[0], "kernel": c[1], "shape": c[2], "gb_per_s": c[3] / max(c[0], 1e-9) / 1e6,
+                                          "tflop_per_s": c[4] / max(c[0], 1e-9) / 1e9} for c in calls]},
+                      open(args.kernel_table, "w"), indent=1)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
