@@ -192,35 +192,43 @@ def conv(ops: Sequence[Op], N: int, dims: Tuple[int, int, int], bias=None, adds:
 
 
 def wgrad(op: Op, dy: torch.Tensor, N: int, dims, gw: torch.Tensor, dy_coff: int = 0):
-    """accx_pw_wgrad: accumulate the weight gradient of one operand into gw (same layout as op.wv.t)."""
+    """accx_pw_wgrad(_tc): accumulate the weight gradient of one operand into gw (same layout as op.wv.t)."""
     B, H, W = dims
     o = Operand()
     _fill(o, op, gw)
     in_dt = dt(op.src.y)
     dy_f32 = 1 if (dy.dtype == torch.float32 and in_dt != F32) else 0
     assert dy_f32 or dt(dy) == in_dt
-    _call("accx_pw_wgrad", in_dt, B, H, W, N, ctypes.byref(o), gw.data_ptr() + op.wv.off * 4,
-          dy.data_ptr() + dy_coff * dy.element_size(),
-          dy.shape[-1], dy_f32, stream(),
-          cost=(B * H * W * (op.K * op.src.y.element_size() + N * dy.element_size()), 2 * B * H * W * N * op.K),
-          tag=f"P={B * H * W} N={N} K={op.K} shift={bool(op.dy or op.dx)}")
+    P = B * H * W
+    cost = (P * (op.K * op.src.y.element_size() + N * dy.element_size()), 2 * P * N * op.K)
+    tag = f"P={P} N={N} K={op.K} shift={bool(op.dy or op.dx)}"
+    dwp = gw.data_ptr() + op.wv.off * 4
+    dyp = dy.data_ptr() + dy_coff * dy.element_size()
+    if (TC and in_dt == BF16 and not dy_f32 and op.K % 8 == 0 and N % 8 == 0 and o.ld % 8 == 0 and dy.shape[-1] % 8 == 0
+            and o.data % 16 == 0 and dyp % 16 == 0):
+        _call("accx_pw_wgrad_tc", B, H, W, N, ctypes.byref(o), dwp, dyp, dy.shape[-1], stream(), cost=cost, tag=tag)
+    else:
+        _call("accx_pw_wgrad", in_dt, B, H, W, N, ctypes.byref(o), dwp, dyp, dy.shape[-1], dy_f32, stream(),
+              cost=cost, tag=tag)
 
 
-def bn_affine(bn: torch.nn.BatchNorm2d, stats, count: float, arena: Arena, training: bool):
+def bn_affine(bn: torch.nn.BatchNorm2d, stats, count: float, arena: Arena, training: bool, conv_bias=None):
     """statistics -> (scale, shift, mean, rstd); updates the running buffers in training."""
     C = bn.num_features
     scale, shift, mean, rstd = arena.take(C), arena.take(C), arena.take(C), arena.take(C)
     mom = 0.1 if bn.momentum is None else bn.momentum
     track = bn.track_running_stats and bn.running_mean is not None
-    _call("accx_bn_finalize", C, float(count), ptr(stats), ptr(f32(bn.weight)), ptr(f32(bn.bias)), float(bn.eps),
+    _call("accx_bn_finalize", C, float(count), ptr(stats), ptr(f32(bn.weight)), ptr(f32(bn.bias)), ptr(f32(conv_bias)),
+          float(bn.eps),
           float(mom), 1 if training else 0, ptr(bn.running_mean) if track else 0, ptr(bn.running_var) if track else 0,
           ptr(bn.num_batches_tracked) if track else 0, ptr(scale), ptr(shift), ptr(mean), ptr(rstd), stream())
     return scale, shift, mean, rstd
 
 
-def bn_lazy(y: torch.Tensor, stats, bn, act: int, arena: Arena, training: bool) -> Lazy:
+def bn_lazy(y: torch.Tensor, stats, bn, act: int, arena: Arena, training: bool, conv_bias=None) -> Lazy:
+    """conv_bias: bias of the conv that produced y and was NOT added to it (folded into the BN here)"""
     count = y.numel() // y.shape[-1]
-    scale, shift, mean, rstd = bn_affine(bn, stats, count, arena, training)
+    scale, shift, mean, rstd = bn_affine(bn, stats, count, arena, training, conv_bias)
     return Lazy(y, scale, shift, act, mean, rstd, bn)
 
 

@@ -89,8 +89,10 @@ def _w(p):
 # =========================================================================================
 def _pw_bn(ops: List[Op], N, dims, conv: nn.Conv2d, bn: nn.BatchNorm2d, act, ar: Arena, training, adds=()):
     st = ar.take(2 * N) if training else None
-    y = E.conv(ops, N, dims, bias=_w(conv.bias), adds=adds, stats=st)
-    return E.bn_lazy(y, st, bn, act, ar, training)
+    # the conv bias is not added to y: a per-channel constant cancels in the BatchNorm that follows, so it is
+    # folded into the BN affine / running mean by accx_bn_finalize and never touches the big tensor
+    y = E.conv(ops, N, dims, adds=adds, stats=st)
+    return E.bn_lazy(y, st, bn, act, ar, training, conv_bias=conv.bias)
 
 
 def _zero_bias_grad(grads, conv):
@@ -136,13 +138,13 @@ def _hanc_core_bwd(hnc, L2: Lazy, pools, dy3: torch.Tensor, grads, ar: Arena, ne
         da2 = E.conv([Op(Lazy(dy3), C, WV(wh, 0, J, J * Ein))], Ein, (B, H, W))
     for l in range(1, k):
         dims_l = (B, H >> l, W >> l)
-        dR = E.pool_sum(dy3, l, 1.0, torch.float32)          # block sums of dY at the pooled resolution
+        dR = E.pool_sum(dy3, l, 1.0)                         # block sums of dY at the pooled resolution
         Pl = Lazy(pools[l - 1])
         if gw is not None:
             E.wgrad(Op(Pl, Ein, WV(wh, l, J * Ein, J), 0), dR, C, dims_l, gw)
             E.wgrad(Op(Pl, Ein, WV(wh, k - 1 + l, J * Ein, J), Ein), dR, C, dims_l, gw)
         if need_da:
-            dP = torch.empty((B, H >> l, W >> l, 2 * Ein), dtype=torch.float32, device=dy3.device)
+            dP = torch.empty((B, H >> l, W >> l, 2 * Ein), dtype=torch.float32, device=dy3.device)   # fp32: feeds unpool
             E.conv([Op(Lazy(dR), C, WV(wh, l, J, J * Ein))], Ein, dims_l, out=dP, out_coff=0)
             E.conv([Op(Lazy(dR), C, WV(wh, k - 1 + l, J, J * Ein))], Ein, dims_l, out=dP, out_coff=Ein)
             E.hanc_unpool_bwd(L2, l, dP, da2, accumulate=True)
@@ -600,7 +602,7 @@ class MLFC(_AccxModule):
                         else:
                             E.upsample_add(g, dxs[src], l - src, 1.0 / float(4 ** (l - src)), accumulate=True)
                 else:         # coarser source, contracted at its own resolution: block-sum dY first
-                    dR = E.pool_sum(dy, src - l, 1.0, torch.float32)
+                    dR = E.pool_sum(dy, src - l, 1.0)
                     if gw is not None:
                         E.wgrad(Op(Lazy(xs[src]), Cs, wv), dR, C, dims[src], gw)
                     g = E.conv([Op(Lazy(dR), C, wvt)], Cs, dims[src], out_dtype=E.dt(xs[src]))

@@ -27,12 +27,14 @@ int check_launch(const char* what) {
 
 // --------------------------------------------------------------------------------------
 __global__ void bn_finalize_kernel(int C, double count, const float* __restrict__ stats,
-                                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   const float* __restrict__ conv_bias, float eps,
                                    float momentum, int training, float* running_mean, float* running_var,
                                    int64_t* nbt, float* scale, float* shift, float* mean_o, float* rstd_o) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c == 0 && training && nbt) *nbt += 1;
   if (c >= C) return;
+  const float cb = conv_bias ? conv_bias[c] : 0.f;   // bias of the producing conv, folded here
   float mean, var;
   if (training) {
     double m = (double)stats[c] / count;
@@ -42,11 +44,11 @@ __global__ void bn_finalize_kernel(int C, double count, const float* __restrict_
     var = (float)v;
     if (running_mean) {
       double unb = count > 1 ? v * count / (count - 1) : v;
-      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (mean + cb);
       running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
     }
   } else {
-    mean = running_mean[c];
+    mean = running_mean[c] - cb;
     var = running_var[c];
   }
   float rstd = rsqrtf(var + eps);
@@ -329,14 +331,15 @@ extern "C" {
 const char* accx_last_error(void) { return g_err; }
 int accx_version(void) { return 100; }
 
-int accx_bn_finalize(int C, double count, const float* stats, const float* gamma, const float* beta, float eps,
-                     float momentum, int training, float* running_mean, float* running_var, int64_t* nbt,
+int accx_bn_finalize(int C, double count, const float* stats, const float* gamma, const float* beta,
+                     const float* conv_bias, float eps, float momentum, int training, float* running_mean, float* running_var, int64_t* nbt,
                      float* scale, float* shift, float* mean, float* rstd, void* stream) {
   ACCX_REQUIRE(C > 0 && gamma && beta && scale && shift, "bn_finalize: bad arguments");
   ACCX_REQUIRE(training ? (stats != nullptr && count > 0) : (running_mean && running_var),
                "bn_finalize: missing statistics");
   bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
-      C, count, stats, gamma, beta, eps, momentum, training, running_mean, running_var, nbt, scale, shift, mean, rstd);
+      C, count, stats, gamma, beta, conv_bias, eps, momentum, training, running_mean, running_var, nbt, scale, shift,
+      mean, rstd);
   return check_launch("bn_finalize");
 }
 

@@ -2,25 +2,27 @@
 // fp32 accumulation.  Same contract as accx_pw_fwd (gemm_simt.cu): several lazy / shifted
 // operands with strided weight views, bias, nearest-upsample-adds, per-channel statistics.
 //
-//   CTA = one 128 x BN output tile (BN <= 256), 192 threads, several CTAs per SM when K is small:
-//     warp 4     TMA producer (one lane): per 64-channel k-block one cp.async.bulk.tensor.2d of the
-//                raw 128 x 64 activation box (128B swizzle, OOB rows/columns zero-filled) and one
-//                cp.async.bulk of the pre-packed bf16 weight tile, both completing on `landed[s]`.
-//     warps 0-3  transform: the pending BatchNorm affine + LeakyReLU of the producing layer is
-//                applied IN PLACE on the landed tile (16 B per thread, same swizzle), and rows whose
-//                3x3 tap falls outside the image are zeroed -- so the normalised/activated tensor
-//                never exists in HBM -- then fence.proxy.async + arrive on `full[s]`.
-//                Afterwards the same warps run the epilogue: tcgen05.ld -> bias / upsample-adds ->
-//                padded smem tile -> per-channel (sum, sum^2) + coalesced 16 B stores.
-//     warp 5     MMA issuer (one lane): tcgen05.mma M=128, N=BN, K=16, four per k-block, accumulators
-//                in TMEM; tcgen05.commit frees the stage / signals the epilogue.  Owns the TMEM alloc.
-#include <cuda.h>
-
-#include "common.cuh"
+//   Persistent kernel: grid = SMs x (1 or 2) CTAs, each CTA walks output tiles of 128 pixels x BN
+//   channels (BN <= 256); 320 threads in four roles that overlap across tiles:
+//     warp 8     TMA producer (one lane): per 64-channel k-block one cp.async.bulk.tensor.2d of the
+//                raw 128 x 64 activation box (128B swizzle, OOB rows/columns zero-filled) completing on
+//                `landed[s]`; the pre-packed bf16 weight tiles come by cp.async.bulk -- once per CTA
+//                when the whole weight matrix fits in shared memory, else one tile per stage.
+//     warps 4-7  transform: the pending BatchNorm affine + LeakyReLU of the producing layer is applied
+//                IN PLACE on the landed tile (16 B per thread, same swizzle), rows whose 3x3 tap falls
+//                outside the image are zeroed -- the normalised/activated tensor never exists in HBM --
+//                then fence.proxy.async + arrive on `full[s]`.
+//     warp 9     MMA issuer (one lane): tcgen05.mma M=128, N=BN, K=16, four per k-block, into one of
+//                two TMEM accumulator buffers; tcgen05.commit frees the smem stage / hands the
+//                accumulator to the epilogue.  Owns the TMEM allocation.
+//     warps 0-3  epilogue: tcgen05.ld -> (+bias, +nearest-upsampled addends) -> padded smem tile ->
+//                coalesced 16 B stores; per-channel (sum, sum^2) accumulate in registers across all the
+//                CTA's tiles and are flushed with one atomicAdd per channel per CTA.
+#include "tc_common.cuh"
 
 namespace accx {
 
-constexpr int TC_BM = 128, TC_BK = 64, TC_THREADS = 192, TC_A_BYTES = TC_BM * TC_BK * 2;
+constexpr int TC_BM = 128, TC_BK = 64, TC_THREADS = 320, TC_A_BYTES = TC_BM * TC_BK * 2;
 
 struct alignas(64) TcParams {
   CUtensorMap tmap[ACCX_MAX_OPERANDS];
@@ -30,6 +32,7 @@ struct alignas(64) TcParams {
   int B, H, W, N;
   int64_t P;
   int bn, stages, tmem_cols, any_transform, out_f32;
+  int m_tiles, n_tiles, b_resident;
   const bf16* wpack;
   const float* bias;
   const float* add[ACCX_MAX_ADDENDS];
@@ -40,84 +43,6 @@ struct alignas(64) TcParams {
   float* stats;
 };
 
-// ---------------------------------------------------------------- PTX helpers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-  } while (!done);
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::
-          "r"(dst),
-      "l"(map), "r"(c0), "r"(c1), "r"(bar)
-      : "memory");
-}
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem]^T, bf16 x bf16 -> fp32
-__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-      : "memory");
-}
-// K-major, 128B swizzle, 8-row groups 1024 B apart (SBO), sm100 descriptor version 1
-__device__ __forceinline__ uint64_t make_desc_k_sw128(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)1 << 16;            // leading byte offset (unused for swizzled K-major) = 1
-  d |= (uint64_t)(1024 >> 4) << 32;  // stride byte offset
-  d |= (uint64_t)1 << 46;            // version
-  d |= (uint64_t)2 << 61;            // SWIZZLE_128B
-  return d;
-}
-__device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
-  uint32_t r[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
 // ---------------------------------------------------------------- weight packing
 // wpack[(n_tile * n_kb + kb) * bn * 64 + swizzled(n_local, kk)] = bf16(W_op[n, k0 + kk])
 __global__ void tc_pack_weights_kernel(const __grid_constant__ TcParams prm, bf16* __restrict__ wpack) {
@@ -127,7 +52,7 @@ __global__ void tc_pack_weights_kernel(const __grid_constant__ TcParams prm, bf1
   const accx_operand_t& op = prm.op[o];
   const int k0 = (kb - prm.kb_start[o]) * TC_BK;
   bf16* tile = wpack + ((int64_t)nt * prm.n_kb + kb) * prm.bn * TC_BK;
-  for (int idx = threadIdx.x; idx < prm.bn * TC_BK; idx += blockDim.x) {
+  for (int idx = blockIdx.z * blockDim.x + threadIdx.x; idx < prm.bn * TC_BK; idx += gridDim.z * blockDim.x) {
     const int nl = idx / TC_BK, kk = idx % TC_BK;
     const int n = nt * prm.bn + nl, k = k0 + kk;
     float v = 0.f;
@@ -186,21 +111,23 @@ __global__ void __launch_bounds__(TC_THREADS) pw_fwd_tc_kernel(const __grid_cons
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
-  const int bn = prm.bn, S = prm.stages;
-  const uint32_t stage_bytes = TC_A_BYTES + bn * 128;
-  const uint32_t pipe_bytes = S * stage_bytes;
+  const int bn = prm.bn, S = prm.stages, n_kb = prm.n_kb;
+  const uint32_t b_tile_bytes = bn * 128;
+  const uint32_t stage_bytes = TC_A_BYTES + (prm.b_resident ? 0 : b_tile_bytes);
+  const uint32_t bres_off = S * stage_bytes;
+  const uint32_t epi_off = bres_off + (prm.b_resident ? n_kb * b_tile_bytes : 0);
   const uint32_t out_pitch = (prm.out_f32 ? bn * 4 : bn * 2) + 16;     // bytes, odd number of 16 B chunks
-  const uint32_t epi_bytes = TC_BM * out_pitch + 2 * bn * 4;          // staged tile + smem statistics
-  const uint32_t bar_off = ((pipe_bytes > epi_bytes ? pipe_bytes : epi_bytes) + 15u) & ~15u;
+  const uint32_t bar_off = (epi_off + TC_BM * out_pitch + 2 * bn * 4 + 15u) & ~15u;
   const uint32_t landed_bar = base + bar_off;            // S x 8 bytes
   const uint32_t full_bar = landed_bar + 8 * S;
   const uint32_t empty_bar = full_bar + 8 * S;
-  const uint32_t tmem_full_bar = empty_bar + 8 * S;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + bar_off + 24 * S + 8);
+  const uint32_t tfull_bar = empty_bar + 8 * S;          // 2 x 8
+  const uint32_t tempty_bar = tfull_bar + 16;            // 2 x 8
+  const uint32_t bres_bar = tempty_bar + 16;             // 8
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + bar_off + 24 * S + 40);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int64_t m0 = (int64_t)blockIdx.x * TC_BM;
-  const int nt = blockIdx.y, n0 = nt * bn;
+  const int total_tiles = prm.m_tiles * prm.n_tiles;
 
   if (tid == 0) {
     for (int s = 0; s < S; ++s) {
@@ -208,10 +135,14 @@ __global__ void __launch_bounds__(TC_THREADS) pw_fwd_tc_kernel(const __grid_cons
       mbar_init(full_bar + 8 * s, 4);     // the four transform warps
       mbar_init(empty_bar + 8 * s, 1);    // tcgen05.commit
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar + 8 * a, 1);    // tcgen05.commit after the last k-block of a tile
+      mbar_init(tempty_bar + 8 * a, 4);   // the four epilogue warps have drained the accumulator
+    }
+    mbar_init(bres_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 5) {
+  if (warp == 9) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"((uint32_t)prm.tmem_cols)
                  : "memory");
@@ -222,142 +153,177 @@ __global__ void __launch_bounds__(TC_THREADS) pw_fwd_tc_kernel(const __grid_cons
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 4) {
+  if (warp == 8) {
     // ============================== TMA producer ==============================
     if (lane == 0) {
-      int o = 0;
-      for (int kb = 0; kb < prm.n_kb; ++kb) {
-        while (o + 1 < prm.n_ops && kb >= prm.kb_start[o + 1]) ++o;
-        const int stage = kb % S;
-        const uint32_t phase = (kb / S) & 1;
-        mbar_wait(empty_bar + 8 * stage, phase ^ 1);
-        const uint32_t a_smem = base + stage * stage_bytes;
-        const uint32_t bar = landed_bar + 8 * stage;
-        mbar_expect_tx(bar, TC_A_BYTES + bn * 128);
-        const accx_operand_t& op = prm.op[o];
-        const int64_t row0 = m0 + (int64_t)op.dy * prm.W + op.dx;     // may be negative: OOB rows are zero-filled
-        tma_load_2d(a_smem, &prm.tmap[o], (kb - prm.kb_start[o]) * TC_BK, (int)row0, bar);
-        bulk_g2s(a_smem + TC_A_BYTES, prm.wpack + ((int64_t)nt * prm.n_kb + kb) * bn * TC_BK, bn * 128, bar);
+      if (prm.b_resident) {
+        mbar_expect_tx(bres_bar, n_kb * b_tile_bytes);
+        for (int kb = 0; kb < n_kb; ++kb)
+          bulk_g2s(base + bres_off + kb * b_tile_bytes, prm.wpack + (int64_t)kb * bn * TC_BK, b_tile_bytes, bres_bar);
+      }
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nt = tile / prm.m_tiles;
+        const int64_t m0 = (int64_t)(tile % prm.m_tiles) * TC_BM;
+        int o = 0;
+        for (int kb = 0; kb < n_kb; ++kb, ++it) {
+          while (o + 1 < prm.n_ops && kb >= prm.kb_start[o + 1]) ++o;
+          const int stage = it % S;
+          const uint32_t phase = (it / S) & 1;
+          mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+          const uint32_t a_smem = base + stage * stage_bytes;
+          const uint32_t bar = landed_bar + 8 * stage;
+          mbar_expect_tx(bar, TC_A_BYTES + (prm.b_resident ? 0 : b_tile_bytes));
+          const accx_operand_t& op = prm.op[o];
+          const int64_t row0 = m0 + (int64_t)op.dy * prm.W + op.dx;   // may be negative: OOB rows are zero-filled
+          tma_load_2d(a_smem, &prm.tmap[o], (kb - prm.kb_start[o]) * TC_BK, (int)row0, bar);
+          if (!prm.b_resident)
+            bulk_g2s(a_smem + TC_A_BYTES, prm.wpack + ((int64_t)nt * n_kb + kb) * bn * TC_BK, b_tile_bytes, bar);
+        }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // ============================== MMA issuer ================================
     if (lane == 0) {
       // instruction descriptor: D fp32, A/B bf16, both K-major, N = bn, M = 128
       const uint32_t idesc =
           (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       const uint32_t ready_bar = prm.any_transform ? full_bar : landed_bar;
-      for (int kb = 0; kb < prm.n_kb; ++kb) {
-        const int stage = kb % S;
-        const uint32_t phase = (kb / S) & 1;
-        mbar_wait(ready_bar + 8 * stage, phase);
+      if (prm.b_resident) mbar_wait(bres_bar, 0);
+      int it = 0, tl = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
+        const int acc = tl & 1;
+        mbar_wait(tempty_bar + 8 * acc, ((tl >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t a_smem = base + stage * stage_bytes;
-        const uint64_t adesc = make_desc_k_sw128(a_smem);
-        const uint64_t bdesc = make_desc_k_sw128(a_smem + TC_A_BYTES);
+        const uint32_t tmem_d = tmem_base + acc * bn;
+        for (int kb = 0; kb < n_kb; ++kb, ++it) {
+          const int stage = it % S;
+          const uint32_t phase = (it / S) & 1;
+          mbar_wait(ready_bar + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t a_smem = base + stage * stage_bytes;
+          const uint64_t adesc = make_desc_k_sw128(a_smem);
+          const uint64_t bdesc =
+              make_desc_k_sw128(prm.b_resident ? base + bres_off + kb * b_tile_bytes : a_smem + TC_A_BYTES);
 #pragma unroll
-        for (int k = 0; k < TC_BK / 16; ++k)
-          tc_mma(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
-        tc_commit(empty_bar + 8 * stage);
+          for (int k = 0; k < TC_BK / 16; ++k)
+            tc_mma(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+          tc_commit(empty_bar + 8 * stage);
+        }
+        tc_commit(tfull_bar + 8 * acc);
       }
-      tc_commit(tmem_full_bar);
     }
-  } else {
+  } else if (warp >= 4) {
     // ============================== transform warps ===========================
     if (prm.any_transform) {
-      const int c = tid & 7, r0 = tid >> 3;
-      int ph[8], pw[8];
+      const int t = tid - 128;
+      const int c = t & 7, r0 = t >> 3;
       const int HWp = prm.H * prm.W;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int64_t m0 = (int64_t)(tile % prm.m_tiles) * TC_BM;
+        int ph[8], pw[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int64_t p = m0 + r0 + 16 * i;
-        const int rem = (int)((p < prm.P ? p : 0) % HWp);
-        ph[i] = rem / prm.W;
-        pw[i] = rem % prm.W;
-      }
-      int o = 0;
-      for (int kb = 0; kb < prm.n_kb; ++kb) {
-        while (o + 1 < prm.n_ops && kb >= prm.kb_start[o + 1]) ++o;
-        const int stage = kb % S;
-        const uint32_t phase = (kb / S) & 1;
-        mbar_wait(landed_bar + 8 * stage, phase);
-        transform_tile(prm, prm.op[o], (kb - prm.kb_start[o]) * TC_BK, m0, c, r0, ph, pw, base + stage * stage_bytes);
-        fence_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(full_bar + 8 * stage);
-      }
-    }
-    // ============================== epilogue ==================================
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    const int row = warp * 32 + lane;
-    const int64_t p = m0 + row;
-    const bool rvalid = p < prm.P;
-    int64_t addrow[ACCX_MAX_ADDENDS];
-    if (prm.n_add > 0 && rvalid) {
-      const int HWp = prm.H * prm.W;
-      const int b = (int)(p / HWp), rem = (int)(p % HWp);
-      const int h = rem / prm.W, w = rem % prm.W;
-      for (int a = 0; a < prm.n_add; ++a) {
-        const int l = prm.add_log2s[a];
-        addrow[a] = (((int64_t)b * (prm.H >> l) + (h >> l)) * (prm.W >> l) + (w >> l)) * prm.N;
+        for (int i = 0; i < 8; ++i) {
+          const int64_t p = m0 + r0 + 16 * i;
+          const int rem = (int)((p < prm.P ? p : 0) % HWp);
+          ph[i] = rem / prm.W;
+          pw[i] = rem % prm.W;
+        }
+        int o = 0;
+        for (int kb = 0; kb < n_kb; ++kb, ++it) {
+          while (o + 1 < prm.n_ops && kb >= prm.kb_start[o + 1]) ++o;
+          const int stage = it % S;
+          const uint32_t phase = (it / S) & 1;
+          mbar_wait(landed_bar + 8 * stage, phase);
+          transform_tile(prm, prm.op[o], (kb - prm.kb_start[o]) * TC_BK, m0, c, r0, ph, pw, base + stage * stage_bytes);
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(full_bar + 8 * stage);
+        }
       }
     }
-    uint8_t* stage_out = smem;                                  // [128][out_pitch]
-    float* sstat = reinterpret_cast<float*>(smem + TC_BM * out_pitch);   // [2][bn]
+  } else {
+    // ============================== epilogue warps ============================
+    uint8_t* stage_out = smem + epi_off;                                   // [128][out_pitch]
+    float* sstat = reinterpret_cast<float*>(stage_out + TC_BM * out_pitch);  // [2][bn]
     for (int j = tid; j < 2 * bn; j += 128) sstat[j] = 0.f;
-    for (int c0 = 0; c0 < bn; c0 += 16) {
-      float v[16];
-      tc_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + c0, v);
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int n = n0 + c0 + j;
-        float x = 0.f;
-        if (rvalid && n < prm.N) {
-          x = v[j];
-          if (prm.bias) x += __ldg(prm.bias + n);
-          for (int a = 0; a < prm.n_add; ++a) x += __ldg(prm.add[a] + addrow[a] + n);
-        }
-        v[j] = x;
-      }
-      if (prm.out_f32) {
-        float4* dst = reinterpret_cast<float4*>(stage_out + row * out_pitch + c0 * 4);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-      } else {
-        uint32_t w[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * q], v[2 * q + 1]);
-          w[q] = *reinterpret_cast<uint32_t*>(&h2);
-        }
-        uint4* dst = reinterpret_cast<uint4*>(stage_out + row * out_pitch + c0 * 2);
-        dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
-        dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
-      }
-    }
-    tc_fence_before();
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    // read-out: thread (tx, ty) owns 8 consecutive columns (chunk tx) of rows ty, ty+TY, ..
-    const int cpr = bn >> 3;                       // 8-column chunks per row
-    const int TX = cpr < 128 ? cpr : 128, TY = 128 / TX;
-    const int tx = tid % TX, ty = tid / TX;
+    const int cpr = bn >> 3;                       // 8-column chunks per row (<= 32)
+    const int TY = 128 / cpr;
+    const int tx = tid % cpr, ty = tid / cpr;      // read-out role: chunk tx of rows ty, ty+TY, ..
     const bool vec_ok = (prm.N % 8 == 0) && (prm.ldy % 8 == 0) && ((reinterpret_cast<uintptr_t>(prm.y) & 15) == 0);
-    if (ty < TY) {
-      for (int cx = tx; cx < cpr; cx += TX) {
-        const int n = n0 + cx * 8;
-        float s1[8], s2[8];
+    const bool flush_per_tile = prm.n_tiles > 1;
+    float s1[8], s2[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+    for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+    const int row = warp * 32 + lane;
+    const int HWp = prm.H * prm.W;
+    int tl = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
+      const int n0 = (tile / prm.m_tiles) * bn;
+      const int64_t m0 = (int64_t)(tile % prm.m_tiles) * TC_BM;
+      const int acc = tl & 1;
+      const int64_t p = m0 + row;
+      const bool rvalid = p < prm.P;
+      int64_t addrow[ACCX_MAX_ADDENDS];
+      if (prm.n_add > 0 && rvalid) {
+        const int b = (int)(p / HWp), rem = (int)(p % HWp);
+        const int h = rem / prm.W, w = rem % prm.W;
+        for (int a = 0; a < prm.n_add; ++a) {
+          const int l = prm.add_log2s[a];
+          addrow[a] = (((int64_t)b * (prm.H >> l) + (h >> l)) * (prm.W >> l) + (w >> l)) * prm.N;
+        }
+      }
+      mbar_wait(tfull_bar + 8 * acc, (tl >> 1) & 1);
+      tc_fence_after();
+      for (int c0 = 0; c0 < bn; c0 += 16) {
+        float v[16];
+        tc_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + acc * bn + c0, v);
+        if (prm.bias != nullptr || prm.n_add > 0 || !rvalid || n0 + bn > prm.N) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int n = n0 + c0 + j;
+            float x = 0.f;
+            if (rvalid && n < prm.N) {
+              x = v[j];
+              if (prm.bias) x += __ldg(prm.bias + n);
+              for (int a = 0; a < prm.n_add; ++a) x += __ldg(prm.add[a] + addrow[a] + n);
+            }
+            v[j] = x;
+          }
+        }
+        if (prm.out_f32) {
+          float4* dst = reinterpret_cast<float4*>(stage_out + row * out_pitch + c0 * 4);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        } else {
+          uint32_t w[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * q], v[2 * q + 1]);
+            w[q] = *reinterpret_cast<uint32_t*>(&h2);
+          }
+          uint4* dst = reinterpret_cast<uint4*>(stage_out + row * out_pitch + c0 * 2);
+          dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+          dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+        }
+      }
+      // accumulator drained: hand the TMEM buffer back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar + 8 * acc);
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (ty < TY) {
+        const int n = n0 + tx * 8;
         for (int r = ty; r < TC_BM; r += TY) {
           const int64_t pp = m0 + r;
           float x[8];
           if (prm.out_f32) {
-            const float4* src = reinterpret_cast<const float4*>(stage_out + r * out_pitch + cx * 32);
+            const float4* src = reinterpret_cast<const float4*>(stage_out + r * out_pitch + tx * 32);
             const float4 a = src[0], b = src[1];
             x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
           } else {
-            const uint4 u = *reinterpret_cast<const uint4*>(stage_out + r * out_pitch + cx * 16);
+            const uint4 u = *reinterpret_cast<const uint4*>(stage_out + r * out_pitch + tx * 16);
             const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -366,8 +332,10 @@ __global__ void __launch_bounds__(TC_THREADS) pw_fwd_tc_kernel(const __grid_cons
             }
             if (vec_ok && pp < prm.P && n < prm.N) *reinterpret_cast<uint4*>((bf16*)prm.y + pp * prm.ldy + n) = u;
           }
+          if (prm.stats) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) { s1[j] += x[j]; s2[j] = fmaf(x[j], x[j], s2[j]); }
+            for (int j = 0; j < 8; ++j) { s1[j] += x[j]; s2[j] = fmaf(x[j], x[j], s2[j]); }
+          }
           if (pp < prm.P && n < prm.N) {
             if (prm.out_f32 && vec_ok) {
               float* dst = (float*)prm.y + pp * prm.ldy + n;
@@ -381,59 +349,63 @@ __global__ void __launch_bounds__(TC_THREADS) pw_fwd_tc_kernel(const __grid_cons
             }
           }
         }
-        if (prm.stats) {
+      }
+      if (prm.stats && flush_per_tile) {     // the channel block changes between this CTA's tiles
+        if (ty < TY) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            atomicAdd(&sstat[cx * 8 + j], s1[j]);
-            atomicAdd(&sstat[bn + cx * 8 + j], s2[j]);
+            atomicAdd(&sstat[tx * 8 + j], s1[j]);
+            atomicAdd(&sstat[bn + tx * 8 + j], s2[j]);
+            s1[j] = s2[j] = 0.f;
           }
         }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int j = tid; j < bn; j += 128) {
+          if (n0 + j < prm.N) {
+            atomicAdd(prm.stats + n0 + j, sstat[j]);
+            atomicAdd(prm.stats + prm.N + n0 + j, sstat[bn + j]);
+          }
+          sstat[j] = 0.f;
+          sstat[bn + j] = 0.f;
+        }
       }
+      asm volatile("bar.sync 1, 128;" ::: "memory");     // staging tile is reused by the next tile
     }
-    if (prm.stats) {
+    if (prm.stats && !flush_per_tile) {
+      if (ty < TY) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          atomicAdd(&sstat[tx * 8 + j], s1[j]);
+          atomicAdd(&sstat[bn + tx * 8 + j], s2[j]);
+        }
+      }
       asm volatile("bar.sync 1, 128;" ::: "memory");
       for (int j = tid; j < bn; j += 128) {
-        if (n0 + j < prm.N) {
-          atomicAdd(prm.stats + n0 + j, sstat[j]);
-          atomicAdd(prm.stats + prm.N + n0 + j, sstat[bn + j]);
+        if (j < prm.N) {
+          atomicAdd(prm.stats + j, sstat[j]);
+          atomicAdd(prm.stats + prm.N + j, sstat[bn + j]);
         }
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 9) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)prm.tmem_cols)
                  : "memory");
   }
 }
 
 // ---------------------------------------------------------------- host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+struct TcLaunch {
+  size_t smem;
+  int ctas_per_sm;
+};
 
-static EncodeTiledFn get_encode() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = (EncodeTiledFn)p;
-  }
-  return fn;
-}
-
-static size_t tc_smem_bytes(const TcParams& prm) {
-  const size_t stage_bytes = TC_A_BYTES + prm.bn * 128;
-  const size_t pipe = prm.stages * stage_bytes;
-  const size_t pitch = (prm.out_f32 ? prm.bn * 4 : prm.bn * 2) + 16;
-  const size_t epi = TC_BM * pitch + 2 * prm.bn * 4;
-  return 1024 + (pipe > epi ? pipe : epi) + 16 + 24 * prm.stages + 32;
-}
-
-static int tc_geometry(int N, const accx_operand_t* ops, int n_ops, TcParams& prm) {
+// Tile / pipeline geometry.  Weights stay resident in shared memory when the whole matrix fits
+// (small K: the HBM-bound layers); 2 CTAs per SM when shared memory and TMEM (2 x BN columns per
+// CTA, 512 per SM) allow it, else 1.
+static TcLaunch tc_geometry(int N, int64_t P, const accx_operand_t* ops, int n_ops, bool out_f32, TcParams& prm) {
   prm.bn = N <= 256 ? (N + 15) / 16 * 16 : 256;
   int kb = 0;
   for (int i = 0; i < n_ops; ++i) {
@@ -442,15 +414,39 @@ static int tc_geometry(int N, const accx_operand_t* ops, int n_ops, TcParams& pr
   }
   prm.kb_start[n_ops] = kb;
   prm.n_kb = kb;
-  // stages: deep enough to keep ~4 k-blocks in flight, shallow enough that several CTAs fit on an SM
-  const int stage_bytes = TC_A_BYTES + prm.bn * 128;
-  int smax = prm.bn > 128 ? 3 : 4;
-  while (smax > 1 && smax * stage_bytes > 100 * 1024) --smax;
-  prm.stages = kb < smax ? kb : smax;
+  prm.n_tiles = (N + prm.bn - 1) / prm.bn;
+  prm.m_tiles = (int)((P + TC_BM - 1) / TC_BM);
   int cols = 32;
-  while (cols < prm.bn) cols <<= 1;
+  while (cols < 2 * prm.bn) cols <<= 1;
   prm.tmem_cols = cols;
-  return (N + prm.bn - 1) / prm.bn;   // n tiles
+  const size_t b_tile = (size_t)prm.bn * 128;
+  const size_t epi = (size_t)TC_BM * ((out_f32 ? prm.bn * 4 : prm.bn * 2) + 16) + 2 * prm.bn * 4;
+  prm.b_resident = (prm.n_tiles == 1 && (size_t)kb * b_tile <= 72 * 1024) ? 1 : 0;
+  const size_t fixed = 1024 + epi + (prm.b_resident ? kb * b_tile : 0) + 256;
+  const size_t stage = TC_A_BYTES + (prm.b_resident ? 0 : b_tile);
+  TcLaunch L;
+  L.ctas_per_sm = 1;
+  int S = 0;
+  if (cols <= 256) {            // try two CTAs per SM with at least 3 stages (or all k-blocks)
+    const size_t budget = 113 * 1024;
+    int want = kb < 3 ? kb : 3;
+    if (fixed + want * stage <= budget) {
+      S = (int)((budget - fixed) / stage);
+      L.ctas_per_sm = 2;
+    }
+  }
+  if (S == 0) {
+    const size_t budget = 226 * 1024;
+    S = (int)((budget - fixed) / stage);
+  }
+  if (S > 6) S = 6;
+  if (S < 1) S = 1;
+  prm.stages = S;
+  L.smem = fixed + (size_t)S * stage;
+  // make the shared-memory footprint itself enforce the intended occupancy (TMEM would otherwise stall a third CTA)
+  const size_t min_smem = (227 * 1024) / (L.ctas_per_sm + 1) + 1024;
+  if (L.smem < min_smem) L.smem = min_smem;
+  return L;
 }
 
 }  // namespace accx
@@ -462,8 +458,8 @@ extern "C" {
 int64_t accx_pw_tc_workspace_bytes(int N, const accx_operand_t* ops, int n_ops) {
   if (!ops || n_ops < 1 || n_ops > ACCX_MAX_OPERANDS) return -1;
   TcParams prm;
-  const int n_tiles = tc_geometry(N, ops, n_ops, prm);
-  return (int64_t)n_tiles * prm.n_kb * prm.bn * TC_BK * 2;
+  tc_geometry(N, 1, ops, n_ops, false, prm);
+  return (int64_t)prm.n_tiles * prm.n_kb * prm.bn * TC_BK * 2;
 }
 
 int accx_pw_fwd_tc(int dtype, int out_dtype, int B, int H, int W, int N, const accx_operand_t* ops, int n_ops,
@@ -474,8 +470,7 @@ int accx_pw_fwd_tc(int dtype, int out_dtype, int B, int H, int W, int N, const a
   ACCX_REQUIRE(n_add >= 0 && n_add <= ACCX_MAX_ADDENDS, "pw_fwd_tc: n_add %d out of range", n_add);
   ACCX_REQUIRE(dtype == ACCX_BF16, "pw_fwd_tc: operands must be bf16 (use accx_pw_fwd for fp32 storage)");
   ACCX_REQUIRE(ldy >= N, "pw_fwd_tc: ldy < N");
-  EncodeTiledFn encode = get_encode();
-  ACCX_REQUIRE(encode != nullptr, "pw_fwd_tc: cuTensorMapEncodeTiled not available from the driver");
+  ACCX_REQUIRE(get_encode() != nullptr, "pw_fwd_tc: cuTensorMapEncodeTiled not available from the driver");
   TcParams prm;
   prm.n_ops = n_ops;
   prm.any_transform = 0;
@@ -488,16 +483,11 @@ int accx_pw_fwd_tc(int dtype, int out_dtype, int B, int H, int W, int N, const a
     ACCX_REQUIRE(ops[i].act == 0 || (ops[i].scale && ops[i].shift && aligned16(ops[i].scale) && aligned16(ops[i].shift)),
                  "pw_fwd_tc: operand %d scale/shift missing or misaligned", i);
     if (ops[i].dy || ops[i].dx || ops[i].act) prm.any_transform = 1;
-    const cuuint64_t gdim[2] = {(cuuint64_t)ops[i].K, (cuuint64_t)P};
-    const cuuint64_t gstr[1] = {(cuuint64_t)ops[i].ld * 2};
-    const cuuint32_t box[2] = {TC_BK, TC_BM};
-    const cuuint32_t estr[2] = {1, 1};
-    CUresult r = encode(&prm.tmap[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ops[i].data), gdim, gstr,
-                        box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    ACCX_REQUIRE(r == CUDA_SUCCESS, "pw_fwd_tc: cuTensorMapEncodeTiled failed (%d) for operand %d", (int)r, i);
+    ACCX_REQUIRE(encode_2d_bf16(&prm.tmap[i], ops[i].data, ops[i].K, P, ops[i].ld, TC_BM),
+                 "pw_fwd_tc: cuTensorMapEncodeTiled failed for operand %d", i);
   }
-  const int n_tiles = tc_geometry(N, ops, n_ops, prm);
+  const TcLaunch L = tc_geometry(N, P, ops, n_ops, out_dtype == ACCX_F32, prm);
+  const int n_tiles = prm.n_tiles;
   const int64_t need = (int64_t)n_tiles * prm.n_kb * prm.bn * TC_BK * 2;
   ACCX_REQUIRE(workspace_bytes >= need && aligned16(workspace), "pw_fwd_tc: workspace too small (%lld < %lld)",
                (long long)workspace_bytes, (long long)need);
@@ -516,7 +506,7 @@ int accx_pw_fwd_tc(int dtype, int out_dtype, int B, int H, int W, int N, const a
   }
   prm.y = y; prm.ldy = ldy; prm.stats = stats;
   cudaStream_t st = (cudaStream_t)stream;
-  tc_pack_weights_kernel<<<dim3(prm.n_kb, n_tiles), 256, 0, st>>>(prm, (bf16*)workspace);
+  tc_pack_weights_kernel<<<dim3(prm.n_kb, n_tiles, (prm.bn * TC_BK + 1023) / 1024), 256, 0, st>>>(prm, (bf16*)workspace);
   int rc = check_launch("tc_pack_weights");
   if (rc) return rc;
   static bool attr_set = false;
@@ -524,8 +514,11 @@ int accx_pw_fwd_tc(int dtype, int out_dtype, int B, int H, int W, int N, const a
     cudaFuncSetAttribute(pw_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr_set = true;
   }
-  dim3 grid((unsigned)((P + TC_BM - 1) / TC_BM), n_tiles);
-  pw_fwd_tc_kernel<<<grid, TC_THREADS, tc_smem_bytes(prm), st>>>(prm);
+  const int n_sm = sm_count();
+  const int64_t total = (int64_t)prm.m_tiles * prm.n_tiles;
+  int64_t grid = (int64_t)n_sm * L.ctas_per_sm;
+  if (grid > total) grid = total;
+  pw_fwd_tc_kernel<<<(unsigned)grid, TC_THREADS, L.smem, st>>>(prm);
   return check_launch("pw_fwd_tc");
 }
 

@@ -243,7 +243,7 @@ __global__ void se_bwd_gate_kernel(int B, int C, int Cr, double HW, const float*
     const float c1 = (float)(a1 / n), c2 = (float)(a2 / n);
     const float g = gate[(int64_t)b * C + c];
     const float s1 = S[(int64_t)b * C + c], s2 = S[BC + (int64_t)b * C + c];
-    const float g1 = G[(int64_t)b * C + c], g2 = G[BC + (int64_t)b * C + c];
+    const float g2 = G[BC + (int64_t)b * C + c];
     const float s = gamma[c] * rs;
     // dgate = sum_hw dz * a with dz = s*(g' - c1 - zhat*c2), zhat = rs*(a*g - mu)
     const float dgate = s * (g2 - c1 * s1 - c2 * rs * (g * s2 - mu * s1));

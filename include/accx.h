@@ -90,14 +90,23 @@ int accx_pw_fwd_tc(int dtype, int out_dtype, int B, int H, int W, int N,
 int accx_pw_wgrad(int dtype, int B, int H, int W, int N, const accx_operand_t* op, float* dw,
                   const void* dy, int64_t ldy, int dy_f32, void* stream);
 
+/* accx_pw_wgrad on the tcgen05 tensor cores: both operands are TMA-loaded as pixel-major (MN-major)
+ * 128B-swizzled tiles, the activation operand is normalised in place, partial tiles are split over
+ * pixels and combined with fp32 atomics.  bf16 operands; K, N, ld multiples of 8. */
+int accx_pw_wgrad_tc(int B, int H, int W, int N, const accx_operand_t* op, float* dw, const void* dy, int64_t ldy,
+                     void* stream);
+
 /* BatchNorm2d statistics -> affine (torch.nn.BatchNorm2d as used at ACC_UNet.py:34,74,178,
  * 244-260,311-319,388-410).  training: mean/var from stats (biased var), running buffers
  * updated with `momentum` and the unbiased variance, num_batches_tracked += 1.  eval: running
- * buffers.  Outputs scale = gamma*rstd, shift = beta - mean*scale, and mean/rstd for backward. */
+ * buffers.  Outputs scale = gamma*rstd, shift = beta - mean*scale, and mean/rstd for backward.
+ * conv_bias (optional): the bias of the convolution that produced the tensor, which was NOT added to
+ * it: a per-channel constant cancels in batch normalisation, so it only enters the running mean
+ * (training) / the shift (eval) here and never touches the activation tensor. */
 int accx_bn_finalize(int C, double count, const float* stats, const float* gamma, const float* beta,
-                     float eps, float momentum, int training, float* running_mean, float* running_var,
-                     int64_t* num_batches_tracked, float* scale, float* shift, float* mean, float* rstd,
-                     void* stream);
+                     const float* conv_bias, float eps, float momentum, int training, float* running_mean,
+                     float* running_var, int64_t* num_batches_tracked, float* scale, float* shift, float* mean,
+                     float* rstd, void* stream);
 
 /* out = post(act(x)) with optional second affine post(u) = u*scale2 + shift2 (ResPath tail
  * BN(lrelu(BN(x))), ACC_UNet.py:328), optional residual add, optional stats of the value

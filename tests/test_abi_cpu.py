@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
 def test_invalid_arguments_return_error_codes_not_crashes():
     from accx import _lib
     lib = _lib.load()
-    rc = lib.accx_bn_finalize(0, 1.0, None, None, None, 1e-5, 0.1, 1, None, None, None, None, None, None, None, None)
+    rc = lib.accx_bn_finalize(0, 1.0, None, None, None, None, 1e-5, 0.1, 1, None, None, None, None, None, None, None, None)
     assert rc == -1 and b"bn_finalize" in lib.accx_last_error()
     with pytest.raises(_lib.AccxError):
         _lib.call("accx_pool_sum", 0, 0, 1, 3, 3, 8, 1, 1.0, 1, 1, 8, None)     # 3x3 not divisible by 2

@@ -115,3 +115,53 @@ def test_tc_large_tile_count_and_k_pipeline():
     ref2 = bf(a2) @ bf(w2).t()
     close(y2.float(), ref2, RT, AT, "tc K=4352")
     close(stats[:128], ref2.sum((0, 1, 2)), 2e-2, 2e-2, "tc K=4352 stats")
+
+
+@pytest.mark.parametrize("P_shape", [(2, 12, 20), (4, 32, 32), (1, 9, 15)])
+@pytest.mark.parametrize("K,N,act", [(32, 96, 0), (96, 32, 2), (64, 64, 1), (128, 272, 2), (320, 128, 2), (16, 8, 0), (1088, 128, 2)])
+def test_tc_wgrad(P_shape, K, N, act):
+    e = E()
+    B, H, W = P_shape
+    L, a = mk_lazy((B, H, W, K), torch.bfloat16, act, 10)
+    g = torch.Generator().manual_seed(11)
+    dy = torch.randn(B, H, W, N, generator=g).to(DEV).to(torch.bfloat16)
+    w = torch.zeros(N, K, device=DEV)
+    gw = torch.zeros(N, K, device=DEV)
+    n0 = e.LAUNCHES
+    e.wgrad(e.Op(L, K, e.WV(w, 0, K, 1)), dy, N, (B, H, W), gw)
+    ref = torch.einsum("bhwn,bhwk->nk", dy.float(), bf(a))
+    close(gw, ref, RT, AT, "tc wgrad")
+
+
+def test_tc_wgrad_strided_weight_view_and_column_slices():
+    """HANC layout: dW[n, e*J + j] for the max half (columns E..2E) of the pooled buffer"""
+    e = E()
+    B, H, W, Ein, N, J = 2, 8, 16, 24, 16, 5
+    L, a = mk_lazy((B, H, W, 2 * Ein), torch.bfloat16, 0, 12)
+    dy = torch.randn(B, H, W, N, generator=torch.Generator().manual_seed(13)).to(DEV).to(torch.bfloat16)
+    w = torch.zeros(N, J * Ein, device=DEV)
+    gw = torch.zeros(N, J * Ein, device=DEV)
+    e.wgrad(e.Op(L, Ein, e.WV(w, 3, J * Ein, J), Ein), dy, N, (B, H, W), gw)
+    ref = torch.einsum("bhwn,bhwk->nk", dy.float(), bf(a[..., Ein:]))
+    close(gw[:, 3::J], ref, RT, AT, "tc wgrad strided")
+    mask = torch.ones(J * Ein, dtype=torch.bool)
+    mask[3::J] = False
+    assert float(gw[:, mask.to(DEV)].abs().max()) == 0
+
+
+@pytest.mark.parametrize("C", [8, 32, 72])
+def test_tc_wgrad_dense3x3_taps(C):
+    e = E()
+    B, H, W = 2, 9, 12
+    L, a = mk_lazy((B, H, W, C), torch.bfloat16, 0, 8)
+    g = torch.Generator().manual_seed(9)
+    w = (torch.randn(C, C, 3, 3, generator=g) / (3 * C ** 0.5)).to(DEV)
+    dy = torch.randn(B, H, W, C, generator=g).to(DEV).to(torch.bfloat16)
+    gw = torch.zeros_like(w)
+    for ky in range(3):
+        for kx in range(3):
+            e.wgrad(e.Op(L, C, e.WV(w, ky * 3 + kx, C * 9, 9), 0, ky - 1, kx - 1), dy, C, (B, H, W), gw)
+    torch.backends.cudnn.allow_tf32 = False
+    w_ = w.clone().requires_grad_(True)
+    F.conv2d(bf(a).permute(0, 3, 1, 2), w_, None, padding=1).backward(dy.float().permute(0, 3, 1, 2))
+    close(gw, w_.grad, RT, AT, "tc conv3x3 wgrad")
