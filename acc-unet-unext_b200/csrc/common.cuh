@@ -50,8 +50,12 @@ __device__ __forceinline__ void ldv(const T* __restrict__ p, float (&v)[VEC]) {
     static_assert(VEC == 4, "fp32 vectors are 4 wide");
     float4 t = *reinterpret_cast<const float4*>(p);
     v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  } else if constexpr (VEC == 4) {      // half-width bf16 access (8 bytes), for register-heavy kernels
+    uint2 t = *reinterpret_cast<const uint2*>(p);
+    v[0] = __uint_as_float(t.x << 16); v[1] = __uint_as_float(t.x & 0xffff0000u);
+    v[2] = __uint_as_float(t.y << 16); v[3] = __uint_as_float(t.y & 0xffff0000u);
   } else {
-    static_assert(VEC == 8, "bf16 vectors are 8 wide");
+    static_assert(VEC == 8, "bf16 vectors are 4 or 8 wide");
     uint4 t = *reinterpret_cast<const uint4*>(p);
     const uint32_t w[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
@@ -68,6 +72,9 @@ __device__ __forceinline__ void stv(T* __restrict__ p, const float (&v)[VEC]) {
     p[0] = from_f<T>(v[0]);
   } else if constexpr (sizeof(T) == 4) {
     *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  } else if constexpr (VEC == 4) {
+    __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
+    *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
   } else {
     uint32_t w[4];
 #pragma unroll
@@ -78,6 +85,31 @@ __device__ __forceinline__ void stv(T* __restrict__ p, const float (&v)[VEC]) {
     *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
   }
 }
+
+// Raw (storage-typed) register vector: issue the load now, unpack to fp32 later -- lets a kernel put
+// many independent loads in flight before the first dependent FMA without paying fp32 registers for them.
+template <typename T, int VEC> struct RawVec;
+template <typename T> struct RawVec<T, 1> {
+  T r;
+  __device__ __forceinline__ void load(const T* p) { r = *p; }
+  __device__ __forceinline__ void zero() { r = from_f<T>(0.f); }
+  __device__ __forceinline__ void unpack(float (&v)[1]) const { v[0] = to_f(r); }
+};
+template <> struct RawVec<float, 4> {
+  float4 r;
+  __device__ __forceinline__ void load(const float* p) { r = *reinterpret_cast<const float4*>(p); }
+  __device__ __forceinline__ void zero() { r = make_float4(0.f, 0.f, 0.f, 0.f); }
+  __device__ __forceinline__ void unpack(float (&v)[4]) const { v[0] = r.x; v[1] = r.y; v[2] = r.z; v[3] = r.w; }
+};
+template <> struct RawVec<bf16, 4> {
+  uint2 r;
+  __device__ __forceinline__ void load(const bf16* p) { r = *reinterpret_cast<const uint2*>(p); }
+  __device__ __forceinline__ void zero() { r = make_uint2(0u, 0u); }
+  __device__ __forceinline__ void unpack(float (&v)[4]) const {
+    v[0] = __uint_as_float(r.x << 16); v[1] = __uint_as_float(r.x & 0xffff0000u);
+    v[2] = __uint_as_float(r.y << 16); v[3] = __uint_as_float(r.y & 0xffff0000u);
+  }
+};
 
 template <int VEC>
 __device__ __forceinline__ void ldf(const float* __restrict__ p, float (&v)[VEC]) {

@@ -11,7 +11,7 @@ namespace accx {
 constexpr int STRIP = 4;
 
 template <typename T, int VEC>
-__global__ void dw3x3_fwd_kernel(int B, int H, int W, int C, const T* __restrict__ x, const float* scale,
+__global__ void __launch_bounds__(256, 2) dw3x3_fwd_kernel(int B, int H, int W, int C, const T* __restrict__ x, const float* scale,
                                  const float* shift, int act, const float* __restrict__ w,
                                  const float* __restrict__ bias, int flip, T* __restrict__ y, float* stats) {
   extern __shared__ float smem[];
@@ -33,12 +33,28 @@ __global__ void dw3x3_fwd_kernel(int B, int H, int W, int C, const T* __restrict
   const int strips_w = (W + STRIP - 1) / STRIP;
   const int64_t n_strips = (int64_t)B * H * strips_w;
   if (active) {
-    for (int64_t sidx = (int64_t)blockIdx.x * blockDim.y + threadIdx.y; sidx < n_strips;
-         sidx += (int64_t)gridDim.x * blockDim.y) {
-      const int w0 = (int)(sidx % strips_w) * STRIP;
-      const int64_t t = sidx / strips_w;
-      const int h = (int)(t % H);
-      const int b = (int)(t / H);
+    for (int sidx = blockIdx.x * blockDim.y + threadIdx.y; sidx < (int)n_strips; sidx += gridDim.x * blockDim.y) {
+      const int w0 = (sidx % strips_w) * STRIP;
+      const int t = sidx / strips_w;
+      const int h = t % H;
+      const int b = t / H;
+      // 1) all 18 window loads first (independent, raw storage type: 2 registers each) ...
+      RawVec<T, VEC> raw[3][STRIP + 2];
+      unsigned inb = 0;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const int hh = h + r - 1;
+        const T* row = x + (((int64_t)b * H + hh) * W) * C + c0;
+#pragma unroll
+        for (int cidx = 0; cidx < STRIP + 2; ++cidx) {
+          const int ww = w0 + cidx - 1;
+          if (hh >= 0 && hh < H && ww >= 0 && ww < W) {
+            raw[r][cidx].load(row + (int64_t)ww * C);
+            inb |= 1u << (r * (STRIP + 2) + cidx);
+          }
+        }
+      }
+      // 2) ... then normalise + accumulate (zero padding applies to the ACTIVATED tensor: skip outside taps)
       float o[STRIP][VEC];
 #pragma unroll
       for (int j = 0; j < STRIP; ++j)
@@ -46,15 +62,11 @@ __global__ void dw3x3_fwd_kernel(int B, int H, int W, int C, const T* __restrict
         for (int i = 0; i < VEC; ++i) o[j][i] = bs[i];
 #pragma unroll
       for (int r = 0; r < 3; ++r) {
-        const int hh = h + r - 1;
-        if (hh < 0 || hh >= H) continue;
-        const T* row = x + (((int64_t)b * H + hh) * W) * C + c0;
 #pragma unroll
         for (int cidx = 0; cidx < STRIP + 2; ++cidx) {
-          const int ww = w0 + cidx - 1;
-          if (ww < 0 || ww >= W) continue;
+          if (!(inb & (1u << (r * (STRIP + 2) + cidx)))) continue;
           float v[VEC];
-          ldv<T, VEC>(row + (int64_t)ww * C, v);
+          raw[r][cidx].unpack(v);
           lz.apply(v);
 #pragma unroll
           for (int j = 0; j < STRIP; ++j) {
@@ -80,7 +92,7 @@ __global__ void dw3x3_fwd_kernel(int B, int H, int W, int C, const T* __restrict
 
 // dw[c, r, t] += sum_p dy[p] * a[p + (r-1, t-1)]
 template <typename T, int VEC>
-__global__ void dw3x3_wgrad_kernel(int B, int H, int W, int C, const T* __restrict__ x, const float* scale,
+__global__ void __launch_bounds__(256, 2) dw3x3_wgrad_kernel(int B, int H, int W, int C, const T* __restrict__ x, const float* scale,
                                    const float* shift, int act, const T* __restrict__ dy, float* dw) {
   extern __shared__ float smem[];
   const int cv = blockIdx.y * blockDim.x + threadIdx.x;
@@ -96,34 +108,42 @@ __global__ void dw3x3_wgrad_kernel(int B, int H, int W, int C, const T* __restri
   const int strips_w = (W + STRIP - 1) / STRIP;
   const int64_t n_strips = (int64_t)B * H * strips_w;
   if (active) {
-    for (int64_t sidx = (int64_t)blockIdx.x * blockDim.y + threadIdx.y; sidx < n_strips;
-         sidx += (int64_t)gridDim.x * blockDim.y) {
-      const int w0 = (int)(sidx % strips_w) * STRIP;
-      const int64_t t = sidx / strips_w;
-      const int h = (int)(t % H);
-      const int b = (int)(t / H);
-      float g[STRIP][VEC];
+    for (int sidx = blockIdx.x * blockDim.y + threadIdx.y; sidx < (int)n_strips; sidx += gridDim.x * blockDim.y) {
+      const int w0 = (sidx % strips_w) * STRIP;
+      const int t = sidx / strips_w;
+      const int h = t % H;
+      const int b = t / H;
+      RawVec<T, VEC> graw[STRIP], raw[3][STRIP + 2];
+      unsigned inb = 0;
       const T* grow = dy + (((int64_t)b * H + h) * W) * C + c0;
 #pragma unroll
       for (int j = 0; j < STRIP; ++j) {
-        if (w0 + j < W) {
-          ldv<T, VEC>(grow + (int64_t)(w0 + j) * C, g[j]);
-        } else {
-#pragma unroll
-          for (int i = 0; i < VEC; ++i) g[j][i] = 0.f;
-        }
+        if (w0 + j < W) graw[j].load(grow + (int64_t)(w0 + j) * C);
+        else graw[j].zero();
       }
 #pragma unroll
       for (int r = 0; r < 3; ++r) {
         const int hh = h + r - 1;
-        if (hh < 0 || hh >= H) continue;
         const T* row = x + (((int64_t)b * H + hh) * W) * C + c0;
 #pragma unroll
         for (int cidx = 0; cidx < STRIP + 2; ++cidx) {
           const int ww = w0 + cidx - 1;
-          if (ww < 0 || ww >= W) continue;
+          if (hh >= 0 && hh < H && ww >= 0 && ww < W) {
+            raw[r][cidx].load(row + (int64_t)ww * C);
+            inb |= 1u << (r * (STRIP + 2) + cidx);
+          }
+        }
+      }
+      float g[STRIP][VEC];
+#pragma unroll
+      for (int j = 0; j < STRIP; ++j) graw[j].unpack(g[j]);
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+#pragma unroll
+        for (int cidx = 0; cidx < STRIP + 2; ++cidx) {
+          if (!(inb & (1u << (r * (STRIP + 2) + cidx)))) continue;
           float v[VEC];
-          ldv<T, VEC>(row + (int64_t)ww * C, v);
+          raw[r][cidx].unpack(v);
           lz.apply(v);
 #pragma unroll
           for (int j = 0; j < STRIP; ++j) {
@@ -163,13 +183,17 @@ int accx_dw3x3_fwd(int dtype, int B, int H, int W, int C, const void* x, const f
   ACCX_REQUIRE(act == 0 || (scale && shift), "dw3x3_fwd: act %d needs scale/shift", act);
   const int64_t n_strips = (int64_t)B * H * ((W + STRIP - 1) / STRIP);
   ACCX_DISPATCH_T(dtype, {
-    Lanes l = make_lanes(C, DT<T>::VEC, aligned16(x) && aligned16(y));
-    dim3 block(l.tx, l.ty), grid(grid_x_for(n_strips, l.ty * 2, 148 * 8), l.gy);
+    // 4 channels per thread for both dtypes: 9 taps x 4 weights + 4 x 4 accumulators stay under ~80 registers,
+    // so three 256-thread CTAs fit on an SM (8-wide bf16 lanes needed 179 registers: one CTA per SM)
+    Lanes l = make_lanes(C, 4, aligned16(x) && aligned16(y));
+    dim3 block(l.tx, l.ty), grid(grid_x_for(n_strips, l.ty * 2, 148 * 12), l.gy);
     size_t sm = (size_t)l.tx * l.ty * l.vec * sizeof(float);
-    ACCX_DISPATCH_VEC(l, {
-      dw3x3_fwd_kernel<T, VEC><<<grid, block, sm, (cudaStream_t)stream>>>(B, H, W, C, (const T*)x, scale, shift, act, w,
-                                                                          bias, flip, (T*)y, stats);
-    });
+    if (l.vec == 1)
+      dw3x3_fwd_kernel<T, 1><<<grid, block, sm, (cudaStream_t)stream>>>(B, H, W, C, (const T*)x, scale, shift, act, w,
+                                                                        bias, flip, (T*)y, stats);
+    else
+      dw3x3_fwd_kernel<T, 4><<<grid, block, sm, (cudaStream_t)stream>>>(B, H, W, C, (const T*)x, scale, shift, act, w,
+                                                                        bias, flip, (T*)y, stats);
   });
   return check_launch("dw3x3_fwd");
 }
@@ -179,13 +203,15 @@ int accx_dw3x3_wgrad(int dtype, int B, int H, int W, int C, const void* x, const
   ACCX_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && x && dy && dw, "dw3x3_wgrad: bad arguments");
   const int64_t n_strips = (int64_t)B * H * ((W + STRIP - 1) / STRIP);
   ACCX_DISPATCH_T(dtype, {
-    Lanes l = make_lanes(C, DT<T>::VEC, aligned16(x) && aligned16(dy));
-    dim3 block(l.tx, l.ty), grid(grid_x_for(n_strips, l.ty * 4, 148 * 2), l.gy);
+    Lanes l = make_lanes(C, 4, aligned16(x) && aligned16(dy));
+    dim3 block(l.tx, l.ty), grid(grid_x_for(n_strips, l.ty * 4, 148 * 3), l.gy);
     size_t sm = (size_t)l.tx * l.ty * l.vec * sizeof(float);
-    ACCX_DISPATCH_VEC(l, {
-      dw3x3_wgrad_kernel<T, VEC><<<grid, block, sm, (cudaStream_t)stream>>>(B, H, W, C, (const T*)x, scale, shift, act,
-                                                                            (const T*)dy, dw);
-    });
+    if (l.vec == 1)
+      dw3x3_wgrad_kernel<T, 1><<<grid, block, sm, (cudaStream_t)stream>>>(B, H, W, C, (const T*)x, scale, shift, act,
+                                                                          (const T*)dy, dw);
+    else
+      dw3x3_wgrad_kernel<T, 4><<<grid, block, sm, (cudaStream_t)stream>>>(B, H, W, C, (const T*)x, scale, shift, act,
+                                                                          (const T*)dy, dw);
   });
   return check_launch("dw3x3_wgrad");
 }

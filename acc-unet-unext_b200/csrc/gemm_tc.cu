@@ -279,12 +279,33 @@ __global__ void __launch_bounds__(TC_THREADS) pw_fwd_tc_kernel(const __grid_cons
       for (int c0 = 0; c0 < bn; c0 += 16) {
         float v[16];
         tc_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + acc * bn + c0, v);
-        if (prm.bias != nullptr || prm.n_add > 0 || !rvalid || n0 + bn > prm.N) {
+        if (!rvalid) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = 0.f;
+        } else if (n0 + c0 + 16 <= prm.N && (prm.N & 3) == 0) {
+          // full chunk: vectorised bias / nearest-upsampled addends (each addend row is contiguous in n)
+          if (prm.bias) {
+            const float4* bp = reinterpret_cast<const float4*>(prm.bias + n0 + c0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float4 b4 = __ldg(bp + q);
+              v[4 * q] += b4.x; v[4 * q + 1] += b4.y; v[4 * q + 2] += b4.z; v[4 * q + 3] += b4.w;
+            }
+          }
+          for (int a = 0; a < prm.n_add; ++a) {
+            const float4* ap = reinterpret_cast<const float4*>(prm.add[a] + addrow[a] + n0 + c0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float4 a4 = __ldg(ap + q);
+              v[4 * q] += a4.x; v[4 * q + 1] += a4.y; v[4 * q + 2] += a4.z; v[4 * q + 3] += a4.w;
+            }
+          }
+        } else {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int n = n0 + c0 + j;
             float x = 0.f;
-            if (rvalid && n < prm.N) {
+            if (n < prm.N) {
               x = v[j];
               if (prm.bias) x += __ldg(prm.bias + n);
               for (int a = 0; a < prm.n_add; ++a) x += __ldg(prm.add[a] + addrow[a] + n);
