@@ -177,7 +177,11 @@ def conv(ops: Sequence[Op], N: int, dims: Tuple[int, int, int], bias=None, adds:
     rd += sum(t.numel() * 4 for t, _ in adds)
     cost = (rd + P * N * out.element_size(), 2 * P * N * sum(op.K for op in ops))
     yptr = out.data_ptr() + out_coff * out.element_size()
-    if TC and in_dt == BF16 and all(o.K % 8 == 0 and o.ld % 8 == 0 and o.data % 16 == 0 for o in arr):
+    tc_ok = (TC and in_dt == BF16 and all(o.K % 8 == 0 and o.ld % 8 == 0 and o.data % 16 == 0 for o in arr)
+             and yptr % 16 == 0 and (out.shape[-1] * out.element_size()) % 16 == 0       # TMA store of the output
+             and not (stats is not None and odt == F32)
+             and all(t.data_ptr() % 16 == 0 for t, _ in adds))
+    if tc_ok:
         ws_bytes = _lib.load().accx_pw_tc_workspace_bytes(N, arr, len(ops))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=out.device)
         LAUNCHES_EXTRA[0] += 1          # the weight re-pack kernel

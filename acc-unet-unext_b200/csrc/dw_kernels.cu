@@ -171,6 +171,13 @@ __global__ void __launch_bounds__(256, 2) dw3x3_wgrad_kernel(int B, int H, int W
   }
 }
 
+// dw_tiled.cu: TMA halo-tile kernels (the fast path whenever the tensor is TMA-addressable)
+bool dw_tiled_ok(int dtype, int C, const void* x, const void* y_or_dy);
+int dw_tiled_fwd(int dtype, int B, int H, int W, int C, const void* x, const float* scale, const float* shift, int act,
+                 const float* w, const float* bias, int flip, void* y, float* stats, cudaStream_t st);
+int dw_tiled_wgrad(int dtype, int B, int H, int W, int C, const void* x, const float* scale, const float* shift,
+                   int act, const void* dy, float* dw, cudaStream_t st);
+
 }  // namespace accx
 
 using namespace accx;
@@ -181,6 +188,9 @@ int accx_dw3x3_fwd(int dtype, int B, int H, int W, int C, const void* x, const f
                    int act, const float* w, const float* bias, int flip, void* y, float* stats, void* stream) {
   ACCX_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && x && w && y, "dw3x3_fwd: bad arguments");
   ACCX_REQUIRE(act == 0 || (scale && shift), "dw3x3_fwd: act %d needs scale/shift", act);
+  ACCX_REQUIRE(dtype == ACCX_F32 || dtype == ACCX_BF16, "dw3x3_fwd: unsupported dtype %d", dtype);
+  if (dw_tiled_ok(dtype, C, x, y))
+    return dw_tiled_fwd(dtype, B, H, W, C, x, scale, shift, act, w, bias, flip, y, stats, (cudaStream_t)stream);
   const int64_t n_strips = (int64_t)B * H * ((W + STRIP - 1) / STRIP);
   ACCX_DISPATCH_T(dtype, {
     // 4 channels per thread for both dtypes: 9 taps x 4 weights + 4 x 4 accumulators stay under ~80 registers,
@@ -201,6 +211,9 @@ int accx_dw3x3_fwd(int dtype, int B, int H, int W, int C, const void* x, const f
 int accx_dw3x3_wgrad(int dtype, int B, int H, int W, int C, const void* x, const float* scale, const float* shift,
                      int act, const void* dy, float* dw, void* stream) {
   ACCX_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && x && dy && dw, "dw3x3_wgrad: bad arguments");
+  ACCX_REQUIRE(dtype == ACCX_F32 || dtype == ACCX_BF16, "dw3x3_wgrad: unsupported dtype %d", dtype);
+  if (dw_tiled_ok(dtype, C, x, dy))
+    return dw_tiled_wgrad(dtype, B, H, W, C, x, scale, shift, act, dy, dw, (cudaStream_t)stream);
   const int64_t n_strips = (int64_t)B * H * ((W + STRIP - 1) / STRIP);
   ACCX_DISPATCH_T(dtype, {
     Lanes l = make_lanes(C, 4, aligned16(x) && aligned16(dy));

@@ -76,24 +76,31 @@ __global__ void act_apply_kernel(int64_t P, int C, const T* __restrict__ x, cons
 #pragma unroll
   for (int i = 0; i < VEC; ++i) acc[0][i] = acc[1][i] = 0.f;
   if (active) {
-    for (int64_t p = (int64_t)blockIdx.x * blockDim.y + threadIdx.y; p < P; p += (int64_t)gridDim.x * blockDim.y) {
-      float v[VEC];
-      ldv<T, VEC>(x + p * C + c0, v);
-      lz.apply(v);
-      if (scale2) {
+    constexpr int U = 4;
+    RawVec<T, VEC> rx[U], rr[U];
+    pixel_loop<U>((int64_t)blockIdx.x * blockDim.y + threadIdx.y, P, (int64_t)gridDim.x * blockDim.y,
+        [&](int u, int64_t p) {
+          rx[u].load(x + p * C + c0);
+          if (residual) rr[u].load(residual + p * C + c0);
+        },
+        [&](int u, int64_t p) {
+          float v[VEC];
+          rx[u].unpack(v);
+          lz.apply(v);
+          if (scale2) {
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) v[i] = fmaf(v[i], s2[i], t2[i]);
-      }
-      if (residual) {
-        float r[VEC];
-        ldv<T, VEC>(residual + p * C + c0, r);
+            for (int i = 0; i < VEC; ++i) v[i] = fmaf(v[i], s2[i], t2[i]);
+          }
+          if (residual) {
+            float r[VEC];
+            rr[u].unpack(r);
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) v[i] += r[i];
-      }
+            for (int i = 0; i < VEC; ++i) v[i] += r[i];
+          }
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) { acc[0][i] += v[i]; acc[1][i] += v[i] * v[i]; }
-      if (out) stv<T, VEC>(out + p * C + c0, v);
-    }
+          for (int i = 0; i < VEC; ++i) { acc[0][i] += v[i]; acc[1][i] += v[i] * v[i]; }
+          if (out) stv<T, VEC>(out + p * C + c0, v);
+        });
   }
   if (stats) reduce_lanes_atomic<2, VEC>(acc, smem, stats, C, c0, active);
 }
@@ -112,19 +119,26 @@ __global__ void add_fwd_kernel(int64_t P, int C, const T* __restrict__ a, const 
 #pragma unroll
   for (int i = 0; i < VEC; ++i) acc[0][i] = acc[1][i] = 0.f;
   if (active) {
-    for (int64_t p = (int64_t)blockIdx.x * blockDim.y + threadIdx.y; p < P; p += (int64_t)gridDim.x * blockDim.y) {
-      float v[VEC], w[VEC];
-      ldv<T, VEC>(a + p * C + c0, v);
-      ldv<T, VEC>(r + p * C + c0, w);
-      lz.apply(v);
+    constexpr int U = 4;
+    RawVec<T, VEC> ra[U], rr[U];
+    pixel_loop<U>((int64_t)blockIdx.x * blockDim.y + threadIdx.y, P, (int64_t)gridDim.x * blockDim.y,
+        [&](int u, int64_t p) {
+          ra[u].load(a + p * C + c0);
+          rr[u].load(r + p * C + c0);
+        },
+        [&](int u, int64_t p) {
+          float v[VEC], w[VEC];
+          ra[u].unpack(v);
+          rr[u].unpack(w);
+          lz.apply(v);
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) {
-        v[i] += w[i];
-        acc[0][i] += v[i];
-        acc[1][i] += v[i] * v[i];
-      }
-      stv<T, VEC>(z + p * C + c0, v);
-    }
+          for (int i = 0; i < VEC; ++i) {
+            v[i] += w[i];
+            acc[0][i] += v[i];
+            acc[1][i] += v[i] * v[i];
+          }
+          stv<T, VEC>(z + p * C + c0, v);
+        });
   }
   if (stats) reduce_lanes_atomic<2, VEC>(acc, smem, stats, C, c0, active);
 }
@@ -147,17 +161,24 @@ __global__ void bn_bwd_reduce_kernel(int64_t P, int C, const T* __restrict__ y, 
 #pragma unroll
   for (int i = 0; i < VEC; ++i) acc[0][i] = acc[1][i] = 0.f;
   if (active) {
-    for (int64_t p = (int64_t)blockIdx.x * blockDim.y + threadIdx.y; p < P; p += (int64_t)gridDim.x * blockDim.y) {
-      float yv[VEC], g[VEC];
-      ldv<T, VEC>(y + p * C + c0, yv);
-      ldv<T, VEC>(da + p * C + c0, g);
+    constexpr int U = 4;
+    RawVec<T, VEC> ry[U], rg[U];
+    pixel_loop<U>((int64_t)blockIdx.x * blockDim.y + threadIdx.y, P, (int64_t)gridDim.x * blockDim.y,
+        [&](int u, int64_t p) {
+          ry[u].load(y + p * C + c0);
+          rg[u].load(da + p * C + c0);
+        },
+        [&](int u, int64_t p) {
+          float yv[VEC], g[VEC];
+          ry[u].unpack(yv);
+          rg[u].unpack(g);
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) {
-        float gi = g[i] * lz.dact(yv[i], i);
-        acc[0][i] += gi;
-        acc[1][i] += gi * (yv[i] - mu[i]) * rs[i];
-      }
-    }
+          for (int i = 0; i < VEC; ++i) {
+            float gi = g[i] * lz.dact(yv[i], i);
+            acc[0][i] += gi;
+            acc[1][i] += gi * (yv[i] - mu[i]) * rs[i];
+          }
+        });
   }
   reduce_lanes_atomic<2, VEC>(acc, smem, sums, C, c0, active);
 }
@@ -187,29 +208,36 @@ __global__ void bn_bwd_apply_kernel(int64_t P, int C, const T* __restrict__ y, c
   }
 #pragma unroll
   for (int i = 0; i < VEC; ++i) { s1[i] *= inv_count; s2[i] *= inv_count; gm[i] *= rs[i]; }
-  for (int64_t p = (int64_t)blockIdx.x * blockDim.y + threadIdx.y; p < P; p += (int64_t)gridDim.x * blockDim.y) {
-    float yv[VEC], g[VEC];
-    ldv<T, VEC>(y + p * C + c0, yv);
-    ldv<T, VEC>(da + p * C + c0, g);
+  constexpr int U = 4;
+  RawVec<T, VEC> ry[U], rg[U];
+  pixel_loop<U>((int64_t)blockIdx.x * blockDim.y + threadIdx.y, P, (int64_t)gridDim.x * blockDim.y,
+      [&](int u, int64_t p) {
+        ry[u].load(y + p * C + c0);
+        rg[u].load(da + p * C + c0);
+      },
+      [&](int u, int64_t p) {
+        float yv[VEC], g[VEC];
+        ry[u].unpack(yv);
+        rg[u].unpack(g);
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) {
-      float gi = g[i] * lz.dact(yv[i], i);
-      float xh = (yv[i] - mu[i]) * rs[i];
-      g[i] = gm[i] * (gi - s1[i] - xh * s2[i]);
-    }
-    stv<T, VEC>(dy + p * C + c0, g);
-  }
+        for (int i = 0; i < VEC; ++i) {
+          float gi = g[i] * lz.dact(yv[i], i);
+          float xh = (yv[i] - mu[i]) * rs[i];
+          g[i] = gm[i] * (gi - s1[i] - xh * s2[i]);
+        }
+        stv<T, VEC>(dy + p * C + c0, g);
+      });
 }
 
 // --------------------------------------------------------------------------------------
 // out[b,ho,wo,c] = mul * sum_{s x s} x[b, ho*s+i, wo*s+j, c]
-template <typename TI, typename TO, int VEC>
+template <typename TI, typename TO, int VEC, int S>
 __global__ void pool_sum_kernel(int B, int H, int W, int C, int log2s, float mul, const TI* __restrict__ x,
                                 TO* __restrict__ out, int64_t out_ld) {
   const int cv = blockIdx.y * blockDim.x + threadIdx.x;
   if (cv * VEC >= C) return;
   const int c0 = cv * VEC;
-  const int s = 1 << log2s, Ho = H >> log2s, Wo = W >> log2s;
+  const int s = S > 0 ? S : 1 << log2s, Ho = H >> log2s, Wo = W >> log2s;
   const int64_t Po = (int64_t)B * Ho * Wo;
   for (int64_t q = (int64_t)blockIdx.x * blockDim.y + threadIdx.y; q < Po; q += (int64_t)gridDim.x * blockDim.y) {
     int wo = (int)(q % Wo);
@@ -219,13 +247,30 @@ __global__ void pool_sum_kernel(int B, int H, int W, int C, int log2s, float mul
     float acc[VEC];
 #pragma unroll
     for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
-    for (int i = 0; i < s; ++i) {
-      const TI* row = x + (((int64_t)b * H + (ho * s + i)) * W + (int64_t)wo * s) * C + c0;
-      for (int j = 0; j < s; ++j) {
+    if constexpr (S > 0) {      // compile-time window: all S*S loads in flight before the first add
+      RawVec<TI, VEC> rx[S * S];
+#pragma unroll
+      for (int i = 0; i < S; ++i) {
+        const TI* row = x + (((int64_t)b * H + (ho * S + i)) * W + (int64_t)wo * S) * C + c0;
+#pragma unroll
+        for (int j = 0; j < S; ++j) rx[i * S + j].load(row + (int64_t)j * C);
+      }
+#pragma unroll
+      for (int k = 0; k < S * S; ++k) {
         float v[VEC];
-        ldv<TI, VEC>(row + (int64_t)j * C, v);
+        rx[k].unpack(v);
 #pragma unroll
         for (int e = 0; e < VEC; ++e) acc[e] += v[e];
+      }
+    } else {
+      for (int i = 0; i < s; ++i) {
+        const TI* row = x + (((int64_t)b * H + (ho * s + i)) * W + (int64_t)wo * s) * C + c0;
+        for (int j = 0; j < s; ++j) {
+          float v[VEC];
+          ldv<TI, VEC>(row + (int64_t)j * C, v);
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) acc[e] += v[e];
+        }
       }
     }
 #pragma unroll
@@ -313,12 +358,17 @@ static int launch_pool_sum(int B, int H, int W, int C, int log2s, float mul, con
   dim3 block(l.tx, l.ty), grid(grid_x_for(Po, l.ty * 4, 148 * 8), l.gy);
   if constexpr (same) {
     if (l.vec != 1) {
-      pool_sum_kernel<TI, TO, DT<TI>::VEC><<<grid, block, 0, st>>>(B, H, W, C, log2s, mul, (const TI*)x, (TO*)out,
-                                                                  out_ld);
+      constexpr int V = DT<TI>::VEC;
+      if (log2s == 1)
+        pool_sum_kernel<TI, TO, V, 2><<<grid, block, 0, st>>>(B, H, W, C, log2s, mul, (const TI*)x, (TO*)out, out_ld);
+      else if (log2s == 2)
+        pool_sum_kernel<TI, TO, V, 4><<<grid, block, 0, st>>>(B, H, W, C, log2s, mul, (const TI*)x, (TO*)out, out_ld);
+      else
+        pool_sum_kernel<TI, TO, V, 0><<<grid, block, 0, st>>>(B, H, W, C, log2s, mul, (const TI*)x, (TO*)out, out_ld);
       return check_launch("pool_sum");
     }
   }
-  pool_sum_kernel<TI, TO, 1><<<grid, block, 0, st>>>(B, H, W, C, log2s, mul, (const TI*)x, (TO*)out, out_ld);
+  pool_sum_kernel<TI, TO, 1, 0><<<grid, block, 0, st>>>(B, H, W, C, log2s, mul, (const TI*)x, (TO*)out, out_ld);
   return check_launch("pool_sum");
 }
 
@@ -380,7 +430,7 @@ int accx_bn_bwd_reduce(int dtype, int64_t P, int C, const void* y, const float* 
   ACCX_REQUIRE(P > 0 && C > 0 && y && da && sums && mean && rstd, "bn_bwd_reduce: bad arguments");
   ACCX_DISPATCH_T(dtype, {
     Lanes l = make_lanes(C, DT<T>::VEC, aligned16(y) && aligned16(da));
-    dim3 block(l.tx, l.ty), grid(grid_x_for(P, l.ty * 8, 148 * 4), l.gy);
+    dim3 block(l.tx, l.ty), grid(grid_x_for(P, l.ty * 8, 148 * 8), l.gy);
     size_t sm = (size_t)l.tx * l.ty * l.vec * sizeof(float);
     ACCX_DISPATCH_VEC(l, {
       bn_bwd_reduce_kernel<T, VEC><<<grid, block, sm, (cudaStream_t)stream>>>(P, C, (const T*)y, scale, shift, act,

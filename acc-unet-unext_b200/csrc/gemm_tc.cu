@@ -2,44 +2,50 @@
 // fp32 accumulation.  Same contract as accx_pw_fwd (gemm_simt.cu): several lazy / shifted
 // operands with strided weight views, bias, nearest-upsample-adds, per-channel statistics.
 //
-//   Persistent kernel: grid = SMs x (1 or 2) CTAs, each CTA walks output tiles of 128 pixels x BN
-//   channels (BN <= 256); 320 threads in four roles that overlap across tiles:
-//     warp 8     TMA producer (one lane): per 64-channel k-block one cp.async.bulk.tensor.2d of the
-//                raw 128 x 64 activation box (128B swizzle, OOB rows/columns zero-filled) completing on
-//                `landed[s]`; the pre-packed bf16 weight tiles come by cp.async.bulk -- once per CTA
-//                when the whole weight matrix fits in shared memory, else one tile per stage.
-//     warps 4-7  transform: the pending BatchNorm affine + LeakyReLU of the producing layer is applied
-//                IN PLACE on the landed tile (16 B per thread, same swizzle), rows whose 3x3 tap falls
-//                outside the image are zeroed -- the normalised/activated tensor never exists in HBM --
-//                then fence.proxy.async + arrive on `full[s]`.
-//     warp 9     MMA issuer (one lane): tcgen05.mma M=128, N=BN, K=16, four per k-block, into one of
-//                two TMEM accumulator buffers; tcgen05.commit frees the smem stage / hands the
-//                accumulator to the epilogue.  Owns the TMEM allocation.
-//     warps 0-3  epilogue: tcgen05.ld -> (+bias, +nearest-upsampled addends) -> padded smem tile ->
-//                coalesced 16 B stores; per-channel (sum, sum^2) accumulate in registers across all the
-//                CTA's tiles and are flushed with one atomicAdd per channel per CTA.
+//   Persistent kernel: one CTA per SM walks output tiles of 128 pixels x BN channels (BN <= 256);
+//   448 threads in four roles that overlap across tiles:
+//     warp 12     TMA producer (one lane): per 64-channel k-block one cp.async.bulk.tensor.2d of the
+//                 raw 128 x 64 activation box (128B swizzle, OOB rows/columns zero-filled) completing on
+//                 `landed[s]`; the pre-packed bf16 weight tiles come by cp.async.bulk -- once per CTA
+//                 when the whole weight matrix fits in shared memory, else one tile per stage.
+//     warps 8-11  transform: the pending BatchNorm affine + LeakyReLU of the producing layer is applied
+//                 IN PLACE on the landed tile (16 B per thread, same swizzle), rows whose 3x3 tap falls
+//                 outside the image are zeroed -- the normalised/activated tensor never exists in HBM --
+//                 then fence.proxy.async + arrive on `full[s]`.
+//     warp 13     MMA issuer (one lane): tcgen05.mma M=128, N=BN, K=16, four per k-block, into one of
+//                 two TMEM accumulator buffers; tcgen05.commit frees the smem stage / hands the
+//                 accumulator to the epilogue.  Owns the TMEM allocation.
+//     warps 0-7   epilogue: two warps per TMEM lane quarter (each takes half of the columns):
+//                 tcgen05.ld (two 16-column loads in flight) -> (+bias, +nearest-upsampled addends) ->
+//                 bf16/fp32 -> 128B-swizzled staging boxes in shared memory -> ONE thread issues the
+//                 TMA stores (cp.async.bulk.tensor.2d.global.shared::cta; rows >= P and columns >= N are
+//                 clipped by the tensor map).  While the store drains, all 256 threads read the staged
+//                 tile back column-wise for the per-channel (sum, sum^2), kept in registers across the
+//                 CTA's tiles and flushed with one atomicAdd per channel when the channel block changes.
 #include "tc_common.cuh"
 
 namespace accx {
 
-constexpr int TC_BM = 128, TC_BK = 64, TC_THREADS = 320, TC_A_BYTES = TC_BM * TC_BK * 2;
+constexpr int TC_BM = 128, TC_BK = 64, TC_A_BYTES = TC_BM * TC_BK * 2;
+constexpr int TC_EPI_THREADS = 256, TC_WARP_XF0 = 8, TC_WARP_TMA = 12, TC_WARP_MMA = 13, TC_THREADS = 14 * 32;
+constexpr int TC_BOX_BYTES = TC_BM * 128;            // one staging box: 128 rows x 128 bytes
+constexpr int TC_SMEM_MAX = 227 * 1024;
 
 struct alignas(64) TcParams {
   CUtensorMap tmap[ACCX_MAX_OPERANDS];
+  CUtensorMap tmap_y;
   accx_operand_t op[ACCX_MAX_OPERANDS];
   int kb_start[ACCX_MAX_OPERANDS + 1];
   int n_ops, n_kb;
   int B, H, W, N;
   int64_t P;
   int bn, stages, tmem_cols, any_transform, out_f32;
-  int m_tiles, n_tiles, b_resident;
+  int m_tiles, n_tiles, b_resident, out_boxes;
   const bf16* wpack;
   const float* bias;
   const float* add[ACCX_MAX_ADDENDS];
   int add_log2s[ACCX_MAX_ADDENDS];
   int n_add;
-  void* y;
-  int64_t ldy;
   float* stats;
 };
 
@@ -62,52 +68,41 @@ __global__ void tc_pack_weights_kernel(const __grid_constant__ TcParams prm, bf1
   }
 }
 
-// ---------------------------------------------------------------- in-place transform of a landed A tile
-__device__ __forceinline__ void transform_tile(const TcParams& prm, const accx_operand_t& op, int k0, int64_t m0,
-                                               int c, int r0, const int* ph, const int* pw, uint32_t a_smem) {
-  const int kcol = k0 + c * 8;
-  const bool shifted = op.dy != 0 || op.dx != 0;
-  if (op.act == 0 && !shifted) return;
-  float s[8], t[8];
-  if (op.act != 0) {
-    if (kcol < op.K) {
-      ldf<8>(op.scale + kcol, s);
-      ldf<8>(op.shift + kcol, t);
-    } else {   // columns beyond K were zero-filled by TMA and must stay zero (their weights are zero too)
+// ---------------------------------------------------------------- epilogue helpers
+// 16 accumulator columns (tile-local column c0) of one row -> staging boxes.
+template <bool F32>
+__device__ __forceinline__ void stage_chunk(const float (&v)[16], uint32_t stage, int row, int c0) {
+  if constexpr (F32) {
+    const uint32_t rowb = stage + (c0 >> 5) * TC_BOX_BYTES + row * 128;
+    const int cc = (c0 & 31) >> 2;
 #pragma unroll
-      for (int e = 0; e < 8; ++e) { s[e] = 0.f; t[e] = 0.f; }
+    for (int q = 0; q < 4; ++q) {
+      const uint32_t addr = rowb + (((cc + q) ^ (row & 7)) << 4);
+      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(__float_as_uint(v[4 * q])),
+                   "r"(__float_as_uint(v[4 * q + 1])), "r"(__float_as_uint(v[4 * q + 2])),
+                   "r"(__float_as_uint(v[4 * q + 3]))
+                   : "memory");
     }
-  }
+  } else {
+    const uint32_t rowb = stage + (c0 >> 6) * TC_BOX_BYTES + row * 128;
+    const int cc = (c0 & 63) >> 3;
+    uint32_t w[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int row = r0 + 16 * i;
-    const uint32_t addr = a_smem + row * 128 + ((c ^ (row & 7)) << 4);
-    bool zero = false;
-    if (shifted) {
-      const int hh = ph[i] + op.dy, ww = pw[i] + op.dx;
-      zero = hh < 0 || hh >= prm.H || ww < 0 || ww >= prm.W || (m0 + row) >= prm.P;
+    for (int q = 0; q < 8; ++q) {
+      __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * q], v[2 * q + 1]);
+      w[q] = *reinterpret_cast<uint32_t*>(&h2);
     }
-    uint32_t w[4];
-    if (zero) {
-      w[0] = w[1] = w[2] = w[3] = 0u;
-    } else {
-      if (op.act == 0) continue;
-      asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(addr));
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        float lo = __uint_as_float(w[e] << 16), hi = __uint_as_float(w[e] & 0xffff0000u);
-        lo = fmaf(lo, s[2 * e], t[2 * e]);
-        hi = fmaf(hi, s[2 * e + 1], t[2 * e + 1]);
-        if (op.act == 2) { lo = lrelu(lo); hi = lrelu(hi); }
-        __nv_bfloat162 h2 = __floats2bfloat162_rn(lo, hi);
-        w[e] = *reinterpret_cast<uint32_t*>(&h2);
-      }
+    for (int q = 0; q < 2; ++q) {
+      const uint32_t addr = rowb + (((cc + q) ^ (row & 7)) << 4);
+      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(w[4 * q]), "r"(w[4 * q + 1]),
+                   "r"(w[4 * q + 2]), "r"(w[4 * q + 3])
+                   : "memory");
     }
-    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
   }
 }
 
-__global__ void __launch_bounds__(TC_THREADS) pw_fwd_tc_kernel(const __grid_constant__ TcParams prm) {
+__global__ void __launch_bounds__(TC_THREADS, 1) pw_fwd_tc_kernel(const __grid_constant__ TcParams prm) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
@@ -115,9 +110,9 @@ __global__ void __launch_bounds__(TC_THREADS) pw_fwd_tc_kernel(const __grid_cons
   const uint32_t b_tile_bytes = bn * 128;
   const uint32_t stage_bytes = TC_A_BYTES + (prm.b_resident ? 0 : b_tile_bytes);
   const uint32_t bres_off = S * stage_bytes;
-  const uint32_t epi_off = bres_off + (prm.b_resident ? n_kb * b_tile_bytes : 0);
-  const uint32_t out_pitch = (prm.out_f32 ? bn * 4 : bn * 2) + 16;     // bytes, odd number of 16 B chunks
-  const uint32_t bar_off = (epi_off + TC_BM * out_pitch + 2 * bn * 4 + 15u) & ~15u;
+  const uint32_t epi_off = bres_off + (prm.b_resident ? n_kb * b_tile_bytes : 0);      // 1024-aligned
+  const uint32_t stat_off = epi_off + prm.out_boxes * TC_BOX_BYTES;                    // float[2 * bn]
+  const uint32_t bar_off = (stat_off + 2 * bn * 4 + 15u) & ~15u;
   const uint32_t landed_bar = base + bar_off;            // S x 8 bytes
   const uint32_t full_bar = landed_bar + 8 * S;
   const uint32_t empty_bar = full_bar + 8 * S;
@@ -137,12 +132,12 @@ __global__ void __launch_bounds__(TC_THREADS) pw_fwd_tc_kernel(const __grid_cons
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar + 8 * a, 1);    // tcgen05.commit after the last k-block of a tile
-      mbar_init(tempty_bar + 8 * a, 4);   // the four epilogue warps have drained the accumulator
+      mbar_init(tempty_bar + 8 * a, 8);   // the eight epilogue warps have drained the accumulator
     }
     mbar_init(bres_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 9) {
+  if (warp == TC_WARP_MMA) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"((uint32_t)prm.tmem_cols)
                  : "memory");
@@ -153,7 +148,7 @@ __global__ void __launch_bounds__(TC_THREADS) pw_fwd_tc_kernel(const __grid_cons
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 8) {
+  if (warp == TC_WARP_TMA) {
     // ============================== TMA producer ==============================
     if (lane == 0) {
       if (prm.b_resident) {
@@ -182,7 +177,7 @@ __global__ void __launch_bounds__(TC_THREADS) pw_fwd_tc_kernel(const __grid_cons
         }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == TC_WARP_MMA) {
     // ============================== MMA issuer ================================
     if (lane == 0) {
       // instruction descriptor: D fp32, A/B bf16, both K-major, N = bn, M = 128
@@ -213,13 +208,16 @@ __global__ void __launch_bounds__(TC_THREADS) pw_fwd_tc_kernel(const __grid_cons
         tc_commit(tfull_bar + 8 * acc);
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= TC_WARP_XF0) {
     // ============================== transform warps ===========================
     if (prm.any_transform) {
-      const int t = tid - 128;
+      const int t = tid - TC_WARP_XF0 * 32;
       const int c = t & 7, r0 = t >> 3;
       const int HWp = prm.H * prm.W;
       int it = 0;
+      // scale/shift of the NEXT k-block are fetched while the current one is transformed
+      float s[8], sh[8];
+      load_affine8(prm.op[0], c * 8, s, sh);
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int64_t m0 = (int64_t)(tile % prm.m_tiles) * TC_BM;
         int ph[8], pw[8];
@@ -228,206 +226,222 @@ __global__ void __launch_bounds__(TC_THREADS) pw_fwd_tc_kernel(const __grid_cons
           const int64_t p = m0 + r0 + 16 * i;
           const int rem = (int)((p < prm.P ? p : 0) % HWp);
           ph[i] = rem / prm.W;
-          pw[i] = rem % prm.W;
+          pw[i] = p < prm.P ? rem % prm.W : -4;        // rows past the end count as outside the image
         }
         int o = 0;
         for (int kb = 0; kb < n_kb; ++kb, ++it) {
           while (o + 1 < prm.n_ops && kb >= prm.kb_start[o + 1]) ++o;
+          const accx_operand_t& op = prm.op[o];
+          // prefetch the affine of the k-block that follows (wraps to the first one of the next tile)
+          int kbn = kb + 1 < n_kb ? kb + 1 : 0, on = kb + 1 < n_kb ? o : 0;
+          while (on + 1 < prm.n_ops && kbn >= prm.kb_start[on + 1]) ++on;
+          float s_n[8], sh_n[8];
+          load_affine8(prm.op[on], (kbn - prm.kb_start[on]) * TC_BK + c * 8, s_n, sh_n);
+          uint32_t zero_mask = 0;
+          if (op.dy != 0 || op.dx != 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int hh = ph[i] + op.dy, ww = pw[i] + op.dx;
+              if (hh < 0 || hh >= prm.H || ww < 0 || ww >= prm.W || pw[i] < 0) zero_mask |= 1u << i;
+            }
+          }
           const int stage = it % S;
           const uint32_t phase = (it / S) & 1;
           mbar_wait(landed_bar + 8 * stage, phase);
-          transform_tile(prm, prm.op[o], (kb - prm.kb_start[o]) * TC_BK, m0, c, r0, ph, pw, base + stage * stage_bytes);
+          if (op.act != 0 || zero_mask != 0) transform_block(base + stage * stage_bytes, c, r0, op.act, s, sh, zero_mask);
           fence_async_smem();
           __syncwarp();
           if (lane == 0) mbar_arrive(full_bar + 8 * stage);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) { s[e] = s_n[e]; sh[e] = sh_n[e]; }
         }
       }
     }
   } else {
     // ============================== epilogue warps ============================
-    uint8_t* stage_out = smem + epi_off;                                   // [128][out_pitch]
-    float* sstat = reinterpret_cast<float*>(stage_out + TC_BM * out_pitch);  // [2][bn]
-    for (int j = tid; j < 2 * bn; j += 128) sstat[j] = 0.f;
-    const int cpr = bn >> 3;                       // 8-column chunks per row (<= 32)
-    const int TY = 128 / cpr;
-    const int tx = tid % cpr, ty = tid / cpr;      // read-out role: chunk tx of rows ty, ty+TY, ..
-    const bool vec_ok = (prm.N % 8 == 0) && (prm.ldy % 8 == 0) && ((reinterpret_cast<uintptr_t>(prm.y) & 15) == 0);
-    const bool flush_per_tile = prm.n_tiles > 1;
+    const uint32_t stage = base + epi_off;
+    float* sstat = reinterpret_cast<float*>(smem + stat_off);   // [2][bn]
+    for (int j = tid; j < 2 * bn; j += TC_EPI_THREADS) sstat[j] = 0.f;
+    const int quarter = warp & 3, half = warp >> 2;
+    const int row = quarter * 32 + lane;
+    const int n_chunks = bn >> 4;
+    const int ch_begin = half ? (n_chunks + 1) >> 1 : 0;
+    const int ch_end = half ? n_chunks : (n_chunks + 1) >> 1;
+    // statistics role: chunk tx (8 columns) of rows ty, ty + TY, ..
+    const int cpr = bn >> 3;
+    const int TY = TC_EPI_THREADS / cpr;
+    const int tx = tid % cpr, ty = tid / cpr;
+    const bool st_on = prm.stats != nullptr && !prm.out_f32;
+    const bool st_active = st_on && ty < TY;
+    const uint32_t st_base = stage + (tx >> 3) * TC_BOX_BYTES;
     float s1[8], s2[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
-    const int row = warp * 32 + lane;
-    const int HWp = prm.H * prm.W;
-    int tl = 0;
+    const int HWp = prm.H * prm.W, N = prm.N, n_add = prm.n_add;
+    const int64_t P = prm.P;
+    const float* bias = prm.bias;
+    const int box_cols = prm.out_f32 ? 32 : 64;
+    int cur_nt = -1, tl = 0;
+
+    auto flush_stats = [&](int nt_flush) {
+      if (st_active) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          atomicAdd(&sstat[tx * 8 + j], s1[j]);
+          atomicAdd(&sstat[bn + tx * 8 + j], s2[j]);
+          s1[j] = s2[j] = 0.f;
+        }
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const int n0f = nt_flush * bn;
+      for (int j = tid; j < bn; j += TC_EPI_THREADS) {
+        if (n0f + j < N) {
+          atomicAdd(prm.stats + n0f + j, sstat[j]);
+          atomicAdd(prm.stats + N + n0f + j, sstat[bn + j]);
+        }
+        sstat[j] = 0.f;
+        sstat[bn + j] = 0.f;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    };
+
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
-      const int n0 = (tile / prm.m_tiles) * bn;
+      const int nt = tile / prm.m_tiles;
+      const int n0 = nt * bn;
       const int64_t m0 = (int64_t)(tile % prm.m_tiles) * TC_BM;
       const int acc = tl & 1;
+      if (st_on && nt != cur_nt && cur_nt >= 0) flush_stats(cur_nt);
+      cur_nt = nt;
       const int64_t p = m0 + row;
-      const bool rvalid = p < prm.P;
-      int64_t addrow[ACCX_MAX_ADDENDS];
-      if (prm.n_add > 0 && rvalid) {
+      const bool rvalid = p < P;
+      const float* ap[ACCX_MAX_ADDENDS];
+#pragma unroll
+      for (int a = 0; a < ACCX_MAX_ADDENDS; ++a) ap[a] = nullptr;
+      if (n_add > 0 && rvalid) {
         const int b = (int)(p / HWp), rem = (int)(p % HWp);
         const int h = rem / prm.W, w = rem % prm.W;
-        for (int a = 0; a < prm.n_add; ++a) {
-          const int l = prm.add_log2s[a];
-          addrow[a] = (((int64_t)b * (prm.H >> l) + (h >> l)) * (prm.W >> l) + (w >> l)) * prm.N;
+#pragma unroll
+        for (int a = 0; a < ACCX_MAX_ADDENDS; ++a) {
+          if (a < n_add) {
+            const int l = prm.add_log2s[a];
+            ap[a] = prm.add[a] + (((int64_t)b * (prm.H >> l) + (h >> l)) * (prm.W >> l) + (w >> l)) * N + n0;
+          }
         }
       }
       mbar_wait(tfull_bar + 8 * acc, (tl >> 1) & 1);
       tc_fence_after();
-      for (int c0 = 0; c0 < bn; c0 += 16) {
-        float v[16];
-        tc_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + acc * bn + c0, v);
-        if (!rvalid) {
+      // the staging boxes are free once the previous tile's TMA stores have read them and every thread has
+      // finished its statistics pass
+      if (tid == 0) bulk_wait_read0();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * bn;
+      for (int ch = ch_begin; ch < ch_end; ch += 2) {
+        const bool two = ch + 1 < ch_end;
+        uint32_t r[2][16];
+        tc_ld16_issue(trow + ch * 16, r[0]);
+        if (two) tc_ld16_issue(trow + ch * 16 + 16, r[1]);
+        tc_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = 0.f;
-        } else if (n0 + c0 + 16 <= prm.N && (prm.N & 3) == 0) {
-          // full chunk: vectorised bias / nearest-upsampled addends (each addend row is contiguous in n)
-          if (prm.bias) {
-            const float4* bp = reinterpret_cast<const float4*>(prm.bias + n0 + c0);
+        for (int u = 0; u < 2; ++u) {
+          if (u == 1 && !two) break;
+          const int c0 = (ch + u) * 16;
+          float v[16];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float4 b4 = __ldg(bp + q);
-              v[4 * q] += b4.x; v[4 * q + 1] += b4.y; v[4 * q + 2] += b4.z; v[4 * q + 3] += b4.w;
+          for (int j = 0; j < 16; ++j) v[j] = rvalid ? __uint_as_float(r[u][j]) : 0.f;
+          if (rvalid && (bias != nullptr || n_add > 0)) {
+            if (n0 + c0 + 16 <= N && (N & 3) == 0) {
+              if (bias) {
+                const float4* bp = reinterpret_cast<const float4*>(bias + n0 + c0);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const float4 b4 = __ldg(bp + q);
+                  v[4 * q] += b4.x; v[4 * q + 1] += b4.y; v[4 * q + 2] += b4.z; v[4 * q + 3] += b4.w;
+                }
+              }
+#pragma unroll
+              for (int a = 0; a < ACCX_MAX_ADDENDS; ++a) {
+                if (a < n_add) {
+                  const float4* a4p = reinterpret_cast<const float4*>(ap[a] + c0);
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) {
+                    const float4 a4 = __ldg(a4p + q);
+                    v[4 * q] += a4.x; v[4 * q + 1] += a4.y; v[4 * q + 2] += a4.z; v[4 * q + 3] += a4.w;
+                  }
+                }
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const int n = n0 + c0 + j;
+                if (n < N) {
+                  if (bias) v[j] += __ldg(bias + n);
+#pragma unroll
+                  for (int a = 0; a < ACCX_MAX_ADDENDS; ++a)
+                    if (a < n_add) v[j] += __ldg(ap[a] + c0 + j);
+                }
+              }
             }
           }
-          for (int a = 0; a < prm.n_add; ++a) {
-            const float4* ap = reinterpret_cast<const float4*>(prm.add[a] + addrow[a] + n0 + c0);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float4 a4 = __ldg(ap + q);
-              v[4 * q] += a4.x; v[4 * q + 1] += a4.y; v[4 * q + 2] += a4.z; v[4 * q + 3] += a4.w;
-            }
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int n = n0 + c0 + j;
-            float x = 0.f;
-            if (n < prm.N) {
-              x = v[j];
-              if (prm.bias) x += __ldg(prm.bias + n);
-              for (int a = 0; a < prm.n_add; ++a) x += __ldg(prm.add[a] + addrow[a] + n);
-            }
-            v[j] = x;
-          }
-        }
-        if (prm.out_f32) {
-          float4* dst = reinterpret_cast<float4*>(stage_out + row * out_pitch + c0 * 4);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-        } else {
-          uint32_t w[8];
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * q], v[2 * q + 1]);
-            w[q] = *reinterpret_cast<uint32_t*>(&h2);
-          }
-          uint4* dst = reinterpret_cast<uint4*>(stage_out + row * out_pitch + c0 * 2);
-          dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
-          dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+          if (prm.out_f32) stage_chunk<true>(v, stage, row, c0);
+          else stage_chunk<false>(v, stage, row, c0);
         }
       }
       // accumulator drained: hand the TMEM buffer back to the MMA warp
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar + 8 * acc);
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (ty < TY) {
-        const int n = n0 + tx * 8;
-        for (int r = ty; r < TC_BM; r += TY) {
-          const int64_t pp = m0 + r;
-          float x[8];
-          if (prm.out_f32) {
-            const float4* src = reinterpret_cast<const float4*>(stage_out + r * out_pitch + tx * 32);
-            const float4 a = src[0], b = src[1];
-            x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
-          } else {
-            const uint4 u = *reinterpret_cast<const uint4*>(stage_out + r * out_pitch + tx * 16);
-            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+      fence_async_smem();                                   // generic-proxy writes -> visible to the TMA store
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (tid == 0) {
+        for (int b = 0; b < prm.out_boxes; ++b)
+          if (n0 + b * box_cols < N) tma_store_2d(&prm.tmap_y, stage + b * TC_BOX_BYTES, n0 + b * box_cols, (int)m0);
+        bulk_commit();
+      }
+      if (st_active) {
+        // column-wise read-back of the staged bf16 tile: this thread's 8 columns over its rows
+        for (int r = ty; r < TC_BM; r += 4 * TY) {
+          uint4 u[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              x[2 * q] = __uint_as_float(w[q] << 16);
-              x[2 * q + 1] = __uint_as_float(w[q] & 0xffff0000u);
+          for (int q = 0; q < 4; ++q) {
+            const int rr = r + q * TY;
+            if (rr < TC_BM) {
+              const uint32_t addr = st_base + rr * 128 + (((tx & 7) ^ (rr & 7)) << 4);
+              asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(u[q].x), "=r"(u[q].y), "=r"(u[q].z), "=r"(u[q].w) : "r"(addr));
+            } else {
+              u[q] = make_uint4(0u, 0u, 0u, 0u);
             }
-            if (vec_ok && pp < prm.P && n < prm.N) *reinterpret_cast<uint4*>((bf16*)prm.y + pp * prm.ldy + n) = u;
           }
-          if (prm.stats) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) { s1[j] += x[j]; s2[j] = fmaf(x[j], x[j], s2[j]); }
-          }
-          if (pp < prm.P && n < prm.N) {
-            if (prm.out_f32 && vec_ok) {
-              float* dst = (float*)prm.y + pp * prm.ldy + n;
-              *reinterpret_cast<float4*>(dst) = make_float4(x[0], x[1], x[2], x[3]);
-              *reinterpret_cast<float4*>(dst + 4) = make_float4(x[4], x[5], x[6], x[7]);
-            } else if (!vec_ok) {
-              for (int j = 0; j < 8 && n + j < prm.N; ++j) {
-                if (prm.out_f32) ((float*)prm.y)[pp * prm.ldy + n + j] = x[j];
-                else ((bf16*)prm.y)[pp * prm.ldy + n + j] = __float2bfloat16_rn(x[j]);
-              }
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t w[4] = {u[q].x, u[q].y, u[q].z, u[q].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float lo = __uint_as_float(w[e] << 16), hi = __uint_as_float(w[e] & 0xffff0000u);
+              s1[2 * e] += lo;
+              s2[2 * e] = fmaf(lo, lo, s2[2 * e]);
+              s1[2 * e + 1] += hi;
+              s2[2 * e + 1] = fmaf(hi, hi, s2[2 * e + 1]);
             }
           }
         }
       }
-      if (prm.stats && flush_per_tile) {     // the channel block changes between this CTA's tiles
-        if (ty < TY) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            atomicAdd(&sstat[tx * 8 + j], s1[j]);
-            atomicAdd(&sstat[bn + tx * 8 + j], s2[j]);
-            s1[j] = s2[j] = 0.f;
-          }
-        }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        for (int j = tid; j < bn; j += 128) {
-          if (n0 + j < prm.N) {
-            atomicAdd(prm.stats + n0 + j, sstat[j]);
-            atomicAdd(prm.stats + prm.N + n0 + j, sstat[bn + j]);
-          }
-          sstat[j] = 0.f;
-          sstat[bn + j] = 0.f;
-        }
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");     // staging tile is reused by the next tile
     }
-    if (prm.stats && !flush_per_tile) {
-      if (ty < TY) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          atomicAdd(&sstat[tx * 8 + j], s1[j]);
-          atomicAdd(&sstat[bn + tx * 8 + j], s2[j]);
-        }
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      for (int j = tid; j < bn; j += 128) {
-        if (j < prm.N) {
-          atomicAdd(prm.stats + j, sstat[j]);
-          atomicAdd(prm.stats + prm.N + j, sstat[bn + j]);
-        }
-      }
-    }
+    if (st_on && cur_nt >= 0) flush_stats(cur_nt);
+    if (tid == 0) bulk_wait0();            // all stores complete before the CTA (and its shared memory) retires
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) {
+  if (warp == TC_WARP_MMA) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)prm.tmem_cols)
                  : "memory");
   }
 }
 
 // ---------------------------------------------------------------- host side
-struct TcLaunch {
-  size_t smem;
-  int ctas_per_sm;
-};
-
-// Tile / pipeline geometry.  Weights stay resident in shared memory when the whole matrix fits
-// (small K: the HBM-bound layers); 2 CTAs per SM when shared memory and TMEM (2 x BN columns per
-// CTA, 512 per SM) allow it, else 1.
-static TcLaunch tc_geometry(int N, int64_t P, const accx_operand_t* ops, int n_ops, bool out_f32, TcParams& prm) {
-  prm.bn = N <= 256 ? (N + 15) / 16 * 16 : 256;
+// Tile / pipeline geometry.  BN: equal column tiles of at most 256 (128 for fp32 outputs, whose staging
+// boxes are twice as large), shrunk further when there are fewer tiles than SMs.  Weights stay resident
+// in shared memory when the whole matrix fits next to >= 3 pipeline stages.
+static size_t tc_geometry(int N, int64_t P, const accx_operand_t* ops, int n_ops, bool out_f32, TcParams& prm) {
   int kb = 0;
   for (int i = 0; i < n_ops; ++i) {
     prm.kb_start[i] = kb;
@@ -435,39 +449,34 @@ static TcLaunch tc_geometry(int N, int64_t P, const accx_operand_t* ops, int n_o
   }
   prm.kb_start[n_ops] = kb;
   prm.n_kb = kb;
-  prm.n_tiles = (N + prm.bn - 1) / prm.bn;
   prm.m_tiles = (int)((P + TC_BM - 1) / TC_BM);
+  const int max_bn = out_f32 ? 128 : 256;
+  int n_tiles = (N + max_bn - 1) / max_bn;
+  // several column tiles: BN must be a whole number of staging boxes, or a tile's last TMA-store box would
+  // spill into its neighbour's columns; a single tile only needs the MMA granularity (the store clips at N)
+  const int box_cols = out_f32 ? 32 : 64;
+  auto bn_for = [&](int nt) {
+    const int g = nt > 1 ? box_cols : 16;
+    return (((N + nt - 1) / nt) + g - 1) / g * g;
+  };
+  const int n_sm = sm_count();
+  while ((int64_t)prm.m_tiles * n_tiles < n_sm && bn_for(n_tiles) > 64) n_tiles *= 2;
+  prm.bn = bn_for(n_tiles);
+  prm.n_tiles = (N + prm.bn - 1) / prm.bn;
   int cols = 32;
   while (cols < 2 * prm.bn) cols <<= 1;
   prm.tmem_cols = cols;
+  prm.out_boxes = (prm.bn + box_cols - 1) / box_cols;
   const size_t b_tile = (size_t)prm.bn * 128;
-  const size_t epi = (size_t)TC_BM * ((out_f32 ? prm.bn * 4 : prm.bn * 2) + 16) + 2 * prm.bn * 4;
-  prm.b_resident = (prm.n_tiles == 1 && (size_t)kb * b_tile <= 72 * 1024) ? 1 : 0;
-  const size_t fixed = 1024 + epi + (prm.b_resident ? kb * b_tile : 0) + 256;
+  const size_t fixed = 1024 + (size_t)prm.out_boxes * TC_BOX_BYTES + 2 * prm.bn * 4 + 512;
+  prm.b_resident = (prm.n_tiles == 1 && fixed + (size_t)kb * b_tile + 3 * TC_A_BYTES <= (size_t)TC_SMEM_MAX) ? 1 : 0;
+  const size_t resident = prm.b_resident ? (size_t)kb * b_tile : 0;
   const size_t stage = TC_A_BYTES + (prm.b_resident ? 0 : b_tile);
-  TcLaunch L;
-  L.ctas_per_sm = 1;
-  int S = 0;
-  if (cols <= 256) {            // try two CTAs per SM with at least 3 stages (or all k-blocks)
-    const size_t budget = 113 * 1024;
-    int want = kb < 3 ? kb : 3;
-    if (fixed + want * stage <= budget) {
-      S = (int)((budget - fixed) / stage);
-      L.ctas_per_sm = 2;
-    }
-  }
-  if (S == 0) {
-    const size_t budget = 226 * 1024;
-    S = (int)((budget - fixed) / stage);
-  }
-  if (S > 6) S = 6;
+  int S = (int)((TC_SMEM_MAX - fixed - resident) / stage);
+  if (S > 8) S = 8;
   if (S < 1) S = 1;
   prm.stages = S;
-  L.smem = fixed + (size_t)S * stage;
-  // make the shared-memory footprint itself enforce the intended occupancy (TMEM would otherwise stall a third CTA)
-  const size_t min_smem = (227 * 1024) / (L.ctas_per_sm + 1) + 1024;
-  if (L.smem < min_smem) L.smem = min_smem;
-  return L;
+  return fixed + resident + (size_t)S * stage;
 }
 
 }  // namespace accx
@@ -478,9 +487,11 @@ extern "C" {
 
 int64_t accx_pw_tc_workspace_bytes(int N, const accx_operand_t* ops, int n_ops) {
   if (!ops || n_ops < 1 || n_ops > ACCX_MAX_OPERANDS) return -1;
-  TcParams prm;
-  tc_geometry(N, 1, ops, n_ops, false, prm);
-  return (int64_t)prm.n_tiles * prm.n_kb * prm.bn * TC_BK * 2;
+  // the packing geometry depends on the output dtype and on P only through BN: reserve for the finest split
+  int64_t kb = 0;
+  for (int i = 0; i < n_ops; ++i) kb += (ops[i].K + TC_BK - 1) / TC_BK;
+  const int64_t n_pad = 2 * (((int64_t)N + 15) / 16 * 16) + 64;
+  return kb * TC_BK * 2 * n_pad;
 }
 
 int accx_pw_fwd_tc(int dtype, int out_dtype, int B, int H, int W, int N, const accx_operand_t* ops, int n_ops,
@@ -491,11 +502,17 @@ int accx_pw_fwd_tc(int dtype, int out_dtype, int B, int H, int W, int N, const a
   ACCX_REQUIRE(n_add >= 0 && n_add <= ACCX_MAX_ADDENDS, "pw_fwd_tc: n_add %d out of range", n_add);
   ACCX_REQUIRE(dtype == ACCX_BF16, "pw_fwd_tc: operands must be bf16 (use accx_pw_fwd for fp32 storage)");
   ACCX_REQUIRE(ldy >= N, "pw_fwd_tc: ldy < N");
+  const bool out_f32 = out_dtype == ACCX_F32;
+  const int esz = out_f32 ? 4 : 2;
+  ACCX_REQUIRE(aligned16(y) && (ldy * esz) % 16 == 0,
+               "pw_fwd_tc: output needs a 16-byte aligned base and row pitch (use accx_pw_fwd)");
+  ACCX_REQUIRE(!(stats && out_f32), "pw_fwd_tc: statistics are produced for bf16 outputs only (use accx_pw_fwd)");
   ACCX_REQUIRE(get_encode() != nullptr, "pw_fwd_tc: cuTensorMapEncodeTiled not available from the driver");
   TcParams prm;
   prm.n_ops = n_ops;
   prm.any_transform = 0;
   const int64_t P = (int64_t)B * H * W;
+  ACCX_REQUIRE(P < (int64_t)1 << 31, "pw_fwd_tc: too many pixels");
   for (int i = 0; i < n_ops; ++i) {
     prm.op[i] = ops[i];
     ACCX_REQUIRE(ops[i].data && ops[i].w && ops[i].K > 0, "pw_fwd_tc: operand %d malformed", i);
@@ -507,39 +524,41 @@ int accx_pw_fwd_tc(int dtype, int out_dtype, int B, int H, int W, int N, const a
     ACCX_REQUIRE(encode_2d_bf16(&prm.tmap[i], ops[i].data, ops[i].K, P, ops[i].ld, TC_BM),
                  "pw_fwd_tc: cuTensorMapEncodeTiled failed for operand %d", i);
   }
-  const TcLaunch L = tc_geometry(N, P, ops, n_ops, out_dtype == ACCX_F32, prm);
+  ACCX_REQUIRE(encode_2d_out(&prm.tmap_y, y, N, P, ldy, esz, TC_BM), "pw_fwd_tc: cuTensorMapEncodeTiled failed for the output");
+  const size_t smem = tc_geometry(N, P, ops, n_ops, out_f32, prm);
   const int n_tiles = prm.n_tiles;
   const int64_t need = (int64_t)n_tiles * prm.n_kb * prm.bn * TC_BK * 2;
   ACCX_REQUIRE(workspace_bytes >= need && aligned16(workspace), "pw_fwd_tc: workspace too small (%lld < %lld)",
                (long long)workspace_bytes, (long long)need);
   prm.B = B; prm.H = H; prm.W = W; prm.N = N;
   prm.P = P;
-  prm.out_f32 = out_dtype == ACCX_F32;
+  prm.out_f32 = out_f32 ? 1 : 0;
   prm.wpack = (const bf16*)workspace;
   prm.bias = bias;
   prm.n_add = n_add;
+  for (int i = 0; i < ACCX_MAX_ADDENDS; ++i) { prm.add[i] = nullptr; prm.add_log2s[i] = 0; }
   for (int i = 0; i < n_add; ++i) {
     prm.add[i] = add[i];
     prm.add_log2s[i] = add_log2s[i];
     ACCX_REQUIRE(add[i] && add_log2s[i] >= 0 && (H >> add_log2s[i]) << add_log2s[i] == H &&
                      (W >> add_log2s[i]) << add_log2s[i] == W,
                  "pw_fwd_tc: addend %d does not tile %dx%d", i, H, W);
+    ACCX_REQUIRE(aligned16(add[i]) || (N & 3) != 0, "pw_fwd_tc: addend %d must be 16-byte aligned", i);
   }
-  prm.y = y; prm.ldy = ldy; prm.stats = stats;
+  prm.stats = stats;
   cudaStream_t st = (cudaStream_t)stream;
   tc_pack_weights_kernel<<<dim3(prm.n_kb, n_tiles, (prm.bn * TC_BK + 1023) / 1024), 256, 0, st>>>(prm, (bf16*)workspace);
   int rc = check_launch("tc_pack_weights");
   if (rc) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(pw_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(pw_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX);
     attr_set = true;
   }
-  const int n_sm = sm_count();
   const int64_t total = (int64_t)prm.m_tiles * prm.n_tiles;
-  int64_t grid = (int64_t)n_sm * L.ctas_per_sm;
+  int64_t grid = sm_count();
   if (grid > total) grid = total;
-  pw_fwd_tc_kernel<<<(unsigned)grid, TC_THREADS, L.smem, st>>>(prm);
+  pw_fwd_tc_kernel<<<(unsigned)grid, TC_THREADS, smem, st>>>(prm);
   return check_launch("pw_fwd_tc");
 }
 

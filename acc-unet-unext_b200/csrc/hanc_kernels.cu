@@ -58,7 +58,8 @@ __global__ void hanc_pool_kernel(int B, int H, int W, int C, int first, const T*
 }
 
 // da[p] (+)= davg[blk]/s^2 + [p == first row-major argmax of blk] * dmax[blk]
-template <typename T, int VEC>
+// S > 0: compile-time window (all S*S loads of a block are issued before the first compare); S == 0: generic.
+template <typename T, int VEC, int S>
 __global__ void hanc_unpool_kernel(int B, int H, int W, int C, int log2s, const T* __restrict__ x, const float* scale,
                                    const float* shift, int act, const float* __restrict__ dpool, T* __restrict__ da,
                                    int accumulate) {
@@ -67,7 +68,7 @@ __global__ void hanc_unpool_kernel(int B, int H, int W, int C, int log2s, const 
   const int c0 = cv * VEC;
   Lazy<VEC> lz;
   lz.init(scale, shift, act, c0);
-  const int s = 1 << log2s, Ho = H >> log2s, Wo = W >> log2s;
+  const int s = S > 0 ? S : 1 << log2s, Ho = H >> log2s, Wo = W >> log2s;
   const float inv = 1.f / (float)(s * s);
   const int64_t Po = (int64_t)B * Ho * Wo;
   for (int64_t q = (int64_t)blockIdx.x * blockDim.y + threadIdx.y; q < Po; q += (int64_t)gridDim.x * blockDim.y) {
@@ -80,32 +81,71 @@ __global__ void hanc_unpool_kernel(int B, int H, int W, int C, int log2s, const 
     int arg[VEC];
 #pragma unroll
     for (int e = 0; e < VEC; ++e) { mx[e] = -FLT_MAX; arg[e] = 0; }
-    for (int i = 0; i < s; ++i)
-      for (int j = 0; j < s; ++j) {
+    float ga[VEC], gm[VEC];
+    if constexpr (S > 0) {
+      constexpr bool PRE = S == 2;        // 2x2: the read-modify-write operand is prefetched as well
+      RawVec<T, VEC> rx[S * S], rd[PRE ? S * S : 1];
+#pragma unroll
+      for (int i = 0; i < S; ++i)
+#pragma unroll
+        for (int j = 0; j < S; ++j) {
+          rx[i * S + j].load(x + base + ((int64_t)i * W + j) * C);
+          if (PRE && accumulate) rd[PRE ? i * S + j : 0].load(da + base + ((int64_t)i * W + j) * C);
+        }
+      ldf<VEC>(dpool + q * 2 * C + c0, ga);
+      ldf<VEC>(dpool + q * 2 * C + C + c0, gm);
+#pragma unroll
+      for (int k = 0; k < S * S; ++k) {
         float v[VEC];
-        ldv<T, VEC>(x + base + ((int64_t)i * W + j) * C, v);
+        rx[k].unpack(v);
         lz.apply(v);
 #pragma unroll
         for (int e = 0; e < VEC; ++e)
-          if (v[e] > mx[e]) { mx[e] = v[e]; arg[e] = i * s + j; }   // strict > keeps the FIRST maximum
+          if (v[e] > mx[e]) { mx[e] = v[e]; arg[e] = k; }   // strict > keeps the FIRST maximum
       }
-    float ga[VEC], gm[VEC];
-    ldf<VEC>(dpool + q * 2 * C + c0, ga);
-    ldf<VEC>(dpool + q * 2 * C + C + c0, gm);
-    for (int i = 0; i < s; ++i)
-      for (int j = 0; j < s; ++j) {
-        float g[VEC];
-        T* dst = da + base + ((int64_t)i * W + j) * C;
-        if (accumulate) {
-          ldv<T, VEC>(dst, g);
-        } else {
 #pragma unroll
-          for (int e = 0; e < VEC; ++e) g[e] = 0.f;
+      for (int i = 0; i < S; ++i)
+#pragma unroll
+        for (int j = 0; j < S; ++j) {
+          float g[VEC];
+          if (accumulate) {
+            if constexpr (PRE) rd[i * S + j].unpack(g);
+            else ldv<T, VEC>(da + base + ((int64_t)i * W + j) * C, g);
+          } else {
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) g[e] = 0.f;
+          }
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) g[e] += ga[e] * inv + (arg[e] == i * S + j ? gm[e] : 0.f);
+          stv<T, VEC>(da + base + ((int64_t)i * W + j) * C, g);
         }
+    } else {
+      for (int i = 0; i < s; ++i)
+        for (int j = 0; j < s; ++j) {
+          float v[VEC];
+          ldv<T, VEC>(x + base + ((int64_t)i * W + j) * C, v);
+          lz.apply(v);
 #pragma unroll
-        for (int e = 0; e < VEC; ++e) g[e] += ga[e] * inv + (arg[e] == i * s + j ? gm[e] : 0.f);
-        stv<T, VEC>(dst, g);
-      }
+          for (int e = 0; e < VEC; ++e)
+            if (v[e] > mx[e]) { mx[e] = v[e]; arg[e] = i * s + j; }
+        }
+      ldf<VEC>(dpool + q * 2 * C + c0, ga);
+      ldf<VEC>(dpool + q * 2 * C + C + c0, gm);
+      for (int i = 0; i < s; ++i)
+        for (int j = 0; j < s; ++j) {
+          float g[VEC];
+          T* dst = da + base + ((int64_t)i * W + j) * C;
+          if (accumulate) {
+            ldv<T, VEC>(dst, g);
+          } else {
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) g[e] = 0.f;
+          }
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) g[e] += ga[e] * inv + (arg[e] == i * s + j ? gm[e] : 0.f);
+          stv<T, VEC>(dst, g);
+        }
+    }
   }
 }
 
@@ -141,8 +181,15 @@ int accx_hanc_unpool_bwd(int dtype, int B, int H, int W, int C, int log2s, const
     Lanes l = make_lanes(C, DT<T>::VEC, aligned16(x) && aligned16(da) && aligned16(dpool));
     dim3 block(l.tx, l.ty), grid(grid_x_for(Po, l.ty * 2, 148 * 8), l.gy);
     ACCX_DISPATCH_VEC(l, {
-      hanc_unpool_kernel<T, VEC><<<grid, block, 0, (cudaStream_t)stream>>>(B, H, W, C, log2s, (const T*)x, scale, shift,
-                                                                           act, dpool, (T*)da, accumulate);
+      if (log2s == 1)
+        hanc_unpool_kernel<T, VEC, 2><<<grid, block, 0, (cudaStream_t)stream>>>(B, H, W, C, log2s, (const T*)x, scale,
+                                                                                shift, act, dpool, (T*)da, accumulate);
+      else if (log2s == 2)
+        hanc_unpool_kernel<T, VEC, 4><<<grid, block, 0, (cudaStream_t)stream>>>(B, H, W, C, log2s, (const T*)x, scale,
+                                                                                shift, act, dpool, (T*)da, accumulate);
+      else
+        hanc_unpool_kernel<T, VEC, 0><<<grid, block, 0, (cudaStream_t)stream>>>(B, H, W, C, log2s, (const T*)x, scale,
+                                                                                shift, act, dpool, (T*)da, accumulate);
     });
   });
   return check_launch("hanc_unpool_bwd");

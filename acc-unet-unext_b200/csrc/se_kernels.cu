@@ -24,13 +24,17 @@ __global__ void se_squeeze_kernel(int B, int HW, int C, int chunks, const T* __r
   for (int i = 0; i < VEC; ++i) acc[0][i] = acc[1][i] = 0.f;
   if (active) {
     const T* img = x + (int64_t)b * HW * C + c0;
-    for (int p = chunk * blockDim.y + threadIdx.y; p < HW; p += chunks * blockDim.y) {
-      float v[VEC];
-      ldv<T, VEC>(img + (int64_t)p * C, v);
-      lz.apply(v);
+    constexpr int U = 8;
+    RawVec<T, VEC> rx[U];
+    pixel_loop<U>(chunk * blockDim.y + threadIdx.y, HW, chunks * blockDim.y,
+        [&](int u, int64_t p) { rx[u].load(img + p * C); },
+        [&](int u, int64_t p) {
+          float v[VEC];
+          rx[u].unpack(v);
+          lz.apply(v);
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) { acc[0][i] += v[i]; acc[1][i] += v[i] * v[i]; }
-    }
+          for (int i = 0; i < VEC; ++i) { acc[0][i] += v[i]; acc[1][i] += v[i] * v[i]; }
+        });
   }
   reduce_lanes_atomic<2, VEC>(acc, smem, S + (int64_t)b * C, (int64_t)B * C, c0, active);
 }
@@ -132,24 +136,31 @@ __global__ void se_apply_kernel(int B, int HW, int C, const T* __restrict__ x, c
   for (int i = 0; i < VEC; ++i) acc[0][i] = acc[1][i] = 0.f;
   const int64_t P = (int64_t)B * HW;
   if (active) {
-    for (int64_t p = (int64_t)blockIdx.x * blockDim.y + threadIdx.y; p < P; p += (int64_t)gridDim.x * blockDim.y) {
-      const int b = (int)(p / HW);
-      float v[VEC], g[VEC];
-      ldv<T, VEC>(x + p * C + c0, v);
-      ldf<VEC>(gate + (int64_t)b * C + c0, g);
-      lz.apply(v);
+    constexpr int U = 4;
+    RawVec<T, VEC> rv[U], rr[U];
+    pixel_loop<U>((int64_t)blockIdx.x * blockDim.y + threadIdx.y, P, (int64_t)gridDim.x * blockDim.y,
+        [&](int u, int64_t p) {
+          rv[u].load(x + p * C + c0);
+          if (residual) rr[u].load(residual + p * C + c0);
+        },
+        [&](int u, int64_t p) {
+          const int b = (int)(p / HW);
+          float v[VEC], g[VEC];
+          rv[u].unpack(v);
+          ldf<VEC>(gate + (int64_t)b * C + c0, g);
+          lz.apply(v);
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) v[i] = lrelu(fmaf(v[i] * g[i], ss[i], st[i]));
-      if (residual) {
-        float r[VEC];
-        ldv<T, VEC>(residual + p * C + c0, r);
+          for (int i = 0; i < VEC; ++i) v[i] = lrelu(fmaf(v[i] * g[i], ss[i], st[i]));
+          if (residual) {
+            float r[VEC];
+            rr[u].unpack(r);
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) v[i] = v[i] * mx + r[i] * rx;
-      }
+            for (int i = 0; i < VEC; ++i) v[i] = v[i] * mx + r[i] * rx;
+          }
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) { acc[0][i] += v[i]; acc[1][i] += v[i] * v[i]; }
-      stv<T, VEC>(out + p * C + c0, v);
-    }
+          for (int i = 0; i < VEC; ++i) { acc[0][i] += v[i]; acc[1][i] += v[i] * v[i]; }
+          stv<T, VEC>(out + p * C + c0, v);
+        });
   }
   if (stats) reduce_lanes_atomic<2, VEC>(acc, smem, stats, C, c0, active);
 }
@@ -178,22 +189,29 @@ __global__ void se_bwd_reduce_kernel(int B, int HW, int C, int chunks, const T* 
   for (int i = 0; i < VEC; ++i) acc[0][i] = acc[1][i] = 0.f;
   if (active) {
     const int64_t off = (int64_t)b * HW * C + c0;
-    for (int p = chunk * blockDim.y + threadIdx.y; p < HW; p += chunks * blockDim.y) {
-      float v[VEC], d[VEC];
-      ldv<T, VEC>(x + off + (int64_t)p * C, v);
-      ldv<T, VEC>(dout + off + (int64_t)p * C, d);
-      lz.apply(v);
-      float r[VEC];
-      if (dmix) ldv<T, VEC>(residual + off + (int64_t)p * C, r);
+    constexpr int U = 4;
+    RawVec<T, VEC> rv[U], rd[U], rr[U];
+    pixel_loop<U>(chunk * blockDim.y + threadIdx.y, HW, chunks * blockDim.y,
+        [&](int u, int64_t p) {
+          rv[u].load(x + off + p * C);
+          rd[u].load(dout + off + p * C);
+          if (dmix) rr[u].load(residual + off + p * C);
+        },
+        [&](int u, int64_t p) {
+          float v[VEC], d[VEC], r[VEC];
+          rv[u].unpack(v);
+          rd[u].unpack(d);
+          if (dmix) rr[u].unpack(r);
+          lz.apply(v);
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) {
-        float u = fmaf(v[i] * g[i], ss[i], st[i]);
-        if (dmix) dm += d[i] * (lrelu(u) - r[i]);
-        float gp = d[i] * mx * (u > 0.f ? 1.f : ACCX_LRELU);
-        acc[0][i] += gp;
-        acc[1][i] += gp * v[i];
-      }
-    }
+          for (int i = 0; i < VEC; ++i) {
+            float uu = fmaf(v[i] * g[i], ss[i], st[i]);
+            if (dmix) dm += d[i] * (lrelu(uu) - r[i]);
+            float gp = d[i] * mx * (uu > 0.f ? 1.f : ACCX_LRELU);
+            acc[0][i] += gp;
+            acc[1][i] += gp * v[i];
+          }
+        });
   }
   reduce_lanes_atomic<2, VEC>(acc, smem, G + (int64_t)b * C, (int64_t)B * C, c0, active);
   if (dmix) {   // block size need not be a multiple of 32: reduce through shared memory
@@ -302,31 +320,39 @@ __global__ void se_bwd_apply_kernel(int B, int HW, int C, const T* __restrict__ 
   ldf<VEC>(se_shift + c0, st);
   const float mx = mix ? *mix : 1.f;
   const int64_t P = (int64_t)B * HW, BC = (int64_t)B * C;
-  for (int64_t p = (int64_t)blockIdx.x * blockDim.y + threadIdx.y; p < P; p += (int64_t)gridDim.x * blockDim.y) {
-    const int b = (int)(p / HW);
-    float v[VEC], d[VEC], g[VEC], cp[VEC], cq[VEC], cr[VEC];
-    ldv<T, VEC>(x + p * C + c0, v);
-    ldv<T, VEC>(dout + p * C + c0, d);
-    ldf<VEC>(gate + (int64_t)b * C + c0, g);
-    ldf<VEC>(PQR + (int64_t)b * C + c0, cp);
-    ldf<VEC>(PQR + BC + (int64_t)b * C + c0, cq);
-    ldf<VEC>(PQR + 2 * BC + (int64_t)b * C + c0, cr);
-    lz.apply(v);
-    float o[VEC];
-    if (accumulate) {
-      ldv<T, VEC>(da + p * C + c0, o);
-    } else {
+  constexpr int U = 4;
+  RawVec<T, VEC> rv[U], rd[U], ro[U];
+  pixel_loop<U>((int64_t)blockIdx.x * blockDim.y + threadIdx.y, P, (int64_t)gridDim.x * blockDim.y,
+      [&](int u, int64_t p) {
+        rv[u].load(x + p * C + c0);
+        rd[u].load(dout + p * C + c0);
+        if (accumulate) ro[u].load(da + p * C + c0);
+      },
+      [&](int u, int64_t p) {
+        const int b = (int)(p / HW);
+        float v[VEC], d[VEC], g[VEC], cp[VEC], cq[VEC], cr[VEC];
+        rv[u].unpack(v);
+        rd[u].unpack(d);
+        ldf<VEC>(gate + (int64_t)b * C + c0, g);
+        ldf<VEC>(PQR + (int64_t)b * C + c0, cp);
+        ldf<VEC>(PQR + BC + (int64_t)b * C + c0, cq);
+        ldf<VEC>(PQR + 2 * BC + (int64_t)b * C + c0, cr);
+        lz.apply(v);
+        float o[VEC];
+        if (accumulate) {
+          ro[u].unpack(o);
+        } else {
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) o[i] = 0.f;
-    }
+          for (int i = 0; i < VEC; ++i) o[i] = 0.f;
+        }
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) {
-      float u = fmaf(v[i] * g[i], ss[i], st[i]);
-      float gp = d[i] * mx * (u > 0.f ? 1.f : ACCX_LRELU);
-      o[i] += cp[i] * gp + cq[i] * v[i] + cr[i];
-    }
-    stv<T, VEC>(da + p * C + c0, o);
-  }
+        for (int i = 0; i < VEC; ++i) {
+          float uu = fmaf(v[i] * g[i], ss[i], st[i]);
+          float gp = d[i] * mx * (uu > 0.f ? 1.f : ACCX_LRELU);
+          o[i] += cp[i] * gp + cq[i] * v[i] + cr[i];
+        }
+        stv<T, VEC>(da + p * C + c0, o);
+      });
 }
 
 static inline int se_chunks(int B, int HW, int ty) {

@@ -141,7 +141,8 @@ def test_pw_wgrad(dtype, K, N, act):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("C,H,W", [(9, 7, 5), (96, 12, 10), (24, 8, 8), (272, 4, 6)])
+@pytest.mark.parametrize("C,H,W", [(9, 7, 5), (96, 12, 10), (24, 8, 8), (272, 4, 6), (64, 32, 64), (384, 24, 24),
+                                   (160, 16, 16), (96, 48, 96), (200, 9, 33)])
 def test_dw3x3(dtype, C, H, W):
     e = E()
     B = 2
