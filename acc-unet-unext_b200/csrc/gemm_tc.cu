@@ -3,16 +3,16 @@
 // operands with strided weight views, bias, nearest-upsample-adds, per-channel statistics.
 //
 //   Persistent kernel: one CTA per SM walks output tiles of 128 pixels x BN channels (BN <= 256);
-//   448 threads in four roles that overlap across tiles:
-//     warp 12     TMA producer (one lane): per 64-channel k-block one cp.async.bulk.tensor.2d of the
+//   576 threads in four roles that overlap across tiles:
+//     warp 16     TMA producer (one lane): per 64-channel k-block one cp.async.bulk.tensor.2d of the
 //                 raw 128 x 64 activation box (128B swizzle, OOB rows/columns zero-filled) completing on
 //                 `landed[s]`; the pre-packed bf16 weight tiles come by cp.async.bulk -- once per CTA
 //                 when the whole weight matrix fits in shared memory, else one tile per stage.
-//     warps 8-11  transform: the pending BatchNorm affine + LeakyReLU of the producing layer is applied
+//     warps 8-15  transform: the pending BatchNorm affine + LeakyReLU of the producing layer is applied
 //                 IN PLACE on the landed tile (16 B per thread, same swizzle), rows whose 3x3 tap falls
 //                 outside the image are zeroed -- the normalised/activated tensor never exists in HBM --
 //                 then fence.proxy.async + arrive on `full[s]`.
-//     warp 13     MMA issuer (one lane): tcgen05.mma M=128, N=BN, K=16, four per k-block, into one of
+//     warp 17     MMA issuer (one lane): tcgen05.mma M=128, N=BN, K=16, four per k-block, into one of
 //                 two TMEM accumulator buffers; tcgen05.commit frees the smem stage / hands the
 //                 accumulator to the epilogue.  Owns the TMEM allocation.
 //     warps 0-7   epilogue: two warps per TMEM lane quarter (each takes half of the columns):
@@ -27,7 +27,8 @@
 namespace accx {
 
 constexpr int TC_BM = 128, TC_BK = 64, TC_A_BYTES = TC_BM * TC_BK * 2;
-constexpr int TC_EPI_THREADS = 256, TC_WARP_XF0 = 8, TC_WARP_TMA = 12, TC_WARP_MMA = 13, TC_THREADS = 14 * 32;
+constexpr int TC_EPI_THREADS = 256, TC_XF_THREADS = 256, TC_WARP_XF0 = 8, TC_WARP_TMA = 16, TC_WARP_MMA = 17;
+constexpr int TC_THREADS = 18 * 32;
 constexpr int TC_BOX_BYTES = TC_BM * 128;            // one staging box: 128 rows x 128 bytes
 constexpr int TC_SMEM_MAX = 227 * 1024;
 
@@ -39,7 +40,7 @@ struct alignas(64) TcParams {
   int n_ops, n_kb;
   int B, H, W, N;
   int64_t P;
-  int bn, stages, tmem_cols, any_transform, out_f32;
+  int bn, stages, tmem_cols, any_transform, any_shift, out_f32;
   int m_tiles, n_tiles, b_resident, out_boxes;
   const bf16* wpack;
   const float* bias;
@@ -112,7 +113,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_fwd_tc_kernel(const __grid_c
   const uint32_t bres_off = S * stage_bytes;
   const uint32_t epi_off = bres_off + (prm.b_resident ? n_kb * b_tile_bytes : 0);      // 1024-aligned
   const uint32_t stat_off = epi_off + prm.out_boxes * TC_BOX_BYTES;                    // float[2 * bn]
-  const uint32_t bar_off = (stat_off + 2 * bn * 4 + 15u) & ~15u;
+  const uint32_t tab_off = (stat_off + 2 * bn * 4 + 15u) & ~15u;                       // float[n_kb][2][64] + int4[n_kb]
+  const uint32_t bar_off = tab_off + (prm.any_transform ? n_kb * (512 + 16) : 0);
   const uint32_t landed_bar = base + bar_off;            // S x 8 bytes
   const uint32_t full_bar = landed_bar + 8 * S;
   const uint32_t empty_bar = full_bar + 8 * S;
@@ -127,7 +129,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_fwd_tc_kernel(const __grid_c
   if (tid == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(landed_bar + 8 * s, 1);   // producer's arrive.expect_tx (+ the TMA transaction bytes)
-      mbar_init(full_bar + 8 * s, 4);     // the four transform warps
+      mbar_init(full_bar + 8 * s, 8);     // the eight transform warps
       mbar_init(empty_bar + 8 * s, 1);    // tcgen05.commit
     }
     for (int a = 0; a < 2; ++a) {
@@ -212,48 +214,65 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_fwd_tc_kernel(const __grid_c
     // ============================== transform warps ===========================
     if (prm.any_transform) {
       const int t = tid - TC_WARP_XF0 * 32;
-      const int c = t & 7, r0 = t >> 3;
+      const int c = t & 7, r0 = t >> 3;                       // rows r0, r0 + 32, r0 + 64, r0 + 96
+      // per-k-block tables in shared memory: scale[64] | shift[64] (zeros beyond K) and {act, dy, dx, -}
+      float* tab = reinterpret_cast<float*>(smem + tab_off);
+      int4* meta = reinterpret_cast<int4*>(smem + tab_off + n_kb * 512);
+      for (int idx = t; idx < n_kb * 64; idx += TC_XF_THREADS) {
+        const int kb = idx >> 6, j = idx & 63;
+        int o = 0;
+        while (o + 1 < prm.n_ops && kb >= prm.kb_start[o + 1]) ++o;
+        const accx_operand_t& op = prm.op[o];
+        const int k = (kb - prm.kb_start[o]) * TC_BK + j;
+        const bool on = op.act != 0 && k < op.K;
+        tab[kb * 128 + j] = on ? __ldg(op.scale + k) : 0.f;
+        tab[kb * 128 + 64 + j] = on ? __ldg(op.shift + k) : 0.f;
+        if (j == 0) meta[kb] = make_int4(op.act, op.dy, op.dx, 0);
+      }
+      asm volatile("bar.sync 2, 256;" ::: "memory");
       const int HWp = prm.H * prm.W;
       int it = 0;
-      // scale/shift of the NEXT k-block are fetched while the current one is transformed
-      float s[8], sh[8];
-      load_affine8(prm.op[0], c * 8, s, sh);
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int64_t m0 = (int64_t)(tile % prm.m_tiles) * TC_BM;
-        int ph[8], pw[8];
+        const int m0 = (tile % prm.m_tiles) * TC_BM;
+        int ph[4], pw[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int64_t p = m0 + r0 + 16 * i;
-          const int rem = (int)((p < prm.P ? p : 0) % HWp);
-          ph[i] = rem / prm.W;
-          pw[i] = p < prm.P ? rem % prm.W : -4;        // rows past the end count as outside the image
+        for (int i = 0; i < 4; ++i) { ph[i] = 0; pw[i] = 0; }
+        if (prm.any_shift) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int p = m0 + r0 + 32 * i;                   // P < 2^31 (checked by the launcher)
+            const int rem = p % HWp;
+            ph[i] = rem / prm.W;
+            pw[i] = p < (int)prm.P ? rem - ph[i] * prm.W : -4;   // rows past the end count as outside the image
+          }
         }
-        int o = 0;
         for (int kb = 0; kb < n_kb; ++kb, ++it) {
-          while (o + 1 < prm.n_ops && kb >= prm.kb_start[o + 1]) ++o;
-          const accx_operand_t& op = prm.op[o];
-          // prefetch the affine of the k-block that follows (wraps to the first one of the next tile)
-          int kbn = kb + 1 < n_kb ? kb + 1 : 0, on = kb + 1 < n_kb ? o : 0;
-          while (on + 1 < prm.n_ops && kbn >= prm.kb_start[on + 1]) ++on;
-          float s_n[8], sh_n[8];
-          load_affine8(prm.op[on], (kbn - prm.kb_start[on]) * TC_BK + c * 8, s_n, sh_n);
-          uint32_t zero_mask = 0;
-          if (op.dy != 0 || op.dx != 0) {
+          const int4 mt = meta[kb];
+          float s[8], sh[8];
+          if (mt.x != 0) {
+            const float4* sp = reinterpret_cast<const float4*>(tab + kb * 128 + c * 8);
+            const float4 a0 = sp[0], a1 = sp[1], b0 = sp[16], b1 = sp[17];
+            s[0] = a0.x; s[1] = a0.y; s[2] = a0.z; s[3] = a0.w; s[4] = a1.x; s[5] = a1.y; s[6] = a1.z; s[7] = a1.w;
+            sh[0] = b0.x; sh[1] = b0.y; sh[2] = b0.z; sh[3] = b0.w; sh[4] = b1.x; sh[5] = b1.y; sh[6] = b1.z; sh[7] = b1.w;
+          } else {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int hh = ph[i] + op.dy, ww = pw[i] + op.dx;
+            for (int e = 0; e < 8; ++e) { s[e] = 1.f; sh[e] = 0.f; }
+          }
+          uint32_t zero_mask = 0;
+          if (mt.y != 0 || mt.z != 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int hh = ph[i] + mt.y, ww = pw[i] + mt.z;
               if (hh < 0 || hh >= prm.H || ww < 0 || ww >= prm.W || pw[i] < 0) zero_mask |= 1u << i;
             }
           }
           const int stage = it % S;
           const uint32_t phase = (it / S) & 1;
           mbar_wait(landed_bar + 8 * stage, phase);
-          if (op.act != 0 || zero_mask != 0) transform_block(base + stage * stage_bytes, c, r0, op.act, s, sh, zero_mask);
+          if (mt.x != 0 || zero_mask != 0) transform_block<4, 32>(base + stage * stage_bytes, c, r0, mt.x, s, sh, zero_mask);
           fence_async_smem();
           __syncwarp();
           if (lane == 0) mbar_arrive(full_bar + 8 * stage);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) { s[e] = s_n[e]; sh[e] = sh_n[e]; }
         }
       }
     }
@@ -468,7 +487,8 @@ static size_t tc_geometry(int N, int64_t P, const accx_operand_t* ops, int n_ops
   prm.tmem_cols = cols;
   prm.out_boxes = (prm.bn + box_cols - 1) / box_cols;
   const size_t b_tile = (size_t)prm.bn * 128;
-  const size_t fixed = 1024 + (size_t)prm.out_boxes * TC_BOX_BYTES + 2 * prm.bn * 4 + 512;
+  const size_t fixed = 1024 + (size_t)prm.out_boxes * TC_BOX_BYTES + 2 * prm.bn * 4 + 512 +
+                       (prm.any_transform ? (size_t)kb * (512 + 16) : 0);
   prm.b_resident = (prm.n_tiles == 1 && fixed + (size_t)kb * b_tile + 3 * TC_A_BYTES <= (size_t)TC_SMEM_MAX) ? 1 : 0;
   const size_t resident = prm.b_resident ? (size_t)kb * b_tile : 0;
   const size_t stage = TC_A_BYTES + (prm.b_resident ? 0 : b_tile);
@@ -511,6 +531,7 @@ int accx_pw_fwd_tc(int dtype, int out_dtype, int B, int H, int W, int N, const a
   TcParams prm;
   prm.n_ops = n_ops;
   prm.any_transform = 0;
+  prm.any_shift = 0;
   const int64_t P = (int64_t)B * H * W;
   ACCX_REQUIRE(P < (int64_t)1 << 31, "pw_fwd_tc: too many pixels");
   for (int i = 0; i < n_ops; ++i) {
@@ -521,6 +542,7 @@ int accx_pw_fwd_tc(int dtype, int out_dtype, int B, int H, int W, int N, const a
     ACCX_REQUIRE(ops[i].act == 0 || (ops[i].scale && ops[i].shift && aligned16(ops[i].scale) && aligned16(ops[i].shift)),
                  "pw_fwd_tc: operand %d scale/shift missing or misaligned", i);
     if (ops[i].dy || ops[i].dx || ops[i].act) prm.any_transform = 1;
+    if (ops[i].dy || ops[i].dx) prm.any_shift = 1;
     ACCX_REQUIRE(encode_2d_bf16(&prm.tmap[i], ops[i].data, ops[i].K, P, ops[i].ld, TC_BM),
                  "pw_fwd_tc: cuTensorMapEncodeTiled failed for operand %d", i);
   }

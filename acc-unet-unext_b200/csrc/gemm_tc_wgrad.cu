@@ -8,7 +8,8 @@
 //
 //   CTA = one 128 (dY channels) x NB (A channels, <= 256) tile of dW over a slice of the pixels
 //   (split-K over pixels across CTAs, fp32 atomicAdd of the partial tiles into dW).
-//   warp 8 TMA producer, warps 4-7 transform, warp 9 MMA issuer + TMEM owner, warps 0-3 epilogue.
+//   warp 8 TMA producer, warps 0-7 transform (scale/shift of the CTA's channels in shared memory), warp 9 MMA
+//   issuer + TMEM owner, warps 0-3 epilogue once the pixel loop is done.
 #include "tc_common.cuh"
 
 namespace accx {
@@ -30,61 +31,14 @@ struct alignas(64) WgParams {
   float* dw;
 };
 
-// in-place BN affine + LeakyReLU (+ zeroing of out-of-image taps) on one landed 128 px x 64 ch block
-__device__ __forceinline__ void wg_transform(const WgParams& prm, int kcol0, int64_t m0, int c, int r0, uint32_t blk) {
-  const accx_operand_t& op = prm.op;
-  const bool shifted = op.dy != 0 || op.dx != 0;
-  if (op.act == 0 && !shifted) return;
-  const int kcol = kcol0 + c * 8;
-  float s[8], t[8];
-  if (op.act != 0) {
-    if (kcol < op.K) {
-      ldf<8>(op.scale + kcol, s);
-      ldf<8>(op.shift + kcol, t);
-    } else {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) { s[e] = 0.f; t[e] = 0.f; }
-    }
-  }
-  const int HWp = prm.H * prm.W;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int row = r0 + 16 * i;
-    const uint32_t addr = blk + row * 128 + ((c ^ (row & 7)) << 4);
-    bool zero = false;
-    if (shifted) {
-      const int64_t p = m0 + row;
-      const int rem = (int)((p < prm.P ? p : 0) % HWp);
-      const int hh = rem / prm.W + op.dy, ww = rem % prm.W + op.dx;
-      zero = hh < 0 || hh >= prm.H || ww < 0 || ww >= prm.W || p >= prm.P;
-    }
-    uint32_t w[4];
-    if (zero) {
-      w[0] = w[1] = w[2] = w[3] = 0u;
-    } else {
-      if (op.act == 0) continue;
-      asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(addr));
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        float lo = __uint_as_float(w[e] << 16), hi = __uint_as_float(w[e] & 0xffff0000u);
-        lo = fmaf(lo, s[2 * e], t[2 * e]);
-        hi = fmaf(hi, s[2 * e + 1], t[2 * e + 1]);
-        if (op.act == 2) { lo = lrelu(lo); hi = lrelu(hi); }
-        __nv_bfloat162 h2 = __floats2bfloat162_rn(lo, hi);
-        w[e] = *reinterpret_cast<uint32_t*>(&h2);
-      }
-    }
-    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
-  }
-}
-
 __global__ void __launch_bounds__(WG_THREADS) pw_wgrad_tc_kernel(const __grid_constant__ WgParams prm) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
   const int S = prm.stages, nb = prm.nb, a_blocks = nb >> 6;
   const uint32_t stage_bytes = (2 + a_blocks) * WG_BLK;       // dY: 2 blocks (128 channels), A: nb/64 blocks
-  const uint32_t bar_off = S * stage_bytes;
+  const uint32_t tab_off = S * stage_bytes;                     // float[2][nb]: scale | shift of this CTA's A channels
+  const uint32_t bar_off = tab_off + 2 * nb * 4;
   const uint32_t landed_bar = base + bar_off;
   const uint32_t full_bar = landed_bar + 8 * S;
   const uint32_t empty_bar = full_bar + 8 * S;
@@ -103,7 +57,7 @@ __global__ void __launch_bounds__(WG_THREADS) pw_wgrad_tc_kernel(const __grid_co
   if (tid == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(landed_bar + 8 * s, 1);
-      mbar_init(full_bar + 8 * s, 4);
+      mbar_init(full_bar + 8 * s, 8);
       mbar_init(empty_bar + 8 * s, 1);
     }
     mbar_init(done_bar, 1);
@@ -160,36 +114,79 @@ __global__ void __launch_bounds__(WG_THREADS) pw_wgrad_tc_kernel(const __grid_co
       }
       tc_commit(done_bar);
     }
-  } else if (warp >= 4) {
+  } else {
+    // warps 0-7: transform during the pixel loop; warps 0-3 then drain the accumulator
     if (prm.any_transform) {
-      const int t = tid - 128;
-      const int c = t & 7, r0 = t >> 3;
+      const int c = tid & 7, r0 = tid >> 3;                       // rows r0, r0 + 32, r0 + 64, r0 + 96
+      float* tab = reinterpret_cast<float*>(smem + tab_off);
+      for (int j = tid; j < nb; j += 256) {
+        const bool on = prm.op.act != 0 && k0 + j < prm.op.K;
+        tab[j] = on ? __ldg(prm.op.scale + k0 + j) : 0.f;
+        tab[nb + j] = on ? __ldg(prm.op.shift + k0 + j) : 0.f;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const bool shifted = prm.op.dy != 0 || prm.op.dx != 0;
+      const int HWp = prm.H * prm.W;
       for (int it = 0; it < n_it; ++it) {
         const int stage = it % S;
+        uint32_t zero_mask = 0;
+        if (shifted) {
+          const int p0 = (int)(pbeg + (int64_t)it * WG_PX);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int p = p0 + r0 + 32 * i;
+            const int rem = p % HWp;
+            const int h = rem / prm.W;
+            const int hh = h + prm.op.dy, ww = rem - h * prm.W + prm.op.dx;
+            if (hh < 0 || hh >= prm.H || ww < 0 || ww >= prm.W || p >= (int)prm.P) zero_mask |= 1u << i;
+          }
+        }
         mbar_wait(landed_bar + 8 * stage, (it / S) & 1);
         const uint32_t st = base + stage * stage_bytes;
-        const int64_t p0 = pbeg + (int64_t)it * WG_PX;
-        for (int j = 0; j < a_blocks; ++j) wg_transform(prm, k0 + 64 * j, p0, c, r0, st + (2 + j) * WG_BLK);
+        if (prm.op.act != 0 || zero_mask != 0) {
+          for (int j = 0; j < a_blocks; ++j) {
+            float sc[8], sh[8];
+            const float4* sp = reinterpret_cast<const float4*>(tab + 64 * j + c * 8);
+            const float4* tp = reinterpret_cast<const float4*>(tab + nb + 64 * j + c * 8);
+            const float4 a0 = sp[0], a1 = sp[1], b0 = tp[0], b1 = tp[1];
+            sc[0] = a0.x; sc[1] = a0.y; sc[2] = a0.z; sc[3] = a0.w; sc[4] = a1.x; sc[5] = a1.y; sc[6] = a1.z; sc[7] = a1.w;
+            sh[0] = b0.x; sh[1] = b0.y; sh[2] = b0.z; sh[3] = b0.w; sh[4] = b1.x; sh[5] = b1.y; sh[6] = b1.z; sh[7] = b1.w;
+            transform_block<4, 32>(st + (2 + j) * WG_BLK, c, r0, prm.op.act, sc, sh, zero_mask);
+          }
+        }
         fence_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(full_bar + 8 * stage);
       }
     }
-  } else if (n_it > 0) {
+    if (warp < 4 && n_it > 0) {
+
     // epilogue: partial dW tile -> global fp32 atomics (strided weight view)
     mbar_wait(done_bar, 0);
     tc_fence_after();
     const int n = n0 + warp * 32 + lane;
+    const bool vec_red = prm.op.w_ks == 1 && (prm.op.w_ld & 3) == 0 && ((reinterpret_cast<uintptr_t>(prm.dw) & 15) == 0);
     for (int c0 = 0; c0 < nb; c0 += 16) {
       float v[16];
       tc_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + c0, v);
       if (n < prm.N) {
+        float* rowp = prm.dw + (int64_t)n * prm.op.w_ld;
+        if (vec_red && k0 + c0 + 16 <= prm.op.K) {
+          // contiguous weight row: four 16-byte vector reductions instead of sixteen scalar atomics
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int k = k0 + c0 + j;
-          if (k < prm.op.K) atomicAdd(prm.dw + (int64_t)n * prm.op.w_ld + (int64_t)k * prm.op.w_ks, v[j]);
+          for (int q = 0; q < 4; ++q)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(rowp + k0 + c0 + 4 * q), "f"(v[4 * q]),
+                         "f"(v[4 * q + 1]), "f"(v[4 * q + 2]), "f"(v[4 * q + 3])
+                         : "memory");
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int k = k0 + c0 + j;
+            if (k < prm.op.K) atomicAdd(rowp + (int64_t)k * prm.op.w_ks, v[j]);
+          }
         }
       }
+    }
     }
   }
   tc_fence_before();
@@ -228,7 +225,8 @@ int accx_pw_wgrad_tc(int B, int H, int W, int N, const accx_operand_t* op, float
   const int pairs = prm.n_tiles * prm.k_tiles;
   const int64_t stages_total = (prm.P + WG_PX - 1) / WG_PX;
   int64_t splits = (2 * (int64_t)sm_count() + pairs - 1) / pairs;
-  if (splits > stages_total) splits = stages_total;
+  // every split ends with 128 x nb fp32 atomics: keep at least 8 stages (1024 pixels) of work behind them
+  if (splits > stages_total / 8) splits = stages_total / 8;
   if (splits < 1) splits = 1;
   int64_t per = (stages_total + splits - 1) / splits;      // stages per split
   splits = (stages_total + per - 1) / per;
@@ -242,7 +240,7 @@ int accx_pw_wgrad_tc(int B, int H, int W, int N, const accx_operand_t* op, float
   prm.stages = S;
   ACCX_REQUIRE(encode_2d_bf16(&prm.map_dy, dy, N, prm.P, ldy, WG_PX), "pw_wgrad_tc: tensor map (dY) failed");
   ACCX_REQUIRE(encode_2d_bf16(&prm.map_a, op->data, op->K, prm.P, op->ld, WG_PX), "pw_wgrad_tc: tensor map (A) failed");
-  const size_t smem = 1024 + S * stage_bytes + 24 * S + 64;
+  const size_t smem = 1024 + S * stage_bytes + 2 * prm.nb * 4 + 24 * S + 64;
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(pw_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);

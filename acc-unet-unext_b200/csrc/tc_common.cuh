@@ -106,21 +106,22 @@ __device__ __forceinline__ void tc_ld16_issue(uint32_t taddr, uint32_t (&r)[16])
 __device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---------------------------------------------------------------- in-place transform of a landed tile
-// One thread owns chunk column c (8 bf16 = 16 B) of rows r0, r0+16, .., r0+112 of a [128 rows][128 B]
-// 128B-swizzled block.  a = act(x*s + t) in place; rows flagged in `zero_mask` (bit i = row r0+16i) become 0.
-// All eight loads are issued before the first dependent instruction (shared-memory latency is paid once).
+// One thread owns chunk column c (8 bf16 = 16 B) of rows r0, r0+RS, .., r0+(NR-1)*RS of a [128 rows][128 B]
+// 128B-swizzled block.  a = act(x*s + t) in place; rows flagged in `zero_mask` (bit i = row r0+RS*i) become 0.
+// All loads are issued before the first dependent instruction (shared-memory latency is paid once).
+template <int NR, int RS>
 __device__ __forceinline__ void transform_block(uint32_t blk, int c, int r0, int act, const float (&s)[8],
                                                 const float (&t)[8], uint32_t zero_mask) {
-  uint4 w[8];
+  uint4 w[NR];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int row = r0 + 16 * i;
+  for (int i = 0; i < NR; ++i) {
+    const int row = r0 + RS * i;
     const uint32_t addr = blk + row * 128 + ((c ^ (row & 7)) << 4);
     asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(w[i].x), "=r"(w[i].y), "=r"(w[i].z), "=r"(w[i].w) : "r"(addr));
   }
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int row = r0 + 16 * i;
+  for (int i = 0; i < NR; ++i) {
+    const int row = r0 + RS * i;
     const uint32_t addr = blk + row * 128 + ((c ^ (row & 7)) << 4);
     uint32_t u[4] = {w[i].x, w[i].y, w[i].z, w[i].w};
     if (zero_mask & (1u << i)) {

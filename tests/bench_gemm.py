@@ -41,7 +41,35 @@ def run(i, reps=5):
           flush=True)
 
 
+def run_wgrad(i, reps=5):
+    """weight gradient of shape i: dW[N, K] = dY[P, N]^T . act(A[P, K])"""
+    P, K, N, act, st = SHAPES[i]
+    x = torch.randn(1, 1, P, K, device="cuda").to(torch.bfloat16)
+    dy = torch.randn(1, 1, P, N, device="cuda").to(torch.bfloat16)
+    s = torch.rand(K, device="cuda") + 0.5
+    t = torch.randn(K, device="cuda") * 0.1
+    L = E.Lazy(x, s, t, act) if act else E.Lazy(x)
+    w = torch.zeros(N, K, device="cuda")
+    gw = torch.zeros(N, K, device="cuda")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    ts = []
+    for _ in range(reps + 2):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        E.wgrad(E.Op(L, K, E.WV(w, 0, K, 1)), dy, N, (1, 1, P), gw)
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ms = sorted(ts[2:])[len(ts[2:]) // 2]
+    byt = P * (K + N) * 2
+    print(f"wgrad P={P:8d} K={K:5d} N={N:5d} act={act}: {ms * 1e3:8.1f} us  {byt / ms / 1e6:7.0f} GB/s  {2 * P * K * N / ms / 1e9:7.1f} TFLOP/s",
+          flush=True)
+
+
 if __name__ == "__main__":
-    idx = [int(a) for a in sys.argv[1:]] or range(len(SHAPES))
+    args = sys.argv[1:]
+    wg = "wgrad" in args
+    idx = [int(a) for a in args if a != "wgrad"] or range(len(SHAPES))
     for i in idx:
-        run(i)
+        (run_wgrad if wg else run)(i)
