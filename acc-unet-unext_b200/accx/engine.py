@@ -272,13 +272,30 @@ def bn_bwd(L: Lazy, da: torch.Tensor, grads: dict, arena: Arena, out: Optional[t
     return dy
 
 
+class GradPool(dict):
+    """id(param) -> fp32 gradient accumulator.  All accumulators of one module backward are allocated up
+    front and zeroed with ONE multi-tensor launch (instead of one fill kernel per parameter); a parameter
+    only appears in the dict once a kernel has asked for its buffer, so parameters the module never
+    touches still report grad=None (ACC_UNet_Lite's unused MLFC convs)."""
+
+    def __init__(self, params=()):
+        super().__init__()
+        self.spare = {id(p): torch.empty(p.shape, dtype=torch.float32, device=p.device)
+                      for p in params if p.requires_grad}
+        if self.spare:
+            torch._foreach_zero_(list(self.spare.values()))
+
+
 def grad_buf(grads: dict, p: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
     """zero-initialised fp32 gradient accumulator for parameter p (None if p takes no gradient)."""
     if p is None or not p.requires_grad:
         return None
     g = grads.get(id(p))
     if g is None:
-        g = torch.zeros(p.shape, dtype=torch.float32, device=p.device)
+        spare = getattr(grads, "spare", None)
+        g = spare.pop(id(p), None) if spare is not None else None
+        if g is None:
+            g = torch.zeros(p.shape, dtype=torch.float32, device=p.device)
         grads[id(p)] = g
     return g
 

@@ -175,7 +175,7 @@ class ChannelSELayer(_AccxModule):
         return [out], ({"se": c, "out_like": _out_like([out])} if need else None)
 
     def _bwd(self, s, douts, in_need):
-        grads = {}
+        grads = E.GradPool(self.parameters())
         ar = Arena(douts[0].device)
         da = E.se_bwd(s["se"], douts[0], grads, ar)
         return [da], grads
@@ -203,7 +203,7 @@ class HANCLayer(_AccxModule):
         return [out], ({"L2": L2, "L3": L3, "pools": pools, "out_like": _out_like([out])} if need else None)
 
     def _bwd(self, s, douts, in_need):
-        grads = {}
+        grads = E.GradPool(self.parameters())
         ar = Arena(douts[0].device)
         dy3 = E.bn_bwd(s["L3"], douts[0], grads, ar, out=torch.empty_like(s["L3"].y))
         da = _hanc_core_bwd(self, s["L2"], s["pools"], dy3, grads, ar, need_da=in_need[0])
@@ -251,7 +251,7 @@ class Conv2d_batchnorm(_AccxModule):
         return [out], ({"X": X, "sv": sv, "out_like": _out_like([out])} if need else None)
 
     def _bwd(self, s, douts, in_need):
-        grads = {}
+        grads = E.GradPool(self.parameters())
         ar = Arena(douts[0].device)
         X = s["X"]
         B, H, W, K = X.y.shape
@@ -313,7 +313,7 @@ class HANCBlock(_AccxModule):
         return [out], saved
 
     def _bwd(self, s, douts, in_need):
-        grads = {}
+        grads = E.GradPool(self.parameters())
         dout = douts[0]
         ar = Arena(dout.device)
         X, L1, L2, L3, L4, L5 = s["X"], s["L1"], s["L2"], s["L3"], s["L4"], s["L5"]
@@ -412,7 +412,7 @@ class ResPath(_AccxModule):
         return [out], saved
 
     def _bwd(self, s, douts, in_need):
-        grads = {}
+        grads = E.GradPool(self.parameters())
         ar = Arena(douts[0].device)
         La, Lb = s["La"], s["Lb"]
         B, H, W, C = La.y.shape
@@ -540,7 +540,7 @@ class MLFC(_AccxModule):
         return outs, saved
 
     def _bwd(self, s, douts, in_need):
-        grads = {}
+        grads = E.GradPool(self.parameters())
         ar = Arena(douts[0].device)
         if self.variant == "lite":
             return [E.se_bwd(c, d, grads, ar) for c, d in zip(s["lite"], douts)], grads

@@ -64,7 +64,7 @@ class TrainStep:
     def __init__(self, model: torch.nn.Module, lr: float = 1e-3, graph: bool = False, graph_warmup: int = 2):
         self.model = model
         self.params = [p for p in model.parameters() if p.requires_grad]
-        self.opt = torch.optim.Adam(self.params, lr=lr, capturable=graph, foreach=True)
+        self.opt = torch.optim.Adam(self.params, lr=lr, capturable=graph, fused=True)     # one multi-tensor kernel chain
         self.avg = GradAverager(self.params)
         self.use_graph = graph
         self.graph: Optional[torch.cuda.CUDAGraph] = None

@@ -224,22 +224,48 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 // Block-level reduction of NS per-channel statistics held as acc[NS][VEC] by every thread
 // of a (TX, TY) block, then one atomicAdd per (stat, channel) into out[s * stride + c].
-// smem must hold blockDim.x * blockDim.y * VEC floats.
+// smem must hold blockDim.x * blockDim.y * VEC floats.  Two-stage tree through shared memory that keeps
+// every thread busy: (column, part) partial sums over TY / nparts rows, then nparts values per column.
 template <int NS, int VEC>
 __device__ __forceinline__ void reduce_lanes_atomic(float (&acc)[NS][VEC], float* smem, float* out,
-                                                    int64_t stride, int c0, bool active) {
+                                                    int64_t stride, int C) {
   const int tx = threadIdx.x, ty = threadIdx.y, TX = blockDim.x, TY = blockDim.y;
+  const int ncol = TX * VEC, t = ty * TX + tx;
+  if (TY == 1) {
+    const int c0 = (blockIdx.y * TX + tx) * VEC;
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+#pragma unroll
+      for (int i = 0; i < VEC; ++i)
+        if (c0 + i < C) atomicAdd(out + s * stride + c0 + i, acc[s][i]);
+    return;
+  }
+  int nparts = (TX * TY) / ncol;          // = TY / VEC
+  if (nparts < 1) nparts = 1;
+  if (nparts > TY) nparts = TY;
 #pragma unroll
   for (int s = 0; s < NS; ++s) {
     __syncthreads();
+    // row ty of the [TY][ncol] matrix; column index = i * TX + tx
 #pragma unroll
     for (int i = 0; i < VEC; ++i) smem[(ty * VEC + i) * TX + tx] = acc[s][i];
     __syncthreads();
-    // thread (tx, ty) sums element i = ty, ty+TY, .. over all rows
-    for (int i = ty; i < VEC; i += TY) {
+    const int nth = TX * TY;
+    if (nparts > 1) {          // nth >= 2 * ncol: every thread owns exactly one (part, column) pair
+      float part = 0.f;
+      const int j = t % ncol, q = t / ncol;
+      if (q < nparts)
+        for (int r = q; r < TY; r += nparts) part += smem[r * ncol + j];
+      __syncthreads();
+      if (q < nparts) smem[q * ncol + j] = part;
+      __syncthreads();
+    }
+    const int rows = nparts > 1 ? nparts : TY;
+    for (int col = t; col < ncol; col += nth) {
       float sum = 0.f;
-      for (int r = 0; r < TY; ++r) sum += smem[(r * VEC + i) * TX + tx];
-      if (active) atomicAdd(out + s * stride + c0 + i, sum);
+      for (int r = 0; r < rows; ++r) sum += smem[r * ncol + col];
+      const int c = (blockIdx.y * TX + (col % TX)) * VEC + col / TX;
+      if (c < C) atomicAdd(out + s * stride + c, sum);
     }
   }
 }

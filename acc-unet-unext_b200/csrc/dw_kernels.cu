@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(256, 2) dw3x3_fwd_kernel(int B, int H, int W, 
       }
     }
   }
-  if (stats) reduce_lanes_atomic<2, VEC>(acc, smem, stats, C, c0, active);
+  if (stats) reduce_lanes_atomic<2, VEC>(acc, smem, stats, C, C);
 }
 
 // dw[c, r, t] += sum_p dy[p] * a[p + (r-1, t-1)]

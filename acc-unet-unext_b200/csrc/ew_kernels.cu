@@ -102,7 +102,7 @@ __global__ void act_apply_kernel(int64_t P, int C, const T* __restrict__ x, cons
           if (out) stv<T, VEC>(out + p * C + c0, v);
         });
   }
-  if (stats) reduce_lanes_atomic<2, VEC>(acc, smem, stats, C, c0, active);
+  if (stats) reduce_lanes_atomic<2, VEC>(acc, smem, stats, C, C);
 }
 
 // z = act(a) + r
@@ -140,7 +140,7 @@ __global__ void add_fwd_kernel(int64_t P, int C, const T* __restrict__ a, const 
           stv<T, VEC>(z + p * C + c0, v);
         });
   }
-  if (stats) reduce_lanes_atomic<2, VEC>(acc, smem, stats, C, c0, active);
+  if (stats) reduce_lanes_atomic<2, VEC>(acc, smem, stats, C, C);
 }
 
 // --------------------------------------------------------------------------------------
@@ -180,7 +180,7 @@ __global__ void bn_bwd_reduce_kernel(int64_t P, int C, const T* __restrict__ y, 
           }
         });
   }
-  reduce_lanes_atomic<2, VEC>(acc, smem, sums, C, c0, active);
+  reduce_lanes_atomic<2, VEC>(acc, smem, sums, C, C);
 }
 
 template <typename T, int VEC>

@@ -6,8 +6,9 @@
 //   576 threads in four roles that overlap across tiles:
 //     warp 16     TMA producer (one lane): per 64-channel k-block one cp.async.bulk.tensor.2d of the
 //                 raw 128 x 64 activation box (128B swizzle, OOB rows/columns zero-filled) completing on
-//                 `landed[s]`; the pre-packed bf16 weight tiles come by cp.async.bulk -- once per CTA
-//                 when the whole weight matrix fits in shared memory, else one tile per stage.
+//                 `landed[s]`.  Weights: when the whole matrix fits in shared memory it is packed there once
+//                 per CTA by the worker warps (fp32 strided view -> swizzled bf16 tiles, no extra launch);
+//                 otherwise a pre-pack kernel writes bf16 tiles that arrive by cp.async.bulk per stage.
 //     warps 8-15  transform: the pending BatchNorm affine + LeakyReLU of the producing layer is applied
 //                 IN PLACE on the landed tile (16 B per thread, same swizzle), rows whose 3x3 tap falls
 //                 outside the image are zeroed -- the normalised/activated tensor never exists in HBM --
@@ -150,14 +151,50 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_fwd_tc_kernel(const __grid_c
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  if (prm.b_resident && warp < TC_WARP_TMA) {
+    // Resident weights are packed straight into shared memory by the 512 epilogue + transform threads:
+    // fp32 strided view -> bf16, K-major 128B-swizzled [bn rows][64] tiles, one per k-block (no pre-pack
+    // launch, no workspace traffic).  Every CTA reads the (small, L2-resident) weight matrix once.
+    // one 16-byte chunk (8 consecutive k of one output row) per thread and step: eight independent loads in flight
+    const int chunks_per_kb = bn * 8;
+    for (int ch = tid; ch < n_kb * chunks_per_kb; ch += TC_WARP_TMA * 32) {
+      const int kb = ch / chunks_per_kb, rem = ch - kb * chunks_per_kb;
+      const int nl = rem >> 3, c8 = rem & 7;
+      int o = 0;
+      while (o + 1 < prm.n_ops && kb >= prm.kb_start[o + 1]) ++o;
+      const accx_operand_t& op = prm.op[o];
+      const int k0 = (kb - prm.kb_start[o]) * TC_BK + c8 * 8;
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = 0.f;
+      if (nl < prm.N && k0 < op.K) {
+        const float* src = op.w + (int64_t)nl * op.w_ld + (int64_t)k0 * op.w_ks;
+        if (op.w_ks == 1 && k0 + 8 <= op.K && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(src)), c = __ldg(reinterpret_cast<const float4*>(src) + 1);
+          v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            if (k0 + e < op.K) v[e] = __ldg(src + (int64_t)e * op.w_ks);
+        }
+      }
+      uint32_t w[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * q], v[2 * q + 1]);
+        w[q] = *reinterpret_cast<uint32_t*>(&h2);
+      }
+      const uint32_t addr = base + bres_off + kb * b_tile_bytes + nl * 128 + ((c8 ^ (nl & 7)) << 4);
+      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+    }
+    fence_async_smem();
+    asm volatile("bar.sync 3, 512;" ::: "memory");
+    if (tid == 0) mbar_arrive(bres_bar);
+  }
+
   if (warp == TC_WARP_TMA) {
     // ============================== TMA producer ==============================
     if (lane == 0) {
-      if (prm.b_resident) {
-        mbar_expect_tx(bres_bar, n_kb * b_tile_bytes);
-        for (int kb = 0; kb < n_kb; ++kb)
-          bulk_g2s(base + bres_off + kb * b_tile_bytes, prm.wpack + (int64_t)kb * bn * TC_BK, b_tile_bytes, bres_bar);
-      }
       int it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int nt = tile / prm.m_tiles;
@@ -478,8 +515,24 @@ static size_t tc_geometry(int N, int64_t P, const accx_operand_t* ops, int n_ops
     const int g = nt > 1 ? box_cols : 16;
     return (((N + nt - 1) / nt) + g - 1) / g * g;
   };
+  // Persistent CTAs: time ~ ceil(tiles / SMs) x per-tile cost, per-tile cost ~ K x (BN + c) (MMA + A tile).
+  // Pick the column split that minimises it (ties: fewer, wider tiles); matters for the small-P layers where
+  // there are only one or two tiles per SM.
   const int n_sm = sm_count();
-  while ((int64_t)prm.m_tiles * n_tiles < n_sm && bn_for(n_tiles) > 64) n_tiles *= 2;
+  {
+    int best_nt = n_tiles;
+    int64_t best_cost = -1;
+    for (int nt = n_tiles; nt <= 64; ++nt) {
+      const int b = bn_for(nt);
+      if (nt > n_tiles && b < 64) break;
+      const int real_nt = (N + b - 1) / b;
+      const int64_t waves = ((int64_t)prm.m_tiles * real_nt + n_sm - 1) / n_sm;
+      const int64_t cost = waves * (b + 96);
+      if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_nt = nt; }
+      if ((int64_t)prm.m_tiles * real_nt >= 4 * (int64_t)n_sm) break;      // many waves: the split no longer matters
+    }
+    n_tiles = best_nt;
+  }
   prm.bn = bn_for(n_tiles);
   prm.n_tiles = (N + prm.bn - 1) / prm.bn;
   int cols = 32;
@@ -550,8 +603,8 @@ int accx_pw_fwd_tc(int dtype, int out_dtype, int B, int H, int W, int N, const a
   const size_t smem = tc_geometry(N, P, ops, n_ops, out_f32, prm);
   const int n_tiles = prm.n_tiles;
   const int64_t need = (int64_t)n_tiles * prm.n_kb * prm.bn * TC_BK * 2;
-  ACCX_REQUIRE(workspace_bytes >= need && aligned16(workspace), "pw_fwd_tc: workspace too small (%lld < %lld)",
-               (long long)workspace_bytes, (long long)need);
+  ACCX_REQUIRE(prm.b_resident || (workspace_bytes >= need && aligned16(workspace)),
+               "pw_fwd_tc: workspace too small (%lld < %lld)", (long long)workspace_bytes, (long long)need);
   prm.B = B; prm.H = H; prm.W = W; prm.N = N;
   prm.P = P;
   prm.out_f32 = out_f32 ? 1 : 0;
@@ -569,9 +622,11 @@ int accx_pw_fwd_tc(int dtype, int out_dtype, int B, int H, int W, int N, const a
   }
   prm.stats = stats;
   cudaStream_t st = (cudaStream_t)stream;
-  tc_pack_weights_kernel<<<dim3(prm.n_kb, n_tiles, (prm.bn * TC_BK + 1023) / 1024), 256, 0, st>>>(prm, (bf16*)workspace);
-  int rc = check_launch("tc_pack_weights");
-  if (rc) return rc;
+  if (!prm.b_resident) {     // streamed weight tiles come from a bf16 re-pack in the workspace
+    tc_pack_weights_kernel<<<dim3(prm.n_kb, n_tiles, (prm.bn * TC_BK + 1023) / 1024), 256, 0, st>>>(prm, (bf16*)workspace);
+    int rc = check_launch("tc_pack_weights");
+    if (rc) return rc;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(pw_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX);

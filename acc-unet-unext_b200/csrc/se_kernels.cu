@@ -36,7 +36,7 @@ __global__ void se_squeeze_kernel(int B, int HW, int C, int chunks, const T* __r
           for (int i = 0; i < VEC; ++i) { acc[0][i] += v[i]; acc[1][i] += v[i] * v[i]; }
         });
   }
-  reduce_lanes_atomic<2, VEC>(acc, smem, S + (int64_t)b * C, (int64_t)B * C, c0, active);
+  reduce_lanes_atomic<2, VEC>(acc, smem, S + (int64_t)b * C, (int64_t)B * C, C);
 }
 
 // grid = B blocks of 256 threads; the last block to finish derives the BatchNorm affine.
@@ -162,7 +162,7 @@ __global__ void se_apply_kernel(int B, int HW, int C, const T* __restrict__ x, c
           stv<T, VEC>(out + p * C + c0, v);
         });
   }
-  if (stats) reduce_lanes_atomic<2, VEC>(acc, smem, stats, C, c0, active);
+  if (stats) reduce_lanes_atomic<2, VEC>(acc, smem, stats, C, C);
 }
 
 // G[0,b,c] += sum_hw g', G[1,b,c] += sum_hw g'*a;  g' = dout*mix*lrelu'(v);  dmix += sum dout*(v_act - r)
@@ -213,7 +213,7 @@ __global__ void se_bwd_reduce_kernel(int B, int HW, int C, int chunks, const T* 
           }
         });
   }
-  reduce_lanes_atomic<2, VEC>(acc, smem, G + (int64_t)b * C, (int64_t)B * C, c0, active);
+  reduce_lanes_atomic<2, VEC>(acc, smem, G + (int64_t)b * C, (int64_t)B * C, C);
   if (dmix) {   // block size need not be a multiple of 32: reduce through shared memory
     const int tid = threadIdx.y * blockDim.x + threadIdx.x, nth = blockDim.x * blockDim.y;
     __syncthreads();

@@ -228,7 +228,7 @@ def test_pool_sum_and_upsample_add(dtype):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("C,act", [(9, 2), (96, 2), (64, 1), (4352, 2)])
+@pytest.mark.parametrize("C,act", [(9, 2), (96, 2), (64, 1), (4352, 2), (8, 2), (768, 2), (1536, 1), (520, 2), (3, 1)])
 def test_batchnorm_forward_stats_and_backward(dtype, C, act):
     e = E()
     B, H, W = 2, 6, 10
