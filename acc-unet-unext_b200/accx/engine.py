@@ -262,13 +262,13 @@ def bn_bwd(L: Lazy, da: torch.Tensor, grads: dict, arena: Arena, out: Optional[t
     dtc = dt(y)
     assert da.dtype == y.dtype and da.is_contiguous()
     _call("accx_bn_bwd_reduce", dtc, P, C, ptr(y), ptr(L.scale), ptr(L.shift), L.act, ptr(L.mean), ptr(L.rstd),
-          ptr(da), ptr(sums), stream(), cost=(nb(y, da), 0))
+          ptr(da), ptr(sums), stream(), cost=(nb(y, da), 0), tag=f"P={P} C={C}")
     dy = da if out is None else out
     gg = grad_buf(grads, L.bn.weight)
     gb = grad_buf(grads, L.bn.bias)
     _call("accx_bn_bwd_apply", dtc, P, C, ptr(y), ptr(L.scale), ptr(L.shift), L.act, ptr(L.mean), ptr(L.rstd),
           ptr(f32(L.bn.weight)), ptr(da), ptr(sums), float(P), ptr(dy), ptr(gg), ptr(gb), stream(),
-          cost=(nb(y, da, dy), 0))
+          cost=(nb(y, da, dy), 0), tag=f"P={P} C={C}")
     return dy
 
 
@@ -305,7 +305,8 @@ def dw_fwd(L: Lazy, w, bias, stats, flip=False):
     B, H, W, C = y.shape
     out = torch.empty_like(y)
     _call("accx_dw3x3_fwd", dt(y), B, H, W, C, ptr(y), ptr(L.scale), ptr(L.shift), L.act, ptr(w), ptr(bias),
-          1 if flip else 0, ptr(out), ptr(stats), stream(), cost=(nb(y, out), 18 * y.numel()))
+          1 if flip else 0, ptr(out), ptr(stats), stream(), cost=(nb(y, out), 18 * y.numel()),
+          tag=f"{B}x{H}x{W}x{C} flip={int(flip)}")
     return out
 
 
@@ -313,7 +314,7 @@ def dw_wgrad(L: Lazy, dy: torch.Tensor, gw: torch.Tensor):
     y = L.y
     B, H, W, C = y.shape
     _call("accx_dw3x3_wgrad", dt(y), B, H, W, C, ptr(y), ptr(L.scale), ptr(L.shift), L.act, ptr(dy), ptr(gw), stream(),
-          cost=(nb(y, dy), 18 * y.numel()))
+          cost=(nb(y, dy), 18 * y.numel()), tag=f"{B}x{H}x{W}x{C}")
 
 
 def hanc_pools(L: Lazy, k: int) -> List[torch.Tensor]:

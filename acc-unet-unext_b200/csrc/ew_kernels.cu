@@ -76,7 +76,7 @@ __global__ void act_apply_kernel(int64_t P, int C, const T* __restrict__ x, cons
 #pragma unroll
   for (int i = 0; i < VEC; ++i) acc[0][i] = acc[1][i] = 0.f;
   if (active) {
-    constexpr int U = 4;
+    constexpr int U = 8;
     RawVec<T, VEC> rx[U], rr[U];
     pixel_loop<U>((int64_t)blockIdx.x * blockDim.y + threadIdx.y, P, (int64_t)gridDim.x * blockDim.y,
         [&](int u, int64_t p) {
@@ -119,7 +119,7 @@ __global__ void add_fwd_kernel(int64_t P, int C, const T* __restrict__ a, const 
 #pragma unroll
   for (int i = 0; i < VEC; ++i) acc[0][i] = acc[1][i] = 0.f;
   if (active) {
-    constexpr int U = 4;
+    constexpr int U = 8;
     RawVec<T, VEC> ra[U], rr[U];
     pixel_loop<U>((int64_t)blockIdx.x * blockDim.y + threadIdx.y, P, (int64_t)gridDim.x * blockDim.y,
         [&](int u, int64_t p) {
@@ -161,7 +161,7 @@ __global__ void bn_bwd_reduce_kernel(int64_t P, int C, const T* __restrict__ y, 
 #pragma unroll
   for (int i = 0; i < VEC; ++i) acc[0][i] = acc[1][i] = 0.f;
   if (active) {
-    constexpr int U = 4;
+    constexpr int U = 8;
     RawVec<T, VEC> ry[U], rg[U];
     pixel_loop<U>((int64_t)blockIdx.x * blockDim.y + threadIdx.y, P, (int64_t)gridDim.x * blockDim.y,
         [&](int u, int64_t p) {
@@ -400,7 +400,9 @@ int accx_act_apply(int dtype, int64_t P, int C, const void* x, const float* scal
   ACCX_REQUIRE(act == 0 || (scale && shift), "act_apply: act %d needs scale/shift", act);
   ACCX_DISPATCH_T(dtype, {
     Lanes l = make_lanes(C, DT<T>::VEC, aligned16(x) && (!out || aligned16(out)) && (!residual || aligned16(residual)));
-    dim3 block(l.tx, l.ty), grid(grid_x_for(P, l.ty * 8, 148 * 8), l.gy);
+    // statistics end in one atomicAdd per channel per block: same-address atomics serialise in L2 (~50 ns each),
+    // so the reducing variants run few, long-lived blocks (8 pixels in flight per thread keep HBM busy)
+    dim3 block(l.tx, l.ty), grid(grid_x_for(P, l.ty * 8, stats ? 148 * 2 : 148 * 8), l.gy);
     size_t sm = (size_t)l.tx * l.ty * l.vec * sizeof(float);
     ACCX_DISPATCH_VEC(l, {
       act_apply_kernel<T, VEC><<<grid, block, sm, (cudaStream_t)stream>>>(
@@ -415,7 +417,7 @@ int accx_add_fwd(int dtype, int64_t P, int C, const void* a, const float* scale,
   ACCX_REQUIRE(P > 0 && C > 0 && a && r && z, "add_fwd: bad arguments");
   ACCX_DISPATCH_T(dtype, {
     Lanes l = make_lanes(C, DT<T>::VEC, aligned16(a) && aligned16(r) && aligned16(z));
-    dim3 block(l.tx, l.ty), grid(grid_x_for(P, l.ty * 8, 148 * 8), l.gy);
+    dim3 block(l.tx, l.ty), grid(grid_x_for(P, l.ty * 8, stats ? 148 * 2 : 148 * 8), l.gy);
     size_t sm = (size_t)l.tx * l.ty * l.vec * sizeof(float);
     ACCX_DISPATCH_VEC(l, {
       add_fwd_kernel<T, VEC><<<grid, block, sm, (cudaStream_t)stream>>>(P, C, (const T*)a, scale, shift, act,
@@ -430,7 +432,7 @@ int accx_bn_bwd_reduce(int dtype, int64_t P, int C, const void* y, const float* 
   ACCX_REQUIRE(P > 0 && C > 0 && y && da && sums && mean && rstd, "bn_bwd_reduce: bad arguments");
   ACCX_DISPATCH_T(dtype, {
     Lanes l = make_lanes(C, DT<T>::VEC, aligned16(y) && aligned16(da));
-    dim3 block(l.tx, l.ty), grid(grid_x_for(P, l.ty * 8, 148 * 8), l.gy);
+    dim3 block(l.tx, l.ty), grid(grid_x_for(P, l.ty * 8, 148 * 2), l.gy);
     size_t sm = (size_t)l.tx * l.ty * l.vec * sizeof(float);
     ACCX_DISPATCH_VEC(l, {
       bn_bwd_reduce_kernel<T, VEC><<<grid, block, sm, (cudaStream_t)stream>>>(P, C, (const T*)y, scale, shift, act,

@@ -136,7 +136,7 @@ __global__ void se_apply_kernel(int B, int HW, int C, const T* __restrict__ x, c
   for (int i = 0; i < VEC; ++i) acc[0][i] = acc[1][i] = 0.f;
   const int64_t P = (int64_t)B * HW;
   if (active) {
-    constexpr int U = 4;
+    constexpr int U = 8;
     RawVec<T, VEC> rv[U], rr[U];
     pixel_loop<U>((int64_t)blockIdx.x * blockDim.y + threadIdx.y, P, (int64_t)gridDim.x * blockDim.y,
         [&](int u, int64_t p) {
@@ -405,7 +405,7 @@ int accx_se_apply(int dtype, int B, int HW, int C, const void* x, const float* s
   const int64_t P = (int64_t)B * HW;
   ACCX_DISPATCH_T(dtype, {
     Lanes l = make_lanes(C, DT<T>::VEC, aligned16(x) && aligned16(out) && (!residual || aligned16(residual)));
-    dim3 block(l.tx, l.ty), grid(grid_x_for(P, l.ty * 8, 148 * 8), l.gy);
+    dim3 block(l.tx, l.ty), grid(grid_x_for(P, l.ty * 8, stats ? 148 * 2 : 148 * 8), l.gy);
     size_t sm = (size_t)l.tx * l.ty * l.vec * sizeof(float);
     ACCX_DISPATCH_VEC(l, {
       se_apply_kernel<T, VEC><<<grid, block, sm, (cudaStream_t)stream>>>(B, HW, C, (const T*)x, scale, shift, act, gate,

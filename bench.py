@@ -235,6 +235,7 @@ def main():
         t_e1.record()
         agg = kernel_table(E.PROFILE)
         calls = sorted(((e0.elapsed_time(e1), n_, tg, nb_, fl_) for n_, e0, e1, nb_, fl_, tg in E.PROFILE), reverse=True)[:40]
+        prof_rows = E.PROFILE
         E.PROFILE = None
         step_ms = t_e0.elapsed_time(t_e1)
         tot = sum(a[1] for a in agg.values())
@@ -253,7 +254,17 @@ def main():
                      "gb_per_s": a[2] / max(a[1], 1e-9) / 1e6, "tflop_per_s": a[3] / max(a[1], 1e-9) / 1e9}
                  for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1])}
         if args.kernel_table:
-            json.dump({"step_ms_eager": step_ms, "accx_ms": tot, "kernels": table,
+            by_shape = {}
+            for n_, e0_, e1_, nb_, fl_, tg in prof_rows:
+                a = by_shape.setdefault(f"{n_} {tg}", [0, 0.0, 0, 0])
+                a[0] += 1
+                a[1] += e0_.elapsed_time(e1_)
+                a[2] += nb_
+                a[3] += fl_
+            shapes = [{"call": k, "n": a[0], "ms": a[1], "gb_per_s": a[2] / max(a[1], 1e-9) / 1e6,
+                       "tflop_per_s": a[3] / max(a[1], 1e-9) / 1e9}
+                      for k, a in sorted(by_shape.items(), key=lambda kv: -kv[1][1])]
+            json.dump({"step_ms_eager": step_ms, "accx_ms": tot, "kernels": table, "by_shape": shapes,
                        "slowest_calls": [{"ms": c[0], "kernel": c[1], "shape": c[2], "gb_per_s": c[3] / max(c[0], 1e-9) / 1e6,
                                           "tflop_per_s": c[4] / max(c[0], 1e-9) / 1e9} for c in calls]},
                       open(args.kernel_table, "w"), indent=1)
