@@ -36,6 +36,67 @@ def _call(name, *args, cost=(0, 0), tag=""):
     PROFILE.append((name, e0, e1, cost[0], cost[1], tag))
 
 
+# ---- weight gradients on a side stream -------------------------------------------------------------
+# In backward, every weight gradient depends only on tensors the main chain has already produced and
+# nothing downstream needs it before the optimiser.  Launching them on a second stream lets the GPU overlap
+# them with the (often latency-bound, partially filled) kernels of the input-gradient chain; under CUDA
+# graph capture the fork/join events become parallel branches of the graph.
+#   SIDE_MODE 0: everything on the caller's stream; 1: join at the end of each module's backward (default);
+#   2: join only when join_side() is called (TrainStep: once, before the optimiser) -- tensors the side
+#   stream reads are kept alive in _KEEP until then so the caching allocator cannot recycle them.
+SIDE_MODE = int(os.environ.get("ACCX_WGRAD_STREAM", "1"))
+_SIDE = {}
+_SIDE_DIRTY = set()
+_KEEP = []
+
+
+class side_stream:
+    """with side_stream(keep=(tensors...)): launches inside go to the side stream, ordered after everything
+    already queued on the current stream."""
+
+    def __init__(self, keep=()):
+        self.keep = keep
+        self.ctx = None
+
+    def __enter__(self):
+        if SIDE_MODE == 0:
+            return self
+        dev = torch.cuda.current_device()
+        s = _SIDE.get(dev)
+        if s is None:
+            s = _SIDE[dev] = torch.cuda.Stream(device=dev)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        s.wait_event(ev)
+        _SIDE_DIRTY.add(dev)
+        if SIDE_MODE == 2:
+            _KEEP.extend(t for t in self.keep if t is not None)
+        self.ctx = torch.cuda.stream(s)
+        self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+        return False
+
+
+def join_side():
+    """make the current stream wait for all side-stream work issued so far"""
+    dev = torch.cuda.current_device()
+    if dev in _SIDE_DIRTY:
+        ev = torch.cuda.Event()
+        ev.record(_SIDE[dev])
+        torch.cuda.current_stream().wait_event(ev)
+        _SIDE_DIRTY.discard(dev)
+    _KEEP.clear()
+
+
+def module_backward_end():
+    if SIDE_MODE == 1:
+        join_side()
+
+
 def nb(*ts) -> int:
     """bytes of the given tensors (algorithmic traffic accounting: each tensor once)"""
     return sum(t.numel() * t.element_size() for t in ts if t is not None)
@@ -208,12 +269,13 @@ def wgrad(op: Op, dy: torch.Tensor, N: int, dims, gw: torch.Tensor, dy_coff: int
     tag = f"P={P} N={N} K={op.K} shift={bool(op.dy or op.dx)}"
     dwp = gw.data_ptr() + op.wv.off * 4
     dyp = dy.data_ptr() + dy_coff * dy.element_size()
-    if (TC and in_dt == BF16 and not dy_f32 and op.K % 8 == 0 and N % 8 == 0 and o.ld % 8 == 0 and dy.shape[-1] % 8 == 0
-            and o.data % 16 == 0 and dyp % 16 == 0):
-        _call("accx_pw_wgrad_tc", B, H, W, N, ctypes.byref(o), dwp, dyp, dy.shape[-1], stream(), cost=cost, tag=tag)
-    else:
-        _call("accx_pw_wgrad", in_dt, B, H, W, N, ctypes.byref(o), dwp, dyp, dy.shape[-1], dy_f32, stream(),
-              cost=cost, tag=tag)
+    with side_stream(keep=(op.src.y, op.src.scale, op.src.shift, dy, gw)):
+        if (TC and in_dt == BF16 and not dy_f32 and op.K % 8 == 0 and N % 8 == 0 and o.ld % 8 == 0
+                and dy.shape[-1] % 8 == 0 and o.data % 16 == 0 and dyp % 16 == 0):
+            _call("accx_pw_wgrad_tc", B, H, W, N, ctypes.byref(o), dwp, dyp, dy.shape[-1], stream(), cost=cost, tag=tag)
+        else:
+            _call("accx_pw_wgrad", in_dt, B, H, W, N, ctypes.byref(o), dwp, dyp, dy.shape[-1], dy_f32, stream(),
+                  cost=cost, tag=tag)
 
 
 def bn_affine(bn: torch.nn.BatchNorm2d, stats, count: float, arena: Arena, training: bool, conv_bias=None):
@@ -313,8 +375,9 @@ def dw_fwd(L: Lazy, w, bias, stats, flip=False):
 def dw_wgrad(L: Lazy, dy: torch.Tensor, gw: torch.Tensor):
     y = L.y
     B, H, W, C = y.shape
-    _call("accx_dw3x3_wgrad", dt(y), B, H, W, C, ptr(y), ptr(L.scale), ptr(L.shift), L.act, ptr(dy), ptr(gw), stream(),
-          cost=(nb(y, dy), 18 * y.numel()), tag=f"{B}x{H}x{W}x{C}")
+    with side_stream(keep=(y, L.scale, L.shift, dy, gw)):
+        _call("accx_dw3x3_wgrad", dt(y), B, H, W, C, ptr(y), ptr(L.scale), ptr(L.shift), L.act, ptr(dy), ptr(gw),
+              stream(), cost=(nb(y, dy), 18 * y.numel()), tag=f"{B}x{H}x{W}x{C}")
 
 
 def hanc_pools(L: Lazy, k: int) -> List[torch.Tensor]:

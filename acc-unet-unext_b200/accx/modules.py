@@ -60,6 +60,7 @@ class _ModuleFn(torch.autograd.Function):
                 d = d.to(like[1])
             dn.append(E.to_nhwc(d))
         dxs, grads = mod._bwd(saved, dn, ctx.in_need)
+        E.module_backward_end()          # weight gradients run on a side stream (engine.side_stream)
         gp = []
         for p in ctx.params:
             g = grads.get(id(p))

@@ -15,6 +15,8 @@ from typing import List, Optional
 import torch
 import torch.distributed as dist
 
+from . import engine as E
+
 
 def dice_bce_loss(logit: torch.Tensor, truth: torch.Tensor, dice_weight: float = 0.5, bce_weight: float = 0.5):
     """WeightedDiceBCE(dice_weight, BCE_weight) with class weights [0.5, 0.5]
@@ -76,7 +78,12 @@ class TrainStep:
         logits = self.model(x)
         loss = dice_bce_loss(logits, m)
         self.opt.zero_grad(set_to_none=True)
-        loss.backward()
+        mode, E.SIDE_MODE = E.SIDE_MODE, (2 if E.SIDE_MODE else 0)     # weight gradients overlap the whole backward ...
+        try:
+            loss.backward()
+        finally:
+            E.join_side()                                              # ... and are joined once, before the optimiser
+            E.SIDE_MODE = mode
         self.avg()
         self.opt.step()
         return loss.detach()
