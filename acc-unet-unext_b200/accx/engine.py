@@ -45,6 +45,7 @@ def _call(name, *args, cost=(0, 0), tag=""):
 #   2: join only when join_side() is called (TrainStep: once, before the optimiser) -- tensors the side
 #   stream reads are kept alive in _KEEP until then so the caching allocator cannot recycle them.
 SIDE_MODE = int(os.environ.get("ACCX_WGRAD_STREAM", "1"))
+BWD_DEPTH = [0]
 _SIDE = {}
 _SIDE_DIRTY = set()
 _KEEP = []
@@ -59,7 +60,9 @@ class side_stream:
         self.ctx = None
 
     def __enter__(self):
-        if SIDE_MODE == 0:
+        # only inside a module backward (which joins at its end) or a TrainStep (which joins before the
+        # optimiser): a direct engine call stays on the caller's stream
+        if SIDE_MODE == 0 or (SIDE_MODE == 1 and BWD_DEPTH[0] == 0):
             return self
         dev = torch.cuda.current_device()
         s = _SIDE.get(dev)

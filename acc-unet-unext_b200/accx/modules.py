@@ -59,8 +59,12 @@ class _ModuleFn(torch.autograd.Function):
             if d.dtype != like[1]:
                 d = d.to(like[1])
             dn.append(E.to_nhwc(d))
-        dxs, grads = mod._bwd(saved, dn, ctx.in_need)
-        E.module_backward_end()          # weight gradients run on a side stream (engine.side_stream)
+        E.BWD_DEPTH[0] += 1
+        try:
+            dxs, grads = mod._bwd(saved, dn, ctx.in_need)
+        finally:
+            E.BWD_DEPTH[0] -= 1
+            E.module_backward_end()      # weight gradients run on a side stream (engine.side_stream)
         gp = []
         for p in ctx.params:
             g = grads.get(id(p))

@@ -16,7 +16,7 @@
 //     warp 17     MMA issuer (one lane): tcgen05.mma M=128, N=BN, K=16, four per k-block, into one of
 //                 two TMEM accumulator buffers; tcgen05.commit frees the smem stage / hands the
 //                 accumulator to the epilogue.  Owns the TMEM allocation.
-//     warps 0-7   epilogue: two warps per TMEM lane quarter (each takes half of the columns):
+//     warps 0-7   epilogue: two groups of four warps, group g drains TMEM buffer g (every second tile):
 //                 tcgen05.ld (two 16-column loads in flight) -> (+bias, +nearest-upsampled addends) ->
 //                 bf16/fp32 -> 128B-swizzled staging boxes in shared memory -> ONE thread issues the
 //                 TMA stores (cp.async.bulk.tensor.2d.global.shared::cta; rows >= P and columns >= N are
@@ -28,7 +28,7 @@
 namespace accx {
 
 constexpr int TC_BM = 128, TC_BK = 64, TC_A_BYTES = TC_BM * TC_BK * 2;
-constexpr int TC_EPI_THREADS = 256, TC_XF_THREADS = 256, TC_WARP_XF0 = 8, TC_WARP_TMA = 16, TC_WARP_MMA = 17;
+constexpr int TC_XF_THREADS = 256, TC_WARP_XF0 = 8, TC_WARP_TMA = 16, TC_WARP_MMA = 17;
 constexpr int TC_THREADS = 18 * 32;
 constexpr int TC_BOX_BYTES = TC_BM * 128;            // one staging box: 128 rows x 128 bytes
 constexpr int TC_SMEM_MAX = 227 * 1024;
@@ -113,8 +113,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_fwd_tc_kernel(const __grid_c
   const uint32_t stage_bytes = TC_A_BYTES + (prm.b_resident ? 0 : b_tile_bytes);
   const uint32_t bres_off = S * stage_bytes;
   const uint32_t epi_off = bres_off + (prm.b_resident ? n_kb * b_tile_bytes : 0);      // 1024-aligned
-  const uint32_t stat_off = epi_off + prm.out_boxes * TC_BOX_BYTES;                    // float[2 * bn]
-  const uint32_t tab_off = (stat_off + 2 * bn * 4 + 15u) & ~15u;                       // float[n_kb][2][64] + int4[n_kb]
+  const uint32_t stat_off = epi_off + 2 * prm.out_boxes * TC_BOX_BYTES;                // float[2 groups][2 * bn]
+  const uint32_t tab_off = (stat_off + 4 * bn * 4 + 15u) & ~15u;                       // float[n_kb][2][64] + int4[n_kb]
   const uint32_t bar_off = tab_off + (prm.any_transform ? n_kb * (512 + 16) : 0);
   const uint32_t landed_bar = base + bar_off;            // S x 8 bytes
   const uint32_t full_bar = landed_bar + 8 * S;
@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_fwd_tc_kernel(const __grid_c
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar + 8 * a, 1);    // tcgen05.commit after the last k-block of a tile
-      mbar_init(tempty_bar + 8 * a, 8);   // the eight epilogue warps have drained the accumulator
+      mbar_init(tempty_bar + 8 * a, 4);   // the four epilogue warps of group a have drained the accumulator
     }
     mbar_init(bres_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -315,18 +315,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_fwd_tc_kernel(const __grid_c
     }
   } else {
     // ============================== epilogue warps ============================
-    const uint32_t stage = base + epi_off;
-    float* sstat = reinterpret_cast<float*>(smem + stat_off);   // [2][bn]
-    for (int j = tid; j < 2 * bn; j += TC_EPI_THREADS) sstat[j] = 0.f;
-    const int quarter = warp & 3, half = warp >> 2;
+    // two groups of four warps; group g drains TMEM buffer g, i.e. every second tile of this CTA, through its own
+    // staging boxes / statistics scratch / named barrier, so the latency chains of consecutive tiles overlap
+    const int grp = warp >> 2, gtid = tid & 127, quarter = warp & 3;
+    const uint32_t stage = base + epi_off + grp * prm.out_boxes * TC_BOX_BYTES;
+    float* sstat = reinterpret_cast<float*>(smem + stat_off) + grp * 2 * bn;   // [2][bn]
+    for (int j = gtid; j < 2 * bn; j += 128) sstat[j] = 0.f;
     const int row = quarter * 32 + lane;
     const int n_chunks = bn >> 4;
-    const int ch_begin = half ? (n_chunks + 1) >> 1 : 0;
-    const int ch_end = half ? n_chunks : (n_chunks + 1) >> 1;
+    const int bar_id = 1 + grp;
     // statistics role: chunk tx (8 columns) of rows ty, ty + TY, ..
     const int cpr = bn >> 3;
-    const int TY = TC_EPI_THREADS / cpr;
-    const int tx = tid % cpr, ty = tid / cpr;
+    const int TY = 128 / cpr;
+    const int tx = gtid % cpr, ty = gtid / cpr;
     const bool st_on = prm.stats != nullptr && !prm.out_f32;
     const bool st_active = st_on && ty < TY;
     const uint32_t st_base = stage + (tx >> 3) * TC_BOX_BYTES;
@@ -337,7 +338,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_fwd_tc_kernel(const __grid_c
     const int64_t P = prm.P;
     const float* bias = prm.bias;
     const int box_cols = prm.out_f32 ? 32 : 64;
-    int cur_nt = -1, tl = 0;
+    int cur_nt = -1;
 
     auto flush_stats = [&](int nt_flush) {
       if (st_active) {
@@ -348,9 +349,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_fwd_tc_kernel(const __grid_c
           s1[j] = s2[j] = 0.f;
         }
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
       const int n0f = nt_flush * bn;
-      for (int j = tid; j < bn; j += TC_EPI_THREADS) {
+      for (int j = gtid; j < bn; j += 128) {
         if (n0f + j < N) {
           atomicAdd(prm.stats + n0f + j, sstat[j]);
           atomicAdd(prm.stats + N + n0f + j, sstat[bn + j]);
@@ -358,14 +359,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_fwd_tc_kernel(const __grid_c
         sstat[j] = 0.f;
         sstat[bn + j] = 0.f;
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
     };
 
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
+    for (int tile = blockIdx.x + grp * gridDim.x, tl = grp; tile < total_tiles; tile += 2 * gridDim.x, tl += 2) {
       const int nt = tile / prm.m_tiles;
       const int n0 = nt * bn;
       const int64_t m0 = (int64_t)(tile % prm.m_tiles) * TC_BM;
-      const int acc = tl & 1;
+      const int acc = grp;
       if (st_on && nt != cur_nt && cur_nt >= 0) flush_stats(cur_nt);
       cur_nt = nt;
       const int64_t p = m0 + row;
@@ -388,11 +389,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_fwd_tc_kernel(const __grid_c
       tc_fence_after();
       // the staging boxes are free once the previous tile's TMA stores have read them and every thread has
       // finished its statistics pass
-      if (tid == 0) bulk_wait_read0();
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (gtid == 0) bulk_wait_read0();
+      asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
       const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * bn;
-      for (int ch = ch_begin; ch < ch_end; ch += 2) {
-        const bool two = ch + 1 < ch_end;
+      for (int ch = 0; ch < n_chunks; ch += 2) {
+        const bool two = ch + 1 < n_chunks;
         uint32_t r[2][16];
         tc_ld16_issue(trow + ch * 16, r[0]);
         if (two) tc_ld16_issue(trow + ch * 16 + 16, r[1]);
@@ -447,8 +448,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_fwd_tc_kernel(const __grid_c
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar + 8 * acc);
       fence_async_smem();                                   // generic-proxy writes -> visible to the TMA store
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (tid == 0) {
+      asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+      if (gtid == 0) {
         for (int b = 0; b < prm.out_boxes; ++b)
           if (n0 + b * box_cols < N) tma_store_2d(&prm.tmap_y, stage + b * TC_BOX_BYTES, n0 + b * box_cols, (int)m0);
         bulk_commit();
@@ -483,7 +484,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_fwd_tc_kernel(const __grid_c
       }
     }
     if (st_on && cur_nt >= 0) flush_stats(cur_nt);
-    if (tid == 0) bulk_wait0();            // all stores complete before the CTA (and its shared memory) retires
+    if (gtid == 0) bulk_wait0();           // all stores complete before the CTA (and its shared memory) retires
   }
   tc_fence_before();
   __syncthreads();
@@ -540,7 +541,7 @@ static size_t tc_geometry(int N, int64_t P, const accx_operand_t* ops, int n_ops
   prm.tmem_cols = cols;
   prm.out_boxes = (prm.bn + box_cols - 1) / box_cols;
   const size_t b_tile = (size_t)prm.bn * 128;
-  const size_t fixed = 1024 + (size_t)prm.out_boxes * TC_BOX_BYTES + 2 * prm.bn * 4 + 512 +
+  const size_t fixed = 1024 + 2 * (size_t)prm.out_boxes * TC_BOX_BYTES + 4 * prm.bn * 4 + 512 +
                        (prm.any_transform ? (size_t)kb * (512 + 16) : 0);
   prm.b_resident = (prm.n_tiles == 1 && fixed + (size_t)kb * b_tile + 3 * TC_A_BYTES <= (size_t)TC_SMEM_MAX) ? 1 : 0;
   const size_t resident = prm.b_resident ? (size_t)kb * b_tile : 0;
