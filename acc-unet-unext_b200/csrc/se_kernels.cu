@@ -58,7 +58,8 @@ __global__ void se_gate_kernel(int B, int C, int Cr, double HW, const float* __r
   const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
   for (int j = warp; j < Cr; j += nw) {
     float a = 0.f;
-    for (int c = lane; c < C; c += 32) a = fmaf(w1[(int64_t)j * C + c], m[c], a);
+#pragma unroll 4
+    for (int c = lane; c < C; c += 32) a = fmaf(__ldg(w1 + (int64_t)j * C + c), m[c], a);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
     if (lane == 0) {
@@ -70,7 +71,21 @@ __global__ void se_gate_kernel(int B, int C, int Cr, double HW, const float* __r
   __syncthreads();
   for (int c = tid; c < C; c += nt) {
     float a = b2[c];
-    for (int j = 0; j < Cr; ++j) a = fmaf(w2[(int64_t)c * Cr + j], h[j], a);
+    const float* wr = w2 + (int64_t)c * Cr;
+    if ((Cr & 3) == 0) {        // row of w2 as independent 16-byte loads (the scalar loop is one dependent chain)
+      float a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 4
+      for (int j = 0; j < Cr; j += 4) {
+        const float4 w = __ldg(reinterpret_cast<const float4*>(wr + j));
+        a = fmaf(w.x, h[j], a);
+        a1 = fmaf(w.y, h[j + 1], a1);
+        a2 = fmaf(w.z, h[j + 2], a2);
+        a3 = fmaf(w.w, h[j + 3], a3);
+      }
+      a += a1 + a2 + a3;
+    } else {
+      for (int j = 0; j < Cr; ++j) a = fmaf(wr[j], h[j], a);
+    }
     gate[(int64_t)b * C + c] = 1.f / (1.f + __expf(-a));
   }
   __threadfence();
@@ -89,6 +104,7 @@ __global__ void se_gate_kernel(int B, int C, int Cr, double HW, const float* __r
     float mean, var;
     if (training) {
       double s1 = 0, s2 = 0;
+#pragma unroll 4
       for (int bb = 0; bb < B; ++bb) {
         float g = __ldcg(gate + (int64_t)bb * C + c);
         s1 += (double)g * S[(int64_t)bb * C + c];
@@ -117,40 +133,47 @@ __global__ void se_gate_kernel(int B, int C, int Cr, double HW, const float* __r
 }
 
 // out = mixf( lrelu(a*gate[b,c]*se_scale[c] + se_shift[c]) , residual )
+// grid.x = B * chunks: a block works inside ONE image, so the gate (folded with the BN scale) lives in registers
 template <typename T, int VEC>
-__global__ void se_apply_kernel(int B, int HW, int C, const T* __restrict__ x, const float* scale, const float* shift,
-                                int act, const float* __restrict__ gate, const float* se_scale, const float* se_shift,
-                                const T* __restrict__ residual, const float* mix, T* __restrict__ out, float* stats) {
+__global__ void se_apply_kernel(int B, int HW, int C, int chunks, const T* __restrict__ x, const float* scale,
+                                const float* shift, int act, const float* __restrict__ gate, const float* se_scale,
+                                const float* se_shift, const T* __restrict__ residual, const float* mix,
+                                T* __restrict__ out, float* stats) {
   extern __shared__ float smem[];
   const int cv = blockIdx.y * blockDim.x + threadIdx.x;
   const bool active = cv * VEC < C;
   const int c0 = active ? cv * VEC : 0;
+  const int b = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
   Lazy<VEC> lz;
   lz.init(scale, shift, act, c0);
-  float ss[VEC], st[VEC];
-  ldf<VEC>(se_scale + c0, ss);
+  float gs[VEC], st[VEC];
+  ldf<VEC>(se_scale + c0, gs);
   ldf<VEC>(se_shift + c0, st);
+  {
+    float g[VEC];
+    ldf<VEC>(gate + (int64_t)b * C + c0, g);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) gs[i] *= g[i];
+  }
   const float mx = mix ? *mix : 1.f, rx = mix ? 1.f - mx : 1.f;
   float acc[2][VEC];
 #pragma unroll
   for (int i = 0; i < VEC; ++i) acc[0][i] = acc[1][i] = 0.f;
-  const int64_t P = (int64_t)B * HW;
   if (active) {
+    const int64_t off = (int64_t)b * HW * C + c0;
     constexpr int U = 8;
     RawVec<T, VEC> rv[U], rr[U];
-    pixel_loop<U>((int64_t)blockIdx.x * blockDim.y + threadIdx.y, P, (int64_t)gridDim.x * blockDim.y,
+    pixel_loop<U>(chunk * blockDim.y + threadIdx.y, HW, chunks * blockDim.y,
         [&](int u, int64_t p) {
-          rv[u].load(x + p * C + c0);
-          if (residual) rr[u].load(residual + p * C + c0);
+          rv[u].load(x + off + p * C);
+          if (residual) rr[u].load(residual + off + p * C);
         },
         [&](int u, int64_t p) {
-          const int b = (int)(p / HW);
-          float v[VEC], g[VEC];
+          float v[VEC];
           rv[u].unpack(v);
-          ldf<VEC>(gate + (int64_t)b * C + c0, g);
           lz.apply(v);
 #pragma unroll
-          for (int i = 0; i < VEC; ++i) v[i] = lrelu(fmaf(v[i] * g[i], ss[i], st[i]));
+          for (int i = 0; i < VEC; ++i) v[i] = lrelu(fmaf(v[i], gs[i], st[i]));
           if (residual) {
             float r[VEC];
             rr[u].unpack(r);
@@ -159,7 +182,7 @@ __global__ void se_apply_kernel(int B, int HW, int C, const T* __restrict__ x, c
           }
 #pragma unroll
           for (int i = 0; i < VEC; ++i) { acc[0][i] += v[i]; acc[1][i] += v[i] * v[i]; }
-          stv<T, VEC>(out + p * C + c0, v);
+          stv<T, VEC>(out + off + p * C, v);
         });
   }
   if (stats) reduce_lanes_atomic<2, VEC>(acc, smem, stats, C, C);
@@ -249,6 +272,7 @@ __global__ void se_bwd_gate_kernel(int B, int C, int Cr, double HW, const float*
   for (int c = tid; c < C; c += nt) {
     const float mu = mean[c], rs = rstd[c];
     double a1 = 0, a2 = 0;
+#pragma unroll 4
     for (int bb = 0; bb < B; ++bb) {
       const float g1 = G[(int64_t)bb * C + c], g2 = G[BC + (int64_t)bb * C + c];
       a1 += g1;
@@ -282,7 +306,8 @@ __global__ void se_bwd_gate_kernel(int B, int C, int Cr, double HW, const float*
   const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
   for (int j = warp; j < Cr; j += nw) {
     float a = 0.f;
-    for (int c = lane; c < C; c += 32) a = fmaf(w2[(int64_t)c * Cr + j], dpre2[c], a);
+#pragma unroll 4
+    for (int c = lane; c < C; c += 32) a = fmaf(__ldg(w2 + (int64_t)c * Cr + j), dpre2[c], a);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
     if (lane == 0) {
@@ -298,14 +323,15 @@ __global__ void se_bwd_gate_kernel(int B, int C, int Cr, double HW, const float*
   }
   for (int c = tid; c < C; c += nt) {
     float dm = 0.f;
-    for (int j = 0; j < Cr; ++j) dm = fmaf(w1[(int64_t)j * C + c], dpre1[j], dm);
+#pragma unroll 4
+    for (int j = 0; j < Cr; ++j) dm = fmaf(__ldg(w1 + (int64_t)j * C + c), dpre1[j], dm);
     PQR[2 * BC + (int64_t)b * C + c] += dm * inv_hw;
   }
 }
 
-// da (+)= P*g' + Q*a + R
+// da (+)= P*g' + Q*a + R;  grid.x = B * chunks (one image per block: gate and P, Q, R in registers)
 template <typename T, int VEC>
-__global__ void se_bwd_apply_kernel(int B, int HW, int C, const T* __restrict__ x, const float* scale,
+__global__ void se_bwd_apply_kernel(int B, int HW, int C, int chunks, const T* __restrict__ x, const float* scale,
                                     const float* shift, int act, const float* __restrict__ gate,
                                     const float* se_scale, const float* se_shift, const T* __restrict__ dout,
                                     const float* mix, const float* __restrict__ PQR, T* __restrict__ da,
@@ -313,32 +339,37 @@ __global__ void se_bwd_apply_kernel(int B, int HW, int C, const T* __restrict__ 
   const int cv = blockIdx.y * blockDim.x + threadIdx.x;
   if (cv * VEC >= C) return;
   const int c0 = cv * VEC;
+  const int b = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
   Lazy<VEC> lz;
   lz.init(scale, shift, act, c0);
-  float ss[VEC], st[VEC];
-  ldf<VEC>(se_scale + c0, ss);
-  ldf<VEC>(se_shift + c0, st);
+  float gs[VEC], st[VEC], cp[VEC], cq[VEC], cr[VEC];
+  const int64_t BC = (int64_t)B * C;
   const float mx = mix ? *mix : 1.f;
-  const int64_t P = (int64_t)B * HW, BC = (int64_t)B * C;
+  ldf<VEC>(se_scale + c0, gs);
+  ldf<VEC>(se_shift + c0, st);
+  ldf<VEC>(PQR + (int64_t)b * C + c0, cp);
+  ldf<VEC>(PQR + BC + (int64_t)b * C + c0, cq);
+  ldf<VEC>(PQR + 2 * BC + (int64_t)b * C + c0, cr);
+  {
+    float g[VEC];
+    ldf<VEC>(gate + (int64_t)b * C + c0, g);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) { gs[i] *= g[i]; cp[i] *= mx; }
+  }
+  const int64_t off = (int64_t)b * HW * C + c0;
   constexpr int U = 4;
   RawVec<T, VEC> rv[U], rd[U], ro[U];
-  pixel_loop<U>((int64_t)blockIdx.x * blockDim.y + threadIdx.y, P, (int64_t)gridDim.x * blockDim.y,
+  pixel_loop<U>(chunk * blockDim.y + threadIdx.y, HW, chunks * blockDim.y,
       [&](int u, int64_t p) {
-        rv[u].load(x + p * C + c0);
-        rd[u].load(dout + p * C + c0);
-        if (accumulate) ro[u].load(da + p * C + c0);
+        rv[u].load(x + off + p * C);
+        rd[u].load(dout + off + p * C);
+        if (accumulate) ro[u].load(da + off + p * C);
       },
       [&](int u, int64_t p) {
-        const int b = (int)(p / HW);
-        float v[VEC], d[VEC], g[VEC], cp[VEC], cq[VEC], cr[VEC];
+        float v[VEC], d[VEC], o[VEC];
         rv[u].unpack(v);
         rd[u].unpack(d);
-        ldf<VEC>(gate + (int64_t)b * C + c0, g);
-        ldf<VEC>(PQR + (int64_t)b * C + c0, cp);
-        ldf<VEC>(PQR + BC + (int64_t)b * C + c0, cq);
-        ldf<VEC>(PQR + 2 * BC + (int64_t)b * C + c0, cr);
         lz.apply(v);
-        float o[VEC];
         if (accumulate) {
           ro[u].unpack(o);
         } else {
@@ -347,18 +378,18 @@ __global__ void se_bwd_apply_kernel(int B, int HW, int C, const T* __restrict__ 
         }
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
-          float uu = fmaf(v[i] * g[i], ss[i], st[i]);
-          float gp = d[i] * mx * (uu > 0.f ? 1.f : ACCX_LRELU);
-          o[i] += cp[i] * gp + cq[i] * v[i] + cr[i];
+          const float uu = fmaf(v[i], gs[i], st[i]);
+          const float gp = d[i] * (uu > 0.f ? 1.f : ACCX_LRELU);
+          o[i] += fmaf(cp[i], gp, fmaf(cq[i], v[i], cr[i]));
         }
-        stv<T, VEC>(da + p * C + c0, o);
+        stv<T, VEC>(da + off + p * C, o);
       });
 }
 
-static inline int se_chunks(int B, int HW, int ty) {
+static inline int se_chunks(int B, int HW, int ty, int target_blocks = 148 * 4) {
   // enough blocks to fill the machine, but keep the number of atomics per (b,c) small
   int per_img = (HW + ty * 8 - 1) / (ty * 8);
-  int want = (148 * 4 + B - 1) / B;
+  int want = (target_blocks + B - 1) / B;
   int c = per_img < want ? per_img : want;
   return c < 1 ? 1 : c;
 }
@@ -405,10 +436,11 @@ int accx_se_apply(int dtype, int B, int HW, int C, const void* x, const float* s
   const int64_t P = (int64_t)B * HW;
   ACCX_DISPATCH_T(dtype, {
     Lanes l = make_lanes(C, DT<T>::VEC, aligned16(x) && aligned16(out) && (!residual || aligned16(residual)));
-    dim3 block(l.tx, l.ty), grid(grid_x_for(P, l.ty * 8, stats ? 148 * 2 : 148 * 8), l.gy);
+    const int chunks = se_chunks(B, HW, l.ty, stats ? 148 * 2 : 148 * 8);
+    dim3 block(l.tx, l.ty), grid(B * chunks, l.gy);
     size_t sm = (size_t)l.tx * l.ty * l.vec * sizeof(float);
     ACCX_DISPATCH_VEC(l, {
-      se_apply_kernel<T, VEC><<<grid, block, sm, (cudaStream_t)stream>>>(B, HW, C, (const T*)x, scale, shift, act, gate,
+      se_apply_kernel<T, VEC><<<grid, block, sm, (cudaStream_t)stream>>>(B, HW, C, chunks, (const T*)x, scale, shift, act, gate,
                                                                          se_scale, se_shift, (const T*)residual, mix,
                                                                          (T*)out, stats);
     });
@@ -454,9 +486,10 @@ int accx_se_bwd_apply(int dtype, int B, int HW, int C, const void* x, const floa
   const int64_t P = (int64_t)B * HW;
   ACCX_DISPATCH_T(dtype, {
     Lanes l = make_lanes(C, DT<T>::VEC, aligned16(x) && aligned16(dout) && aligned16(da));
-    dim3 block(l.tx, l.ty), grid(grid_x_for(P, l.ty * 8, 148 * 8), l.gy);
+    const int chunks = se_chunks(B, HW, l.ty, 148 * 8);
+    dim3 block(l.tx, l.ty), grid(B * chunks, l.gy);
     ACCX_DISPATCH_VEC(l, {
-      se_bwd_apply_kernel<T, VEC><<<grid, block, 0, (cudaStream_t)stream>>>(B, HW, C, (const T*)x, scale, shift, act,
+      se_bwd_apply_kernel<T, VEC><<<grid, block, 0, (cudaStream_t)stream>>>(B, HW, C, chunks, (const T*)x, scale, shift, act,
                                                                             gate, se_scale, se_shift, (const T*)dout,
                                                                             mix, PQR, (T*)da, accumulate);
     });
