@@ -99,8 +99,10 @@ __device__ __forceinline__ void dw_activate_tile(const DwParams& prm, uint32_t t
   }
   const int step = DW_THREADS / vpp;
   const bool lre = prm.act == 2;
-  for (int pos = threadIdx.x / vpp; pos < n_pos; pos += step) {
-    const int hy = pos / halo_w, hx = pos - hy * halo_w;
+  int pos = threadIdx.x / vpp;
+  int hy = pos / halo_w, hx = pos - hy * halo_w;          // advanced incrementally: no division in the loop
+  for (; pos < n_pos; pos += step, hx += step) {
+    while (hx >= halo_w) { hx -= halo_w; ++hy; }
     const int h = h0 - 1 + hy, w = w0 - 1 + hx;
     const bool inside = h >= 0 && h < prm.H && w >= 0 && w < prm.W;
     const uint32_t addr = tile + (uint32_t)(pos * prm.CC + sub * EPV) * sizeof(T);
@@ -344,7 +346,7 @@ static bool encode_4d(CUtensorMap* map, const void* data, int esz, int B, int H,
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   return encode(map, esz == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
                 const_cast<void*>(data), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+                CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 // Tile geometry: TW in {32, 16, 8} (CC = 1024 / TW) minimising the padded work, ties to the wider tile.
