@@ -226,6 +226,7 @@ def main():
         hbm, tflops, which = peaks()
         eager = TrainStep(model, lr=1e-3, graph=False)
         eager.opt = step.opt if not args.graph else eager.opt
+        eager.avg.world = 1              # rank-0-only instrumentation: no collective (the other ranks are not in it)
         eager(x_dev, m_dev)
         torch.cuda.synchronize()
         E.PROFILE = []
