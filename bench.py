@@ -293,9 +293,17 @@ def main():
             "gpu_launches": launches_per_step * K,
             "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "loss": float(loss_host),
         }
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Leave without tearing NCCL down: destroying a communicator whose collectives were captured into a
+        # still-alive CUDA graph can block at exit.  Everything that matters (the JSON line) is already out.
+        try:
+            dist.barrier()
+        except Exception:
+            pass
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def traffic_from_profiles(kernel):
