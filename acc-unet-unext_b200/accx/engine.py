@@ -317,17 +317,20 @@ def add_fwd(L: Lazy, r: torch.Tensor, stats):
     return z
 
 
-def bn_bwd(L: Lazy, da: torch.Tensor, grads: dict, arena: Arena, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+def bn_bwd(L: Lazy, da: torch.Tensor, grads: dict, arena: Arena, out: Optional[torch.Tensor] = None,
+           sums: Optional[torch.Tensor] = None) -> torch.Tensor:
     """gradient w.r.t. the raw tensor L.y given the gradient w.r.t. act(BN(L.y)); accumulates
-    dgamma/dbeta into grads[bn.weight]/grads[bn.bias].  In place on `da` unless `out` is given."""
+    dgamma/dbeta into grads[bn.weight]/grads[bn.bias].  In place on `da` unless `out` is given.
+    `sums`: the (sum g, sum g*xhat) reduction if the producer of `da` already made it (hanc_unpool_bnred)."""
     y = L.y
     C = y.shape[-1]
     P = y.numel() // C
-    sums = arena.take(2 * C)
     dtc = dt(y)
     assert da.dtype == y.dtype and da.is_contiguous()
-    _call("accx_bn_bwd_reduce", dtc, P, C, ptr(y), ptr(L.scale), ptr(L.shift), L.act, ptr(L.mean), ptr(L.rstd),
-          ptr(da), ptr(sums), stream(), cost=(nb(y, da), 0), tag=f"P={P} C={C}")
+    if sums is None:
+        sums = arena.take(2 * C)
+        _call("accx_bn_bwd_reduce", dtc, P, C, ptr(y), ptr(L.scale), ptr(L.shift), L.act, ptr(L.mean), ptr(L.rstd),
+              ptr(da), ptr(sums), stream(), cost=(nb(y, da), 0), tag=f"P={P} C={C}")
     dy = da if out is None else out
     gg = grad_buf(grads, L.bn.weight)
     gb = grad_buf(grads, L.bn.bias)
@@ -402,6 +405,23 @@ def hanc_unpool_bwd(L: Lazy, l: int, dpool: torch.Tensor, da: torch.Tensor, accu
     assert dpool.dtype == torch.float32
     _call("accx_hanc_unpool_bwd", dt(L.y), B, H, W, C, l, ptr(L.y), ptr(L.scale), ptr(L.shift), L.act, ptr(dpool),
           ptr(da), 1 if accumulate else 0, stream(), cost=(nb(L.y, dpool, da) + (nb(da) if accumulate else 0), 0))
+
+
+def hanc_unpool_bnred(L: Lazy, dpools: List[torch.Tensor], da: torch.Tensor, arena: Arena) -> torch.Tensor:
+    """all pyramid levels of a k = 2 / 3 HANC backward added into `da` in one pass + the BN-backward reduction of
+    L's BatchNorm on the result; returns the sums for bn_bwd(..., sums=)."""
+    B, H, W, C = L.y.shape
+    sums = arena.take(2 * C)
+    levels = len(dpools)
+    _call("accx_hanc_unpool_bnred", dt(L.y), B, H, W, C, levels, ptr(L.y), ptr(L.scale), ptr(L.shift), L.act,
+          ptr(dpools[0]), ptr(dpools[1]) if levels > 1 else 0, ptr(da), ptr(L.mean), ptr(L.rstd), ptr(sums), stream(),
+          cost=(nb(L.y, da, da, *dpools), 0), tag=f"{B}x{H}x{W}x{C} levels={levels}")
+    return sums
+
+
+def hanc_unpool_fusable(L: Lazy, k: int) -> bool:
+    return (k in (2, 3) and L.y.dtype == torch.bfloat16 and L.C % 4 == 0 and L.mean is not None and L.rstd is not None
+            and L.y.data_ptr() % 8 == 0)
 
 
 def pool_sum(x: torch.Tensor, l: int, mul: float, out_dtype: Optional[torch.dtype] = None):

@@ -127,8 +127,9 @@ def _hanc_core_fwd(hnc, L2: Lazy, ar: Arena, training):
     return L3, pools
 
 
-def _hanc_core_bwd(hnc, L2: Lazy, pools, dy3: torch.Tensor, grads, ar: Arena, need_da=True):
-    """dy3 = gradient w.r.t. the raw conv output.  Returns the gradient w.r.t. the activated input."""
+def _hanc_core_bwd(hnc, L2: Lazy, pools, dy3: torch.Tensor, grads, ar: Arena, need_da=True, fuse_bn=False):
+    """dy3 = gradient w.r.t. the raw conv output.  Returns the gradient w.r.t. the activated input
+    (fuse_bn: -> (gradient, BN-backward sums of L2's BatchNorm or None), see engine.hanc_unpool_bnred)."""
     B, H, W, Ein = L2.y.shape
     k = hnc.k
     J = 2 * k - 1
@@ -141,6 +142,8 @@ def _hanc_core_bwd(hnc, L2: Lazy, pools, dy3: torch.Tensor, grads, ar: Arena, ne
     da2 = None
     if need_da:
         da2 = E.conv([Op(Lazy(dy3), C, WV(wh, 0, J, J * Ein))], Ein, (B, H, W))
+    fused = fuse_bn and need_da and E.hanc_unpool_fusable(L2, k)
+    dPs = []
     for l in range(1, k):
         dims_l = (B, H >> l, W >> l)
         dR = E.pool_sum(dy3, l, 1.0)                         # block sums of dY at the pooled resolution
@@ -152,7 +155,12 @@ def _hanc_core_bwd(hnc, L2: Lazy, pools, dy3: torch.Tensor, grads, ar: Arena, ne
             dP = torch.empty((B, H >> l, W >> l, 2 * Ein), dtype=torch.float32, device=dy3.device)   # fp32: feeds unpool
             E.conv([Op(Lazy(dR), C, WV(wh, l, J, J * Ein))], Ein, dims_l, out=dP, out_coff=0)
             E.conv([Op(Lazy(dR), C, WV(wh, k - 1 + l, J, J * Ein))], Ein, dims_l, out=dP, out_coff=Ein)
-            E.hanc_unpool_bwd(L2, l, dP, da2, accumulate=True)
+            if fused:
+                dPs.append(dP)
+            else:
+                E.hanc_unpool_bwd(L2, l, dP, da2, accumulate=True)
+    if fuse_bn:
+        return da2, (E.hanc_unpool_bnred(L2, dPs, da2, ar) if fused else None)
     return da2
 
 
@@ -337,8 +345,8 @@ class HANCBlock(_AccxModule):
         # norm(x + inp): dz feeds both the HANC branch and the residual
         dz = E.bn_bwd(L4, da4, grads, ar)
         dy3 = E.bn_bwd(L3, dz, grads, ar, out=torch.empty_like(dz))
-        da2 = _hanc_core_bwd(self.hnc, L2, s["pools"], dy3, grads, ar)
-        dy2 = E.bn_bwd(L2, da2, grads, ar)
+        da2, sums2 = _hanc_core_bwd(self.hnc, L2, s["pools"], dy3, grads, ar, fuse_bn=True)
+        dy2 = E.bn_bwd(L2, da2, grads, ar, sums=sums2)
         # depthwise
         _zero_bias_grad(grads, self.conv2)
         g2 = E.grad_buf(grads, self.conv2.weight)

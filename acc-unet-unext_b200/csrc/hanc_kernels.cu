@@ -149,6 +149,118 @@ __global__ void hanc_unpool_kernel(int B, int H, int W, int C, int log2s, const 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Fused HANC backward for k = 2 / 3 (LEVELS = 1 / 2) + BatchNorm-backward reduction of the layer in front:
+//   da (+)= sum over levels of [ davg[blk]/s^2 + (p is the FIRST row-major maximum of blk ? dmax[blk] : 0) ]
+//   sums[c] += sum_p g, sums[C+c] += sum_p g * xhat,   g = da_total * act'(y),  xhat = (y - mean) * rstd
+// One thread owns a 2^LEVELS-square window of 4 channels: y and da are read ONCE (the per-level kernels read y
+// and read-modify-write da once per level, and the BN reduction reads both again), every load of the window is
+// in flight before the first compare.  bf16 storage.
+template <int LEVELS>
+__global__ void __launch_bounds__(128) hanc_unpool_bnred_kernel(int B, int H, int W, int C, const bf16* __restrict__ y,
+                                                                const float* scale, const float* shift, int act,
+                                                                const float* __restrict__ dp1,
+                                                                const float* __restrict__ dp2, bf16* __restrict__ da,
+                                                                const float* mean, const float* rstd, float* sums) {
+  constexpr int S = 1 << LEVELS, NPX = S * S, VEC = 4;
+  extern __shared__ float smem[];
+  const int cv = blockIdx.y * blockDim.x + threadIdx.x;
+  const bool active = cv * VEC < C;
+  const int c0 = active ? cv * VEC : 0;
+  Lazy<VEC> lz;
+  lz.init(scale, shift, act, c0);
+  float mu[VEC];
+  ldf<VEC>(mean + c0, mu);
+  float acc[2][VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) acc[0][i] = acc[1][i] = 0.f;
+  const int Ho = H / S, Wo = W / S;
+  const int64_t n_win = (int64_t)B * Ho * Wo;
+  if (active) {
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.y + threadIdx.y; q < n_win; q += (int64_t)gridDim.x * blockDim.y) {
+      const int wo = (int)(q % Wo);
+      const int64_t t = q / Wo;
+      const int ho = (int)(t % Ho);
+      const int b = (int)(t / Ho);
+      const int64_t base = (((int64_t)b * H + (int64_t)ho * S) * W + (int64_t)wo * S) * C + c0;
+      RawVec<bf16, VEC> ry[NPX], rd[NPX];
+#pragma unroll
+      for (int i = 0; i < S; ++i)
+#pragma unroll
+        for (int j = 0; j < S; ++j) {
+          ry[i * S + j].load(y + base + ((int64_t)i * W + j) * C);
+          rd[i * S + j].load(da + base + ((int64_t)i * W + j) * C);
+        }
+      // level-1 gradients of the (S/2)^2 2x2 sub-windows, level-2 gradient of the whole 4x4 window
+      constexpr int NSUB = (S / 2) * (S / 2);
+      float ga1[NSUB][VEC], gm1[NSUB][VEC], ga2[VEC], gm2[VEC];
+#pragma unroll
+      for (int si = 0; si < S / 2; ++si)
+#pragma unroll
+        for (int sj = 0; sj < S / 2; ++sj) {
+          const int64_t q1 = (((int64_t)b * (H >> 1) + (ho * (S / 2) + si)) * (W >> 1) + (wo * (S / 2) + sj)) * 2 * C + c0;
+          ldf<VEC>(dp1 + q1, ga1[si * (S / 2) + sj]);
+          ldf<VEC>(dp1 + q1 + C, gm1[si * (S / 2) + sj]);
+        }
+      if constexpr (LEVELS == 2) {
+        ldf<VEC>(dp2 + q * 2 * C + c0, ga2);
+        ldf<VEC>(dp2 + q * 2 * C + C + c0, gm2);
+      }
+      // ---- pass 1: arg-maxima (first maximum in row-major order of each window) ----
+      float mx4[VEC];
+      int arg4[VEC], arg2[NSUB][VEC];
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) { mx4[e] = -FLT_MAX; arg4[e] = 0; }
+#pragma unroll
+      for (int sub = 0; sub < NSUB; ++sub) {
+        const int si = sub / (S / 2), sj = sub % (S / 2);
+        float mx2[VEC];
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) { mx2[e] = -FLT_MAX; arg2[sub][e] = 0; }
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq) {
+          const int idx = (2 * si + (qq >> 1)) * S + 2 * sj + (qq & 1);
+          float v[VEC];
+          ry[idx].unpack(v);
+          lz.apply(v);
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) {
+            if (v[e] > mx2[e]) { mx2[e] = v[e]; arg2[sub][e] = qq; }
+            if (LEVELS == 2 && (v[e] > mx4[e] || (v[e] == mx4[e] && idx < arg4[e]))) { mx4[e] = v[e]; arg4[e] = idx; }
+          }
+        }
+      }
+      // ---- pass 2: total gradient, store, BatchNorm-backward partial sums ----
+#pragma unroll
+      for (int i = 0; i < S; ++i)
+#pragma unroll
+        for (int j = 0; j < S; ++j) {
+          const int idx = i * S + j, sub = (i >> 1) * (S / 2) + (j >> 1), qq = (i & 1) * 2 + (j & 1);
+          float g[VEC], yv[VEC];
+          rd[idx].unpack(g);
+          ry[idx].unpack(yv);
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) {
+            g[e] += ga1[sub][e] * 0.25f + (arg2[sub][e] == qq ? gm1[sub][e] : 0.f);
+            if (LEVELS == 2) g[e] += ga2[e] * 0.0625f + (arg4[e] == idx ? gm2[e] : 0.f);
+          }
+          stv<bf16, VEC>(da + base + ((int64_t)i * W + j) * C, g);
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) {
+            const float gi = g[e] * lz.dact(yv[e], e);
+            acc[0][e] += gi;
+            acc[1][e] = fmaf(gi, yv[e] - mu[e], acc[1][e]);
+          }
+        }
+    }
+  }
+  float rs[VEC];
+  ldf<VEC>(rstd + c0, rs);
+#pragma unroll
+  for (int e = 0; e < VEC; ++e) acc[1][e] *= rs[e];
+  reduce_lanes_atomic<2, VEC>(acc, smem, sums, C, C);
+}
+
 }  // namespace accx
 
 using namespace accx;
@@ -194,5 +306,38 @@ int accx_hanc_unpool_bwd(int dtype, int B, int H, int W, int C, int log2s, const
   });
   return check_launch("hanc_unpool_bwd");
 }
+
+int accx_hanc_unpool_bnred(int dtype, int B, int H, int W, int C, int levels, const void* y, const float* scale,
+                           const float* shift, int act, const float* dpool1, const float* dpool2, void* da,
+                           const float* mean, const float* rstd, float* sums, void* stream) {
+  ACCX_REQUIRE(B > 0 && C > 0 && y && dpool1 && da && mean && rstd && sums, "hanc_unpool_bnred: bad arguments");
+  ACCX_REQUIRE(dtype == ACCX_BF16, "hanc_unpool_bnred: bf16 storage only (use accx_hanc_unpool_bwd + accx_bn_bwd_reduce)");
+  ACCX_REQUIRE(levels == 1 || (levels == 2 && dpool2), "hanc_unpool_bnred: levels must be 1 or 2 (k = 2 or 3)");
+  const int S = 1 << levels;
+  ACCX_REQUIRE(H % S == 0 && W % S == 0, "hanc_unpool_bnred: %dx%d not divisible by %d", H, W, S);
+  ACCX_REQUIRE(C % 4 == 0 && aligned16(dpool1) && (!dpool2 || aligned16(dpool2)) &&
+                   (reinterpret_cast<uintptr_t>(y) & 7) == 0 && (reinterpret_cast<uintptr_t>(da) & 7) == 0,
+               "hanc_unpool_bnred: needs C %% 4 == 0 and aligned tensors");
+  ACCX_REQUIRE(act == 0 || (scale && shift), "hanc_unpool_bnred: act %d needs scale/shift", act);
+  const int64_t n_win = (int64_t)B * (H / S) * (W / S);
+  Lanes l;                                       // 128-thread blocks: the window state is register heavy
+  l.vec = 4;
+  l.cvn = C / 4;
+  l.tx = l.cvn <= 128 ? l.cvn : 128;
+  for (int d = 128; l.cvn > 128 && d >= 32; --d)
+    if (l.cvn % d == 0) { l.tx = d; break; }
+  l.ty = 128 / l.tx;
+  l.gy = (l.cvn + l.tx - 1) / l.tx;
+  dim3 block(l.tx, l.ty), grid(grid_x_for(n_win, l.ty, 148 * 3), l.gy);
+  const size_t sm = (size_t)l.tx * l.ty * l.vec * sizeof(float);
+  if (levels == 1)
+    hanc_unpool_bnred_kernel<1><<<grid, block, sm, (cudaStream_t)stream>>>(B, H, W, C, (const bf16*)y, scale, shift, act,
+                                                                            dpool1, dpool2, (bf16*)da, mean, rstd, sums);
+  else
+    hanc_unpool_bnred_kernel<2><<<grid, block, sm, (cudaStream_t)stream>>>(B, H, W, C, (const bf16*)y, scale, shift, act,
+                                                                            dpool1, dpool2, (bf16*)da, mean, rstd, sums);
+  return check_launch("hanc_unpool_bnred");
+}
+
 
 }  // extern "C"

@@ -144,6 +144,14 @@ int accx_hanc_pool_fwd(int dtype, int B, int H, int W, int C, int first, const v
 int accx_hanc_unpool_bwd(int dtype, int B, int H, int W, int C, int log2s, const void* x, const float* scale,
                          const float* shift, int act, const float* dpool, void* da, int accumulate, void* stream);
 
+/* The same gradient for ALL levels of a k = 2 / 3 pyramid (levels = 1 / 2; dpool1 = level-1 gradients
+ * [B,H/2,W/2,2C], dpool2 = level-2 [B,H/4,W/4,2C], fp32) accumulated into da in ONE pass, fused with the
+ * BatchNorm-backward reduction of the layer in front (accx_bn_bwd_reduce on the updated da):
+ * sums[c] += sum g, sums[C+c] += sum g*xhat.  bf16 storage, C % 4 == 0. */
+int accx_hanc_unpool_bnred(int dtype, int B, int H, int W, int C, int levels, const void* y, const float* scale,
+                           const float* shift, int act, const float* dpool1, const float* dpool2, void* da,
+                           const float* mean, const float* rstd, float* sums, void* stream);
+
 /* out[b, h, w, coff + c] = mul * sum over the s x s block of x (MLFC's chained AvgPool2d(2),
  * ACC_UNet.py:361,448-480 with mul = 1/s^2; block sums of gradients with mul = 1). */
 int accx_pool_sum(int in_dtype, int out_dtype, int B, int H, int W, int C, int log2s, float mul, const void* x,

@@ -193,6 +193,38 @@ def test_hanc_pools_and_unpool(dtype, k):
     close(da.float(), a_.grad, rt, at, "unpool bwd")
 
 
+@pytest.mark.parametrize("k", [2, 3])
+@pytest.mark.parametrize("C,H,W", [(24, 16, 32), (96, 8, 12), (272, 4, 8)])
+def test_hanc_unpool_fused_with_bn_reduce_matches_separate_kernels(k, C, H, W):
+    """accx_hanc_unpool_bnred == accx_hanc_unpool_bwd per level followed by accx_bn_bwd_reduce (bf16);
+    ties inside a window (frequent in bf16) must be routed identically: first maximum in row-major order."""
+    e = E()
+    B = 2
+    g = torch.Generator().manual_seed(31)
+    y = torch.randn(B, H, W, C, generator=g).to(DEV).to(torch.bfloat16)
+    y[:, ::2, 1::2, :] = y[:, ::2, ::2, :]            # force exact ties inside every 2x2 / 4x4 window
+    scale = (torch.rand(C, generator=g) + 0.5).to(DEV)
+    shift = (torch.randn(C, generator=g) * 0.3).to(DEV)
+    mean = (torch.randn(C, generator=g) * 0.2).to(DEV)
+    rstd = (torch.rand(C, generator=g) + 0.5).to(DEV)
+    L = e.Lazy(y, scale, shift, 2, mean, rstd, None)
+    da0 = torch.randn(B, H, W, C, generator=g).to(DEV).to(torch.bfloat16)
+    dps = [torch.randn(B, H >> l, W >> l, 2 * C, generator=g).to(DEV) for l in range(1, k)]
+    ar = e.Arena(DEV)
+    # separate kernels (fp32 copy of da so that the reference carries no intermediate bf16 rounding)
+    ref = da0.float().clone()
+    Lf = e.Lazy(y.float(), scale, shift, 2, mean, rstd, None)
+    for l, dp in enumerate(dps, start=1):
+        e.hanc_unpool_bwd(Lf, l, dp, ref, accumulate=True)
+    sums_ref = torch.zeros(2 * C, device=DEV)
+    e._call("accx_bn_bwd_reduce", e.F32, B * H * W, C, e.ptr(Lf.y), e.ptr(scale), e.ptr(shift), 2, e.ptr(mean), e.ptr(rstd),
+            e.ptr(ref), e.ptr(sums_ref), e.stream())
+    da = da0.clone()
+    sums = e.hanc_unpool_bnred(L, dps, da, ar)
+    close(da.float(), ref, 1e-2, 1e-2, "fused unpool da")
+    close(sums, sums_ref, 2e-3, 2e-3, "fused bn-backward sums")
+
+
 def test_unpool_routes_ties_to_first_maximum():
     """ATen MaxPool2d sends the gradient to the first maximal element in row-major window order."""
     e = E()
