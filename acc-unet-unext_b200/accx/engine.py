@@ -378,6 +378,24 @@ def dw_fwd(L: Lazy, w, bias, stats, flip=False):
     return out
 
 
+def dw_dgrad_bnred_ok(L: Lazy, dy: torch.Tensor) -> bool:
+    y = L.y
+    return (L.mean is not None and L.rstd is not None and (y.shape[-1] * y.element_size()) % 16 == 0
+            and y.data_ptr() % 16 == 0 and dy.data_ptr() % 16 == 0)
+
+
+def dw_dgrad_bnred(L: Lazy, dy: torch.Tensor, w, arena: Arena):
+    """input gradient of the depthwise conv whose input was the lazy tensor L, fused with the BatchNorm-backward
+    reduction of L's BatchNorm -> (da, sums) for bn_bwd(L, da, ..., sums=)"""
+    y = L.y
+    B, H, W, C = y.shape
+    da = torch.empty_like(y)
+    sums = arena.take(2 * C)
+    _call("accx_dw3x3_dgrad_bnred", dt(y), B, H, W, C, ptr(dy), ptr(w), ptr(da), ptr(y), ptr(L.scale), ptr(L.shift), L.act,
+          ptr(L.mean), ptr(L.rstd), ptr(sums), stream(), cost=(nb(dy, y, da), 18 * y.numel()), tag=f"{B}x{H}x{W}x{C}")
+    return da, sums
+
+
 def dw_wgrad(L: Lazy, dy: torch.Tensor, gw: torch.Tensor):
     y = L.y
     B, H, W, C = y.shape
@@ -481,9 +499,11 @@ def se_fwd(L: Lazy, se, arena: Arena, training: bool, residual=None, mix=None, s
 
 
 def se_bwd(c: SECtx, dout: torch.Tensor, grads: dict, arena: Arena, da: Optional[torch.Tensor] = None,
-           accumulate=False) -> torch.Tensor:
+           accumulate=False, bn_sums=False):
     """gradient w.r.t. the activated SE input given d(out); parameter grads accumulate in `grads`.
-    (The residual branch, if any, simply receives dout * (1 - mix) -- handled by the caller.)"""
+    (The residual branch, if any, simply receives dout * (1 - mix) -- handled by the caller.)
+    bn_sums=True: -> (da, sums) where sums is the BatchNorm-backward reduction of the SE input's own
+    BatchNorm on da (made in the same pass; hand it to bn_bwd(..., sums=)), or None if the input has no BN."""
     L, se = c.L, c.mod
     y = L.y
     B, H, W, C = y.shape
@@ -504,10 +524,11 @@ def se_bwd(c: SECtx, dout: torch.Tensor, grads: dict, arena: Arena, da: Optional
     if da is None:
         da = torch.empty_like(y)
         accumulate = False
+    sums = arena.take(2 * C) if (bn_sums and L.mean is not None and L.rstd is not None) else None
     _call("accx_se_bwd_apply", d, B, H * W, C, ptr(y), ptr(L.scale), ptr(L.shift), L.act, ptr(c.gate), ptr(c.scale),
-          ptr(c.shift), ptr(dout), ptr(c.mix), ptr(PQR), ptr(da), 1 if accumulate else 0, stream(),
-          cost=(nb(y, dout, da), 0))
-    return da
+          ptr(c.shift), ptr(dout), ptr(c.mix), ptr(PQR), ptr(da), 1 if accumulate else 0, ptr(L.mean) if sums is not None else 0,
+          ptr(L.rstd) if sums is not None else 0, ptr(sums), stream(), cost=(nb(y, dout, da), 0))
+    return (da, sums) if bn_sums else da
 
 
 def to_nhwc(x: torch.Tensor) -> torch.Tensor:

@@ -250,9 +250,9 @@ class Conv2d_batchnorm(_AccxModule):
     def _core_bwd(self, saved, dout, grads, ar):
         """-> gradient w.r.t. the raw conv output"""
         L, c = saved
-        da = E.se_bwd(c, dout, grads, ar)
+        da, sums = E.se_bwd(c, dout, grads, ar, bn_sums=True)
         _zero_bias_grad(grads, self.conv1)
-        return E.bn_bwd(L, da, grads, ar)
+        return E.bn_bwd(L, da, grads, ar, sums=sums)
 
     def _fwd(self, xs, training, need):
         x = xs[0]
@@ -335,8 +335,8 @@ class HANCBlock(_AccxModule):
         Ex, Cout = self.conv1.out_channels, self.conv3.out_channels
         w1, w3 = _w(self.conv1.weight), _w(self.conv3.weight)
         # SE -> norm3 -> conv3
-        da5 = E.se_bwd(s["se"], dout, grads, ar)
-        dy5 = E.bn_bwd(L5, da5, grads, ar)
+        da5, sums5 = E.se_bwd(s["se"], dout, grads, ar, bn_sums=True)
+        dy5 = E.bn_bwd(L5, da5, grads, ar, sums=sums5)
         _zero_bias_grad(grads, self.conv3)
         g3 = E.grad_buf(grads, self.conv3.weight)
         if g3 is not None:
@@ -352,8 +352,11 @@ class HANCBlock(_AccxModule):
         g2 = E.grad_buf(grads, self.conv2.weight)
         if g2 is not None:
             E.dw_wgrad(L1, dy2, g2)
-        da1 = E.dw_fwd(Lazy(dy2), _w(self.conv2.weight), None, None, flip=True)
-        dy1 = E.bn_bwd(L1, da1, grads, ar)
+        if E.dw_dgrad_bnred_ok(L1, dy2):       # input gradient + norm1's backward reduction in one pass
+            da1, sums1 = E.dw_dgrad_bnred(L1, dy2, _w(self.conv2.weight), ar)
+        else:
+            da1, sums1 = E.dw_fwd(Lazy(dy2), _w(self.conv2.weight), None, None, flip=True), None
+        dy1 = E.bn_bwd(L1, da1, grads, ar, sums=sums1)
         # conv1
         _zero_bias_grad(grads, self.conv1)
         g1 = E.grad_buf(grads, self.conv1.weight)
@@ -435,8 +438,8 @@ class ResPath(_AccxModule):
         for i in reversed(range(len(self.convs))):
             X, L, sec = s["levels"][i]
             w = _w(self.convs[i].weight)
-            da = E.se_bwd(sec, dx, grads, ar)
-            dy = E.bn_bwd(L, da, grads, ar)
+            da, sums = E.se_bwd(sec, dx, grads, ar, bn_sums=True)
+            dy = E.bn_bwd(L, da, grads, ar, sums=sums)
             _zero_bias_grad(grads, self.convs[i])
             gw = E.grad_buf(grads, self.convs[i].weight)
             if gw is not None:
@@ -573,8 +576,8 @@ class MLFC(_AccxModule):
             C = filt[l]
             cm = getattr(self, f"cnv_mrg{l + 1}")[i]
             wm = _w(cm.conv1.weight)
-            da = E.se_bwd(s["fin"][l], douts[l], grads, ar)                 # final SE
-            dt_ = E.bn_bwd(Lm[l], da, grads, ar)                            # bns_mrg: grad wrt (SE_out*mix + x*(1-mix))
+            da, sums = E.se_bwd(s["fin"][l], douts[l], grads, ar, bn_sums=True)       # final SE
+            dt_ = E.bn_bwd(Lm[l], da, grads, ar, sums=sums)                 # bns_mrg: grad wrt (SE_out*mix + x*(1-mix))
             # residual branch
             if mix is None:
                 acc(l, dt_)          # aliasing is safe: dt_ is only read by the launches queued below

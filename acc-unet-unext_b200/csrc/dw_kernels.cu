@@ -178,11 +178,29 @@ int dw_tiled_fwd(int dtype, int B, int H, int W, int C, const void* x, const flo
 int dw_tiled_wgrad(int dtype, int B, int H, int W, int C, const void* x, const float* scale, const float* shift,
                    int act, const void* dy, float* dw, cudaStream_t st);
 
+int dw_tiled_dgrad_bnred(int dtype, int B, int H, int W, int C, const void* dy, const float* w, void* da, const void* y1,
+                         const float* bn_scale, const float* bn_shift, int bn_act, const float* bn_mean,
+                         const float* bn_rstd, float* sums, cudaStream_t st);
+
 }  // namespace accx
 
 using namespace accx;
 
 extern "C" {
+
+int accx_dw3x3_dgrad_bnred(int dtype, int B, int H, int W, int C, const void* dy, const float* w, void* da,
+                           const void* y1, const float* bn_scale, const float* bn_shift, int bn_act,
+                           const float* bn_mean, const float* bn_rstd, float* sums, void* stream) {
+  ACCX_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && dy && w && da && y1 && bn_mean && bn_rstd && sums,
+               "dw3x3_dgrad_bnred: bad arguments");
+  ACCX_REQUIRE(dtype == ACCX_F32 || dtype == ACCX_BF16, "dw3x3_dgrad_bnred: unsupported dtype %d", dtype);
+  ACCX_REQUIRE(bn_act == 0 || (bn_scale && bn_shift), "dw3x3_dgrad_bnred: act %d needs scale/shift", bn_act);
+  ACCX_REQUIRE(dw_tiled_ok(dtype, C, dy, da) && dw_tiled_ok(dtype, C, y1, da),
+               "dw3x3_dgrad_bnred: tensors must be TMA-addressable (16-byte aligned, C*elem %% 16 == 0); use "
+               "accx_dw3x3_fwd(flip) + accx_bn_bwd_reduce");
+  return dw_tiled_dgrad_bnred(dtype, B, H, W, C, dy, w, da, y1, bn_scale, bn_shift, bn_act, bn_mean, bn_rstd, sums,
+                              (cudaStream_t)stream);
+}
 
 int accx_dw3x3_fwd(int dtype, int B, int H, int W, int C, const void* x, const float* scale, const float* shift,
                    int act, const float* w, const float* bias, int flip, void* y, float* stats, void* stream) {

@@ -37,6 +37,13 @@ struct alignas(64) DwParams {
   float* stats;
   const void* dy;
   float* dw;
+  // MODE 2 (input gradient + BatchNorm-backward reduction of the layer in front): raw forward input y1 comes in
+  // through map_dy; g = da * act'(y1*bn_scale + bn_shift); stats[c] += sum g, stats[C+c] += sum g * xhat
+  const float* bn_scale;
+  const float* bn_shift;
+  const float* bn_mean;
+  const float* bn_rstd;
+  int bn_act;
 };
 
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
@@ -158,15 +165,17 @@ __device__ __forceinline__ void dw_flush(const DwParams& prm, float (&acc)[NV][4
   }
 }
 
-template <typename T, int TH, bool WGRAD>
+// MODE 0: forward / input gradient (flip);  1: weight gradient;  2: input gradient + BN-backward reduction
+template <typename T, int TH, int MODE>
 __global__ void __launch_bounds__(DW_THREADS, 2) dw3x3_tiled_kernel(const __grid_constant__ DwParams prm) {
+  constexpr bool WGRAD = MODE == 1, BOX2 = MODE != 0;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
   const int TW = prm.TW, CC = prm.CC, lanes_c = prm.lanes_c;
   const int halo_w = TW + 2, n_pos = (TH + 2) * halo_w;
   const uint32_t x_bytes = (uint32_t)n_pos * CC * sizeof(T);
   const uint32_t x_bytes_al = (x_bytes + 127u) & ~127u;
-  const uint32_t g_bytes = WGRAD ? (uint32_t)TH * TW * CC * sizeof(T) : 0u;     // multiple of 128
+  const uint32_t g_bytes = BOX2 ? (uint32_t)TH * TW * CC * sizeof(T) : 0u;      // multiple of 128
   const uint32_t stage_bytes = x_bytes_al + g_bytes;
   const uint32_t bar0 = base + 2 * stage_bytes;                                 // two mbarriers
   float* red = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw)) + 2 * stage_bytes + 16);
@@ -197,7 +206,7 @@ __global__ void __launch_bounds__(DW_THREADS, 2) dw3x3_tiled_kernel(const __grid
     const uint32_t dst = base + stage * stage_bytes, bar = bar0 + 8 * stage;
     mbar_expect_tx(bar, x_bytes + g_bytes);
     tma_load_4d(dst, &prm.map_x, chunk * CC, w0 - 1, h0 - 1, b, bar);
-    if (WGRAD) tma_load_4d(dst + x_bytes_al, &prm.map_dy, chunk * CC, w0, h0, b, bar);
+    if (BOX2) tma_load_4d(dst + x_bytes_al, &prm.map_dy, chunk * CC, w0, h0, b, bar);
   };
 
   if (tid == 0 && (int64_t)blockIdx.x < total) issue(blockIdx.x, 0);
@@ -214,6 +223,9 @@ __global__ void __launch_bounds__(DW_THREADS, 2) dw3x3_tiled_kernel(const __grid
 #pragma unroll
     for (int t = 0; t < 9; ++t) acc_w[t][i] = 0.f;
   }
+  float bn_s[4], bn_t[4], bn_mu[4], bn_rs[4];   // MODE 2
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { bn_s[i] = 1.f; bn_t[i] = 0.f; bn_mu[i] = 0.f; bn_rs[i] = 0.f; }
   int cur_chunk = -1;
   int it = 0;
   for (int64_t tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
@@ -227,10 +239,24 @@ __global__ void __launch_bounds__(DW_THREADS, 2) dw3x3_tiled_kernel(const __grid
     const int c = c0 + cl * 4;
     if (chunk != cur_chunk) {
       if (cur_chunk >= 0) {
+        if (MODE == 2) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) acc_st[1][i] *= bn_rs[i];
+        }
         if (WGRAD) dw_flush<9>(prm, acc_w, red, cl, col, cur_chunk * CC, prm.dw, 9, 1);
         else if (prm.stats) dw_flush<2>(prm, acc_st, red, cl, col, cur_chunk * CC, prm.stats, 1, prm.C);
       }
       cur_chunk = chunk;
+      if (MODE == 2) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const bool ok = c + i < prm.C;
+          bn_s[i] = (ok && prm.bn_act != 0) ? __ldg(prm.bn_scale + c + i) : 1.f;
+          bn_t[i] = (ok && prm.bn_act != 0) ? __ldg(prm.bn_shift + c + i) : 0.f;
+          bn_mu[i] = ok ? __ldg(prm.bn_mean + c + i) : 0.f;
+          bn_rs[i] = ok ? __ldg(prm.bn_rstd + c + i) : 0.f;
+        }
+      }
       if (!WGRAD) {
         float wf[4][9];
 #pragma unroll
@@ -284,10 +310,25 @@ __global__ void __launch_bounds__(DW_THREADS, 2) dw3x3_tiled_kernel(const __grid
           unpack2(o[2][0], v[0], v[1]);
           unpack2(o[2][1], v[2], v[3]);
           if (col_ok && h < prm.H) {
+            if constexpr (MODE == 2) {
+              f32x2 y01, y23;
+              lds4<T>(xt + x_bytes_al + (uint32_t)(((r - 2) * TW + col) * CC + cl * 4) * sizeof(T), y01, y23);
+              float yv[4];
+              unpack2(y01, yv[0], yv[1]);
+              unpack2(y23, yv[2], yv[3]);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              acc_st[0][i] += v[i];
-              acc_st[1][i] = fmaf(v[i], v[i], acc_st[1][i]);
+              for (int i = 0; i < 4; ++i) {
+                const float dact = (prm.bn_act == 2 && fmaf(yv[i], bn_s[i], bn_t[i]) <= 0.f) ? ACCX_LRELU : 1.f;
+                const float gi = v[i] * dact;
+                acc_st[0][i] += gi;
+                acc_st[1][i] = fmaf(gi, yv[i] - bn_mu[i], acc_st[1][i]);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                acc_st[0][i] += v[i];
+                acc_st[1][i] = fmaf(v[i], v[i], acc_st[1][i]);
+              }
             }
             T* dst = (T*)prm.y + ((((int64_t)b * prm.H + h) * prm.W + (w0 + col)) * prm.C + c);
             stv<T, 4>(dst, v);
@@ -331,6 +372,10 @@ __global__ void __launch_bounds__(DW_THREADS, 2) dw3x3_tiled_kernel(const __grid
     __syncthreads();                     // everyone is done reading this stage before it is refilled
   }
   if (cur_chunk >= 0) {
+    if (MODE == 2) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc_st[1][i] *= bn_rs[i];
+    }
     if (WGRAD) dw_flush<9>(prm, acc_w, red, cl, col, cur_chunk * CC, prm.dw, 9, 1);
     else if (prm.stats) dw_flush<2>(prm, acc_st, red, cl, col, cur_chunk * CC, prm.stats, 1, prm.C);
   }
@@ -367,22 +412,23 @@ static void dw_geometry(int B, int H, int W, int C, int TH, DwParams& prm) {
   prm.n_spatial = (int64_t)B * prm.tiles_h * prm.tiles_w;
 }
 
-template <typename T, int TH, bool WGRAD>
+template <typename T, int TH, int MODE>
 static int dw_launch(DwParams& prm, const void* x, const void* dy, cudaStream_t st) {
+  constexpr bool BOX2 = MODE != 0;
   const int esz = sizeof(T);
   dw_geometry(prm.B, prm.H, prm.W, prm.C, TH, prm);
   if (!encode_4d(&prm.map_x, x, esz, prm.B, prm.H, prm.W, prm.C, prm.CC, prm.TW + 2, TH + 2)) {
     set_error("dw3x3: cuTensorMapEncodeTiled failed for the input");
     return ACCX_ERR_CUDA;
   }
-  if (WGRAD && !encode_4d(&prm.map_dy, dy, esz, prm.B, prm.H, prm.W, prm.C, prm.CC, prm.TW, TH)) {
-    set_error("dw3x3: cuTensorMapEncodeTiled failed for dY");
+  if (BOX2 && !encode_4d(&prm.map_dy, dy, esz, prm.B, prm.H, prm.W, prm.C, prm.CC, prm.TW, TH)) {
+    set_error("dw3x3: cuTensorMapEncodeTiled failed for the second operand");
     return ACCX_ERR_CUDA;
   }
   const size_t x_bytes = ((size_t)(TH + 2) * (prm.TW + 2) * prm.CC * esz + 127) & ~(size_t)127;
-  const size_t g_bytes = WGRAD ? (size_t)TH * prm.TW * prm.CC * esz : 0;
+  const size_t g_bytes = BOX2 ? (size_t)TH * prm.TW * prm.CC * esz : 0;
   const size_t smem = 128 + 2 * (x_bytes + g_bytes) + 16 + DW_THREADS * sizeof(float);
-  auto kern = dw3x3_tiled_kernel<T, TH, WGRAD>;
+  auto kern = dw3x3_tiled_kernel<T, TH, MODE>;
   static bool attr_set = false;       // one flag per template instantiation
   if (!attr_set) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -407,13 +453,28 @@ int dw_tiled_fwd(int dtype, int B, int H, int W, int C, const void* x, const flo
   prm.B = B; prm.H = H; prm.W = W; prm.C = C;
   prm.scale = scale; prm.shift = shift; prm.act = act; prm.flip = flip;
   prm.w = w; prm.bias = bias; prm.y = y; prm.stats = stats; prm.dy = nullptr; prm.dw = nullptr;
+  prm.bn_scale = prm.bn_shift = prm.bn_mean = prm.bn_rstd = nullptr; prm.bn_act = 0;
   int rc;
   if (dtype == ACCX_BF16) {
-    rc = (H % 16 == 0) ? dw_launch<bf16, 16, false>(prm, x, nullptr, st) : dw_launch<bf16, 8, false>(prm, x, nullptr, st);
+    rc = (H % 16 == 0) ? dw_launch<bf16, 16, 0>(prm, x, nullptr, st) : dw_launch<bf16, 8, 0>(prm, x, nullptr, st);
   } else {
-    rc = dw_launch<float, 8, false>(prm, x, nullptr, st);
+    rc = dw_launch<float, 8, 0>(prm, x, nullptr, st);
   }
   return rc ? rc : check_launch("dw3x3_fwd(tiled)");
+}
+
+int dw_tiled_dgrad_bnred(int dtype, int B, int H, int W, int C, const void* dy, const float* w, void* da, const void* y1,
+                         const float* bn_scale, const float* bn_shift, int bn_act, const float* bn_mean,
+                         const float* bn_rstd, float* sums, cudaStream_t st) {
+  DwParams prm;
+  prm.B = B; prm.H = H; prm.W = W; prm.C = C;
+  prm.scale = nullptr; prm.shift = nullptr; prm.act = 0; prm.flip = 1;
+  prm.w = w; prm.bias = nullptr; prm.y = da; prm.stats = sums; prm.dy = y1; prm.dw = nullptr;
+  prm.bn_scale = bn_scale; prm.bn_shift = bn_shift; prm.bn_act = bn_act; prm.bn_mean = bn_mean; prm.bn_rstd = bn_rstd;
+  int rc;
+  if (dtype == ACCX_BF16) rc = dw_launch<bf16, 8, 2>(prm, dy, y1, st);
+  else rc = dw_launch<float, 8, 2>(prm, dy, y1, st);
+  return rc ? rc : check_launch("dw3x3_dgrad_bnred(tiled)");
 }
 
 int dw_tiled_wgrad(int dtype, int B, int H, int W, int C, const void* x, const float* scale, const float* shift,
@@ -422,9 +483,10 @@ int dw_tiled_wgrad(int dtype, int B, int H, int W, int C, const void* x, const f
   prm.B = B; prm.H = H; prm.W = W; prm.C = C;
   prm.scale = scale; prm.shift = shift; prm.act = act; prm.flip = 0;
   prm.w = nullptr; prm.bias = nullptr; prm.y = nullptr; prm.stats = nullptr; prm.dy = dy; prm.dw = dw;
+  prm.bn_scale = prm.bn_shift = prm.bn_mean = prm.bn_rstd = nullptr; prm.bn_act = 0;
   int rc;
-  if (dtype == ACCX_BF16) rc = dw_launch<bf16, 8, true>(prm, x, dy, st);
-  else rc = dw_launch<float, 8, true>(prm, x, dy, st);
+  if (dtype == ACCX_BF16) rc = dw_launch<bf16, 8, 1>(prm, x, dy, st);
+  else rc = dw_launch<float, 8, 1>(prm, x, dy, st);
   return rc ? rc : check_launch("dw3x3_wgrad(tiled)");
 }
 

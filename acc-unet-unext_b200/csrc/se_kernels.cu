@@ -335,11 +335,19 @@ __global__ void se_bwd_apply_kernel(int B, int HW, int C, int chunks, const T* _
                                     const float* shift, int act, const float* __restrict__ gate,
                                     const float* se_scale, const float* se_shift, const T* __restrict__ dout,
                                     const float* mix, const float* __restrict__ PQR, T* __restrict__ da,
-                                    int accumulate) {
+                                    int accumulate, const float* bn_mean, const float* bn_rstd, float* bn_sums) {
+  // bn_sums != NULL: also the BatchNorm-backward reduction of the lazy input's own BatchNorm on the gradient
+  // just produced (sum g, sum g*xhat with g = da*act'(x)) -- saves the separate accx_bn_bwd_reduce pass
+  extern __shared__ float smem[];
   const int cv = blockIdx.y * blockDim.x + threadIdx.x;
-  if (cv * VEC >= C) return;
-  const int c0 = cv * VEC;
+  const bool active = cv * VEC < C;
+  if (!active && bn_sums == nullptr) return;
+  const int c0 = active ? cv * VEC : 0;
   const int b = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
+  float bacc[2][VEC], bmu[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) { bacc[0][i] = bacc[1][i] = 0.f; bmu[i] = 0.f; }
+  if (bn_sums) ldf<VEC>(bn_mean + c0, bmu);
   Lazy<VEC> lz;
   lz.init(scale, shift, act, c0);
   float gs[VEC], st[VEC], cp[VEC], cq[VEC], cr[VEC];
@@ -359,6 +367,7 @@ __global__ void se_bwd_apply_kernel(int B, int HW, int C, int chunks, const T* _
   const int64_t off = (int64_t)b * HW * C + c0;
   constexpr int U = 4;
   RawVec<T, VEC> rv[U], rd[U], ro[U];
+  if (active)
   pixel_loop<U>(chunk * blockDim.y + threadIdx.y, HW, chunks * blockDim.y,
       [&](int u, int64_t p) {
         rv[u].load(x + off + p * C);
@@ -366,9 +375,11 @@ __global__ void se_bwd_apply_kernel(int B, int HW, int C, int chunks, const T* _
         if (accumulate) ro[u].load(da + off + p * C);
       },
       [&](int u, int64_t p) {
-        float v[VEC], d[VEC], o[VEC];
+        float v[VEC], d[VEC], o[VEC], raw[VEC];
         rv[u].unpack(v);
         rd[u].unpack(d);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) raw[i] = v[i];
         lz.apply(v);
         if (accumulate) {
           ro[u].unpack(o);
@@ -383,7 +394,22 @@ __global__ void se_bwd_apply_kernel(int B, int HW, int C, int chunks, const T* _
           o[i] += fmaf(cp[i], gp, fmaf(cq[i], v[i], cr[i]));
         }
         stv<T, VEC>(da + off + p * C, o);
+        if (bn_sums) {
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) {
+            const float gi = o[i] * lz.dact(raw[i], i);
+            bacc[0][i] += gi;
+            bacc[1][i] = fmaf(gi, raw[i] - bmu[i], bacc[1][i]);
+          }
+        }
       });
+  if (bn_sums) {
+    float rs[VEC];
+    ldf<VEC>(bn_rstd + c0, rs);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) bacc[1][i] *= rs[i];
+    reduce_lanes_atomic<2, VEC>(bacc, smem, bn_sums, C, C);
+  }
 }
 
 static inline int se_chunks(int B, int HW, int ty, int target_blocks = 148 * 4) {
@@ -481,17 +507,20 @@ int accx_se_bwd_gate(int B, int C, int Cr, double HW, const float* S, const floa
 
 int accx_se_bwd_apply(int dtype, int B, int HW, int C, const void* x, const float* scale, const float* shift, int act,
                       const float* gate, const float* se_scale, const float* se_shift, const void* dout,
-                      const float* mix, const float* PQR, void* da, int accumulate, void* stream) {
+                      const float* mix, const float* PQR, void* da, int accumulate, const float* bn_mean,
+                      const float* bn_rstd, float* bn_sums, void* stream) {
   ACCX_REQUIRE(B > 0 && HW > 0 && C > 0 && x && gate && dout && PQR && da, "se_bwd_apply: bad arguments");
+  ACCX_REQUIRE(!bn_sums || (bn_mean && bn_rstd), "se_bwd_apply: bn_sums needs bn_mean and bn_rstd");
   const int64_t P = (int64_t)B * HW;
   ACCX_DISPATCH_T(dtype, {
     Lanes l = make_lanes(C, DT<T>::VEC, aligned16(x) && aligned16(dout) && aligned16(da));
-    const int chunks = se_chunks(B, HW, l.ty, 148 * 8);
+    const int chunks = se_chunks(B, HW, l.ty, bn_sums ? 148 * 2 : 148 * 8);     // reducing: few blocks (atomics)
     dim3 block(l.tx, l.ty), grid(B * chunks, l.gy);
+    const size_t sm = bn_sums ? (size_t)l.tx * l.ty * l.vec * sizeof(float) : 0;
     ACCX_DISPATCH_VEC(l, {
-      se_bwd_apply_kernel<T, VEC><<<grid, block, 0, (cudaStream_t)stream>>>(B, HW, C, chunks, (const T*)x, scale, shift, act,
-                                                                            gate, se_scale, se_shift, (const T*)dout,
-                                                                            mix, PQR, (T*)da, accumulate);
+      se_bwd_apply_kernel<T, VEC><<<grid, block, sm, (cudaStream_t)stream>>>(
+          B, HW, C, chunks, (const T*)x, scale, shift, act, gate, se_scale, se_shift, (const T*)dout, mix, PQR, (T*)da,
+          accumulate, bn_mean, bn_rstd, bn_sums);
     });
   });
   return check_launch("se_bwd_apply");

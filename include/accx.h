@@ -132,6 +132,12 @@ int accx_dw3x3_fwd(int dtype, int B, int H, int W, int C, const void* x, const f
                    int act, const float* w, const float* bias, int flip, void* y, float* stats, void* stream);
 int accx_dw3x3_wgrad(int dtype, int B, int H, int W, int C, const void* x, const float* scale, const float* shift,
                      int act, const void* dy, float* dw, void* stream);
+/* Input gradient da = dwconv(dy, rot180(w)) fused with the BatchNorm-backward reduction of the layer in front of
+ * the depthwise conv (norm1, ACC_UNet.py:244,270): y1 is that layer's raw output, g = da*act'(y1*bn_scale+bn_shift),
+ * sums[c] += sum g, sums[C+c] += sum g*(y1-mean)*rstd.  Needs TMA-addressable tensors (C*elem % 16 == 0). */
+int accx_dw3x3_dgrad_bnred(int dtype, int B, int H, int W, int C, const void* dy, const float* w, void* da,
+                           const void* y1, const float* bn_scale, const float* bn_shift, int bn_act,
+                           const float* bn_mean, const float* bn_rstd, float* sums, void* stream);
 
 /* HANC pyramid (HANCLayer.forward, ACC_UNet.py:83-136), one 2x level per call.
  * first != 0: x is the lazy [B,H,W,C] map, else x is the previous level [B,H,W,2C] (avg | max).
@@ -179,7 +185,8 @@ int accx_se_apply(int dtype, int B, int HW, int C, const void* x, const float* s
 /* backward: G[0,b,c] += sum_hw g', G[1,b,c] += sum_hw g'*a with g' = dout*lrelu'(v)  (reduce);
  * the tiny gate kernel turns G into per-(b,c) coefficients PQR and all parameter gradients;
  * apply: da (+)= P*g' + Q*a + R.  With mix: g' carries the factor mix and
- * dmix += sum dout*(v - residual). */
+ * dmix += sum dout*(v - residual).  bn_sums != NULL (apply): the lazy input's own BatchNorm-backward reduction
+ * (accx_bn_bwd_reduce on the da just written) is accumulated in the same pass. */
 int accx_se_bwd_reduce(int dtype, int B, int HW, int C, const void* x, const float* scale, const float* shift, int act,
                        const float* gate, const float* se_scale, const float* se_shift, const void* dout,
                        const float* mix, const void* residual, float* dmix, float* G, void* stream);
@@ -189,7 +196,8 @@ int accx_se_bwd_gate(int B, int C, int Cr, double HW, const float* S, const floa
                      float* PQR, void* stream);
 int accx_se_bwd_apply(int dtype, int B, int HW, int C, const void* x, const float* scale, const float* shift, int act,
                       const float* gate, const float* se_scale, const float* se_shift, const void* dout,
-                      const float* mix, const float* PQR, void* da, int accumulate, void* stream);
+                      const float* mix, const float* PQR, void* da, int accumulate, const float* bn_mean,
+                      const float* bn_rstd, float* bn_sums, void* stream);
 
 /* z = act(a) + r with stats (HANCBlock: norm(x + inp), ACC_UNet.py:279). */
 int accx_add_fwd(int dtype, int64_t P, int C, const void* a, const float* scale, const float* shift, int act,

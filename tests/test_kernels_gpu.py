@@ -193,6 +193,30 @@ def test_hanc_pools_and_unpool(dtype, k):
     close(da.float(), a_.grad, rt, at, "unpool bwd")
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("C,H,W", [(96, 12, 10), (24, 8, 8), (64, 32, 64), (384, 24, 24), (200, 9, 33)])
+def test_dw3x3_dgrad_fused_with_bn_reduce(dtype, C, H, W):
+    """accx_dw3x3_dgrad_bnred == accx_dw3x3_fwd(flip) followed by accx_bn_bwd_reduce"""
+    e = E()
+    B = 2
+    L1, _ = mk_lazy((B, H, W, C), dtype, 2, 21)
+    g = torch.Generator().manual_seed(22)
+    L1.mean = (torch.randn(C, generator=g) * 0.2).to(DEV)
+    L1.rstd = (torch.rand(C, generator=g) + 0.5).to(DEV)
+    w = (torch.randn(C, 1, 3, 3, generator=g) / 3).to(DEV)
+    dy = torch.randn(B, H, W, C, generator=g).to(DEV).to(dtype)
+    ar = e.Arena(DEV)
+    assert e.dw_dgrad_bnred_ok(L1, dy)
+    da, sums = e.dw_dgrad_bnred(L1, dy, w, ar)
+    ref = e.dw_fwd(e.Lazy(dy), w, None, None, flip=True)
+    assert torch.equal(da, ref)
+    sums_ref = torch.zeros(2 * C, device=DEV)
+    e._call("accx_bn_bwd_reduce", e.dt(ref), B * H * W, C, e.ptr(L1.y), e.ptr(L1.scale), e.ptr(L1.shift), 2, e.ptr(L1.mean),
+            e.ptr(L1.rstd), e.ptr(ref), e.ptr(sums_ref), e.stream())
+    rt = 1e-3 if dtype == torch.float32 else 1e-2
+    close(sums, sums_ref, rt, rt, "fused dw dgrad bn-backward sums")
+
+
 @pytest.mark.parametrize("k", [2, 3])
 @pytest.mark.parametrize("C,H,W", [(24, 16, 32), (96, 8, 12), (272, 4, 8)])
 def test_hanc_unpool_fused_with_bn_reduce_matches_separate_kernels(k, C, H, W):
