@@ -100,6 +100,62 @@ def module_backward_end():
         join_side()
 
 
+# ---- independent chains on parallel streams --------------------------------------------------------
+# MLFC's four pyramid levels (and the model's four ResPaths) are independent chains of small, latency-bound
+# kernels.  Inside ONE module call they are issued on separate streams between a fork and a join, so the GPU
+# (and the captured CUDA graph) runs them concurrently.  Every tensor a lane allocates stays referenced until
+# after the join, and a lane starts by waiting for the caller's stream, so the caching allocator never hands
+# memory to a stream that could still race with a pending reader.
+LANES = int(os.environ.get("ACCX_LANES", "1"))
+_LANE_STREAMS = {}
+
+
+class fork_lanes:
+    def __init__(self, n):
+        self.n = n
+        self.used = set()
+        self.enabled = LANES != 0
+
+    def __enter__(self):
+        if self.enabled:
+            self.main = torch.cuda.current_stream()
+            dev = torch.cuda.current_device()
+            pool = _LANE_STREAMS.setdefault(dev, [])
+            while len(pool) < self.n:
+                pool.append(torch.cuda.Stream(device=dev))
+            self.pool = pool
+            self.ev = torch.cuda.Event()
+            self.ev.record(self.main)
+        return self
+
+    def lane(self, i):
+        """context manager: launches inside go to lane i (ordered after everything queued before the fork and
+        after this lane's earlier work)"""
+        if not self.enabled:
+            return _NullCtx()
+        s = self.pool[i]
+        if i not in self.used:
+            s.wait_event(self.ev)
+            self.used.add(i)
+        return torch.cuda.stream(s)
+
+    def __exit__(self, *exc):
+        if self.enabled:
+            for i in self.used:
+                ev = torch.cuda.Event()
+                ev.record(self.pool[i])
+                self.main.wait_event(ev)
+        return False
+
+
+class _NullCtx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
 def nb(*ts) -> int:
     """bytes of the given tensors (algorithmic traffic accounting: each tensor once)"""
     return sum(t.numel() * t.element_size() for t in ts if t is not None)

@@ -14,7 +14,7 @@ import torch
 from torch import nn
 
 from . import engine as E
-from .modules import HANCBlock, MLFC, ResPath
+from .modules import HANCBlock, MLFC, ResPath, run_parallel
 
 
 class _ACCUNetBase(nn.Module):
@@ -75,10 +75,8 @@ class _ACCUNetBase(nn.Module):
             x4 = self.cnv32(self.cnv31(self.pool(x3)))
             x5 = self.cnv42(self.cnv41(self.pool(x4)))
             x6 = self.cnv52(self.cnv51(self.pool(x5)))
-            x2 = self.rspth1(x2)
-            x3 = self.rspth2(x3)
-            x4 = self.rspth3(x4)
-            x5 = self.rspth4(x5)
+            # the four ResPaths are independent of each other: one autograd node, four stream lanes
+            x2, x3, x4, x5 = run_parallel([self.rspth1, self.rspth2, self.rspth3, self.rspth4], [x2, x3, x4, x5])
             x2, x3, x4, x5 = self.mlfc1(x2, x3, x4, x5)
             x2, x3, x4, x5 = self.mlfc2(x2, x3, x4, x5)
             x2, x3, x4, x5 = self.mlfc3(x2, x3, x4, x5)

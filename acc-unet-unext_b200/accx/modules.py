@@ -75,6 +75,73 @@ class _ModuleFn(torch.autograd.Function):
         return (None, None, *gx, *gp)
 
 
+class _GroupFn(torch.autograd.Function):
+    """Several single-input / single-output accx modules that do not depend on each other (the model's four
+    ResPaths) as ONE autograd node: forward and backward of the members run on parallel stream lanes."""
+
+    @staticmethod
+    def forward(ctx, mods, *tensors):
+        n = len(mods)
+        xs = tensors[:n]
+        E.require_cuda(xs[0])
+        need = any(ctx.needs_input_grad[1:])
+        outs, saved = [None] * n, [None] * n
+        xs_n = [E.to_nhwc(x.detach()) for x in xs]
+        with E.fork_lanes(n) as lanes:
+            for i, m in enumerate(mods):
+                with lanes.lane(i):
+                    o, saved[i] = m._fwd([xs_n[i]], m.training, need)
+                    outs[i] = o[0]
+        ctx.mods, ctx.saved = mods, saved
+        ctx.counts = [len(list(m.parameters())) for m in mods]
+        ctx.params = tensors[n:]
+        ctx.training = all(m.training for m in mods)
+        ctx.in_need = ctx.needs_input_grad[1:1 + n]
+        return tuple(E.to_nchw_view(o) for o in outs)
+
+    @staticmethod
+    def backward(ctx, *douts):
+        if not ctx.training:
+            raise E._lib.AccxError("accx backward implements training-mode BatchNorm only (call .train())")
+        mods, saved, n = ctx.mods, ctx.saved, len(ctx.mods)
+        ctx.saved = None
+        dn = []
+        for d, sv in zip(douts, saved):
+            like = sv["out_like"][0]
+            if d is None:
+                d = torch.zeros(like[0], dtype=like[1], device=like[2]).permute(0, 3, 1, 2)
+            if d.dtype != like[1]:
+                d = d.to(like[1])
+            dn.append(E.to_nhwc(d))
+        gx, gp_all = [None] * n, []
+        pools = [E.GradPool(m.parameters()) for m in mods]       # zeroed on the caller's stream, before the fork
+        E.BWD_DEPTH[0] += 1
+        try:
+            results = [None] * n
+            with E.fork_lanes(n) as lanes:
+                for i, m in enumerate(mods):
+                    with lanes.lane(i):
+                        results[i] = m._bwd(saved[i], [dn[i]], [ctx.in_need[i]], grads=pools[i])
+        finally:
+            E.BWD_DEPTH[0] -= 1
+            E.module_backward_end()
+        off = 0
+        for i, m in enumerate(mods):
+            dxs, grads = results[i]
+            gx[i] = None if dxs[0] is None else E.to_nchw_view(dxs[0])
+            for p in ctx.params[off:off + ctx.counts[i]]:
+                g = grads.get(id(p))
+                gp_all.append(g if g is None or g.dtype == p.dtype else g.to(p.dtype))
+            off += ctx.counts[i]
+        return (None, *gx, *gp_all)
+
+
+def run_parallel(mods, xs):
+    """y_i = mods[i](xs[i]) for independent accx modules, issued concurrently (see _GroupFn)"""
+    params = [p for m in mods for p in m.parameters()]
+    return _GroupFn.apply(list(mods), *xs, *params)
+
+
 class _AccxModule(nn.Module):
     def _run(self, *xs):
         params = [p for p in self.parameters()]
@@ -427,8 +494,8 @@ class ResPath(_AccxModule):
         saved = {"levels": levels, "La": La, "Lb": Lb, "out_like": _out_like([out])} if need else None
         return [out], saved
 
-    def _bwd(self, s, douts, in_need):
-        grads = E.GradPool(self.parameters())
+    def _bwd(self, s, douts, in_need, grads=None):
+        grads = E.GradPool(self.parameters()) if grads is None else grads
         ar = Arena(douts[0].device)
         La, Lb = s["La"], s["Lb"]
         B, H, W, C = La.y.shape
@@ -516,39 +583,42 @@ class MLFC(_AccxModule):
         lenn = len(self.cnv_blks1)
         saved_it = None
         Lm = None
-        for i in range(lenn):
-            blk, mrg = [], []
-            Lc = []
+        outs, fin = [None] * 4, [None] * 4
+        # the four target levels are independent chains (gather conv -> SE -> bns -> merge conv -> SE -> bns_mrg ->
+        # final SE): one stream lane and one scratch arena per level
+        ars = [Arena(xs[0].device) for _ in range(4)]
+        with E.fork_lanes(4) as lanes:
+            for i in range(lenn):
+                blk, mrg, Lc, Lm = [None] * 4, [None] * 4, [None] * 4, [None] * 4
+                for l in range(4):
+                    with lanes.lane(l):
+                        arl = ars[l]
+                        cb = getattr(self, f"cnv_blks{l + 1}")[i]
+                        wb = _w(cb.conv1.weight)                                  # [C_l, tot], block order
+                        adds = []
+                        for s in range(l + 1, 4):                                 # coarser sources
+                            r = E.conv([Op(Lazy(xs[s]), filt[s], WV(wb, offs[s], tot, 1))], filt[l], dims[s],
+                                       out_dtype=E.F32)
+                            adds.append((r, s - l))
+                        ops = [Op(Lazy(pooled[(s, l)] if s < l else xs[l]), filt[s], WV(wb, offs[s], tot, 1))
+                               for s in range(l + 1)]
+                        stt = arl.take(2 * filt[l]) if training else None
+                        t, sv = cb._core_fwd(ops, dims[l], arl, training, adds=adds, stats=stt)
+                        Lc[l] = E.bn_lazy(t, stt, getattr(self, f"bns{l + 1}")[i], 2, arl, training)
+                        blk[l] = sv
+                        cm = getattr(self, f"cnv_mrg{l + 1}")[i]
+                        wm = _w(cm.conv1.weight)                                  # [C_l, 2*C_l], K index 2c + j
+                        C = filt[l]
+                        ops = [Op(Lc[l], C, WV(wm, 0, 2 * C, 2)), Op(Lazy(xs[l]), C, WV(wm, 1, 2 * C, 2))]
+                        stt = arl.take(2 * C) if training else None
+                        t, sv = cm._core_fwd(ops, dims[l], arl, training, residual=xs[l], mix=mix, stats=stt,
+                                             mix_param=self.W if mix is not None else None)
+                        Lm[l] = E.bn_lazy(t, stt, getattr(self, f"bns_mrg{l + 1}")[i], 2, arl, training)
+                        mrg[l] = sv
+                saved_it = (i, blk, Lc, mrg)      # only the last repeat reaches the output (as in the reference)
             for l in range(4):
-                cb = getattr(self, f"cnv_blks{l + 1}")[i]
-                wb = _w(cb.conv1.weight)                                  # [C_l, tot], block order
-                adds = []
-                for s in range(l + 1, 4):                                 # coarser sources
-                    r = E.conv([Op(Lazy(xs[s]), filt[s], WV(wb, offs[s], tot, 1))], filt[l], dims[s], out_dtype=E.F32)
-                    adds.append((r, s - l))
-                ops = [Op(Lazy(pooled[(s, l)] if s < l else xs[l]), filt[s], WV(wb, offs[s], tot, 1))
-                       for s in range(l + 1)]
-                stt = ar.take(2 * filt[l]) if training else None
-                t, sv = cb._core_fwd(ops, dims[l], ar, training, adds=adds, stats=stt)
-                Lc.append(E.bn_lazy(t, stt, getattr(self, f"bns{l + 1}")[i], 2, ar, training))
-                blk.append(sv)
-            Lm = []
-            for l in range(4):
-                cm = getattr(self, f"cnv_mrg{l + 1}")[i]
-                wm = _w(cm.conv1.weight)                                  # [C_l, 2*C_l], K index 2c + j
-                C = filt[l]
-                ops = [Op(Lc[l], C, WV(wm, 0, 2 * C, 2)), Op(Lazy(xs[l]), C, WV(wm, 1, 2 * C, 2))]
-                stt = ar.take(2 * C) if training else None
-                t, sv = cm._core_fwd(ops, dims[l], ar, training, residual=xs[l], mix=mix, stats=stt,
-                                     mix_param=self.W if mix is not None else None)
-                Lm.append(E.bn_lazy(t, stt, getattr(self, f"bns_mrg{l + 1}")[i], 2, ar, training))
-                mrg.append(sv)
-            saved_it = (i, blk, Lc, mrg)          # only the last repeat reaches the output (as in the reference)
-        outs, fin = [], []
-        for l in range(4):
-            o, c = E.se_fwd(Lm[l], getattr(self, f"sqe{l + 1}"), ar, training)
-            outs.append(o)
-            fin.append(c)
+                with lanes.lane(l):
+                    outs[l], fin[l] = E.se_fwd(Lm[l], getattr(self, f"sqe{l + 1}"), ars[l], training)
         saved = None
         if need:
             saved = {"xs": xs, "pooled": pooled, "it": saved_it, "Lm": Lm, "fin": fin, "out_like": _out_like(outs),
@@ -571,58 +641,63 @@ class MLFC(_AccxModule):
         def acc(l, g):
             dxs[l] = g if dxs[l] is None else E.add_inplace(dxs[l], g)
 
-        dys_blk = []
-        for l in range(4):
-            C = filt[l]
-            cm = getattr(self, f"cnv_mrg{l + 1}")[i]
-            wm = _w(cm.conv1.weight)
-            da, sums = E.se_bwd(s["fin"][l], douts[l], grads, ar, bn_sums=True)       # final SE
-            dt_ = E.bn_bwd(Lm[l], da, grads, ar, sums=sums)                 # bns_mrg: grad wrt (SE_out*mix + x*(1-mix))
-            # residual branch
-            if mix is None:
-                acc(l, dt_)          # aliasing is safe: dt_ is only read by the launches queued below
-            else:
-                acc(l, self._scaled(dt_, mix, one_minus=True))
-            dy = cm._core_bwd(mrg[l], dt_, grads, ar)                       # through SE(mix inside) + BN
-            gw = E.grad_buf(grads, cm.conv1.weight)
-            if gw is not None:
-                E.wgrad(Op(Lc[l], C, WV(wm, 0, 2 * C, 2)), dy, C, dims[l], gw)
-                E.wgrad(Op(Lazy(xs[l]), C, WV(wm, 1, 2 * C, 2)), dy, C, dims[l], gw)
-            acc(l, E.conv([Op(Lazy(dy), C, WV(wm, 1, 2, 2 * C))], C, dims[l]))       # d wrt x (odd K)
-            dac = E.conv([Op(Lazy(dy), C, WV(wm, 0, 2, 2 * C))], C, dims[l])         # d wrt x_c (even K)
-            dtc = E.bn_bwd(Lc[l], dac, grads, ar)                                     # bns
-            cb = getattr(self, f"cnv_blks{l + 1}")[i]
-            dys_blk.append(cb._core_bwd(blk[l], dtc, grads, ar))
-        # gather conv backward
-        for l in range(4):
-            cb = getattr(self, f"cnv_blks{l + 1}")[i]
-            wb = _w(cb.conv1.weight)
-            gw = E.grad_buf(grads, cb.conv1.weight)
-            dy = dys_blk[l]
-            C = filt[l]
+        # phase A: the four level chains are independent (lane l only touches dxs[l]) -> parallel lanes
+        dys_blk = [None] * 4
+        ars = [ar] + [Arena(douts[0].device) for _ in range(3)]
+        with E.fork_lanes(4) as lanes:
+            for l in range(4):
+                with lanes.lane(l):
+                    arl = ars[l]
+                    C = filt[l]
+                    cm = getattr(self, f"cnv_mrg{l + 1}")[i]
+                    wm = _w(cm.conv1.weight)
+                    da, sums = E.se_bwd(s["fin"][l], douts[l], grads, arl, bn_sums=True)      # final SE
+                    dt_ = E.bn_bwd(Lm[l], da, grads, arl, sums=sums)        # bns_mrg: grad wrt (SE_out*mix + x*(1-mix))
+                    # residual branch
+                    if mix is None:
+                        acc(l, dt_)          # aliasing is safe: dt_ is only read by the launches queued below
+                    else:
+                        acc(l, self._scaled(dt_, mix, one_minus=True))
+                    dy = cm._core_bwd(mrg[l], dt_, grads, arl)                      # through SE(mix inside) + BN
+                    gw = E.grad_buf(grads, cm.conv1.weight)
+                    if gw is not None:
+                        E.wgrad(Op(Lc[l], C, WV(wm, 0, 2 * C, 2)), dy, C, dims[l], gw)
+                        E.wgrad(Op(Lazy(xs[l]), C, WV(wm, 1, 2 * C, 2)), dy, C, dims[l], gw)
+                    acc(l, E.conv([Op(Lazy(dy), C, WV(wm, 1, 2, 2 * C))], C, dims[l]))       # d wrt x (odd K)
+                    dac = E.conv([Op(Lazy(dy), C, WV(wm, 0, 2, 2 * C))], C, dims[l])         # d wrt x_c (even K)
+                    dtc = E.bn_bwd(Lc[l], dac, grads, arl)                                    # bns
+                    cb = getattr(self, f"cnv_blks{l + 1}")[i]
+                    dys_blk[l] = cb._core_bwd(blk[l], dtc, grads, arl)
+        # phase B: gather conv backward; lane `src` owns dxs[src] and collects the contributions of every target level
+        gws = [E.grad_buf(grads, getattr(self, f"cnv_blks{l + 1}")[i].conv1.weight) for l in range(4)]
+        with E.fork_lanes(4) as lanes:
             for src in range(4):
-                Cs = filt[src]
-                wv = WV(wb, offs[src], tot, 1)
-                wvt = WV(wb, offs[src], 1, tot)
-                if src <= l:
-                    A = Lazy(pooled[(src, l)] if src < l else xs[l])
-                    if gw is not None:
-                        E.wgrad(Op(A, Cs, wv), dy, C, dims[l], gw)
-                    g = E.conv([Op(Lazy(dy), C, wvt)], Cs, dims[l])
-                    if src == l:
-                        acc(l, g)
-                    else:     # gradient of the average pool: broadcast / s^2
-                        if dxs[src] is None:
-                            dxs[src] = torch.empty_like(xs[src])
-                            E.upsample_add(g, dxs[src], l - src, 1.0 / float(4 ** (l - src)), accumulate=False)
-                        else:
-                            E.upsample_add(g, dxs[src], l - src, 1.0 / float(4 ** (l - src)), accumulate=True)
-                else:         # coarser source, contracted at its own resolution: block-sum dY first
-                    dR = E.pool_sum(dy, src - l, 1.0)
-                    if gw is not None:
-                        E.wgrad(Op(Lazy(xs[src]), Cs, wv), dR, C, dims[src], gw)
-                    g = E.conv([Op(Lazy(dR), C, wvt)], Cs, dims[src], out_dtype=E.dt(xs[src]))
-                    acc(src, g)
+                with lanes.lane(src):
+                    Cs = filt[src]
+                    for l in range(4):
+                        cb = getattr(self, f"cnv_blks{l + 1}")[i]
+                        wb = _w(cb.conv1.weight)
+                        gw, dy, C = gws[l], dys_blk[l], filt[l]
+                        wv = WV(wb, offs[src], tot, 1)
+                        wvt = WV(wb, offs[src], 1, tot)
+                        if src <= l:
+                            A = Lazy(pooled[(src, l)] if src < l else xs[l])
+                            if gw is not None:
+                                E.wgrad(Op(A, Cs, wv), dy, C, dims[l], gw)
+                            g = E.conv([Op(Lazy(dy), C, wvt)], Cs, dims[l])
+                            if src == l:
+                                acc(l, g)
+                            else:     # gradient of the average pool: broadcast / s^2
+                                first = dxs[src] is None
+                                if first:
+                                    dxs[src] = torch.empty_like(xs[src])
+                                E.upsample_add(g, dxs[src], l - src, 1.0 / float(4 ** (l - src)), accumulate=not first)
+                        else:         # coarser source, contracted at its own resolution: block-sum dY first
+                            dR = E.pool_sum(dy, src - l, 1.0)
+                            if gw is not None:
+                                E.wgrad(Op(Lazy(xs[src]), Cs, wv), dR, C, dims[src], gw)
+                            g = E.conv([Op(Lazy(dR), C, wvt)], Cs, dims[src], out_dtype=E.dt(xs[src]))
+                            acc(src, g)
         return dxs, grads
 
     @staticmethod
