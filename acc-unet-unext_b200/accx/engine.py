@@ -111,12 +111,17 @@ _LANE_STREAMS = {}
 
 
 class fork_lanes:
+    depth = 0          # forks do not nest: an inner fork (a module used inside a lane) runs in its caller's lane
+
     def __init__(self, n):
         self.n = n
         self.used = set()
-        self.enabled = LANES != 0
+        self.enabled = LANES != 0 and n > 1
 
     def __enter__(self):
+        if fork_lanes.depth > 0:
+            self.enabled = False
+        fork_lanes.depth += 1
         if self.enabled:
             self.main = torch.cuda.current_stream()
             dev = torch.cuda.current_device()
@@ -140,6 +145,7 @@ class fork_lanes:
         return torch.cuda.stream(s)
 
     def __exit__(self, *exc):
+        fork_lanes.depth -= 1
         if self.enabled:
             for i in self.used:
                 ev = torch.cuda.Event()

@@ -207,25 +207,30 @@ def _hanc_core_bwd(hnc, L2: Lazy, pools, dy3: torch.Tensor, grads, ar: Arena, ne
     if gw is not None:
         E.wgrad(Op(L2, Ein, WV(wh, 0, J * Ein, J)), dy3, C, (B, H, W), gw)
     da2 = None
-    if need_da:
-        da2 = E.conv([Op(Lazy(dy3), C, WV(wh, 0, J, J * Ein))], Ein, (B, H, W))
     fused = fuse_bn and need_da and E.hanc_unpool_fusable(L2, k)
     dPs = []
-    for l in range(1, k):
-        dims_l = (B, H >> l, W >> l)
-        dR = E.pool_sum(dy3, l, 1.0)                         # block sums of dY at the pooled resolution
-        Pl = Lazy(pools[l - 1])
-        if gw is not None:
-            E.wgrad(Op(Pl, Ein, WV(wh, l, J * Ein, J), 0), dR, C, dims_l, gw)
-            E.wgrad(Op(Pl, Ein, WV(wh, k - 1 + l, J * Ein, J), Ein), dR, C, dims_l, gw)
+    # the full-resolution input gradient and the (small) per-level chains only meet in the unpool step:
+    # lane 0 = main contraction, lane l = level l (block sums of dY -> weight gradients -> dP contractions)
+    with E.fork_lanes(k if fused else 1) as lanes:
         if need_da:
-            dP = torch.empty((B, H >> l, W >> l, 2 * Ein), dtype=torch.float32, device=dy3.device)   # fp32: feeds unpool
-            E.conv([Op(Lazy(dR), C, WV(wh, l, J, J * Ein))], Ein, dims_l, out=dP, out_coff=0)
-            E.conv([Op(Lazy(dR), C, WV(wh, k - 1 + l, J, J * Ein))], Ein, dims_l, out=dP, out_coff=Ein)
-            if fused:
-                dPs.append(dP)
-            else:
-                E.hanc_unpool_bwd(L2, l, dP, da2, accumulate=True)
+            with lanes.lane(0):
+                da2 = E.conv([Op(Lazy(dy3), C, WV(wh, 0, J, J * Ein))], Ein, (B, H, W))
+        for l in range(1, k):
+            with lanes.lane(l if fused else 0):
+                dims_l = (B, H >> l, W >> l)
+                dR = E.pool_sum(dy3, l, 1.0)                         # block sums of dY at the pooled resolution
+                Pl = Lazy(pools[l - 1])
+                if gw is not None:
+                    E.wgrad(Op(Pl, Ein, WV(wh, l, J * Ein, J), 0), dR, C, dims_l, gw)
+                    E.wgrad(Op(Pl, Ein, WV(wh, k - 1 + l, J * Ein, J), Ein), dR, C, dims_l, gw)
+                if need_da:
+                    dP = torch.empty((B, H >> l, W >> l, 2 * Ein), dtype=torch.float32, device=dy3.device)   # fp32
+                    E.conv([Op(Lazy(dR), C, WV(wh, l, J, J * Ein))], Ein, dims_l, out=dP, out_coff=0)
+                    E.conv([Op(Lazy(dR), C, WV(wh, k - 1 + l, J, J * Ein))], Ein, dims_l, out=dP, out_coff=Ein)
+                    if fused:
+                        dPs.append(dP)
+                    else:
+                        E.hanc_unpool_bwd(L2, l, dP, da2, accumulate=True)
     if fuse_bn:
         return da2, (E.hanc_unpool_bnred(L2, dPs, da2, ar) if fused else None)
     return da2
