@@ -74,9 +74,11 @@ class _ACCUNetBase(nn.Module):
             x3 = self.cnv22(self.cnv21(self.pool(x2)))
             x4 = self.cnv32(self.cnv31(self.pool(x3)))
             x5 = self.cnv42(self.cnv41(self.pool(x4)))
-            x6 = self.cnv52(self.cnv51(self.pool(x5)))
-            # the four ResPaths are independent of each other: one autograd node, four stream lanes
-            x2, x3, x4, x5 = run_parallel([self.rspth1, self.rspth2, self.rspth3, self.rspth4], [x2, x3, x4, x5])
+            # the bottleneck pair and the four ResPaths are independent of each other: one autograd node whose five
+            # chains run on parallel stream lanes (forward and backward)
+            x6, x2, x3, x4, x5 = run_parallel(
+                [[self.cnv51, self.cnv52], self.rspth1, self.rspth2, self.rspth3, self.rspth4],
+                [self.pool(x5), x2, x3, x4, x5])
             x2, x3, x4, x5 = self.mlfc1(x2, x3, x4, x5)
             x2, x3, x4, x5 = self.mlfc2(x2, x3, x4, x5)
             x2, x3, x4, x5 = self.mlfc3(x2, x3, x4, x5)

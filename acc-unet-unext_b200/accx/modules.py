@@ -76,26 +76,29 @@ class _ModuleFn(torch.autograd.Function):
 
 
 class _GroupFn(torch.autograd.Function):
-    """Several single-input / single-output accx modules that do not depend on each other (the model's four
-    ResPaths) as ONE autograd node: forward and backward of the members run on parallel stream lanes."""
+    """Independent CHAINS of single-input / single-output accx modules (the model's four ResPaths, the bottleneck
+    pair cnv51 -> cnv52) as ONE autograd node: the chains run forward and backward on parallel stream lanes."""
 
     @staticmethod
-    def forward(ctx, mods, *tensors):
-        n = len(mods)
+    def forward(ctx, chains, *tensors):
+        n = len(chains)
         xs = tensors[:n]
         E.require_cuda(xs[0])
         need = any(ctx.needs_input_grad[1:])
         outs, saved = [None] * n, [None] * n
         xs_n = [E.to_nhwc(x.detach()) for x in xs]
         with E.fork_lanes(n) as lanes:
-            for i, m in enumerate(mods):
+            for i, chain in enumerate(chains):
                 with lanes.lane(i):
-                    o, saved[i] = m._fwd([xs_n[i]], m.training, need)
-                    outs[i] = o[0]
-        ctx.mods, ctx.saved = mods, saved
-        ctx.counts = [len(list(m.parameters())) for m in mods]
+                    cur, sv = xs_n[i], []
+                    for m in chain:
+                        o, s_ = m._fwd([cur], m.training, need)
+                        cur = o[0]
+                        sv.append(s_)
+                    outs[i], saved[i] = cur, sv
+        ctx.chains, ctx.saved = chains, saved
         ctx.params = tensors[n:]
-        ctx.training = all(m.training for m in mods)
+        ctx.training = all(m.training for c in chains for m in c)
         ctx.in_need = ctx.needs_input_grad[1:1 + n]
         return tuple(E.to_nchw_view(o) for o in outs)
 
@@ -103,43 +106,49 @@ class _GroupFn(torch.autograd.Function):
     def backward(ctx, *douts):
         if not ctx.training:
             raise E._lib.AccxError("accx backward implements training-mode BatchNorm only (call .train())")
-        mods, saved, n = ctx.mods, ctx.saved, len(ctx.mods)
+        chains, saved, n = ctx.chains, ctx.saved, len(ctx.chains)
         ctx.saved = None
         dn = []
         for d, sv in zip(douts, saved):
-            like = sv["out_like"][0]
+            like = sv[-1]["out_like"][0]
             if d is None:
                 d = torch.zeros(like[0], dtype=like[1], device=like[2]).permute(0, 3, 1, 2)
             if d.dtype != like[1]:
                 d = d.to(like[1])
             dn.append(E.to_nhwc(d))
-        gx, gp_all = [None] * n, []
-        pools = [E.GradPool(m.parameters()) for m in mods]       # zeroed on the caller's stream, before the fork
+        # gradient accumulators are zeroed on the caller's stream, before the fork
+        pools = [[E.GradPool(m.parameters()) for m in chain] for chain in chains]
+        gx = [None] * n
         E.BWD_DEPTH[0] += 1
         try:
-            results = [None] * n
             with E.fork_lanes(n) as lanes:
-                for i, m in enumerate(mods):
+                for i, chain in enumerate(chains):
                     with lanes.lane(i):
-                        results[i] = m._bwd(saved[i], [dn[i]], [ctx.in_need[i]], grads=pools[i])
+                        cur = dn[i]
+                        for j in reversed(range(len(chain))):
+                            need_in = True if j > 0 else ctx.in_need[i]
+                            dxs, _ = chain[j]._bwd(saved[i][j], [cur], [need_in], grads=pools[i][j])
+                            cur = dxs[0]
+                        gx[i] = cur
         finally:
             E.BWD_DEPTH[0] -= 1
             E.module_backward_end()
-        off = 0
-        for i, m in enumerate(mods):
-            dxs, grads = results[i]
-            gx[i] = None if dxs[0] is None else E.to_nchw_view(dxs[0])
-            for p in ctx.params[off:off + ctx.counts[i]]:
-                g = grads.get(id(p))
-                gp_all.append(g if g is None or g.dtype == p.dtype else g.to(p.dtype))
-            off += ctx.counts[i]
-        return (None, *gx, *gp_all)
+        grads = {}
+        for chain_pools in pools:
+            for gp in chain_pools:
+                grads.update(gp)
+        gp_all = []
+        for p in ctx.params:
+            g = grads.get(id(p))
+            gp_all.append(g if g is None or g.dtype == p.dtype else g.to(p.dtype))
+        return (None, *[None if g is None else E.to_nchw_view(g) for g in gx], *gp_all)
 
 
-def run_parallel(mods, xs):
-    """y_i = mods[i](xs[i]) for independent accx modules, issued concurrently (see _GroupFn)"""
-    params = [p for m in mods for p in m.parameters()]
-    return _GroupFn.apply(list(mods), *xs, *params)
+def run_parallel(chains, xs):
+    """y_i = chain_i(xs[i]) for independent chains (lists) of accx modules, issued concurrently (see _GroupFn)"""
+    chains = [list(c) if isinstance(c, (list, tuple)) else [c] for c in chains]
+    params = [p for c in chains for m in c for p in m.parameters()]
+    return _GroupFn.apply(chains, *xs, *params)
 
 
 class _AccxModule(nn.Module):
@@ -397,8 +406,8 @@ class HANCBlock(_AccxModule):
                      "out_like": _out_like([out])}
         return [out], saved
 
-    def _bwd(self, s, douts, in_need):
-        grads = E.GradPool(self.parameters())
+    def _bwd(self, s, douts, in_need, grads=None):
+        grads = E.GradPool(self.parameters()) if grads is None else grads
         dout = douts[0]
         ar = Arena(dout.device)
         X, L1, L2, L3, L4, L5 = s["X"], s["L1"], s["L2"], s["L3"], s["L4"], s["L5"]
