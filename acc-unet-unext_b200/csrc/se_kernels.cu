@@ -431,7 +431,7 @@ int accx_se_squeeze(int dtype, int B, int HW, int C, const void* x, const float*
   ACCX_REQUIRE(B > 0 && HW > 0 && C > 0 && x && S, "se_squeeze: bad arguments");
   ACCX_DISPATCH_T(dtype, {
     Lanes l = make_lanes(C, DT<T>::VEC, aligned16(x));
-    int chunks = se_chunks(B, HW, l.ty);
+    int chunks = se_chunks(B, HW, l.ty, 148 * 2);
     dim3 block(l.tx, l.ty), grid(B * chunks, l.gy);
     size_t sm = (size_t)l.tx * l.ty * l.vec * sizeof(float);
     ACCX_DISPATCH_VEC(l, {
@@ -481,7 +481,7 @@ int accx_se_bwd_reduce(int dtype, int B, int HW, int C, const void* x, const flo
   ACCX_REQUIRE(!dmix || (mix && residual), "se_bwd_reduce: dmix needs mix and residual");
   ACCX_DISPATCH_T(dtype, {
     Lanes l = make_lanes(C, DT<T>::VEC, aligned16(x) && aligned16(dout) && (!residual || aligned16(residual)));
-    int chunks = se_chunks(B, HW, l.ty);
+    int chunks = se_chunks(B, HW, l.ty, 148 * 2);
     dim3 block(l.tx, l.ty), grid(B * chunks, l.gy);
     size_t sm = (size_t)l.tx * l.ty * l.vec * sizeof(float);
     ACCX_DISPATCH_VEC(l, {
