@@ -392,16 +392,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_fwd_tc_kernel(const __grid_c
       if (gtid == 0) bulk_wait_read0();
       asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
       const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * bn;
-      for (int ch = 0; ch < n_chunks; ch += 2) {
-        const bool two = ch + 1 < n_chunks;
-        uint32_t r[2][16];
+      for (int ch = 0; ch < n_chunks; ++ch) {
+        uint32_t r[1][16];
         tc_ld16_issue(trow + ch * 16, r[0]);
-        if (two) tc_ld16_issue(trow + ch * 16 + 16, r[1]);
         tc_ld_wait();
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          if (u == 1 && !two) break;
-          const int c0 = (ch + u) * 16;
+        {
+          constexpr int u = 0;
+          const int c0 = ch * 16;
           float v[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = rvalid ? __uint_as_float(r[u][j]) : 0.f;

@@ -249,6 +249,7 @@ def main():
             roof = {"bound": "hbm", "achieved": nbytes / (tms / 1e3) / 1e9, "peak": hbm, "unit": "GB/s"}
         roof["frac"] = roof["achieved"] / roof["peak"]
         roof.update({"kernel": name, "launches_per_step": n, "avg_launch_us": tms / n * 1e3,
+                     "algorithmic_bytes_per_launch": nbytes / n,
                      "share_of_accx_time": tms / tot, "accx_kernel_ms_per_step": tot, "eager_step_ms": step_ms,
                      "peak_source": which, "traffic": traffic_from_profiles(name)})
         table = {k: {"launches": a[0], "ms": a[1], "alg_gbytes": a[2] / 1e9, "gflop": a[3] / 1e9,
@@ -310,7 +311,8 @@ def traffic_from_profiles(kernel):
     """dram bytes per launch of `kernel` from the committed ncu --set full summary, if any"""
     path = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(path):
-        return json.load(open(path)).get(kernel)
+        d = json.load(open(path)).get(kernel)
+        return d["dram_bytes_per_launch"] if isinstance(d, dict) else d
     return None
 
 
