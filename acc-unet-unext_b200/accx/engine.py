@@ -42,8 +42,8 @@ def _call(name, *args, cost=(0, 0), tag=""):
 # them with the (often latency-bound, partially filled) kernels of the input-gradient chain; under CUDA
 # graph capture the fork/join events become parallel branches of the graph.
 #   SIDE_MODE 0: everything on the caller's stream; 1: join at the end of each module's backward (default);
-#   2: join only when join_side() is called (TrainStep: once, before the optimiser) -- tensors the side
-#   stream reads are kept alive in _KEEP until then so the caching allocator cannot recycle them.
+#   2: join only when join_side() is called (TrainStep: once, before the optimiser).  Tensors the side
+#   stream reads are kept alive in _KEEP until the join so the caching allocator cannot recycle them.
 SIDE_MODE = int(os.environ.get("ACCX_WGRAD_STREAM", "1"))
 BWD_DEPTH = [0]
 _SIDE = {}
@@ -72,8 +72,9 @@ class side_stream:
         ev.record(torch.cuda.current_stream())
         s.wait_event(ev)
         _SIDE_DIRTY.add(dev)
-        if SIDE_MODE == 2:
-            _KEEP.extend(t for t in self.keep if t is not None)
+        # whatever the side stream reads must outlive the join: a temporary the caller drops right after this
+        # call would otherwise go back to the allocator and be handed to the next kernel on the caller's stream
+        _KEEP.extend(t for t in self.keep if t is not None)
         self.ctx = torch.cuda.stream(s)
         self.ctx.__enter__()
         return self

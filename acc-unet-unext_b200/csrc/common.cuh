@@ -270,6 +270,26 @@ __device__ __forceinline__ void reduce_lanes_atomic(float (&acc)[NS][VEC], float
   }
 }
 
+// ---- tiny-channel contraction kernels (gemm_narrow.cu), dispatched from accx_pw_fwd / accx_pw_wgrad ----
+struct NarrowParams {
+  accx_operand_t op[ACCX_MAX_OPERANDS];
+  int n_ops, k_total;
+  int B, H, W, N;
+  int64_t P;
+  const float* bias;
+  const float* add[ACCX_MAX_ADDENDS];
+  int add_log2s[ACCX_MAX_ADDENDS];
+  int n_add;
+  void* y;
+  int64_t ldy;
+  float* stats;
+};
+bool narrow_fwd_ok(int k_total, int N);
+bool narrow_wgrad_ok(int K, int N);
+int pw_fwd_narrow(int dtype, int out_dtype, const NarrowParams& prm, cudaStream_t st);
+int pw_wgrad_narrow(int dtype, int dy_f32, const accx_operand_t& op, int N, int64_t P, const void* dy, int64_t ldy,
+                    float* dw, cudaStream_t st);
+
 #define ACCX_DISPATCH_T(dtype, ...)                       \
   do {                                                    \
     if ((dtype) == ACCX_F32) {                            \

@@ -326,6 +326,24 @@ int accx_pw_fwd(int dtype, int out_dtype, int B, int H, int W, int N, const accx
   }
   prm.y = y; prm.ldy = ldy; prm.stats = stats;
   cudaStream_t st = (cudaStream_t)stream;
+  {   // tiny channel counts (ACC-UNet's first block, C = 3): whole pixels per thread instead of GEMM tiles
+    int k_total = 0;
+    bool plain = !(dtype == ACCX_F32 && out_dtype == ACCX_BF16);
+    for (int i = 0; i < n_ops; ++i) {
+      k_total += ops[i].K;
+      plain = plain && ops[i].dy == 0 && ops[i].dx == 0;
+    }
+    if (plain && narrow_fwd_ok(k_total, N)) {
+      NarrowParams np;
+      for (int i = 0; i < n_ops; ++i) np.op[i] = ops[i];
+      np.n_ops = n_ops; np.k_total = k_total;
+      np.B = B; np.H = H; np.W = W; np.N = N; np.P = prm.P;
+      np.bias = bias; np.n_add = n_add;
+      for (int i = 0; i < ACCX_MAX_ADDENDS; ++i) { np.add[i] = i < n_add ? add[i] : nullptr; np.add_log2s[i] = i < n_add ? add_log2s[i] : 0; }
+      np.y = y; np.ldy = ldy; np.stats = stats;
+      return pw_fwd_narrow(dtype, out_dtype, np, st);
+    }
+  }
   if (dtype == ACCX_F32 && out_dtype == ACCX_F32) return launch_pw<float, float>(prm, st);
   if (dtype == ACCX_BF16 && out_dtype == ACCX_BF16) return launch_pw<bf16, bf16>(prm, st);
   if (dtype == ACCX_BF16 && out_dtype == ACCX_F32) return launch_pw<bf16, float>(prm, st);
@@ -339,6 +357,8 @@ int accx_pw_wgrad(int dtype, int B, int H, int W, int N, const accx_operand_t* o
   ACCX_REQUIRE(B > 0 && H > 0 && W > 0 && N > 0 && op && op->data && dw && dy, "pw_wgrad: bad arguments");
   ACCX_REQUIRE(op->act == 0 || (op->scale && op->shift), "pw_wgrad: act without scale/shift");
   const int64_t P = (int64_t)B * H * W;
+  if (op->dy == 0 && op->dx == 0 && narrow_wgrad_ok(op->K, N) && (dtype == ACCX_F32 || dtype == ACCX_BF16))
+    return pw_wgrad_narrow(dtype, dy_f32, *op, N, P, dy, ldy, dw, (cudaStream_t)stream);
   const int gx = (op->K + WG_T - 1) / WG_T, gy = (N + WG_T - 1) / WG_T;
   int64_t splits = (148 * 4 + gx * gy - 1) / (gx * gy);
   const int64_t max_splits = (P + 255) / 256;
