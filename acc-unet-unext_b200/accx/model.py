@@ -70,15 +70,14 @@ class _ACCUNetBase(nn.Module):
             x = E.to_nchw_view(E.input_to_nhwc(x, cd)) if not x.requires_grad else \
                 x.to(cd).contiguous(memory_format=torch.channels_last)
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=(cd == torch.bfloat16)):
-            x2 = self.cnv12(self.cnv11(x))
-            x3 = self.cnv22(self.cnv21(self.pool(x2)))
-            x4 = self.cnv32(self.cnv31(self.pool(x3)))
-            x5 = self.cnv42(self.cnv41(self.pool(x4)))
-            # the bottleneck pair and the four ResPaths are independent of each other: one autograd node whose five
-            # chains run on parallel stream lanes (forward and backward)
-            x6, x2, x3, x4, x5 = run_parallel(
-                [[self.cnv51, self.cnv52], self.rspth1, self.rspth2, self.rspth3, self.rspth4],
-                [self.pool(x5), x2, x3, x4, x5])
+            # Same dataflow as ACC_UNet.forward (ACC_UNet.py:605-631), issued so that independent chains overlap: the
+            # ResPath of level l only needs that level's encoder output, so it runs (forward AND backward, one
+            # autograd node per pair) on a parallel stream lane next to the encoder blocks of level l+1.
+            e2 = self.cnv12(self.cnv11(x))
+            x2, e3 = run_parallel([self.rspth1, [self.cnv21, self.cnv22]], [e2, self.pool(e2)])
+            x3, e4 = run_parallel([self.rspth2, [self.cnv31, self.cnv32]], [e3, self.pool(e3)])
+            x4, e5 = run_parallel([self.rspth3, [self.cnv41, self.cnv42]], [e4, self.pool(e4)])
+            x5, x6 = run_parallel([self.rspth4, [self.cnv51, self.cnv52]], [e5, self.pool(e5)])
             x2, x3, x4, x5 = self.mlfc1(x2, x3, x4, x5)
             x2, x3, x4, x5 = self.mlfc2(x2, x3, x4, x5)
             x2, x3, x4, x5 = self.mlfc3(x2, x3, x4, x5)
