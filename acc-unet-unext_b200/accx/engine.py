@@ -322,8 +322,13 @@ def conv(ops: Sequence[Op], N: int, dims: Tuple[int, int, int], bias=None, adds:
     return out
 
 
+_SKIP_WGRAD = os.environ.get("ACCX_EXPERIMENT_SKIP_WGRAD", "0") == "1"    # timing experiments only (wrong gradients)
+
+
 def wgrad(op: Op, dy: torch.Tensor, N: int, dims, gw: torch.Tensor, dy_coff: int = 0):
     """accx_pw_wgrad(_tc): accumulate the weight gradient of one operand into gw (same layout as op.wv.t)."""
+    if _SKIP_WGRAD:
+        return
     B, H, W = dims
     o = Operand()
     _fill(o, op, gw)
@@ -342,6 +347,37 @@ def wgrad(op: Op, dy: torch.Tensor, N: int, dims, gw: torch.Tensor, dy_coff: int
         else:
             _call("accx_pw_wgrad", in_dt, B, H, W, N, ctypes.byref(o), dwp, dyp, dy.shape[-1], dy_f32, stream(),
                   cost=cost, tag=tag)
+
+
+def wgrad_conv3x3(X: Lazy, C_in: int, w: torch.Tensor, dy: torch.Tensor, N: int, dims, gw: torch.Tensor):
+    """weight gradient of a dense 3x3 convolution (weight [N, C_in, 3, 3], padding 1) whose input was the lazy
+    tensor X: the nine taps in groups of up to five per launch (accx_pw_wgrad_taps_tc: dY and the activation are
+    read once per group instead of once per tap), or tap by tap where the tensor cores cannot be used."""
+    B, H, W = dims
+    taps = [(ky * 3 + kx, ky - 1, kx - 1) for ky in range(3) for kx in range(3)]
+    in_dt = dt(X.y)
+    y = X.y
+    nbk = 64 if C_in >= 64 else (C_in + 15) // 16 * 16
+    tc_ok = (TC and in_dt == BF16 and dy.dtype == torch.bfloat16 and C_in % 8 == 0 and N % 8 == 0 and y.shape[-1] % 8 == 0
+             and dy.shape[-1] % 8 == 0 and y.data_ptr() % 16 == 0 and dy.data_ptr() % 16 == 0 and not _SKIP_WGRAD)
+    if not tc_ok:
+        for t, ddy, ddx in taps:
+            wgrad(Op(X, C_in, WV(w, t, C_in * 9, 9), 0, ddy, ddx), dy, N, dims, gw)
+        return
+    per = max(1, min(5, 512 // nbk))
+    o = Operand()
+    _fill(o, Op(X, C_in, WV(w, 0, C_in * 9, 9)), gw)
+    P = B * H * W
+    with side_stream(keep=(y, X.scale, X.shift, dy, gw)):
+        for g0 in range(0, 9, per):
+            grp = taps[g0:g0 + per]
+            n = len(grp)
+            tdy = (ctypes.c_int * n)(*[g[1] for g in grp])
+            tdx = (ctypes.c_int * n)(*[g[2] for g in grp])
+            tof = (ctypes.c_int64 * n)(*[g[0] for g in grp])
+            _call("accx_pw_wgrad_taps_tc", B, H, W, N, ctypes.byref(o), n, tdy, tdx, tof, gw.data_ptr(), dy.data_ptr(),
+                  dy.shape[-1], stream(), cost=(P * (C_in + N) * 2, 2 * P * N * C_in * n),
+                  tag=f"P={P} N={N} K={C_in} taps={n}")
 
 
 def bn_affine(bn: torch.nn.BatchNorm2d, stats, count: float, arena: Arena, training: bool, conv_bias=None):

@@ -524,8 +524,7 @@ class ResPath(_AccxModule):
             _zero_bias_grad(grads, self.convs[i])
             gw = E.grad_buf(grads, self.convs[i].weight)
             if gw is not None:
-                for op in self._taps(X, w, C):
-                    E.wgrad(op, dy, C, dims, gw)
+                E.wgrad_conv3x3(X, C, w, dy, C, dims, gw)
             if i > 0 or in_need[0]:
                 dxi = E.conv(self._taps(Lazy(dy), w, C, transpose=True), C, dims)
                 dx = E.add_inplace(dxi, dx)

@@ -29,16 +29,23 @@ struct alignas(64) WgParams {
   int64_t px_per_split;   // multiple of WG_PX
   int stages, tmem_cols, any_transform;
   float* dw;
+  // several filter taps of a dense 3x3 convolution in ONE pass over dY and the activation (ResPath): tap t reads
+  // the activation shifted by (tap_dy[t], tap_dx[t]) and accumulates into dw + tap_woff[t]; each tap owns nb TMEM
+  // columns.  A plain contraction is the single tap (op.dy, op.dx) with offset 0.
+  int n_taps, dy_blocks;
+  int tap_dy[9], tap_dx[9];
+  int64_t tap_woff[9];
 };
 
 __global__ void __launch_bounds__(WG_THREADS) pw_wgrad_tc_kernel(const __grid_constant__ WgParams prm) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
-  const int S = prm.stages, nb = prm.nb, a_blocks = nb >> 6;
-  const uint32_t stage_bytes = (2 + a_blocks) * WG_BLK;       // dY: 2 blocks (128 channels), A: nb/64 blocks
+  const int S = prm.stages, nb = prm.nb, a_blocks = (nb + 63) >> 6, nbp = a_blocks * 64;
+  const int n_taps = prm.n_taps, dyb = prm.dy_blocks;
+  const uint32_t stage_bytes = (dyb + n_taps * a_blocks) * WG_BLK;   // dY: 1-2 blocks (64 ch each), A: nb/64 blocks per tap
   const uint32_t tab_off = S * stage_bytes;                     // float[2][nb]: scale | shift of this CTA's A channels
-  const uint32_t bar_off = tab_off + 2 * nb * 4;
+  const uint32_t bar_off = tab_off + 2 * nbp * 4;
   const uint32_t landed_bar = base + bar_off;
   const uint32_t full_bar = landed_bar + 8 * S;
   const uint32_t empty_bar = full_bar + 8 * S;
@@ -76,7 +83,6 @@ __global__ void __launch_bounds__(WG_THREADS) pw_wgrad_tc_kernel(const __grid_co
 
   if (warp == 8) {
     if (lane == 0) {
-      const int64_t shift = (int64_t)prm.op.dy * prm.W + prm.op.dx;
       for (int it = 0; it < n_it; ++it) {
         const int stage = it % S;
         mbar_wait(empty_bar + 8 * stage, ((it / S) & 1) ^ 1);
@@ -87,10 +93,12 @@ __global__ void __launch_bounds__(WG_THREADS) pw_wgrad_tc_kernel(const __grid_co
         // NOTE rows >= pend of the last stage belong to the next split: they are masked below by loading
         // them anyway and letting the NEXT split skip them -- instead we clip: the box is only ever
         // partially valid at the very end of the tensor (px_per_split is a multiple of the stage size).
-        tma_load_2d(st, &prm.map_dy, n0, (int)p0, bar);
-        tma_load_2d(st + WG_BLK, &prm.map_dy, n0 + 64, (int)p0, bar);
-        for (int j = 0; j < a_blocks; ++j)
-          tma_load_2d(st + (2 + j) * WG_BLK, &prm.map_a, k0 + 64 * j, (int)(p0 + shift), bar);
+        for (int j = 0; j < dyb; ++j) tma_load_2d(st + j * WG_BLK, &prm.map_dy, n0 + 64 * j, (int)p0, bar);
+        for (int t = 0; t < n_taps; ++t) {
+          const int64_t shift = (int64_t)prm.tap_dy[t] * prm.W + prm.tap_dx[t];
+          for (int j = 0; j < a_blocks; ++j)
+            tma_load_2d(st + (dyb + t * a_blocks + j) * WG_BLK, &prm.map_a, k0 + 64 * j, (int)(p0 + shift), bar);
+        }
       }
     }
   } else if (warp == 9) {
@@ -104,11 +112,15 @@ __global__ void __launch_bounds__(WG_THREADS) pw_wgrad_tc_kernel(const __grid_co
         mbar_wait(ready_bar + 8 * stage, (it / S) & 1);
         tc_fence_after();
         const uint32_t st = base + stage * stage_bytes;
+        // (with a single dY block the "second block" of the M = 128 operand aliases the first activation block:
+        //  accumulator rows >= 64 are garbage and are never read back, the epilogue stops at row N <= 64)
+        for (int t = 0; t < n_taps; ++t) {
 #pragma unroll
-        for (int k = 0; k < WG_PX / 16; ++k) {
-          const uint64_t adesc = make_desc_mn_sw128(st + k * 2048, WG_BLK);
-          const uint64_t bdesc = make_desc_mn_sw128(st + 2 * WG_BLK + k * 2048, WG_BLK);
-          tc_mma(tmem_base, adesc, bdesc, idesc, (it | k) ? 1u : 0u);
+          for (int k = 0; k < WG_PX / 16; ++k) {
+            const uint64_t adesc = make_desc_mn_sw128(st + k * 2048, WG_BLK);
+            const uint64_t bdesc = make_desc_mn_sw128(st + (dyb + t * a_blocks) * WG_BLK + k * 2048, WG_BLK);
+            tc_mma(tmem_base + t * nb, adesc, bdesc, idesc, (it | k) ? 1u : 0u);
+          }
         }
         tc_commit(empty_bar + 8 * stage);
       }
@@ -119,39 +131,50 @@ __global__ void __launch_bounds__(WG_THREADS) pw_wgrad_tc_kernel(const __grid_co
     if (prm.any_transform) {
       const int c = tid & 7, r0 = tid >> 3;                       // rows r0, r0 + 32, r0 + 64, r0 + 96
       float* tab = reinterpret_cast<float*>(smem + tab_off);
-      for (int j = tid; j < nb; j += 256) {
-        const bool on = prm.op.act != 0 && k0 + j < prm.op.K;
+      for (int j = tid; j < nbp; j += 256) {
+        const bool on = prm.op.act != 0 && j < nb && k0 + j < prm.op.K;
         tab[j] = on ? __ldg(prm.op.scale + k0 + j) : 0.f;
-        tab[nb + j] = on ? __ldg(prm.op.shift + k0 + j) : 0.f;
+        tab[nbp + j] = on ? __ldg(prm.op.shift + k0 + j) : 0.f;
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      const bool shifted = prm.op.dy != 0 || prm.op.dx != 0;
+      bool shifted = false;
+      for (int t = 0; t < n_taps; ++t) shifted = shifted || prm.tap_dy[t] != 0 || prm.tap_dx[t] != 0;
       const int HWp = prm.H * prm.W;
       for (int it = 0; it < n_it; ++it) {
         const int stage = it % S;
-        uint32_t zero_mask = 0;
+        int ph[4], pw[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { ph[i] = 0; pw[i] = 0; }
         if (shifted) {
           const int p0 = (int)(pbeg + (int64_t)it * WG_PX);
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int p = p0 + r0 + 32 * i;
             const int rem = p % HWp;
-            const int h = rem / prm.W;
-            const int hh = h + prm.op.dy, ww = rem - h * prm.W + prm.op.dx;
-            if (hh < 0 || hh >= prm.H || ww < 0 || ww >= prm.W || p >= (int)prm.P) zero_mask |= 1u << i;
+            ph[i] = rem / prm.W;
+            pw[i] = p < (int)prm.P ? rem - ph[i] * prm.W : -4;       // rows past the end count as outside the image
           }
         }
         mbar_wait(landed_bar + 8 * stage, (it / S) & 1);
         const uint32_t st = base + stage * stage_bytes;
-        if (prm.op.act != 0 || zero_mask != 0) {
+        for (int t = 0; t < n_taps; ++t) {
+          uint32_t zero_mask = 0;
+          if (prm.tap_dy[t] != 0 || prm.tap_dx[t] != 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int hh = ph[i] + prm.tap_dy[t], ww = pw[i] + prm.tap_dx[t];
+              if (hh < 0 || hh >= prm.H || ww < 0 || ww >= prm.W || pw[i] < 0) zero_mask |= 1u << i;
+            }
+          }
+          if (prm.op.act == 0 && zero_mask == 0) continue;
           for (int j = 0; j < a_blocks; ++j) {
             float sc[8], sh[8];
             const float4* sp = reinterpret_cast<const float4*>(tab + 64 * j + c * 8);
-            const float4* tp = reinterpret_cast<const float4*>(tab + nb + 64 * j + c * 8);
+            const float4* tp = reinterpret_cast<const float4*>(tab + nbp + 64 * j + c * 8);
             const float4 a0 = sp[0], a1 = sp[1], b0 = tp[0], b1 = tp[1];
             sc[0] = a0.x; sc[1] = a0.y; sc[2] = a0.z; sc[3] = a0.w; sc[4] = a1.x; sc[5] = a1.y; sc[6] = a1.z; sc[7] = a1.w;
             sh[0] = b0.x; sh[1] = b0.y; sh[2] = b0.z; sh[3] = b0.w; sh[4] = b1.x; sh[5] = b1.y; sh[6] = b1.z; sh[7] = b1.w;
-            transform_block<4, 32>(st + (2 + j) * WG_BLK, c, r0, prm.op.act, sc, sh, zero_mask);
+            transform_block<4, 32>(st + (dyb + t * a_blocks + j) * WG_BLK, c, r0, prm.op.act, sc, sh, zero_mask);
           }
         }
         fence_async_smem();
@@ -166,11 +189,12 @@ __global__ void __launch_bounds__(WG_THREADS) pw_wgrad_tc_kernel(const __grid_co
     tc_fence_after();
     const int n = n0 + warp * 32 + lane;
     const bool vec_red = prm.op.w_ks == 1 && (prm.op.w_ld & 3) == 0 && ((reinterpret_cast<uintptr_t>(prm.dw) & 15) == 0);
+    for (int t = 0; t < n_taps; ++t)
     for (int c0 = 0; c0 < nb; c0 += 16) {
       float v[16];
-      tc_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + c0, v);
+      tc_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + t * nb + c0, v);
       if (n < prm.N) {
-        float* rowp = prm.dw + (int64_t)n * prm.op.w_ld;
+        float* rowp = prm.dw + prm.tap_woff[t] + (int64_t)n * prm.op.w_ld;
         if (vec_red && k0 + c0 + 16 <= prm.op.K) {
           // contiguous weight row: four 16-byte vector reductions instead of sixteen scalar atomics
 #pragma unroll
@@ -203,44 +227,61 @@ using namespace accx;
 
 extern "C" {
 
-int accx_pw_wgrad_tc(int B, int H, int W, int N, const accx_operand_t* op, float* dw, const void* dy, int64_t ldy,
-                     void* stream) {
+static int wgrad_tc_launch(int B, int H, int W, int N, const accx_operand_t* op, int n_taps, const int* taps_dy,
+                           const int* taps_dx, const int64_t* taps_woff, float* dw, const void* dy, int64_t ldy,
+                           void* stream) {
   ACCX_REQUIRE(B > 0 && H > 0 && W > 0 && N > 0 && op && op->data && dw && dy, "pw_wgrad_tc: bad arguments");
   ACCX_REQUIRE(op->K % 8 == 0 && op->ld % 8 == 0 && aligned16(op->data) && ldy % 8 == 0 && aligned16(dy) && N % 8 == 0,
                "pw_wgrad_tc: needs K, N, ld multiples of 8 and 16-byte aligned bases (use accx_pw_wgrad)");
   ACCX_REQUIRE(op->act == 0 || (op->scale && op->shift && aligned16(op->scale) && aligned16(op->shift)),
                "pw_wgrad_tc: scale/shift missing or misaligned");
+  ACCX_REQUIRE(n_taps >= 1 && n_taps <= 9, "pw_wgrad_tc: n_taps %d out of range", n_taps);
   WgParams prm;
   prm.op = *op;
   prm.B = B; prm.H = H; prm.W = W; prm.N = N;
   prm.P = (int64_t)B * H * W;
+  ACCX_REQUIRE(prm.P < (int64_t)1 << 31, "pw_wgrad_tc: too many pixels");
   prm.dw = dw;
-  prm.any_transform = (op->act || op->dy || op->dx) ? 1 : 0;
-  prm.nb = op->K >= 256 ? 256 : (op->K + 63) / 64 * 64;
+  prm.n_taps = n_taps;
+  prm.any_transform = op->act ? 1 : 0;
+  for (int t = 0; t < 9; ++t) { prm.tap_dy[t] = 0; prm.tap_dx[t] = 0; prm.tap_woff[t] = 0; }
+  for (int t = 0; t < n_taps; ++t) {
+    prm.tap_dy[t] = taps_dy[t]; prm.tap_dx[t] = taps_dx[t]; prm.tap_woff[t] = taps_woff[t];
+    if (taps_dy[t] || taps_dx[t]) prm.any_transform = 1;
+  }
+  if (n_taps == 1) {
+    prm.nb = op->K >= 256 ? 256 : (op->K + 63) / 64 * 64;
+  } else {               // every tap owns nb TMEM columns and one 64-channel activation block per stage
+    prm.nb = op->K >= 64 ? 64 : (op->K + 15) / 16 * 16;
+    ACCX_REQUIRE(n_taps * prm.nb <= 512, "pw_wgrad_tc: %d taps x %d channels exceed the 512 TMEM columns", n_taps, prm.nb);
+  }
+  const int a_blocks = (prm.nb + 63) / 64;
+  prm.dy_blocks = N <= 64 ? 1 : 2;
   prm.n_tiles = (N + 127) / 128;
   prm.k_tiles = (op->K + prm.nb - 1) / prm.nb;
   int cols = 32;
-  while (cols < prm.nb) cols <<= 1;
+  while (cols < n_taps * prm.nb) cols <<= 1;
   prm.tmem_cols = cols;
   const int pairs = prm.n_tiles * prm.k_tiles;
   const int64_t stages_total = (prm.P + WG_PX - 1) / WG_PX;
   int64_t splits = (2 * (int64_t)sm_count() + pairs - 1) / pairs;
-  // every split ends with 128 x nb fp32 atomics: keep at least 8 stages (1024 pixels) of work behind them
+  // every split ends with 128 x nb fp32 atomics per tap: keep at least 8 stages (1024 pixels) of work behind them
   if (splits > stages_total / 8) splits = stages_total / 8;
   if (splits < 1) splits = 1;
   int64_t per = (stages_total + splits - 1) / splits;      // stages per split
   splits = (stages_total + per - 1) / per;
   prm.splits = (int)splits;
   prm.px_per_split = per * WG_PX;
-  const size_t stage_bytes = (size_t)(2 + (prm.nb >> 6)) * WG_BLK;
-  int S = (int)((200 * 1024) / stage_bytes);
+  const size_t stage_bytes = (size_t)(prm.dy_blocks + n_taps * a_blocks) * WG_BLK;
+  const size_t fixed = 1024 + 2 * (size_t)a_blocks * 64 * 4 + 24 * 4 + 64;
+  int S = (int)((227 * 1024 - fixed) / stage_bytes);
   if (S > 4) S = 4;
   if (S > per) S = (int)per;
-  if (S < 1) S = 1;
+  ACCX_REQUIRE(S >= 1, "pw_wgrad_tc: one pipeline stage (%zu bytes) does not fit in shared memory", stage_bytes);
   prm.stages = S;
   ACCX_REQUIRE(encode_2d_bf16(&prm.map_dy, dy, N, prm.P, ldy, WG_PX), "pw_wgrad_tc: tensor map (dY) failed");
   ACCX_REQUIRE(encode_2d_bf16(&prm.map_a, op->data, op->K, prm.P, op->ld, WG_PX), "pw_wgrad_tc: tensor map (A) failed");
-  const size_t smem = 1024 + S * stage_bytes + 2 * prm.nb * 4 + 24 * S + 64;
+  const size_t smem = 1024 + S * stage_bytes + 2 * (size_t)a_blocks * 64 * 4 + 24 * S + 64;
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(pw_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -248,6 +289,21 @@ int accx_pw_wgrad_tc(int B, int H, int W, int N, const accx_operand_t* op, float
   }
   pw_wgrad_tc_kernel<<<(unsigned)(pairs * splits), WG_THREADS, smem, (cudaStream_t)stream>>>(prm);
   return check_launch("pw_wgrad_tc");
+}
+
+int accx_pw_wgrad_tc(int B, int H, int W, int N, const accx_operand_t* op, float* dw, const void* dy, int64_t ldy,
+                     void* stream) {
+  ACCX_REQUIRE(op, "pw_wgrad_tc: bad arguments");
+  const int tdy = op->dy, tdx = op->dx;
+  const int64_t off = 0;
+  return wgrad_tc_launch(B, H, W, N, op, 1, &tdy, &tdx, &off, dw, dy, ldy, stream);
+}
+
+int accx_pw_wgrad_taps_tc(int B, int H, int W, int N, const accx_operand_t* op, int n_taps, const int* taps_dy,
+                          const int* taps_dx, const int64_t* taps_woff, float* dw, const void* dy, int64_t ldy,
+                          void* stream) {
+  ACCX_REQUIRE(op && taps_dy && taps_dx && taps_woff, "pw_wgrad_taps_tc: bad arguments");
+  return wgrad_tc_launch(B, H, W, N, op, n_taps, taps_dy, taps_dx, taps_woff, dw, dy, ldy, stream);
 }
 
 }  // extern "C"

@@ -227,6 +227,9 @@ def main():
         eager = TrainStep(model, lr=1e-3, graph=False)
         eager.opt = step.opt if not args.graph else eager.opt
         eager.avg.world = 1              # rank-0-only instrumentation: no collective (the other ranks are not in it)
+        # per-kernel timing needs kernels that run alone: no side stream, no parallel lanes in this step
+        side_mode, lanes_mode = E.SIDE_MODE, E.LANES
+        E.SIDE_MODE, E.LANES = 0, 0
         eager(x_dev, m_dev)
         torch.cuda.synchronize()
         E.PROFILE = []
@@ -238,6 +241,7 @@ def main():
         calls = sorted(((e0.elapsed_time(e1), n_, tg, nb_, fl_) for n_, e0, e1, nb_, fl_, tg in E.PROFILE), reverse=True)[:40]
         prof_rows = E.PROFILE
         E.PROFILE = None
+        E.SIDE_MODE, E.LANES = side_mode, lanes_mode
         step_ms = t_e0.elapsed_time(t_e1)
         tot = sum(a[1] for a in agg.values())
         top = max(agg.items(), key=lambda kv: kv[1][1])

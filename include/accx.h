@@ -95,6 +95,13 @@ int accx_pw_wgrad(int dtype, int B, int H, int W, int N, const accx_operand_t* o
  * pixels and combined with fp32 atomics.  bf16 operands; K, N, ld multiples of 8. */
 int accx_pw_wgrad_tc(int B, int H, int W, int N, const accx_operand_t* op, float* dw, const void* dy, int64_t ldy,
                      void* stream);
+/* Several taps of a dense k x k convolution's weight gradient (ResPath 3x3, ACC_UNet.py:316-318) in ONE pass over dY
+ * and the activation: tap t reads the activation shifted by (taps_dy[t], taps_dx[t]) (zero outside the image) and
+ * accumulates into dw + taps_woff[t] (floats; the [C, C, 3, 3] weight has w_ld = 9C, w_ks = 9, offset = tap index).
+ * op->dy/dx are ignored.  n_taps x min(round16(K), 64) must fit the 512 TMEM columns. */
+int accx_pw_wgrad_taps_tc(int B, int H, int W, int N, const accx_operand_t* op, int n_taps, const int* taps_dy,
+                          const int* taps_dx, const int64_t* taps_woff, float* dw, const void* dy, int64_t ldy,
+                          void* stream);
 
 /* BatchNorm2d statistics -> affine (torch.nn.BatchNorm2d as used at ACC_UNet.py:34,74,178,
  * 244-260,311-319,388-410).  training: mean/var from stats (biased var), running buffers

@@ -165,3 +165,22 @@ def test_tc_wgrad_dense3x3_taps(C):
     w_ = w.clone().requires_grad_(True)
     F.conv2d(bf(a).permute(0, 3, 1, 2), w_, None, padding=1).backward(dy.float().permute(0, 3, 1, 2))
     close(gw, w_.grad, RT, AT, "tc conv3x3 wgrad")
+
+
+@pytest.mark.parametrize("C", [8, 32, 64, 72, 136])
+def test_tc_wgrad_conv3x3_grouped_taps(C):
+    """accx_pw_wgrad_taps_tc (several taps per pass over dY / the activation) against autograd of F.conv2d"""
+    e = E()
+    B, H, W = 2, 20, 24
+    L, a = mk_lazy((B, H, W, C), torch.bfloat16, 2, 18)
+    g = torch.Generator().manual_seed(19)
+    w = (torch.randn(C, C, 3, 3, generator=g) / (3 * C ** 0.5)).to(DEV)
+    dy = torch.randn(B, H, W, C, generator=g).to(DEV).to(torch.bfloat16)
+    gw = torch.zeros_like(w)
+    n0 = e.LAUNCHES
+    e.wgrad_conv3x3(L, C, w, dy, C, (B, H, W), gw)
+    assert e.LAUNCHES - n0 <= 3, "taps were not grouped"
+    torch.backends.cudnn.allow_tf32 = False
+    w_ = w.clone().requires_grad_(True)
+    F.conv2d(bf(a).permute(0, 3, 1, 2), w_, None, padding=1).backward(dy.float().permute(0, 3, 1, 2))
+    close(gw, w_.grad, RT, AT, "tc conv3x3 grouped wgrad")
