@@ -157,6 +157,8 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"       # the version banner goes to stdout; stdout carries ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     accx.load_library()
     W = max(args.warmup, 3)
