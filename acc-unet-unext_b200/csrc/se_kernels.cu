@@ -514,7 +514,7 @@ int accx_se_bwd_apply(int dtype, int B, int HW, int C, const void* x, const floa
   const int64_t P = (int64_t)B * HW;
   ACCX_DISPATCH_T(dtype, {
     Lanes l = make_lanes(C, DT<T>::VEC, aligned16(x) && aligned16(dout) && aligned16(da));
-    const int chunks = se_chunks(B, HW, l.ty, bn_sums ? 148 * 2 : 148 * 8);     // reducing: few blocks (atomics)
+    const int chunks = se_chunks(B, HW, l.ty, bn_sums ? 148 * 4 : 148 * 8);     // reducing: few blocks (atomics)
     dim3 block(l.tx, l.ty), grid(B * chunks, l.gy);
     const size_t sm = bn_sums ? (size_t)l.tx * l.ty * l.vec * sizeof(float) : 0;
     ACCX_DISPATCH_VEC(l, {
