@@ -322,13 +322,8 @@ def conv(ops: Sequence[Op], N: int, dims: Tuple[int, int, int], bias=None, adds:
     return out
 
 
-_SKIP_WGRAD = os.environ.get("ACCX_EXPERIMENT_SKIP_WGRAD", "0") == "1"    # timing experiments only (wrong gradients)
-
-
 def wgrad(op: Op, dy: torch.Tensor, N: int, dims, gw: torch.Tensor, dy_coff: int = 0):
     """accx_pw_wgrad(_tc): accumulate the weight gradient of one operand into gw (same layout as op.wv.t)."""
-    if _SKIP_WGRAD:
-        return
     B, H, W = dims
     o = Operand()
     _fill(o, op, gw)
@@ -359,7 +354,7 @@ def wgrad_conv3x3(X: Lazy, C_in: int, w: torch.Tensor, dy: torch.Tensor, N: int,
     y = X.y
     nbk = 64 if C_in >= 64 else (C_in + 15) // 16 * 16
     tc_ok = (TC and in_dt == BF16 and dy.dtype == torch.bfloat16 and C_in % 8 == 0 and N % 8 == 0 and y.shape[-1] % 8 == 0
-             and dy.shape[-1] % 8 == 0 and y.data_ptr() % 16 == 0 and dy.data_ptr() % 16 == 0 and not _SKIP_WGRAD)
+             and dy.shape[-1] % 8 == 0 and y.data_ptr() % 16 == 0 and dy.data_ptr() % 16 == 0)
     if not tc_ok:
         for t, ddy, ddx in taps:
             wgrad(Op(X, C_in, WV(w, t, C_in * 9, 9), 0, ddy, ddx), dy, N, dims, gw)
