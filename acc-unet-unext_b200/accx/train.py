@@ -48,13 +48,19 @@ class GradAverager:
     def __call__(self):
         if self.world == 1:
             return
-        live = [p for p in self.params if p.grad is not None]
         # ranks must agree on the bucket layout: ACC_UNet_Lite leaves the same parameters unused everywhere
-        flat = torch._utils._flatten_dense_tensors([p.grad for p in live])
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
-        flat.div_(self.world)
-        for p, g in zip(live, torch._utils._unflatten_dense_tensors(flat, [p.grad for p in live])):
-            p.grad.copy_(g)
+        grads = [p.grad for p in self.params if p.grad is not None]
+        flat = torch.cat([g.reshape(-1) for g in grads])            # one gather kernel for the ~900 tensors
+        if dist.get_backend(self.group) == "nccl":
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.group)
+        else:
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+            flat.div_(self.world)
+        views, off = [], 0
+        for g in grads:
+            views.append(flat[off:off + g.numel()].view_as(g))
+            off += g.numel()
+        torch._foreach_copy_(grads, views)                          # scatter back with multi-tensor kernels
 
 
 class TrainStep:
