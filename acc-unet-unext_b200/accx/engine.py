@@ -23,12 +23,20 @@ PROFILE = None        # list -> every launch is bracketed by CUDA events on the 
                       # appended as (kernel, start, end, algorithmic_bytes, flops); see bench.py
 
 
+PROFILE_LEAD = None   # (every, cycles): while profiling, a spin kernel of `cycles` SM clocks is queued before every
+                      # `every`-th launch (outside the event pairs).  Eager launching is CPU-bound (~45 us per launch vs
+                      # ~25 us per kernel); without the lead the GPU idles between an event and the kernel that follows,
+                      # and that idle time would be booked to the kernel.
+
+
 def _call(name, *args, cost=(0, 0), tag=""):
     global LAUNCHES
     LAUNCHES += 1
     if PROFILE is None:
         _lib.call(name, *args)
         return
+    if PROFILE_LEAD is not None and len(PROFILE) % PROFILE_LEAD[0] == 0:
+        torch.cuda._sleep(PROFILE_LEAD[1])
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     _lib.call(name, *args)
@@ -400,14 +408,15 @@ def materialize(L: Lazy, scale2=None, shift2=None, residual=None, stats=None, ou
     if out is None and not stats_only:
         out = torch.empty_like(y)
     _call("accx_act_apply", dt(y), y.numel() // y.shape[-1], y.shape[-1], ptr(y), ptr(L.scale), ptr(L.shift), L.act,
-          ptr(scale2), ptr(shift2), ptr(residual), ptr(out), ptr(stats), stream(), cost=(nb(y, residual, out), 0))
+          ptr(scale2), ptr(shift2), ptr(residual), ptr(out), ptr(stats), stream(), cost=(nb(y, residual, out), 0),
+          tag=f"P={y.numel() // y.shape[-1]} C={y.shape[-1]} stats={int(stats is not None)} out={int(out is not None)}")
     return out
 
 
 def add_fwd(L: Lazy, r: torch.Tensor, stats):
     z = torch.empty_like(r)
     _call("accx_add_fwd", dt(r), r.numel() // r.shape[-1], r.shape[-1], ptr(L.y), ptr(L.scale), ptr(L.shift), L.act,
-          ptr(r), ptr(z), ptr(stats), stream(), cost=(nb(L.y, r, z), 0))
+          ptr(r), ptr(z), ptr(stats), stream(), cost=(nb(L.y, r, z), 0), tag=f"P={r.numel() // r.shape[-1]} C={r.shape[-1]}")
     return z
 
 
@@ -434,6 +443,12 @@ def bn_bwd(L: Lazy, da: torch.Tensor, grads: dict, arena: Arena, out: Optional[t
     return dy
 
 
+# Set by accx.train.FlatState for the duration of a training step: parameter gradients are then accumulated
+# straight into ONE flat fp32 buffer (zeroed by one memset per step) that the all-reduce and the Adam kernel
+# consume as is.  An object with .serves(p) -> bool and .take(p) -> zero-initialised view or None.
+GRAD_ARENA = None
+
+
 class GradPool(dict):
     """id(param) -> fp32 gradient accumulator.  All accumulators of one module backward are allocated up
     front and zeroed with ONE multi-tensor launch (instead of one fill kernel per parameter); a parameter
@@ -442,8 +457,9 @@ class GradPool(dict):
 
     def __init__(self, params=()):
         super().__init__()
+        ga = GRAD_ARENA
         self.spare = {id(p): torch.empty(p.shape, dtype=torch.float32, device=p.device)
-                      for p in params if p.requires_grad}
+                      for p in params if p.requires_grad and (ga is None or not ga.serves(p))}
         if self.spare:
             torch._foreach_zero_(list(self.spare.values()))
 
@@ -453,6 +469,10 @@ def grad_buf(grads: dict, p: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
     if p is None or not p.requires_grad:
         return None
     g = grads.get(id(p))
+    if g is None and GRAD_ARENA is not None:
+        g = GRAD_ARENA.take(p)       # a view into the step's flat gradient buffer (already zero), or None
+        if g is not None:
+            grads[id(p)] = g
     if g is None:
         spare = getattr(grads, "spare", None)
         g = spare.pop(id(p), None) if spare is not None else None
@@ -539,7 +559,8 @@ def hanc_unpool_fusable(L: Lazy, k: int) -> bool:
 def pool_sum(x: torch.Tensor, l: int, mul: float, out_dtype: Optional[torch.dtype] = None):
     B, H, W, C = x.shape
     out = torch.empty((B, H >> l, W >> l, C), dtype=out_dtype or x.dtype, device=x.device)
-    _call("accx_pool_sum", dt(x), dt(out), B, H, W, C, l, float(mul), ptr(x), ptr(out), C, stream(), cost=(nb(x, out), 0))
+    _call("accx_pool_sum", dt(x), dt(out), B, H, W, C, l, float(mul), ptr(x), ptr(out), C, stream(), cost=(nb(x, out), 0),
+          tag=f"{B}x{H}x{W}x{C} l={l}")
     return out
 
 
@@ -579,7 +600,7 @@ def se_fwd(L: Lazy, se, arena: Arena, training: bool, residual=None, mix=None, s
     counter = arena.take(1)
     d = dt(y)
     _call("accx_se_squeeze", d, B, H * W, C, ptr(y), ptr(L.scale), ptr(L.shift), L.act, ptr(c.S), stream(),
-          cost=(nb(y), 0))
+          cost=(nb(y), 0), tag=f"B={B} HW={H * W} C={C}")
     bn = se.bn
     mom = 0.1 if bn.momentum is None else bn.momentum
     _call("accx_se_gate", B, C, Cr, float(H * W), ptr(c.S), ptr(f32(se.fc1.weight)), ptr(f32(se.fc1.bias)),
@@ -588,7 +609,8 @@ def se_fwd(L: Lazy, se, arena: Arena, training: bool, residual=None, mix=None, s
           ptr(c.gate), ptr(c.hidden), ptr(c.scale), ptr(c.shift), ptr(c.mean), ptr(c.rstd), ptr(counter), stream())
     out = torch.empty_like(y)
     _call("accx_se_apply", d, B, H * W, C, ptr(y), ptr(L.scale), ptr(L.shift), L.act, ptr(c.gate), ptr(c.scale),
-          ptr(c.shift), ptr(residual), ptr(mix), ptr(out), ptr(stats), stream(), cost=(nb(y, residual, out), 0))
+          ptr(c.shift), ptr(residual), ptr(mix), ptr(out), ptr(stats), stream(), cost=(nb(y, residual, out), 0),
+          tag=f"B={B} HW={H * W} C={C} res={int(residual is not None)} stats={int(stats is not None)}")
     return out, c
 
 
@@ -609,7 +631,7 @@ def se_bwd(c: SECtx, dout: torch.Tensor, grads: dict, arena: Arena, da: Optional
     gmix = grad_buf(grads, c.mix_param) if c.mix_param is not None else None
     _call("accx_se_bwd_reduce", d, B, H * W, C, ptr(y), ptr(L.scale), ptr(L.shift), L.act, ptr(c.gate), ptr(c.scale),
           ptr(c.shift), ptr(dout), ptr(c.mix), ptr(c.residual) if gmix is not None else 0, ptr(gmix), ptr(G), stream(),
-          cost=(nb(y, dout), 0))
+          cost=(nb(y, dout), 0), tag=f"B={B} HW={H * W} C={C}")
     _call("accx_se_bwd_gate", B, C, Cr, float(H * W), ptr(c.S), ptr(G), ptr(c.gate), ptr(c.hidden),
           ptr(f32(se.fc1.weight)), ptr(f32(se.fc2.weight)), ptr(f32(se.bn.weight)), ptr(c.mean), ptr(c.rstd),
           ptr(grad_buf(grads, se.fc1.weight)), ptr(grad_buf(grads, se.fc1.bias)), ptr(grad_buf(grads, se.fc2.weight)),
@@ -621,7 +643,8 @@ def se_bwd(c: SECtx, dout: torch.Tensor, grads: dict, arena: Arena, da: Optional
     sums = arena.take(2 * C) if (bn_sums and L.mean is not None and L.rstd is not None) else None
     _call("accx_se_bwd_apply", d, B, H * W, C, ptr(y), ptr(L.scale), ptr(L.shift), L.act, ptr(c.gate), ptr(c.scale),
           ptr(c.shift), ptr(dout), ptr(c.mix), ptr(PQR), ptr(da), 1 if accumulate else 0, ptr(L.mean) if sums is not None else 0,
-          ptr(L.rstd) if sums is not None else 0, ptr(sums), stream(), cost=(nb(y, dout, da), 0))
+          ptr(L.rstd) if sums is not None else 0, ptr(sums), stream(), cost=(nb(y, dout, da), 0),
+          tag=f"B={B} HW={H * W} C={C} acc={int(bool(accumulate))} bn={int(sums is not None)}")
     return (da, sums) if bn_sums else da
 
 
@@ -651,3 +674,50 @@ def input_to_nhwc(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     out = torch.empty((B, H, W, C), dtype=dtype, device=x.device)
     _call("accx_nchw_to_nhwc", dt(x), dt(out), B, C, H * W, ptr(x), ptr(out), stream())
     return out
+
+
+# ---- the steps either side of the blocks inside a training step (include/accx.h, rows f1/f2) -----------------
+def maxpool2(x: torch.Tensor) -> torch.Tensor:
+    """MaxPool2d(2) on a contiguous [B,H,W,C] tensor"""
+    B, H, W, C = x.shape
+    out = torch.empty((B, H // 2, W // 2, C), dtype=x.dtype, device=x.device)
+    _call("accx_maxpool2_fwd", dt(x), B, H, W, C, ptr(x), ptr(out), stream(), cost=(nb(x, out), 0),
+          tag=f"{B}x{H}x{W}x{C}")
+    return out
+
+
+def maxpool2_bwd(x: torch.Tensor, dy: torch.Tensor) -> torch.Tensor:
+    B, H, W, C = x.shape
+    assert dy.dtype == x.dtype and dy.is_contiguous()
+    dx = torch.empty_like(x)
+    _call("accx_maxpool2_bwd", dt(x), B, H, W, C, ptr(x), ptr(dy), ptr(dx), stream(), cost=(nb(x, dy, dx), 0),
+          tag=f"{B}x{H}x{W}x{C}")
+    return dx
+
+
+def dice_bce_fwd(logit: torch.Tensor, truth: torch.Tensor, dice_w: float, bce_w: float):
+    """logit [B, N] (fp32 / bf16), truth [B, N] fp32 -> (loss scalar tensor, sums for the backward)"""
+    B, N = logit.shape
+    sums = torch.zeros(8 * B + 8, dtype=torch.float32, device=logit.device)
+    loss = torch.empty((), dtype=torch.float32, device=logit.device)
+    _call("accx_dice_bce_fwd", dt(logit), B, N, ptr(logit), ptr(truth), float(dice_w), float(bce_w), ptr(sums), ptr(loss),
+          stream(), cost=(nb(logit, truth), 0))
+    return loss, sums
+
+
+def dice_bce_bwd(logit, truth, sums, dice_w, bce_w, gscale: Optional[torch.Tensor], grad_dtype: torch.dtype):
+    B, N = logit.shape
+    d = torch.empty((B, N), dtype=grad_dtype, device=logit.device)
+    _call("accx_dice_bce_bwd", dt(logit), dt(d), B, N, ptr(logit), ptr(truth), ptr(sums), float(dice_w), float(bce_w),
+          ptr(gscale), ptr(d), stream(), cost=(nb(logit, truth, d), 0))
+    return d
+
+
+def adam_step(param, grad, exp_avg, exp_avg_sq, state, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0,
+              grad_scale=1.0):
+    """one Adam step over flat fp32 buffers (state[0] = device-side step count, incremented by the call)"""
+    n = param.numel()
+    global LAUNCHES
+    LAUNCHES += 1                      # the step-count tick
+    _call("accx_adam_step", n, ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), ptr(state), float(lr), float(beta1),
+          float(beta2), float(eps), float(weight_decay), float(grad_scale), stream(), cost=(7 * 4 * n, 0))

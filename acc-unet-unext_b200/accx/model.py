@@ -1,9 +1,9 @@
 """ACC-UNet assembled from the accx drop-in blocks (caller glue of ACC_UNet.py:530-659).
 
-The five hot-path module types run the accx kernels; the glue around them that the reference
-also delegates to ATen -- MaxPool2d(2), ConvTranspose2d(2, 2, stride 2), the skip torch.cat and
-the final 1x1 conv (+ sigmoid) -- stays on torch here (SURVEY.md section 8, row a8 / f1 "next"),
-operating on channels_last tensors so no layout change happens between blocks.
+The five hot-path module types run the accx kernels, and so do MaxPool2d(2) and the final 1x1 conv
+(SURVEY.md section 8, row f1).  ConvTranspose2d(2, 2, stride 2), the skip torch.cat and the optional
+sigmoid stay on torch as in the reference (row a8), operating on channels_last tensors so no layout
+change happens between blocks.
 
 `compute_dtype=torch.bfloat16` stores activations in bf16 (fp32 accumulation, statistics and
 parameters); default None follows the input's dtype (fp32 = the reference's arithmetic).
@@ -14,7 +14,7 @@ import torch
 from torch import nn
 
 from . import engine as E
-from .modules import HANCBlock, MLFC, ResPath, run_parallel
+from .modules import HANCBlock, MLFC, ResPath, maxpool2, out_conv, run_parallel
 
 
 class _ACCUNetBase(nn.Module):
@@ -74,10 +74,10 @@ class _ACCUNetBase(nn.Module):
             # ResPath of level l only needs that level's encoder output, so it runs (forward AND backward, one
             # autograd node per pair) on a parallel stream lane next to the encoder blocks of level l+1.
             e2 = self.cnv12(self.cnv11(x))
-            x2, e3 = run_parallel([self.rspth1, [self.cnv21, self.cnv22]], [e2, self.pool(e2)])
-            x3, e4 = run_parallel([self.rspth2, [self.cnv31, self.cnv32]], [e3, self.pool(e3)])
-            x4, e5 = run_parallel([self.rspth3, [self.cnv41, self.cnv42]], [e4, self.pool(e4)])
-            x5, x6 = run_parallel([self.rspth4, [self.cnv51, self.cnv52]], [e5, self.pool(e5)])
+            x2, e3 = run_parallel([self.rspth1, [self.cnv21, self.cnv22]], [e2, maxpool2(e2)])
+            x3, e4 = run_parallel([self.rspth2, [self.cnv31, self.cnv32]], [e3, maxpool2(e3)])
+            x4, e5 = run_parallel([self.rspth3, [self.cnv41, self.cnv42]], [e4, maxpool2(e4)])
+            x5, x6 = run_parallel([self.rspth4, [self.cnv51, self.cnv52]], [e5, maxpool2(e5)])
             x2, x3, x4, x5 = self.mlfc1(x2, x3, x4, x5)
             x2, x3, x4, x5 = self.mlfc2(x2, x3, x4, x5)
             x2, x3, x4, x5 = self.mlfc3(x2, x3, x4, x5)
@@ -85,8 +85,7 @@ class _ACCUNetBase(nn.Module):
             x8 = self.cnv72(self.cnv71(torch.cat([self.up7(x7), x4], dim=1)))
             x9 = self.cnv82(self.cnv81(torch.cat([self.up8(x8), x3], dim=1)))
             x10 = self.cnv92(self.cnv91(torch.cat([self.up9(x9), x2], dim=1)))
-            logits = self.out(x10)
-        logits = logits.float()
+            logits = out_conv(x10, self.out)                       # fp32 logits
         if self.last_activation is not None:
             logits = self.last_activation(logits)
         return logits

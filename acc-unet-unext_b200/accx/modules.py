@@ -151,6 +151,72 @@ def run_parallel(chains, xs):
     return _GroupFn.apply(chains, *xs, *params)
 
 
+class _MaxPool2Fn(torch.autograd.Function):
+    """nn.MaxPool2d(2) between the encoder levels (ACC_UNet.py:552,608-618) on the accx kernels; backward
+    recomputes the arg-max from the saved input (no index tensor)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        E.require_cuda(x)
+        xn = E.to_nhwc(x.detach())
+        if xn.shape[1] % 2 or xn.shape[2] % 2:
+            raise ValueError(f"accx MaxPool2d(2) needs even H, W, got {xn.shape[1]}x{xn.shape[2]}")
+        ctx.xn = xn
+        return E.to_nchw_view(E.maxpool2(xn))
+
+    @staticmethod
+    def backward(ctx, dy):
+        xn, ctx.xn = ctx.xn, None
+        dn = E.to_nhwc(dy if dy.dtype == xn.dtype else dy.to(xn.dtype))
+        return E.to_nchw_view(E.maxpool2_bwd(xn, dn))
+
+
+def maxpool2(x):
+    return _MaxPool2Fn.apply(x)
+
+
+class _OutConvFn(torch.autograd.Function):
+    """the model's final 1x1 conv (ACC_UNet.py:596-599,653) -> fp32 logits, on the tiny-channel contraction kernels"""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        E.require_cuda(x)
+        xn = E.to_nhwc(x.detach())
+        B, H, W, C = xn.shape
+        N = weight.shape[0]
+        w = E.f32(weight)
+        y = E.conv([Op(Lazy(xn), C, WV(w, 0, C, 1))], N, (B, H, W), bias=E.f32(bias), out_dtype=E.F32)
+        ctx.xn, ctx.weight, ctx.bias = xn, weight, bias
+        return E.to_nchw_view(y)
+
+    @staticmethod
+    def backward(ctx, dy):
+        xn, weight, bias = ctx.xn, ctx.weight, ctx.bias
+        ctx.xn = None
+        B, H, W, C = xn.shape
+        N = weight.shape[0]
+        dims = (B, H, W)
+        w = E.f32(weight)
+        dn = E.to_nhwc(dy.float())
+        grads = E.GradPool([weight] + ([bias] if bias is not None else []))
+        gw, gb = None, None
+        if ctx.needs_input_grad[1]:
+            gw = E.grad_buf(grads, weight)
+            E.wgrad(Op(Lazy(xn), C, WV(w, 0, C, 1)), dn, N, dims, gw)
+        if bias is not None and ctx.needs_input_grad[2]:
+            gb = E.grad_buf(grads, bias)
+            torch.sum(dn.view(-1, N), dim=0, out=gb)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dl = dn if dn.dtype == xn.dtype else dn.to(xn.dtype)
+            dx = E.to_nchw_view(E.conv([Op(Lazy(dl), N, WV(w, 0, 1, C))], C, dims))
+        return dx, gw, gb
+
+
+def out_conv(x, conv: nn.Conv2d):
+    return _OutConvFn.apply(x, conv.weight, conv.bias)
+
+
 class _AccxModule(nn.Module):
     def _run(self, *xs):
         params = [p for p in self.parameters()]

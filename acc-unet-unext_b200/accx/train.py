@@ -3,10 +3,16 @@ gradient averaging, optional whole-step CUDA-graph capture.
 
 Mirrors the reference harness (Experiments/Train_one_epoch.py:107-129, train_model.py:647,719):
     preds = model(images); loss = WeightedDiceBCE(0.5, 0.5)(preds, masks); zero_grad; backward; Adam(lr=1e-3).step
-Data parallel (new functionality -- the reference has no distributed code): one
-process per GPU, rank-local BatchNorm statistics, gradients averaged with ONE NCCL all-reduce of a
-flat fp32 buffer per step; parameters whose gradient is None on every rank (ACC_UNet_Lite's unused
-MLFC convs) are left out of the bucket.
+
+Memory layout of the optimiser state (`FlatState`): ALL parameters live back to back in one flat fp32 buffer
+(every `p.data` is a view into it), and so do the gradients, `exp_avg` and `exp_avg_sq`.  Per step:
+  * one memset zeroes the flat gradient buffer; the accx backward kernels accumulate every parameter gradient
+    straight into its slice (`engine.GRAD_ARENA`), so `p.grad` IS a view of the flat buffer;
+  * data parallel (new functionality -- the reference has no distributed code): one process per
+    GPU, rank-local BatchNorm statistics, ONE in-place NCCL all-reduce (average) of the flat gradient buffer --
+    no gather / scatter copies; parameters that receive no gradient on any rank (ACC_UNet_Lite's unused MLFC
+    convs) keep a zero gradient, which leaves them and their Adam state untouched;
+  * one `accx_adam_step` launch updates all parameters (4 reads + 3 writes per element).
 """
 from __future__ import annotations
 
@@ -18,10 +24,11 @@ import torch.distributed as dist
 from . import engine as E
 
 
-def dice_bce_loss(logit: torch.Tensor, truth: torch.Tensor, dice_weight: float = 0.5, bce_weight: float = 0.5):
-    """WeightedDiceBCE(dice_weight, BCE_weight) with class weights [0.5, 0.5]
-    (Experiments/utils.py:21-74 BCE-with-logits normalised over positives / negatives,
-    :109-138 weighted soft Dice on sigmoid(logit), :140-171 the sum)."""
+def dice_bce_loss_torch(logit: torch.Tensor, truth: torch.Tensor, dice_weight: float = 0.5, bce_weight: float = 0.5):
+    """WeightedDiceBCE(dice_weight, BCE_weight) with class weights [0.5, 0.5] as a chain of torch operators
+    (Experiments/utils.py:21-74 BCE-with-logits normalised over positives / negatives, :109-138 weighted soft
+    Dice on sigmoid(logit), :140-171 the sum).  Host-logic tests (gloo, CPU) and the parity test of the fused
+    kernels use it; the train step does not."""
     B = logit.shape[0]
     lg = logit.reshape(B, -1).float()
     tr = truth.reshape(B, -1).float()
@@ -37,30 +44,149 @@ def dice_bce_loss(logit: torch.Tensor, truth: torch.Tensor, dice_weight: float =
     return dice_weight * dice + bce_weight * bce
 
 
-class GradAverager:
-    """Average gradients over the ranks of `group` with one all-reduce of a flat buffer."""
+class _DiceBCEFn(torch.autograd.Function):
+    """the same loss as two accx kernels: one reduction pass (per-image partial sums + the scalar), one
+    element-wise pass for d loss / d logit"""
 
-    def __init__(self, params: List[torch.nn.Parameter], group=None):
+    @staticmethod
+    def forward(ctx, logit, truth, dice_w, bce_w):
+        E.require_cuda(logit)
+        if logit.dim() == 4 and logit.shape[1] != 1:
+            raise E._lib.AccxError("accx dice_bce_loss implements the one-class case (n_classes = 1)")
+        B = logit.shape[0]
+        lg = logit.detach().reshape(B, -1)
+        if lg.dtype not in (torch.float32, torch.bfloat16):
+            lg = lg.float()
+        lg = lg.contiguous()
+        tr = truth.detach().reshape(B, -1).float().contiguous()
+        if tr.shape != lg.shape:
+            raise ValueError(f"dice_bce_loss: logits {tuple(logit.shape)} vs masks {tuple(truth.shape)}")
+        loss, sums = E.dice_bce_fwd(lg, tr, dice_w, bce_w)
+        ctx.saved = (lg, tr, sums)
+        ctx.w = (dice_w, bce_w)
+        ctx.shape, ctx.dtype = logit.shape, logit.dtype
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        lg, tr, sums = ctx.saved
+        ctx.saved = None
+        gs = g.detach().float().reshape(1).contiguous()
+        gdt = ctx.dtype if ctx.dtype in (torch.float32, torch.bfloat16) else torch.float32
+        d = E.dice_bce_bwd(lg, tr, sums, ctx.w[0], ctx.w[1], gs, gdt)
+        d = d.view(ctx.shape)
+        return (d if d.dtype == ctx.dtype else d.to(ctx.dtype)), None, None, None
+
+
+def dice_bce_loss(logit: torch.Tensor, truth: torch.Tensor, dice_weight: float = 0.5, bce_weight: float = 0.5):
+    """WeightedDiceBCE(dice_weight, BCE_weight) on one-class logits [B, 1, H, W] (CUDA, accx kernels; see
+    dice_bce_loss_torch for the formula and the reference lines)."""
+    return _DiceBCEFn.apply(logit, truth, float(dice_weight), float(bce_weight))
+
+
+class FlatState:
+    """Parameters, gradients and Adam moments of a model as four flat fp32 buffers (see the module docstring).
+    While `active()` the accx backward kernels write parameter gradients into the flat gradient buffer."""
+
+    ALIGN = 64          # elements: every slice starts 256-byte aligned (vector loads, TMA-able weight views)
+
+    def __init__(self, params: List[torch.nn.Parameter]):
+        self.params = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError("FlatState: no trainable parameters")
+        dev = self.params[0].device
+        for p in self.params:
+            if p.dtype != torch.float32 or p.device != dev:
+                raise TypeError("FlatState expects fp32 parameters on one device")
+        self.offsets, off = {}, 0
+        for p in self.params:
+            self.offsets[id(p)] = off
+            off += (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        self.n = off
+        self.param = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.exp_avg = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.step_state = torch.zeros(4, dtype=torch.float32, device=dev)      # [0] = step count
+        with torch.no_grad():
+            for p in self.params:
+                v = self._view(self.param, p)
+                v.copy_(p.data)
+                p.data = v                                                     # the parameter now lives in the flat buffer
+        self.taken = set()
+
+    def _view(self, flat, p):
+        o = self.offsets[id(p)]
+        return flat[o:o + p.numel()].view(p.shape)
+
+    # ---- engine.GRAD_ARENA protocol ------------------------------------------------------------------
+    def serves(self, p) -> bool:
+        return id(p) in self.offsets and id(p) not in self.taken
+
+    def take(self, p):
+        """fresh view of p's (zeroed) gradient slice; None if p is not ours or was already handed out this step
+        (a second use of the parameter then accumulates through autograd into the same slice)"""
+        if id(p) not in self.offsets or id(p) in self.taken:
+            return None
+        self.taken.add(id(p))
+        return self._view(self.grad, p)
+
+    def begin_step(self):
+        """zero the flat gradients (one memset) and drop the p.grad views of the previous step"""
+        for p in self.params:
+            p.grad = None
+        self.grad.zero_()
+        self.taken.clear()
+
+    def collect(self):
+        """after backward: gradients that autograd produced outside the flat buffer (parameters of torch-native
+        layers such as ConvTranspose2d) are copied into their slices, and p.grad is pointed at the slice"""
+        for p in self.params:
+            g = p.grad
+            if g is None:
+                continue
+            v = self._view(self.grad, p)
+            if g.data_ptr() != v.data_ptr():
+                v.copy_(g)
+                p.grad = v
+
+    def adam(self, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        E.adam_step(self.param, self.grad, self.exp_avg, self.exp_avg_sq, self.step_state, lr, betas[0], betas[1], eps,
+                    weight_decay)
+
+
+class GradAverager:
+    """Average gradients over the ranks of `group`: one in-place all-reduce of a flat buffer."""
+
+    def __init__(self, params: List[torch.nn.Parameter], group=None, flat: Optional[FlatState] = None):
         self.params = list(params)
         self.group = group
+        self.flat = flat
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+
+    def _allreduce_avg(self, buf):
+        if dist.get_backend(self.group) == "nccl":
+            dist.all_reduce(buf, op=dist.ReduceOp.AVG, group=self.group)
+        else:
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group)
+            buf.div_(self.world)
 
     def __call__(self):
         if self.world == 1:
             return
-        # ranks must agree on the bucket layout: ACC_UNet_Lite leaves the same parameters unused everywhere
+        if self.flat is not None:                  # gradients already live in one buffer: reduce it in place
+            self._allreduce_avg(self.flat.grad)
+            return
+        # loose gradients: ranks must agree on the bucket layout (ACC_UNet_Lite leaves the same parameters unused
+        # everywhere); one gather kernel, one all-reduce, multi-tensor scatter
         grads = [p.grad for p in self.params if p.grad is not None]
-        flat = torch.cat([g.reshape(-1) for g in grads])            # one gather kernel for the ~900 tensors
-        if dist.get_backend(self.group) == "nccl":
-            dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.group)
-        else:
-            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
-            flat.div_(self.world)
+        flat = torch.cat([g.reshape(-1) for g in grads])
+        self._allreduce_avg(flat)
         views, off = [], 0
         for g in grads:
             views.append(flat[off:off + g.numel()].view_as(g))
             off += g.numel()
-        torch._foreach_copy_(grads, views)                          # scatter back with multi-tensor kernels
+        torch._foreach_copy_(grads, views)
 
 
 class TrainStep:
@@ -69,29 +195,39 @@ class TrainStep:
     graph=True captures forward + loss + backward + (all-reduce) + Adam in a CUDA graph after
     `graph_warmup` eager steps; inputs are then copied into static buffers each step."""
 
-    def __init__(self, model: torch.nn.Module, lr: float = 1e-3, graph: bool = False, graph_warmup: int = 2):
+    def __init__(self, model: torch.nn.Module, lr: float = 1e-3, graph: bool = False, graph_warmup: int = 3,
+                 betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0):
         self.model = model
         self.params = [p for p in model.parameters() if p.requires_grad]
-        self.opt = torch.optim.Adam(self.params, lr=lr, capturable=graph, fused=True)     # one multi-tensor kernel chain
-        self.avg = GradAverager(self.params)
+        E.require_cuda(self.params[0])
+        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
+        self.flat = FlatState(self.params)
+        self.avg = GradAverager(self.params, flat=self.flat)
         self.use_graph = graph
         self.graph: Optional[torch.cuda.CUDAGraph] = None
-        self.graph_warmup = graph_warmup
+        self.graph_warmup = max(1, graph_warmup)
         self.calls = 0
         self.static_x = self.static_m = self.static_loss = None
 
     def _eager(self, x, m):
-        logits = self.model(x)
-        loss = dice_bce_loss(logits, m)
-        self.opt.zero_grad(set_to_none=True)
-        mode, E.SIDE_MODE = E.SIDE_MODE, (2 if E.SIDE_MODE else 0)     # weight gradients overlap the whole backward ...
+        flat = self.flat
+        flat.begin_step()
+        arena, E.GRAD_ARENA = E.GRAD_ARENA, flat
+        mode = E.SIDE_MODE
         try:
-            loss.backward()
+            logits = self.model(x)
+            loss = dice_bce_loss(logits, m)
+            E.SIDE_MODE = 2 if mode else 0             # weight gradients overlap the whole backward ...
+            try:
+                loss.backward()
+            finally:
+                E.join_side()                          # ... and are joined once, before the optimiser
+                E.SIDE_MODE = mode
         finally:
-            E.join_side()                                              # ... and are joined once, before the optimiser
-            E.SIDE_MODE = mode
+            E.GRAD_ARENA = arena
+        flat.collect()
         self.avg()
-        self.opt.step()
+        flat.adam(self.lr, self.betas, self.eps, self.weight_decay)
         return loss.detach()
 
     def __call__(self, x: torch.Tensor, m: torch.Tensor) -> torch.Tensor:
@@ -101,12 +237,9 @@ class TrainStep:
         if self.graph is None:
             if self.calls <= self.graph_warmup:
                 return self._eager(x, m)
+            # the eager warm-up steps above have created every stream / lazily initialised handle the step uses;
+            # capturing records the step without running it, the replay below is this call's ONE optimisation step
             self.static_x, self.static_m = x.clone(), m.clone()
-            s = torch.cuda.Stream()
-            s.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(s):            # one more eager step on the side stream (allocator warm-up)
-                self._eager(self.static_x, self.static_m)
-            torch.cuda.current_stream().wait_stream(s)
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph):
                 self.static_loss = self._eager(self.static_x, self.static_m)

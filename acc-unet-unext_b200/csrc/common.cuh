@@ -21,6 +21,17 @@ namespace accx {
 void set_error(const char* fmt, ...);
 int check_launch(const char* what);
 
+// Launch-geometry tuning knobs (accx_set_knob): 0 = the built-in default.  Used by tests/bench_knobs.py to sweep
+// blocks-per-SM / pixels-in-flight on the GPU; the defaults in the launchers are the winners of those sweeps.
+enum {
+  KNOB_SE_SQUEEZE_BLOCKS = 0, KNOB_SE_SQUEEZE_U, KNOB_SE_APPLY_BLOCKS, KNOB_SE_APPLY_STATS_BLOCKS, KNOB_SE_APPLY_U,
+  KNOB_SE_BWD_REDUCE_BLOCKS, KNOB_SE_BWD_REDUCE_U, KNOB_SE_BWD_APPLY_BLOCKS, KNOB_SE_BWD_APPLY_BN_BLOCKS,
+  KNOB_SE_BWD_APPLY_U, KNOB_BN_REDUCE_BLOCKS, KNOB_EW_BLOCKS, KNOB_POOL_BLOCKS, KNOB_SPARE0, KNOB_SPARE1, KNOB_SPARE2,
+  KNOB_COUNT
+};
+extern int g_knobs[KNOB_COUNT];
+inline int knob(int idx, int dflt) { return g_knobs[idx] > 0 ? g_knobs[idx] : dflt; }
+
 #define ACCX_REQUIRE(cond, ...)          \
   do {                                   \
     if (!(cond)) {                       \

@@ -8,6 +8,7 @@
 namespace accx {
 
 static thread_local char g_err[512] = "";
+int g_knobs[KNOB_COUNT] = {0};
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -378,6 +379,12 @@ using namespace accx;
 
 extern "C" {
 
+int accx_set_knob(int index, int value) {
+  ACCX_REQUIRE(index >= 0 && index < KNOB_COUNT, "set_knob: index %d out of range [0, %d)", index, (int)KNOB_COUNT);
+  g_knobs[index] = value;
+  return ACCX_OK;
+}
+
 const char* accx_last_error(void) { return g_err; }
 int accx_version(void) { return 100; }
 
@@ -432,7 +439,7 @@ int accx_bn_bwd_reduce(int dtype, int64_t P, int C, const void* y, const float* 
   ACCX_REQUIRE(P > 0 && C > 0 && y && da && sums && mean && rstd, "bn_bwd_reduce: bad arguments");
   ACCX_DISPATCH_T(dtype, {
     Lanes l = make_lanes(C, DT<T>::VEC, aligned16(y) && aligned16(da));
-    dim3 block(l.tx, l.ty), grid(grid_x_for(P, l.ty * 8, 148 * 2), l.gy);
+    dim3 block(l.tx, l.ty), grid(grid_x_for(P, l.ty * 8, 148 * knob(KNOB_BN_REDUCE_BLOCKS, 2)), l.gy);
     size_t sm = (size_t)l.tx * l.ty * l.vec * sizeof(float);
     ACCX_DISPATCH_VEC(l, {
       bn_bwd_reduce_kernel<T, VEC><<<grid, block, sm, (cudaStream_t)stream>>>(P, C, (const T*)y, scale, shift, act,

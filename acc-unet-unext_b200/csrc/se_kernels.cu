@@ -9,7 +9,7 @@
 namespace accx {
 
 // grid.x = B * chunks; each block reduces a slice of one image
-template <typename T, int VEC>
+template <typename T, int VEC, int U>
 __global__ void se_squeeze_kernel(int B, int HW, int C, int chunks, const T* __restrict__ x, const float* scale,
                                   const float* shift, int act, float* S) {
   extern __shared__ float smem[];
@@ -24,7 +24,6 @@ __global__ void se_squeeze_kernel(int B, int HW, int C, int chunks, const T* __r
   for (int i = 0; i < VEC; ++i) acc[0][i] = acc[1][i] = 0.f;
   if (active) {
     const T* img = x + (int64_t)b * HW * C + c0;
-    constexpr int U = 8;
     RawVec<T, VEC> rx[U];
     pixel_loop<U>(chunk * blockDim.y + threadIdx.y, HW, chunks * blockDim.y,
         [&](int u, int64_t p) { rx[u].load(img + p * C); },
@@ -134,7 +133,7 @@ __global__ void se_gate_kernel(int B, int C, int Cr, double HW, const float* __r
 
 // out = mixf( lrelu(a*gate[b,c]*se_scale[c] + se_shift[c]) , residual )
 // grid.x = B * chunks: a block works inside ONE image, so the gate (folded with the BN scale) lives in registers
-template <typename T, int VEC>
+template <typename T, int VEC, int U>
 __global__ void se_apply_kernel(int B, int HW, int C, int chunks, const T* __restrict__ x, const float* scale,
                                 const float* shift, int act, const float* __restrict__ gate, const float* se_scale,
                                 const float* se_shift, const T* __restrict__ residual, const float* mix,
@@ -161,7 +160,6 @@ __global__ void se_apply_kernel(int B, int HW, int C, int chunks, const T* __res
   for (int i = 0; i < VEC; ++i) acc[0][i] = acc[1][i] = 0.f;
   if (active) {
     const int64_t off = (int64_t)b * HW * C + c0;
-    constexpr int U = 8;
     RawVec<T, VEC> rv[U], rr[U];
     pixel_loop<U>(chunk * blockDim.y + threadIdx.y, HW, chunks * blockDim.y,
         [&](int u, int64_t p) {
@@ -189,7 +187,7 @@ __global__ void se_apply_kernel(int B, int HW, int C, int chunks, const T* __res
 }
 
 // G[0,b,c] += sum_hw g', G[1,b,c] += sum_hw g'*a;  g' = dout*mix*lrelu'(v);  dmix += sum dout*(v_act - r)
-template <typename T, int VEC>
+template <typename T, int VEC, int U>
 __global__ void se_bwd_reduce_kernel(int B, int HW, int C, int chunks, const T* __restrict__ x, const float* scale,
                                      const float* shift, int act, const float* __restrict__ gate,
                                      const float* se_scale, const float* se_shift, const T* __restrict__ dout,
@@ -212,7 +210,6 @@ __global__ void se_bwd_reduce_kernel(int B, int HW, int C, int chunks, const T* 
   for (int i = 0; i < VEC; ++i) acc[0][i] = acc[1][i] = 0.f;
   if (active) {
     const int64_t off = (int64_t)b * HW * C + c0;
-    constexpr int U = 4;
     RawVec<T, VEC> rv[U], rd[U], rr[U];
     pixel_loop<U>(chunk * blockDim.y + threadIdx.y, HW, chunks * blockDim.y,
         [&](int u, int64_t p) {
@@ -330,7 +327,7 @@ __global__ void se_bwd_gate_kernel(int B, int C, int Cr, double HW, const float*
 }
 
 // da (+)= P*g' + Q*a + R;  grid.x = B * chunks (one image per block: gate and P, Q, R in registers)
-template <typename T, int VEC>
+template <typename T, int VEC, int U>
 __global__ void se_bwd_apply_kernel(int B, int HW, int C, int chunks, const T* __restrict__ x, const float* scale,
                                     const float* shift, int act, const float* __restrict__ gate,
                                     const float* se_scale, const float* se_shift, const T* __restrict__ dout,
@@ -365,7 +362,6 @@ __global__ void se_bwd_apply_kernel(int B, int HW, int C, int chunks, const T* _
     for (int i = 0; i < VEC; ++i) { gs[i] *= g[i]; cp[i] *= mx; }
   }
   const int64_t off = (int64_t)b * HW * C + c0;
-  constexpr int U = 4;
   RawVec<T, VEC> rv[U], rd[U], ro[U];
   if (active)
   pixel_loop<U>(chunk * blockDim.y + threadIdx.y, HW, chunks * blockDim.y,
@@ -412,6 +408,14 @@ __global__ void se_bwd_apply_kernel(int B, int HW, int C, int chunks, const T* _
   }
 }
 
+// pixels in flight per thread: a compile-time unroll chosen at launch (tuning knob, else the per-kernel default)
+#define ACCX_DISPATCH_U(u, ...)                         \
+  do {                                                  \
+    if ((u) >= 16) { constexpr int U = 16; __VA_ARGS__ }  \
+    else if ((u) >= 8) { constexpr int U = 8; __VA_ARGS__ } \
+    else { constexpr int U = 4; __VA_ARGS__ }           \
+  } while (0)
+
 static inline int se_chunks(int B, int HW, int ty, int target_blocks = 148 * 4) {
   // enough blocks to fill the machine, but keep the number of atomics per (b,c) small
   int per_img = (HW + ty * 8 - 1) / (ty * 8);
@@ -431,12 +435,15 @@ int accx_se_squeeze(int dtype, int B, int HW, int C, const void* x, const float*
   ACCX_REQUIRE(B > 0 && HW > 0 && C > 0 && x && S, "se_squeeze: bad arguments");
   ACCX_DISPATCH_T(dtype, {
     Lanes l = make_lanes(C, DT<T>::VEC, aligned16(x));
-    int chunks = se_chunks(B, HW, l.ty, 148 * 2);
+    int chunks = se_chunks(B, HW, l.ty, 148 * knob(KNOB_SE_SQUEEZE_BLOCKS, 2));
     dim3 block(l.tx, l.ty), grid(B * chunks, l.gy);
     size_t sm = (size_t)l.tx * l.ty * l.vec * sizeof(float);
+    const int u = knob(KNOB_SE_SQUEEZE_U, 8);
     ACCX_DISPATCH_VEC(l, {
-      se_squeeze_kernel<T, VEC><<<grid, block, sm, (cudaStream_t)stream>>>(B, HW, C, chunks, (const T*)x, scale, shift,
-                                                                           act, S);
+      ACCX_DISPATCH_U(u, {
+        se_squeeze_kernel<T, VEC, U><<<grid, block, sm, (cudaStream_t)stream>>>(B, HW, C, chunks, (const T*)x, scale,
+                                                                                shift, act, S);
+      });
     });
   });
   return check_launch("se_squeeze");
@@ -459,16 +466,18 @@ int accx_se_apply(int dtype, int B, int HW, int C, const void* x, const float* s
                   const float* gate, const float* se_scale, const float* se_shift, const void* residual,
                   const float* mix, void* out, float* stats, void* stream) {
   ACCX_REQUIRE(B > 0 && HW > 0 && C > 0 && x && gate && se_scale && se_shift && out, "se_apply: bad arguments");
-  const int64_t P = (int64_t)B * HW;
   ACCX_DISPATCH_T(dtype, {
     Lanes l = make_lanes(C, DT<T>::VEC, aligned16(x) && aligned16(out) && (!residual || aligned16(residual)));
-    const int chunks = se_chunks(B, HW, l.ty, stats ? 148 * 2 : 148 * 8);
+    const int chunks = se_chunks(B, HW, l.ty, 148 * (stats ? knob(KNOB_SE_APPLY_STATS_BLOCKS, 2) : knob(KNOB_SE_APPLY_BLOCKS, 8)));
     dim3 block(l.tx, l.ty), grid(B * chunks, l.gy);
     size_t sm = (size_t)l.tx * l.ty * l.vec * sizeof(float);
+    const int u = knob(KNOB_SE_APPLY_U, 8);
     ACCX_DISPATCH_VEC(l, {
-      se_apply_kernel<T, VEC><<<grid, block, sm, (cudaStream_t)stream>>>(B, HW, C, chunks, (const T*)x, scale, shift, act, gate,
-                                                                         se_scale, se_shift, (const T*)residual, mix,
-                                                                         (T*)out, stats);
+      ACCX_DISPATCH_U(u, {
+        se_apply_kernel<T, VEC, U><<<grid, block, sm, (cudaStream_t)stream>>>(B, HW, C, chunks, (const T*)x, scale, shift, act,
+                                                                              gate, se_scale, se_shift, (const T*)residual,
+                                                                              mix, (T*)out, stats);
+      });
     });
   });
   return check_launch("se_apply");
@@ -481,13 +490,16 @@ int accx_se_bwd_reduce(int dtype, int B, int HW, int C, const void* x, const flo
   ACCX_REQUIRE(!dmix || (mix && residual), "se_bwd_reduce: dmix needs mix and residual");
   ACCX_DISPATCH_T(dtype, {
     Lanes l = make_lanes(C, DT<T>::VEC, aligned16(x) && aligned16(dout) && (!residual || aligned16(residual)));
-    int chunks = se_chunks(B, HW, l.ty, 148 * 2);
+    int chunks = se_chunks(B, HW, l.ty, 148 * knob(KNOB_SE_BWD_REDUCE_BLOCKS, 2));
     dim3 block(l.tx, l.ty), grid(B * chunks, l.gy);
     size_t sm = (size_t)l.tx * l.ty * l.vec * sizeof(float);
+    const int u = knob(KNOB_SE_BWD_REDUCE_U, 4);
     ACCX_DISPATCH_VEC(l, {
-      se_bwd_reduce_kernel<T, VEC><<<grid, block, sm, (cudaStream_t)stream>>>(
-          B, HW, C, chunks, (const T*)x, scale, shift, act, gate, se_scale, se_shift, (const T*)dout, mix,
-          (const T*)residual, dmix, G);
+      ACCX_DISPATCH_U(u, {
+        se_bwd_reduce_kernel<T, VEC, U><<<grid, block, sm, (cudaStream_t)stream>>>(
+            B, HW, C, chunks, (const T*)x, scale, shift, act, gate, se_scale, se_shift, (const T*)dout, mix,
+            (const T*)residual, dmix, G);
+      });
     });
   });
   return check_launch("se_bwd_reduce");
@@ -511,16 +523,19 @@ int accx_se_bwd_apply(int dtype, int B, int HW, int C, const void* x, const floa
                       const float* bn_rstd, float* bn_sums, void* stream) {
   ACCX_REQUIRE(B > 0 && HW > 0 && C > 0 && x && gate && dout && PQR && da, "se_bwd_apply: bad arguments");
   ACCX_REQUIRE(!bn_sums || (bn_mean && bn_rstd), "se_bwd_apply: bn_sums needs bn_mean and bn_rstd");
-  const int64_t P = (int64_t)B * HW;
   ACCX_DISPATCH_T(dtype, {
     Lanes l = make_lanes(C, DT<T>::VEC, aligned16(x) && aligned16(dout) && aligned16(da));
-    const int chunks = se_chunks(B, HW, l.ty, bn_sums ? 148 * 4 : 148 * 8);     // reducing: few blocks (atomics)
+    // reducing variant: few blocks (atomics)
+    const int chunks = se_chunks(B, HW, l.ty, 148 * (bn_sums ? knob(KNOB_SE_BWD_APPLY_BN_BLOCKS, 4) : knob(KNOB_SE_BWD_APPLY_BLOCKS, 8)));
     dim3 block(l.tx, l.ty), grid(B * chunks, l.gy);
     const size_t sm = bn_sums ? (size_t)l.tx * l.ty * l.vec * sizeof(float) : 0;
+    const int u = knob(KNOB_SE_BWD_APPLY_U, 4);
     ACCX_DISPATCH_VEC(l, {
-      se_bwd_apply_kernel<T, VEC><<<grid, block, sm, (cudaStream_t)stream>>>(
-          B, HW, C, chunks, (const T*)x, scale, shift, act, gate, se_scale, se_shift, (const T*)dout, mix, PQR, (T*)da,
-          accumulate, bn_mean, bn_rstd, bn_sums);
+      ACCX_DISPATCH_U(u, {
+        se_bwd_apply_kernel<T, VEC, U><<<grid, block, sm, (cudaStream_t)stream>>>(
+            B, HW, C, chunks, (const T*)x, scale, shift, act, gate, se_scale, se_shift, (const T*)dout, mix, PQR, (T*)da,
+            accumulate, bn_mean, bn_rstd, bn_sums);
+      });
     });
   });
   return check_launch("se_bwd_apply");

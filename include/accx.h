@@ -39,6 +39,9 @@ extern "C" {
 
 const char* accx_last_error(void);
 int accx_version(void);
+/* Launch-geometry tuning knob `index` (see KNOB_* in csrc/common.cuh) := value; 0 restores the built-in default.
+ * Process-global, meant for the sweeps in tests/bench_knobs.py -- results never depend on it. */
+int accx_set_knob(int index, int value);
 
 /* One A-operand of a pointwise contraction together with its weight slice.
  *   value(p, k) = act(data[p'*ld + k]*scale[k] + shift[k]),  p' = pixel p shifted by (dy, dx)
@@ -213,6 +216,30 @@ int accx_add_fwd(int dtype, int64_t P, int C, const void* a, const float* scale,
 /* NCHW <-> NHWC with optional dtype change (model entry / exit only). */
 int accx_nchw_to_nhwc(int in_dtype, int out_dtype, int B, int C, int HW, const void* src, void* dst, void* stream);
 int accx_nhwc_to_nchw(int in_dtype, int out_dtype, int B, int C, int HW, const void* src, void* dst, void* stream);
+
+/* ---- the steps either side of the blocks inside one training step ---- */
+
+/* MaxPool2d(2) between encoder levels (ACC_UNet.py:552,608-618), NHWC.  Backward recomputes the arg-max from
+ * the input and routes the gradient to the first maximum in row-major window order (ATen's tie rule);
+ * it writes every element of dx (H, W even). */
+int accx_maxpool2_fwd(int dtype, int B, int H, int W, int C, const void* x, void* out, void* stream);
+int accx_maxpool2_bwd(int dtype, int B, int H, int W, int C, const void* x, const void* dy, void* dx, void* stream);
+
+/* WeightedDiceBCE(dice_weight, BCE_weight) on one-class logits (Experiments/utils.py:21-74 BCE normalised over
+ * positives / negatives, :109-138 soft Dice on sigmoid(logit) with class weights [0.5, 0.5], :140-171 the sum).
+ * logit [B, N] (dtype), truth [B, N] fp32.  sums: float[8*B + 8], ZEROED by the caller (per-image partial sums
+ * + a block counter); loss: one float, written by the last block.  bwd: dlogit = gscale[0] * dloss/dlogit in
+ * grad_dtype (gscale may be NULL = 1). */
+int accx_dice_bce_fwd(int dtype, int B, int64_t N, const void* logit, const float* truth, float dice_w, float bce_w,
+                      float* sums, float* loss, void* stream);
+int accx_dice_bce_bwd(int dtype, int grad_dtype, int B, int64_t N, const void* logit, const float* truth,
+                      const float* sums, float dice_w, float bce_w, const float* gscale, void* dlogit, void* stream);
+
+/* torch.optim.Adam(lr) step (train_model.py:647) over ONE flat fp32 buffer holding all parameters back to
+ * back (n a multiple of 4, 16-byte aligned buffers).  state[0] = step count, kept on the device and incremented
+ * by the call (graph-capturable).  grad is multiplied by grad_scale first; weight_decay is torch's L2 form. */
+int accx_adam_step(int64_t n, float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* state,
+                   float lr, float beta1, float beta2, float eps, float weight_decay, float grad_scale, void* stream);
 
 #ifdef __cplusplus
 }

@@ -3,6 +3,8 @@
 The kernels need a GPU, the gradient exchange does not: GradAverager must average every live
 gradient over the ranks with one flat all-reduce, skip parameters whose gradient is None on every
 rank (ACC_UNet_Lite's unused MLFC convs, ACC_UNet_lite.py:424-427) and leave ranks bit-identical.
+Both layouts are covered: loose p.grad tensors (gather / all-reduce / scatter) and the train step's
+FlatState (gradients live in ONE flat buffer that is all-reduced in place).
 """
 import os
 import socket
@@ -24,14 +26,14 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, use_flat=False):
     for p in (ROOT, os.path.join(ROOT, "acc-unet-unext_b200")):
         if p not in sys.path:
             sys.path.insert(0, p)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from accx.train import GradAverager, dice_bce_loss
+    from accx.train import FlatState, GradAverager, dice_bce_loss_torch as dice_bce_loss
 
     torch.manual_seed(2)                                  # identical replicas
     net = torch.nn.Sequential(torch.nn.Conv2d(3, 4, 1), torch.nn.LeakyReLU(), torch.nn.Conv2d(4, 1, 1))
@@ -41,9 +43,17 @@ def _worker(rank, world, port, out_dir):
     x = torch.randn(2, 3, 8, 8, generator=g)
     m = (torch.rand(2, 1, 8, 8, generator=g) > 0.5).float()
     loss = dice_bce_loss(net(x), m)
+    flat = None
+    if use_flat:
+        flat = FlatState(params)                          # parameters / gradients move into flat buffers
+        flat.begin_step()
+        loss = dice_bce_loss(net(x), m)
     loss.backward()
     local = [None if p.grad is None else p.grad.clone() for p in params]
-    GradAverager(params)()
+    if use_flat:
+        flat.collect()                                    # autograd's loose gradients -> slices of flat.grad
+        assert all(p.grad is None or p.grad.data_ptr() == flat._view(flat.grad, p).data_ptr() for p in params)
+    GradAverager(params, flat=flat)()
     torch.save({"local": local, "avg": [None if p.grad is None else p.grad.clone() for p in params],
                 "loss": loss.detach()}, os.path.join(out_dir, f"r{rank}.pt"))
     dist.barrier()
@@ -51,9 +61,10 @@ def _worker(rank, world, port, out_dir):
 
 
 @pytest.mark.timeout(120)
-def test_grad_averager_world2_gloo(tmp_path):
+@pytest.mark.parametrize("use_flat", [False, True], ids=["loose", "flat"])
+def test_grad_averager_world2_gloo(tmp_path, use_flat):
     world = 2
-    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), use_flat), nprocs=world, join=True)
     r = [torch.load(os.path.join(tmp_path, f"r{i}.pt")) for i in range(world)]
     n = len(r[0]["local"])
     assert r[0]["avg"][-1] is None and r[1]["avg"][-1] is None          # unused parameter stays grad=None
@@ -72,3 +83,36 @@ def test_reference_arm_other_ranks_do_no_work(monkeypatch, capsys):
     import argparse
     bench.run_reference(argparse.Namespace(gpus=2, steps=1, warmup=1), rank=1)
     assert capsys.readouterr().out == ""
+
+
+def test_flat_state_layout_cpu():
+    """FlatState host logic: aligned slices, parameters become views, one-shot gradient hand-out per step"""
+    for p in (ROOT, os.path.join(ROOT, "acc-unet-unext_b200")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    from accx.train import FlatState
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Conv2d(3, 5, 3), torch.nn.BatchNorm2d(5), torch.nn.Linear(7, 3))
+    before = [p.detach().clone() for p in net.parameters()]
+    params = list(net.parameters())
+    fs = FlatState(params)
+    assert fs.n % FlatState.ALIGN == 0 and all(o % FlatState.ALIGN == 0 for o in fs.offsets.values())
+    for p, b in zip(params, before):
+        assert torch.equal(p.detach(), b)                                       # values preserved
+        o = fs.offsets[id(p)]
+        assert p.data_ptr() == fs.param.data_ptr() + 4 * o                      # p lives in the flat buffer
+    assert list(net.state_dict().keys())[:2] == ["0.weight", "0.bias"]          # names / shapes untouched
+    fs.begin_step()
+    p0 = params[0]
+    assert fs.serves(p0)
+    g = fs.take(p0)
+    assert g.shape == p0.shape and g.data_ptr() == fs.grad.data_ptr() + 4 * fs.offsets[id(p0)]
+    assert not fs.serves(p0) and fs.take(p0) is None                            # handed out once per step
+    assert fs.take(torch.nn.Parameter(torch.zeros(2))) is None                  # foreign parameter
+    g.add_(1.0)
+    params[1].grad = torch.full_like(params[1], 2.0)                            # a loose gradient made by autograd
+    fs.collect()
+    assert params[1].grad.data_ptr() == fs._view(fs.grad, params[1]).data_ptr()
+    assert float(fs.grad.sum()) == p0.numel() * 1.0 + params[1].numel() * 2.0   # padding stays zero
+    fs.begin_step()
+    assert float(fs.grad.abs().sum()) == 0.0 and all(p.grad is None for p in params) and fs.serves(p0)
