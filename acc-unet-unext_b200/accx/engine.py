@@ -53,6 +53,10 @@ def _call(name, *args, cost=(0, 0), tag=""):
 #   2: join only when join_side() is called (TrainStep: once, before the optimiser).  Tensors the side
 #   stream reads are kept alive in _KEEP until the join so the caching allocator cannot recycle them.
 SIDE_MODE = int(os.environ.get("ACCX_WGRAD_STREAM", "1"))
+# CUDA stream priorities (lower number = scheduled first): the chain of input gradients is the critical path, the
+# weight gradients only have to be done before the optimiser, so the side stream yields to the main stream / lanes
+SIDE_PRIORITY = int(os.environ.get("ACCX_SIDE_PRIO", "0"))
+MAIN_PRIORITY = int(os.environ.get("ACCX_MAIN_PRIO", "-3"))
 BWD_DEPTH = [0]
 _SIDE = {}
 _SIDE_DIRTY = set()
@@ -75,7 +79,7 @@ class side_stream:
         dev = torch.cuda.current_device()
         s = _SIDE.get(dev)
         if s is None:
-            s = _SIDE[dev] = torch.cuda.Stream(device=dev)
+            s = _SIDE[dev] = torch.cuda.Stream(device=dev, priority=SIDE_PRIORITY)
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream())
         s.wait_event(ev)
@@ -136,7 +140,7 @@ class fork_lanes:
             dev = torch.cuda.current_device()
             pool = _LANE_STREAMS.setdefault(dev, [])
             while len(pool) < self.n:
-                pool.append(torch.cuda.Stream(device=dev))
+                pool.append(torch.cuda.Stream(device=dev, priority=MAIN_PRIORITY))
             self.pool = pool
             self.ev = torch.cuda.Event()
             self.ev.record(self.main)

@@ -241,7 +241,8 @@ class TrainStep:
             # capturing records the step without running it, the replay below is this call's ONE optimisation step
             self.static_x, self.static_m = x.clone(), m.clone()
             self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph):
+            cap = torch.cuda.Stream(priority=E.MAIN_PRIORITY)       # kernel nodes inherit the capture stream's priority
+            with torch.cuda.graph(self.graph, stream=cap):
                 self.static_loss = self._eager(self.static_x, self.static_m)
         self.static_x.copy_(x, non_blocking=True)
         self.static_m.copy_(m, non_blocking=True)

@@ -11,6 +11,10 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <utility>
 
 #include "../../include/accx.h"
 
@@ -31,6 +35,45 @@ enum {
 };
 extern int g_knobs[KNOB_COUNT];
 inline int knob(int idx, int dflt) { return g_knobs[idx] > 0 ? g_knobs[idx] : dflt; }
+
+// ---- programmatic dependent launch -----------------------------------------------------------------------------
+// A training step is a chain of ~2000 dependent launches; ~500 of them are tiny single-wave kernels (BatchNorm
+// finalize, the SE gate kernels, weight re-packs) whose cost is launch latency.  Kernels launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization start with pdl_sync(): their blocks are scheduled while the
+// previous kernel drains and park in griddepcontrol.wait until it (and, transitively, everything before it) has
+// completed and flushed.  The trigger comes after the wait, so at most ONE dependent grid is parked at a time.
+// Captured into the step's CUDA graph as programmatic edges.  Measured on B200 (bench step, ms): attribute on every
+// launch 41.0 (parked blocks of big grids take SM slots from the concurrent lanes), never 38.26, grids <= 148 blocks
+// 38.19, grids <= 32 blocks 37.87 -> the default.  ACCX_PDL: 0 = never, 1 = every launch, N > 1 = grids <= N blocks.
+__device__ __forceinline__ void pdl_sync() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+inline int pdl_mode() {
+  static const int mode = [] {
+    const char* e = getenv("ACCX_PDL");
+    return e ? atoi(e) : 32;
+  }();
+  return mode;
+}
+
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1] = {};
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  const int mode = pdl_mode();
+  const unsigned long long blocks = (unsigned long long)grid.x * grid.y * grid.z;
+  cfg.numAttrs = (mode == 1 || (mode > 1 && blocks <= (unsigned long long)mode)) ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(std::forward<Args>(args))...);
+}
 
 #define ACCX_REQUIRE(cond, ...)          \
   do {                                   \

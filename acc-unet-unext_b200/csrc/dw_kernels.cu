@@ -14,6 +14,7 @@ template <typename T, int VEC>
 __global__ void __launch_bounds__(256, 2) dw3x3_fwd_kernel(int B, int H, int W, int C, const T* __restrict__ x, const float* scale,
                                  const float* shift, int act, const float* __restrict__ w,
                                  const float* __restrict__ bias, int flip, T* __restrict__ y, float* stats) {
+  pdl_sync();
   extern __shared__ float smem[];
   const int cv = blockIdx.y * blockDim.x + threadIdx.x;
   const bool active = cv * VEC < C;
@@ -94,6 +95,7 @@ __global__ void __launch_bounds__(256, 2) dw3x3_fwd_kernel(int B, int H, int W, 
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256, 2) dw3x3_wgrad_kernel(int B, int H, int W, int C, const T* __restrict__ x, const float* scale,
                                    const float* shift, int act, const T* __restrict__ dy, float* dw) {
+  pdl_sync();
   extern __shared__ float smem[];
   const int cv = blockIdx.y * blockDim.x + threadIdx.x;
   const bool active = cv * VEC < C;
@@ -217,10 +219,10 @@ int accx_dw3x3_fwd(int dtype, int B, int H, int W, int C, const void* x, const f
     dim3 block(l.tx, l.ty), grid(grid_x_for(n_strips, l.ty * 2, 148 * 12), l.gy);
     size_t sm = (size_t)l.tx * l.ty * l.vec * sizeof(float);
     if (l.vec == 1)
-      dw3x3_fwd_kernel<T, 1><<<grid, block, sm, (cudaStream_t)stream>>>(B, H, W, C, (const T*)x, scale, shift, act, w,
+      launch_k(dw3x3_fwd_kernel<T, 1>, grid, block, sm, (cudaStream_t)stream, B, H, W, C, (const T*)x, scale, shift, act, w,
                                                                         bias, flip, (T*)y, stats);
     else
-      dw3x3_fwd_kernel<T, 4><<<grid, block, sm, (cudaStream_t)stream>>>(B, H, W, C, (const T*)x, scale, shift, act, w,
+      launch_k(dw3x3_fwd_kernel<T, 4>, grid, block, sm, (cudaStream_t)stream, B, H, W, C, (const T*)x, scale, shift, act, w,
                                                                         bias, flip, (T*)y, stats);
   });
   return check_launch("dw3x3_fwd");
@@ -238,10 +240,10 @@ int accx_dw3x3_wgrad(int dtype, int B, int H, int W, int C, const void* x, const
     dim3 block(l.tx, l.ty), grid(grid_x_for(n_strips, l.ty * 4, 148 * 3), l.gy);
     size_t sm = (size_t)l.tx * l.ty * l.vec * sizeof(float);
     if (l.vec == 1)
-      dw3x3_wgrad_kernel<T, 1><<<grid, block, sm, (cudaStream_t)stream>>>(B, H, W, C, (const T*)x, scale, shift, act,
+      launch_k(dw3x3_wgrad_kernel<T, 1>, grid, block, sm, (cudaStream_t)stream, B, H, W, C, (const T*)x, scale, shift, act,
                                                                           (const T*)dy, dw);
     else
-      dw3x3_wgrad_kernel<T, 4><<<grid, block, sm, (cudaStream_t)stream>>>(B, H, W, C, (const T*)x, scale, shift, act,
+      launch_k(dw3x3_wgrad_kernel<T, 4>, grid, block, sm, (cudaStream_t)stream, B, H, W, C, (const T*)x, scale, shift, act,
                                                                           (const T*)dy, dw);
   });
   return check_launch("dw3x3_wgrad");

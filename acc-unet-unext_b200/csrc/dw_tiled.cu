@@ -168,6 +168,7 @@ __device__ __forceinline__ void dw_flush(const DwParams& prm, float (&acc)[NV][4
 // MODE 0: forward / input gradient (flip);  1: weight gradient;  2: input gradient + BN-backward reduction
 template <typename T, int TH, int MODE>
 __global__ void __launch_bounds__(DW_THREADS, 2) dw3x3_tiled_kernel(const __grid_constant__ DwParams prm) {
+  pdl_sync();
   constexpr bool WGRAD = MODE == 1, BOX2 = MODE != 0;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
@@ -437,7 +438,7 @@ static int dw_launch(DwParams& prm, const void* x, const void* dy, cudaStream_t 
   const int64_t total = prm.n_spatial * prm.n_chunks;
   int64_t grid = 2 * (int64_t)sm_count();
   if (grid > total) grid = total;
-  kern<<<(unsigned)grid, DW_THREADS, smem, st>>>(prm);
+  launch_k(kern, (unsigned)grid, DW_THREADS, smem, st, prm);
   return ACCX_OK;
 }
 

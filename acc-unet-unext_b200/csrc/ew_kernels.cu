@@ -32,6 +32,7 @@ __global__ void bn_finalize_kernel(int C, double count, const float* __restrict_
                                    const float* __restrict__ conv_bias, float eps,
                                    float momentum, int training, float* running_mean, float* running_var,
                                    int64_t* nbt, float* scale, float* shift, float* mean_o, float* rstd_o) {
+  pdl_sync();
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c == 0 && training && nbt) *nbt += 1;
   if (c >= C) return;
@@ -65,6 +66,7 @@ template <typename T, int VEC>
 __global__ void act_apply_kernel(int64_t P, int C, const T* __restrict__ x, const float* scale, const float* shift,
                                  int act, const float* scale2, const float* shift2, const T* __restrict__ residual,
                                  T* __restrict__ out, float* stats) {
+  pdl_sync();
   extern __shared__ float smem[];
   const int cv = blockIdx.y * blockDim.x + threadIdx.x;
   const bool active = cv * VEC < C;
@@ -110,6 +112,7 @@ __global__ void act_apply_kernel(int64_t P, int C, const T* __restrict__ x, cons
 template <typename T, int VEC>
 __global__ void add_fwd_kernel(int64_t P, int C, const T* __restrict__ a, const float* scale, const float* shift,
                                int act, const T* __restrict__ r, T* __restrict__ z, float* stats) {
+  pdl_sync();
   extern __shared__ float smem[];
   const int cv = blockIdx.y * blockDim.x + threadIdx.x;
   const bool active = cv * VEC < C;
@@ -149,6 +152,7 @@ template <typename T, int VEC>
 __global__ void bn_bwd_reduce_kernel(int64_t P, int C, const T* __restrict__ y, const float* scale,
                                      const float* shift, int act, const float* mean, const float* rstd,
                                      const T* __restrict__ da, float* sums) {
+  pdl_sync();
   extern __shared__ float smem[];
   const int cv = blockIdx.y * blockDim.x + threadIdx.x;
   const bool active = cv * VEC < C;
@@ -189,6 +193,7 @@ __global__ void bn_bwd_apply_kernel(int64_t P, int C, const T* __restrict__ y, c
                                     int act, const float* mean, const float* rstd, const float* gamma,
                                     const T* __restrict__ da, const float* __restrict__ sums, float inv_count,
                                     T* __restrict__ dy, float* dgamma, float* dbeta) {
+  pdl_sync();
   const int cv = blockIdx.y * blockDim.x + threadIdx.x;
   if (cv * VEC >= C) return;
   const int c0 = cv * VEC;
@@ -235,6 +240,7 @@ __global__ void bn_bwd_apply_kernel(int64_t P, int C, const T* __restrict__ y, c
 template <typename TI, typename TO, int VEC, int S>
 __global__ void pool_sum_kernel(int B, int H, int W, int C, int log2s, float mul, const TI* __restrict__ x,
                                 TO* __restrict__ out, int64_t out_ld) {
+  pdl_sync();
   const int cv = blockIdx.y * blockDim.x + threadIdx.x;
   if (cv * VEC >= C) return;
   const int c0 = cv * VEC;
@@ -284,6 +290,7 @@ __global__ void pool_sum_kernel(int B, int H, int W, int C, int log2s, float mul
 template <typename TI, typename TO, int VEC>
 __global__ void upsample_add_kernel(int B, int H, int W, int C, int log2s, float mul, const TI* __restrict__ src,
                                     int64_t src_ld, TO* __restrict__ dst, int accumulate) {
+  pdl_sync();
   const int cv = blockIdx.y * blockDim.x + threadIdx.x;
   if (cv * VEC >= C) return;
   const int c0 = cv * VEC;
@@ -313,6 +320,7 @@ __global__ void upsample_add_kernel(int B, int H, int W, int C, int log2s, float
 // [B, C, HW] <-> [B, HW, C] through a 32x32 shared tile
 template <typename TI, typename TO>
 __global__ void transpose_kernel(int rows, int cols, const TI* __restrict__ src, TO* __restrict__ dst) {
+  pdl_sync();
   // per batch: src [rows, cols] -> dst [cols, rows]
   __shared__ float tile[32][33];
   const TI* s = src + (int64_t)blockIdx.z * rows * cols;
@@ -333,7 +341,7 @@ __global__ void transpose_kernel(int rows, int cols, const TI* __restrict__ src,
 template <typename TI, typename TO>
 static int launch_transpose(int B, int rows, int cols, const void* src, void* dst, cudaStream_t st) {
   dim3 grid((cols + 31) / 32, (rows + 31) / 32, B), block(32, 8);
-  transpose_kernel<TI, TO><<<grid, block, 0, st>>>(rows, cols, (const TI*)src, (TO*)dst);
+  launch_k(transpose_kernel<TI, TO>, grid, block, 0, st, rows, cols, (const TI*)src, (TO*)dst);
   return check_launch("transpose");
 }
 
@@ -361,15 +369,15 @@ static int launch_pool_sum(int B, int H, int W, int C, int log2s, float mul, con
     if (l.vec != 1) {
       constexpr int V = DT<TI>::VEC;
       if (log2s == 1)
-        pool_sum_kernel<TI, TO, V, 2><<<grid, block, 0, st>>>(B, H, W, C, log2s, mul, (const TI*)x, (TO*)out, out_ld);
+        launch_k(pool_sum_kernel<TI, TO, V, 2>, grid, block, 0, st, B, H, W, C, log2s, mul, (const TI*)x, (TO*)out, out_ld);
       else if (log2s == 2)
-        pool_sum_kernel<TI, TO, V, 4><<<grid, block, 0, st>>>(B, H, W, C, log2s, mul, (const TI*)x, (TO*)out, out_ld);
+        launch_k(pool_sum_kernel<TI, TO, V, 4>, grid, block, 0, st, B, H, W, C, log2s, mul, (const TI*)x, (TO*)out, out_ld);
       else
-        pool_sum_kernel<TI, TO, V, 0><<<grid, block, 0, st>>>(B, H, W, C, log2s, mul, (const TI*)x, (TO*)out, out_ld);
+        launch_k(pool_sum_kernel<TI, TO, V, 0>, grid, block, 0, st, B, H, W, C, log2s, mul, (const TI*)x, (TO*)out, out_ld);
       return check_launch("pool_sum");
     }
   }
-  pool_sum_kernel<TI, TO, 1, 0><<<grid, block, 0, st>>>(B, H, W, C, log2s, mul, (const TI*)x, (TO*)out, out_ld);
+  launch_k(pool_sum_kernel<TI, TO, 1, 0>, grid, block, 0, st, B, H, W, C, log2s, mul, (const TI*)x, (TO*)out, out_ld);
   return check_launch("pool_sum");
 }
 
@@ -394,7 +402,7 @@ int accx_bn_finalize(int C, double count, const float* stats, const float* gamma
   ACCX_REQUIRE(C > 0 && gamma && beta && scale && shift, "bn_finalize: bad arguments");
   ACCX_REQUIRE(training ? (stats != nullptr && count > 0) : (running_mean && running_var),
                "bn_finalize: missing statistics");
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+  launch_k(bn_finalize_kernel, (C + 127) / 128, 128, 0, (cudaStream_t)stream, 
       C, count, stats, gamma, beta, conv_bias, eps, momentum, training, running_mean, running_var, nbt, scale, shift,
       mean, rstd);
   return check_launch("bn_finalize");
@@ -412,7 +420,7 @@ int accx_act_apply(int dtype, int64_t P, int C, const void* x, const float* scal
     dim3 block(l.tx, l.ty), grid(grid_x_for(P, l.ty * 8, stats ? 148 * 2 : 148 * 8), l.gy);
     size_t sm = (size_t)l.tx * l.ty * l.vec * sizeof(float);
     ACCX_DISPATCH_VEC(l, {
-      act_apply_kernel<T, VEC><<<grid, block, sm, (cudaStream_t)stream>>>(
+      launch_k(act_apply_kernel<T, VEC>, grid, block, sm, (cudaStream_t)stream, 
           P, C, (const T*)x, scale, shift, act, scale2, shift2, (const T*)residual, (T*)out, stats);
     });
   });
@@ -427,7 +435,7 @@ int accx_add_fwd(int dtype, int64_t P, int C, const void* a, const float* scale,
     dim3 block(l.tx, l.ty), grid(grid_x_for(P, l.ty * 8, stats ? 148 * 2 : 148 * 8), l.gy);
     size_t sm = (size_t)l.tx * l.ty * l.vec * sizeof(float);
     ACCX_DISPATCH_VEC(l, {
-      add_fwd_kernel<T, VEC><<<grid, block, sm, (cudaStream_t)stream>>>(P, C, (const T*)a, scale, shift, act,
+      launch_k(add_fwd_kernel<T, VEC>, grid, block, sm, (cudaStream_t)stream, P, C, (const T*)a, scale, shift, act,
                                                                         (const T*)r, (T*)z, stats);
     });
   });
@@ -442,7 +450,7 @@ int accx_bn_bwd_reduce(int dtype, int64_t P, int C, const void* y, const float* 
     dim3 block(l.tx, l.ty), grid(grid_x_for(P, l.ty * 8, 148 * knob(KNOB_BN_REDUCE_BLOCKS, 2)), l.gy);
     size_t sm = (size_t)l.tx * l.ty * l.vec * sizeof(float);
     ACCX_DISPATCH_VEC(l, {
-      bn_bwd_reduce_kernel<T, VEC><<<grid, block, sm, (cudaStream_t)stream>>>(P, C, (const T*)y, scale, shift, act,
+      launch_k(bn_bwd_reduce_kernel<T, VEC>, grid, block, sm, (cudaStream_t)stream, P, C, (const T*)y, scale, shift, act,
                                                                               mean, rstd, (const T*)da, sums);
     });
   });
@@ -457,7 +465,7 @@ int accx_bn_bwd_apply(int dtype, int64_t P, int C, const void* y, const float* s
     Lanes l = make_lanes(C, DT<T>::VEC, aligned16(y) && aligned16(da) && aligned16(dy));
     dim3 block(l.tx, l.ty), grid(grid_x_for(P, l.ty * 8, 148 * 8), l.gy);
     ACCX_DISPATCH_VEC(l, {
-      bn_bwd_apply_kernel<T, VEC><<<grid, block, 0, (cudaStream_t)stream>>>(
+      launch_k(bn_bwd_apply_kernel<T, VEC>, grid, block, 0, (cudaStream_t)stream, 
           P, C, (const T*)y, scale, shift, act, mean, rstd, gamma, (const T*)da, sums, (float)(1.0 / count), (T*)dy,
           dgamma, dbeta);
     });
@@ -501,10 +509,10 @@ int accx_upsample_add(int in_dtype, int out_dtype, int B, int H, int W, int C, i
     Lanes l = make_lanes(C, DT<TI>::VEC, al);
     dim3 block(l.tx, l.ty), grid(grid_x_for(P, l.ty * 8, 148 * 8), l.gy);
     if (l.vec == 1) {
-      upsample_add_kernel<TI, TO, 1><<<grid, block, 0, (cudaStream_t)stream>>>(B, H, W, C, log2s, mul, (const TI*)src,
+      launch_k(upsample_add_kernel<TI, TO, 1>, grid, block, 0, (cudaStream_t)stream, B, H, W, C, log2s, mul, (const TI*)src,
                                                                               src_ld, (TO*)dst, accumulate);
     } else {
-      upsample_add_kernel<TI, TI, DT<TI>::VEC><<<grid, block, 0, (cudaStream_t)stream>>>(
+      launch_k(upsample_add_kernel<TI, TI, DT<TI>::VEC>, grid, block, 0, (cudaStream_t)stream, 
           B, H, W, C, log2s, mul, (const TI*)src, src_ld, (TI*)dst, accumulate);
     }
   });

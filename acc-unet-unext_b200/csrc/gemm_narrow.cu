@@ -34,6 +34,7 @@ __device__ __forceinline__ void narrow_block_reduce_atomic(float (&v)[NV], float
 
 template <typename T, typename TO, int KT, int NT>
 __global__ void __launch_bounds__(NAR_THREADS) pw_fwd_narrow_kernel(const __grid_constant__ NarrowParams prm) {
+  pdl_sync();
   __shared__ float Ws[NT][KT];                 // weights, zero padded
   __shared__ float sc[KT], sh[KT], slope[KT];  // pending affine + LeakyReLU slope per concatenated k
   __shared__ const T* kptr[KT];                // operand base (+ column) per concatenated k
@@ -122,6 +123,7 @@ template <typename T, typename TG, int KT, int NT>
 __global__ void __launch_bounds__(NAR_THREADS) pw_wgrad_narrow_kernel(accx_operand_t op, int N, int64_t P,
                                                                       const TG* __restrict__ dy, int64_t ldy,
                                                                       float* dw) {
+  pdl_sync();
   __shared__ float sc[KT], sh[KT];
   __shared__ float red[(NAR_THREADS / 32) * NT * KT];
   __shared__ int widx[NT * KT];
@@ -170,7 +172,7 @@ static int launch_fwd_narrow(const NarrowParams& prm, cudaStream_t st) {
   const int K = prm.k_total, N = prm.N;
 #define ACCX_NARROW_FWD(KT, NT)                                                        \
   if (K <= KT && N <= NT) {                                                            \
-    pw_fwd_narrow_kernel<T, TO, KT, NT><<<blocks, NAR_THREADS, 0, st>>>(prm);          \
+    launch_k(pw_fwd_narrow_kernel<T, TO, KT, NT>, blocks, NAR_THREADS, 0, st, prm);          \
     return check_launch("pw_fwd(narrow)");                                             \
   }
   ACCX_NARROW_FWD(4, 12)
@@ -210,7 +212,7 @@ static int launch_wgrad_narrow(const accx_operand_t& op, int N, int64_t P, const
   const int K = op.K;
 #define ACCX_NARROW_WG(KT, NT)                                                                               \
   if (K <= KT && N <= NT) {                                                                                  \
-    pw_wgrad_narrow_kernel<T, TG, KT, NT><<<blocks, NAR_THREADS, 0, st>>>(op, N, P, (const TG*)dy, ldy, dw); \
+    launch_k(pw_wgrad_narrow_kernel<T, TG, KT, NT>, blocks, NAR_THREADS, 0, st, op, N, P, (const TG*)dy, ldy, dw); \
     return check_launch("pw_wgrad(narrow)");                                                                 \
   }
   ACCX_NARROW_WG(4, 12)

@@ -46,6 +46,7 @@ __device__ __forceinline__ void load8(const T* __restrict__ src, int k, int K, b
 
 template <typename T, typename TO, int TN>
 __global__ void __launch_bounds__(NTHREADS) pw_fwd_kernel(const __grid_constant__ PwParams prm) {
+  pdl_sync();
   constexpr int BN = 16 * TN;
   __shared__ __align__(16) float As[BK][BM];
   __shared__ __align__(16) float Ws[BK][BN];
@@ -196,6 +197,7 @@ template <typename T, typename TG>
 __global__ void __launch_bounds__(NTHREADS) pw_wgrad_kernel(accx_operand_t op, int B, int H, int W, int N, int64_t P,
                                                             const TG* __restrict__ dy, int64_t ldy, float* dw,
                                                             int64_t p_per_split) {
+  pdl_sync();
   __shared__ __align__(16) float Gs[WG_P][WG_T];   // dY tile  [pixel][n]
   __shared__ __align__(16) float Xs[WG_P][WG_T];   // A tile   [pixel][k]
   const int tid = threadIdx.x;
@@ -282,13 +284,13 @@ static int launch_pw(const PwParams& prm, cudaStream_t st) {
   const int gx = (int)((prm.P + BM - 1) / BM);
   if (prm.N <= 32) {
     dim3 grid(gx, (prm.N + 31) / 32);
-    pw_fwd_kernel<T, TO, 2><<<grid, NTHREADS, 0, st>>>(prm);
+    launch_k(pw_fwd_kernel<T, TO, 2>, grid, NTHREADS, 0, st, prm);
   } else if (prm.N <= 64 || prm.N % 128 != 0) {
     dim3 grid(gx, (prm.N + 63) / 64);
-    pw_fwd_kernel<T, TO, 4><<<grid, NTHREADS, 0, st>>>(prm);
+    launch_k(pw_fwd_kernel<T, TO, 4>, grid, NTHREADS, 0, st, prm);
   } else {
     dim3 grid(gx, (prm.N + 127) / 128);
-    pw_fwd_kernel<T, TO, 8><<<grid, NTHREADS, 0, st>>>(prm);
+    launch_k(pw_fwd_kernel<T, TO, 8>, grid, NTHREADS, 0, st, prm);
   }
   return check_launch("pw_fwd");
 }
@@ -370,11 +372,11 @@ int accx_pw_wgrad(int dtype, int B, int H, int W, int N, const accx_operand_t* o
   dim3 grid(gx, gy, (unsigned)splits);
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == ACCX_F32) {
-    pw_wgrad_kernel<float, float><<<grid, NTHREADS, 0, st>>>(*op, B, H, W, N, P, (const float*)dy, ldy, dw, per);
+    launch_k(pw_wgrad_kernel<float, float>, grid, NTHREADS, 0, st, *op, B, H, W, N, P, (const float*)dy, ldy, dw, per);
   } else if (dtype == ACCX_BF16 && dy_f32) {
-    pw_wgrad_kernel<bf16, float><<<grid, NTHREADS, 0, st>>>(*op, B, H, W, N, P, (const float*)dy, ldy, dw, per);
+    launch_k(pw_wgrad_kernel<bf16, float>, grid, NTHREADS, 0, st, *op, B, H, W, N, P, (const float*)dy, ldy, dw, per);
   } else if (dtype == ACCX_BF16) {
-    pw_wgrad_kernel<bf16, bf16><<<grid, NTHREADS, 0, st>>>(*op, B, H, W, N, P, (const bf16*)dy, ldy, dw, per);
+    launch_k(pw_wgrad_kernel<bf16, bf16>, grid, NTHREADS, 0, st, *op, B, H, W, N, P, (const bf16*)dy, ldy, dw, per);
   } else {
     set_error("pw_wgrad: bad dtype %d", dtype);
     return ACCX_ERR_INVALID;

@@ -54,6 +54,7 @@ struct alignas(64) TcParams {
 // ---------------------------------------------------------------- weight packing
 // wpack[(n_tile * n_kb + kb) * bn * 64 + swizzled(n_local, kk)] = bf16(W_op[n, k0 + kk])
 __global__ void tc_pack_weights_kernel(const __grid_constant__ TcParams prm, bf16* __restrict__ wpack) {
+  pdl_sync();
   const int kb = blockIdx.x, nt = blockIdx.y;
   int o = 0;
   while (o + 1 < prm.n_ops && kb >= prm.kb_start[o + 1]) ++o;
@@ -105,6 +106,7 @@ __device__ __forceinline__ void stage_chunk(const float (&v)[16], uint32_t stage
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1) pw_fwd_tc_kernel(const __grid_constant__ TcParams prm) {
+  pdl_sync();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
@@ -621,7 +623,7 @@ int accx_pw_fwd_tc(int dtype, int out_dtype, int B, int H, int W, int N, const a
   prm.stats = stats;
   cudaStream_t st = (cudaStream_t)stream;
   if (!prm.b_resident) {     // streamed weight tiles come from a bf16 re-pack in the workspace
-    tc_pack_weights_kernel<<<dim3(prm.n_kb, n_tiles, (prm.bn * TC_BK + 1023) / 1024), 256, 0, st>>>(prm, (bf16*)workspace);
+    launch_k(tc_pack_weights_kernel, dim3(prm.n_kb, n_tiles, (prm.bn * TC_BK + 1023) / 1024), 256, 0, st, prm, (bf16*)workspace);
     int rc = check_launch("tc_pack_weights");
     if (rc) return rc;
   }
@@ -633,7 +635,7 @@ int accx_pw_fwd_tc(int dtype, int out_dtype, int B, int H, int W, int N, const a
   const int64_t total = (int64_t)prm.m_tiles * prm.n_tiles;
   int64_t grid = sm_count();
   if (grid > total) grid = total;
-  pw_fwd_tc_kernel<<<(unsigned)grid, TC_THREADS, smem, st>>>(prm);
+  launch_k(pw_fwd_tc_kernel, (unsigned)grid, TC_THREADS, smem, st, prm);
   return check_launch("pw_fwd_tc");
 }
 

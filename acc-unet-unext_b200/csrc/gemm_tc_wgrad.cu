@@ -38,6 +38,7 @@ struct alignas(64) WgParams {
 };
 
 __global__ void __launch_bounds__(WG_THREADS) pw_wgrad_tc_kernel(const __grid_constant__ WgParams prm) {
+  pdl_sync();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
@@ -287,7 +288,7 @@ static int wgrad_tc_launch(int B, int H, int W, int N, const accx_operand_t* op,
     cudaFuncSetAttribute(pw_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr_set = true;
   }
-  pw_wgrad_tc_kernel<<<(unsigned)(pairs * splits), WG_THREADS, smem, (cudaStream_t)stream>>>(prm);
+  launch_k(pw_wgrad_tc_kernel, (unsigned)(pairs * splits), WG_THREADS, smem, (cudaStream_t)stream, prm);
   return check_launch("pw_wgrad_tc");
 }
 

@@ -15,6 +15,7 @@ namespace accx {
 template <typename T, int VEC>
 __global__ void hanc_pool_kernel(int B, int H, int W, int C, int first, const T* __restrict__ x, const float* scale,
                                  const float* shift, int act, T* __restrict__ out) {
+  pdl_sync();
   const int cv = blockIdx.y * blockDim.x + threadIdx.x;
   if (cv * VEC >= C) return;
   const int c0 = cv * VEC;
@@ -63,6 +64,7 @@ template <typename T, int VEC, int S>
 __global__ void hanc_unpool_kernel(int B, int H, int W, int C, int log2s, const T* __restrict__ x, const float* scale,
                                    const float* shift, int act, const float* __restrict__ dpool, T* __restrict__ da,
                                    int accumulate) {
+  pdl_sync();
   const int cv = blockIdx.y * blockDim.x + threadIdx.x;
   if (cv * VEC >= C) return;
   const int c0 = cv * VEC;
@@ -162,6 +164,7 @@ __global__ void __launch_bounds__(128) hanc_unpool_bnred_kernel(int B, int H, in
                                                                 const float* __restrict__ dp1,
                                                                 const float* __restrict__ dp2, bf16* __restrict__ da,
                                                                 const float* mean, const float* rstd, float* sums) {
+  pdl_sync();
   constexpr int S = 1 << LEVELS, NPX = S * S, VEC = 4;
   extern __shared__ float smem[];
   const int cv = blockIdx.y * blockDim.x + threadIdx.x;
@@ -276,7 +279,7 @@ int accx_hanc_pool_fwd(int dtype, int B, int H, int W, int C, int first, const v
     Lanes l = make_lanes(C, DT<T>::VEC, aligned16(x) && aligned16(out));
     dim3 block(l.tx, l.ty), grid(grid_x_for(Po, l.ty * 4, 148 * 8), l.gy);
     ACCX_DISPATCH_VEC(l, {
-      hanc_pool_kernel<T, VEC><<<grid, block, 0, (cudaStream_t)stream>>>(B, H, W, C, first, (const T*)x, scale, shift,
+      launch_k(hanc_pool_kernel<T, VEC>, grid, block, 0, (cudaStream_t)stream, B, H, W, C, first, (const T*)x, scale, shift,
                                                                          act, (T*)out);
     });
   });
@@ -294,13 +297,13 @@ int accx_hanc_unpool_bwd(int dtype, int B, int H, int W, int C, int log2s, const
     dim3 block(l.tx, l.ty), grid(grid_x_for(Po, l.ty * 2, 148 * 8), l.gy);
     ACCX_DISPATCH_VEC(l, {
       if (log2s == 1)
-        hanc_unpool_kernel<T, VEC, 2><<<grid, block, 0, (cudaStream_t)stream>>>(B, H, W, C, log2s, (const T*)x, scale,
+        launch_k(hanc_unpool_kernel<T, VEC, 2>, grid, block, 0, (cudaStream_t)stream, B, H, W, C, log2s, (const T*)x, scale,
                                                                                 shift, act, dpool, (T*)da, accumulate);
       else if (log2s == 2)
-        hanc_unpool_kernel<T, VEC, 4><<<grid, block, 0, (cudaStream_t)stream>>>(B, H, W, C, log2s, (const T*)x, scale,
+        launch_k(hanc_unpool_kernel<T, VEC, 4>, grid, block, 0, (cudaStream_t)stream, B, H, W, C, log2s, (const T*)x, scale,
                                                                                 shift, act, dpool, (T*)da, accumulate);
       else
-        hanc_unpool_kernel<T, VEC, 0><<<grid, block, 0, (cudaStream_t)stream>>>(B, H, W, C, log2s, (const T*)x, scale,
+        launch_k(hanc_unpool_kernel<T, VEC, 0>, grid, block, 0, (cudaStream_t)stream, B, H, W, C, log2s, (const T*)x, scale,
                                                                                 shift, act, dpool, (T*)da, accumulate);
     });
   });
@@ -331,10 +334,10 @@ int accx_hanc_unpool_bnred(int dtype, int B, int H, int W, int C, int levels, co
   dim3 block(l.tx, l.ty), grid(grid_x_for(n_win, l.ty, 148 * 3), l.gy);
   const size_t sm = (size_t)l.tx * l.ty * l.vec * sizeof(float);
   if (levels == 1)
-    hanc_unpool_bnred_kernel<1><<<grid, block, sm, (cudaStream_t)stream>>>(B, H, W, C, (const bf16*)y, scale, shift, act,
+    launch_k(hanc_unpool_bnred_kernel<1>, grid, block, sm, (cudaStream_t)stream, B, H, W, C, (const bf16*)y, scale, shift, act,
                                                                             dpool1, dpool2, (bf16*)da, mean, rstd, sums);
   else
-    hanc_unpool_bnred_kernel<2><<<grid, block, sm, (cudaStream_t)stream>>>(B, H, W, C, (const bf16*)y, scale, shift, act,
+    launch_k(hanc_unpool_bnred_kernel<2>, grid, block, sm, (cudaStream_t)stream, B, H, W, C, (const bf16*)y, scale, shift, act,
                                                                             dpool1, dpool2, (bf16*)da, mean, rstd, sums);
   return check_launch("hanc_unpool_bnred");
 }

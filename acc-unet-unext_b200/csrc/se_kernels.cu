@@ -12,6 +12,7 @@ namespace accx {
 template <typename T, int VEC, int U>
 __global__ void se_squeeze_kernel(int B, int HW, int C, int chunks, const T* __restrict__ x, const float* scale,
                                   const float* shift, int act, float* S) {
+  pdl_sync();
   extern __shared__ float smem[];
   const int cv = blockIdx.y * blockDim.x + threadIdx.x;
   const bool active = cv * VEC < C;
@@ -38,14 +39,19 @@ __global__ void se_squeeze_kernel(int B, int HW, int C, int chunks, const T* __r
   reduce_lanes_atomic<2, VEC>(acc, smem, S + (int64_t)b * C, (int64_t)B * C, C);
 }
 
-// grid = B blocks of 256 threads; the last block to finish derives the BatchNorm affine.
-__global__ void se_gate_kernel(int B, int C, int Cr, double HW, const float* __restrict__ S,
+// The two per-batch kernels are chains of dependent L2 round trips over tiny matrices (one image per block); wider
+// blocks (1024 threads) and deeper unrolling were measured and did not help (B200, round 1).
+constexpr int SE_GATE_THREADS = 256;
+
+// grid = B blocks; the last block to finish derives the BatchNorm affine.
+__global__ void __launch_bounds__(SE_GATE_THREADS) se_gate_kernel(int B, int C, int Cr, double HW, const float* __restrict__ S,
                                const float* __restrict__ w1, const float* __restrict__ b1,
                                const float* __restrict__ w2, const float* __restrict__ b2,
                                const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                float momentum, int training, float* running_mean, float* running_var, int64_t* nbt,
                                float* gate, float* hidden, float* scale, float* shift, float* mean_o, float* rstd_o,
                                unsigned int* counter) {
+  pdl_sync();
   extern __shared__ float sm[];
   float* m = sm;            // [C]
   float* h = sm + C;        // [Cr]
@@ -138,6 +144,7 @@ __global__ void se_apply_kernel(int B, int HW, int C, int chunks, const T* __res
                                 const float* shift, int act, const float* __restrict__ gate, const float* se_scale,
                                 const float* se_shift, const T* __restrict__ residual, const float* mix,
                                 T* __restrict__ out, float* stats) {
+  pdl_sync();
   extern __shared__ float smem[];
   const int cv = blockIdx.y * blockDim.x + threadIdx.x;
   const bool active = cv * VEC < C;
@@ -192,6 +199,7 @@ __global__ void se_bwd_reduce_kernel(int B, int HW, int C, int chunks, const T* 
                                      const float* shift, int act, const float* __restrict__ gate,
                                      const float* se_scale, const float* se_shift, const T* __restrict__ dout,
                                      const float* mix, const T* __restrict__ residual, float* dmix, float* G) {
+  pdl_sync();
   extern __shared__ float smem[];
   const int cv = blockIdx.y * blockDim.x + threadIdx.x;
   const bool active = cv * VEC < C;
@@ -250,12 +258,13 @@ __global__ void se_bwd_reduce_kernel(int B, int HW, int C, int chunks, const T* 
 // One block per image.  Every block first derives the per-channel BN-backward constants
 // (c1 = mean g', c2 = mean g'*zhat) from G over ALL images (cheap: B*C values), then runs the
 // two tiny FC backward products for its image and emits the per-(b,c) apply coefficients.
-__global__ void se_bwd_gate_kernel(int B, int C, int Cr, double HW, const float* __restrict__ S,
+__global__ void __launch_bounds__(SE_GATE_THREADS) se_bwd_gate_kernel(int B, int C, int Cr, double HW, const float* __restrict__ S,
                                    const float* __restrict__ G, const float* __restrict__ gate,
                                    const float* __restrict__ hidden, const float* __restrict__ w1,
                                    const float* __restrict__ w2, const float* __restrict__ gamma,
                                    const float* __restrict__ mean, const float* __restrict__ rstd, float* dw1,
                                    float* db1, float* dw2, float* db2, float* dgamma, float* dbeta, float* PQR) {
+  pdl_sync();
   extern __shared__ float sm[];
   float* dpre2 = sm;            // [C]
   float* m = sm + C;            // [C]
@@ -333,6 +342,7 @@ __global__ void se_bwd_apply_kernel(int B, int HW, int C, int chunks, const T* _
                                     const float* se_scale, const float* se_shift, const T* __restrict__ dout,
                                     const float* mix, const float* __restrict__ PQR, T* __restrict__ da,
                                     int accumulate, const float* bn_mean, const float* bn_rstd, float* bn_sums) {
+  pdl_sync();
   // bn_sums != NULL: also the BatchNorm-backward reduction of the lazy input's own BatchNorm on the gradient
   // just produced (sum g, sum g*xhat with g = da*act'(x)) -- saves the separate accx_bn_bwd_reduce pass
   extern __shared__ float smem[];
@@ -435,13 +445,13 @@ int accx_se_squeeze(int dtype, int B, int HW, int C, const void* x, const float*
   ACCX_REQUIRE(B > 0 && HW > 0 && C > 0 && x && S, "se_squeeze: bad arguments");
   ACCX_DISPATCH_T(dtype, {
     Lanes l = make_lanes(C, DT<T>::VEC, aligned16(x));
-    int chunks = se_chunks(B, HW, l.ty, 148 * knob(KNOB_SE_SQUEEZE_BLOCKS, 2));
+    int chunks = se_chunks(B, HW, l.ty, 148 * knob(KNOB_SE_SQUEEZE_BLOCKS, 4));
     dim3 block(l.tx, l.ty), grid(B * chunks, l.gy);
     size_t sm = (size_t)l.tx * l.ty * l.vec * sizeof(float);
-    const int u = knob(KNOB_SE_SQUEEZE_U, 8);
+    const int u = knob(KNOB_SE_SQUEEZE_U, 4);
     ACCX_DISPATCH_VEC(l, {
       ACCX_DISPATCH_U(u, {
-        se_squeeze_kernel<T, VEC, U><<<grid, block, sm, (cudaStream_t)stream>>>(B, HW, C, chunks, (const T*)x, scale,
+        launch_k(se_squeeze_kernel<T, VEC, U>, grid, block, sm, (cudaStream_t)stream, B, HW, C, chunks, (const T*)x, scale,
                                                                                 shift, act, S);
       });
     });
@@ -456,7 +466,7 @@ int accx_se_gate(int B, int C, int Cr, double HW, const float* S, const float* w
   ACCX_REQUIRE(B > 0 && C > 0 && Cr > 0 && S && w1 && b1 && w2 && b2 && gate && hidden && scale && shift && counter,
                "se_gate: bad arguments (C=%d Cr=%d)", C, Cr);
   size_t sm = (size_t)(C + Cr) * sizeof(float);
-  se_gate_kernel<<<B, 256, sm, (cudaStream_t)stream>>>(B, C, Cr, HW, S, w1, b1, w2, b2, gamma, beta, eps, momentum,
+  launch_k(se_gate_kernel, B, SE_GATE_THREADS, sm, (cudaStream_t)stream, B, C, Cr, HW, S, w1, b1, w2, b2, gamma, beta, eps, momentum,
                                                        training, running_mean, running_var, nbt, gate, hidden, scale,
                                                        shift, mean, rstd, counter);
   return check_launch("se_gate");
@@ -468,13 +478,13 @@ int accx_se_apply(int dtype, int B, int HW, int C, const void* x, const float* s
   ACCX_REQUIRE(B > 0 && HW > 0 && C > 0 && x && gate && se_scale && se_shift && out, "se_apply: bad arguments");
   ACCX_DISPATCH_T(dtype, {
     Lanes l = make_lanes(C, DT<T>::VEC, aligned16(x) && aligned16(out) && (!residual || aligned16(residual)));
-    const int chunks = se_chunks(B, HW, l.ty, 148 * (stats ? knob(KNOB_SE_APPLY_STATS_BLOCKS, 2) : knob(KNOB_SE_APPLY_BLOCKS, 8)));
+    const int chunks = se_chunks(B, HW, l.ty, 148 * (stats ? knob(KNOB_SE_APPLY_STATS_BLOCKS, 4) : knob(KNOB_SE_APPLY_BLOCKS, 4)));
     dim3 block(l.tx, l.ty), grid(B * chunks, l.gy);
     size_t sm = (size_t)l.tx * l.ty * l.vec * sizeof(float);
-    const int u = knob(KNOB_SE_APPLY_U, 8);
+    const int u = knob(KNOB_SE_APPLY_U, 4);
     ACCX_DISPATCH_VEC(l, {
       ACCX_DISPATCH_U(u, {
-        se_apply_kernel<T, VEC, U><<<grid, block, sm, (cudaStream_t)stream>>>(B, HW, C, chunks, (const T*)x, scale, shift, act,
+        launch_k(se_apply_kernel<T, VEC, U>, grid, block, sm, (cudaStream_t)stream, B, HW, C, chunks, (const T*)x, scale, shift, act,
                                                                               gate, se_scale, se_shift, (const T*)residual,
                                                                               mix, (T*)out, stats);
       });
@@ -490,13 +500,13 @@ int accx_se_bwd_reduce(int dtype, int B, int HW, int C, const void* x, const flo
   ACCX_REQUIRE(!dmix || (mix && residual), "se_bwd_reduce: dmix needs mix and residual");
   ACCX_DISPATCH_T(dtype, {
     Lanes l = make_lanes(C, DT<T>::VEC, aligned16(x) && aligned16(dout) && (!residual || aligned16(residual)));
-    int chunks = se_chunks(B, HW, l.ty, 148 * knob(KNOB_SE_BWD_REDUCE_BLOCKS, 2));
+    int chunks = se_chunks(B, HW, l.ty, 148 * knob(KNOB_SE_BWD_REDUCE_BLOCKS, 4));
     dim3 block(l.tx, l.ty), grid(B * chunks, l.gy);
     size_t sm = (size_t)l.tx * l.ty * l.vec * sizeof(float);
-    const int u = knob(KNOB_SE_BWD_REDUCE_U, 4);
+    const int u = knob(KNOB_SE_BWD_REDUCE_U, 8);
     ACCX_DISPATCH_VEC(l, {
       ACCX_DISPATCH_U(u, {
-        se_bwd_reduce_kernel<T, VEC, U><<<grid, block, sm, (cudaStream_t)stream>>>(
+        launch_k(se_bwd_reduce_kernel<T, VEC, U>, grid, block, sm, (cudaStream_t)stream, 
             B, HW, C, chunks, (const T*)x, scale, shift, act, gate, se_scale, se_shift, (const T*)dout, mix,
             (const T*)residual, dmix, G);
       });
@@ -512,7 +522,7 @@ int accx_se_bwd_gate(int B, int C, int Cr, double HW, const float* S, const floa
   ACCX_REQUIRE(B > 0 && C > 0 && Cr > 0 && S && G && gate && hidden && w1 && w2 && gamma && mean && rstd && PQR,
                "se_bwd_gate: bad arguments");
   size_t sm = (size_t)(2 * C + 2 * Cr) * sizeof(float);
-  se_bwd_gate_kernel<<<B, 256, sm, (cudaStream_t)stream>>>(B, C, Cr, HW, S, G, gate, hidden, w1, w2, gamma, mean, rstd,
+  launch_k(se_bwd_gate_kernel, B, SE_GATE_THREADS, sm, (cudaStream_t)stream, B, C, Cr, HW, S, G, gate, hidden, w1, w2, gamma, mean, rstd,
                                                            dw1, db1, dw2, db2, dgamma, dbeta, PQR);
   return check_launch("se_bwd_gate");
 }
@@ -529,10 +539,10 @@ int accx_se_bwd_apply(int dtype, int B, int HW, int C, const void* x, const floa
     const int chunks = se_chunks(B, HW, l.ty, 148 * (bn_sums ? knob(KNOB_SE_BWD_APPLY_BN_BLOCKS, 4) : knob(KNOB_SE_BWD_APPLY_BLOCKS, 8)));
     dim3 block(l.tx, l.ty), grid(B * chunks, l.gy);
     const size_t sm = bn_sums ? (size_t)l.tx * l.ty * l.vec * sizeof(float) : 0;
-    const int u = knob(KNOB_SE_BWD_APPLY_U, 4);
+    const int u = knob(KNOB_SE_BWD_APPLY_U, 8);
     ACCX_DISPATCH_VEC(l, {
       ACCX_DISPATCH_U(u, {
-        se_bwd_apply_kernel<T, VEC, U><<<grid, block, sm, (cudaStream_t)stream>>>(
+        launch_k(se_bwd_apply_kernel<T, VEC, U>, grid, block, sm, (cudaStream_t)stream, 
             B, HW, C, chunks, (const T*)x, scale, shift, act, gate, se_scale, se_shift, (const T*)dout, mix, PQR, (T*)da,
             accumulate, bn_mean, bn_rstd, bn_sums);
       });

@@ -13,6 +13,7 @@ namespace accx {
 // routes the gradient to the FIRST maximum in row-major window order (ATen's tie rule: strict '>').
 template <typename T, int VEC>
 __global__ void maxpool2_fwd_kernel(int B, int H, int W, int C, const T* __restrict__ x, T* __restrict__ out) {
+  pdl_sync();
   const int cv = blockIdx.y * blockDim.x + threadIdx.x;
   if (cv * VEC >= C) return;
   const int c0 = cv * VEC;
@@ -48,6 +49,7 @@ __global__ void maxpool2_fwd_kernel(int B, int H, int W, int C, const T* __restr
 template <typename T, int VEC>
 __global__ void maxpool2_bwd_kernel(int B, int H, int W, int C, const T* __restrict__ x, const T* __restrict__ dy,
                                     T* __restrict__ dx) {
+  pdl_sync();
   const int cv = blockIdx.y * blockDim.x + threadIdx.x;
   if (cv * VEC >= C) return;
   const int c0 = cv * VEC;
@@ -130,6 +132,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) dice_bce_fwd_kernel(int B, int64_t N, const T* __restrict__ logit,
                                                            const float* __restrict__ truth, float dice_w, float bce_w,
                                                            float* sums, unsigned int* counter, float* loss) {
+  pdl_sync();
   __shared__ float red[8][LOSS_NS];
   __shared__ bool is_last;
   const int b = blockIdx.y;
@@ -185,6 +188,7 @@ __global__ void __launch_bounds__(256) dice_bce_bwd_kernel(int B, int64_t N, con
                                                            const float* __restrict__ truth,
                                                            const float* __restrict__ sums, float dice_w, float bce_w,
                                                            const float* gscale, TG* __restrict__ dlogit) {
+  pdl_sync();
   __shared__ LossTotals tot;
   const int b = blockIdx.y;
   if (threadIdx.x == 0) tot = loss_totals(sums, B, N);
@@ -212,12 +216,14 @@ __global__ void __launch_bounds__(256) dice_bce_bwd_kernel(int B, int64_t N, con
 // Adam over one flat fp32 buffer (all parameters of the model back to back): 4 reads + 3 writes per element in
 // ONE launch instead of a multi-tensor launch chain over ~900 tensors.  state[0] = step count (device side, so
 // the launch is graph-capturable); same arithmetic as torch.optim.Adam (no amsgrad, L2 weight decay).
-__global__ void adam_tick_kernel(float* state) { state[0] += 1.f; }
+__global__ void adam_tick_kernel(float* state) {
+  pdl_sync(); state[0] += 1.f; }
 
 __global__ void __launch_bounds__(256) adam_flat_kernel(int64_t n4, float4* __restrict__ p, const float4* __restrict__ g,
                                                         float4* __restrict__ m, float4* __restrict__ v,
                                                         const float* __restrict__ state, float lr, float b1, float b2,
                                                         float eps, float wd, float gscale) {
+  pdl_sync();
   const double t = (double)state[0];
   const float bc1 = (float)(1.0 - pow((double)b1, t));
   const float bc2s = (float)sqrt(1.0 - pow((double)b2, t));
@@ -266,7 +272,7 @@ int accx_maxpool2_fwd(int dtype, int B, int H, int W, int C, const void* x, void
     Lanes l = make_lanes(C, DT<T>::VEC, aligned16(x) && aligned16(out));
     dim3 block(l.tx, l.ty), grid(grid_x_for(Po, l.ty * 2, 148 * 16), l.gy);
     ACCX_DISPATCH_VEC(l, {
-      maxpool2_fwd_kernel<T, VEC><<<grid, block, 0, (cudaStream_t)stream>>>(B, H, W, C, (const T*)x, (T*)out);
+      launch_k(maxpool2_fwd_kernel<T, VEC>, grid, block, 0, (cudaStream_t)stream, B, H, W, C, (const T*)x, (T*)out);
     });
   });
   return check_launch("maxpool2_fwd");
@@ -280,7 +286,7 @@ int accx_maxpool2_bwd(int dtype, int B, int H, int W, int C, const void* x, cons
     Lanes l = make_lanes(C, DT<T>::VEC, aligned16(x) && aligned16(dy) && aligned16(dx));
     dim3 block(l.tx, l.ty), grid(grid_x_for(Po, l.ty * 2, 148 * 16), l.gy);
     ACCX_DISPATCH_VEC(l, {
-      maxpool2_bwd_kernel<T, VEC><<<grid, block, 0, (cudaStream_t)stream>>>(B, H, W, C, (const T*)x, (const T*)dy, (T*)dx);
+      launch_k(maxpool2_bwd_kernel<T, VEC>, grid, block, 0, (cudaStream_t)stream, B, H, W, C, (const T*)x, (const T*)dy, (T*)dx);
     });
   });
   return check_launch("maxpool2_bwd");
@@ -299,7 +305,7 @@ int accx_dice_bce_fwd(int dtype, int B, int64_t N, const void* logit, const floa
   dim3 grid(loss_grid_x(B, N), B);
   unsigned int* counter = reinterpret_cast<unsigned int*>(sums + (int64_t)B * LOSS_STRIDE);
   ACCX_DISPATCH_T(dtype, {
-    dice_bce_fwd_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(B, N, (const T*)logit, truth, dice_w, bce_w, sums,
+    launch_k(dice_bce_fwd_kernel<T>, grid, 256, 0, (cudaStream_t)stream, B, N, (const T*)logit, truth, dice_w, bce_w, sums,
                                                                     counter, loss);
   });
   return check_launch("dice_bce_fwd");
@@ -312,10 +318,10 @@ int accx_dice_bce_bwd(int dtype, int grad_dtype, int B, int64_t N, const void* l
   cudaStream_t st = (cudaStream_t)stream;
   ACCX_DISPATCH_T(dtype, {
     if (grad_dtype == ACCX_F32)
-      dice_bce_bwd_kernel<T, float><<<grid, 256, 0, st>>>(B, N, (const T*)logit, truth, sums, dice_w, bce_w, gscale,
+      launch_k(dice_bce_bwd_kernel<T, float>, grid, 256, 0, st, B, N, (const T*)logit, truth, sums, dice_w, bce_w, gscale,
                                                           (float*)dlogit);
     else if (grad_dtype == ACCX_BF16)
-      dice_bce_bwd_kernel<T, bf16><<<grid, 256, 0, st>>>(B, N, (const T*)logit, truth, sums, dice_w, bce_w, gscale,
+      launch_k(dice_bce_bwd_kernel<T, bf16>, grid, 256, 0, st, B, N, (const T*)logit, truth, sums, dice_w, bce_w, gscale,
                                                          (bf16*)dlogit);
     else {
       set_error("dice_bce_bwd: unsupported gradient dtype %d", grad_dtype);
@@ -332,10 +338,10 @@ int accx_adam_step(int64_t n, float* param, const float* grad, float* exp_avg, f
   ACCX_REQUIRE(aligned16(param) && aligned16(grad) && aligned16(exp_avg) && aligned16(exp_avg_sq),
                "adam_step: buffers must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
-  adam_tick_kernel<<<1, 1, 0, st>>>(state);
+  launch_k(adam_tick_kernel, 1, 1, 0, st, state);
   const int64_t n4 = n / 4;
   int grid = grid_x_for(n4, 256 * 2, 148 * 8);
-  adam_flat_kernel<<<grid, 256, 0, st>>>(n4, (float4*)param, (const float4*)grad, (float4*)exp_avg, (float4*)exp_avg_sq,
+  launch_k(adam_flat_kernel, grid, 256, 0, st, n4, (float4*)param, (const float4*)grad, (float4*)exp_avg, (float4*)exp_avg_sq,
                                          state, lr, beta1, beta2, eps, weight_decay, grad_scale);
   return check_launch("adam_step");
 }
