@@ -79,6 +79,10 @@ def load():
         fn.restype = ret
         fn.argtypes = types
     _lib = lib
+    # whole-step experiments: ACCX_KNOBS="index=value,index=value" (see KNOB_* in csrc/common.cuh)
+    for kv in filter(None, os.environ.get("ACCX_KNOBS", "").split(",")):
+        k, v = kv.split("=")
+        lib.accx_set_knob(int(k), int(v))
     return lib
 
 

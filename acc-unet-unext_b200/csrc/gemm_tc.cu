@@ -545,8 +545,15 @@ static size_t tc_geometry(int N, int64_t P, const accx_operand_t* ops, int n_ops
   prm.b_resident = (prm.n_tiles == 1 && fixed + (size_t)kb * b_tile + 3 * TC_A_BYTES <= (size_t)TC_SMEM_MAX) ? 1 : 0;
   const size_t resident = prm.b_resident ? (size_t)kb * b_tile : 0;
   const size_t stage = TC_A_BYTES + (prm.b_resident ? 0 : b_tile);
-  int S = (int)((TC_SMEM_MAX - fixed - resident) / stage);
-  if (S > 8) S = 8;
+  // pipeline depth: as many stages as fit under the cap, at most 8.  The cap (160 KB, whole-step sweep on B200:
+  // 227 KB 38.29 ms, 160 KB 37.82 ms, 112 KB 38.44 ms) leaves room for kernels of the other stream lanes on the SM
+  size_t cap = (size_t)knob(KNOB_TC_SMEM_KB, 160) * 1024;
+  if (cap > (size_t)TC_SMEM_MAX) cap = TC_SMEM_MAX;
+  if (cap < fixed + resident + 2 * stage) cap = fixed + resident + 2 * stage;
+  if (cap > (size_t)TC_SMEM_MAX) cap = TC_SMEM_MAX;
+  int S = (int)((cap - fixed - resident) / stage);
+  const int max_stages = knob(KNOB_TC_MAX_STAGES, 8);
+  if (S > max_stages) S = max_stages;
   if (S < 1) S = 1;
   prm.stages = S;
   return fixed + resident + (size_t)S * stage;

@@ -267,7 +267,8 @@ static int wgrad_tc_launch(int B, int H, int W, int N, const accx_operand_t* op,
   const int64_t stages_total = (prm.P + WG_PX - 1) / WG_PX;
   int64_t splits = (2 * (int64_t)sm_count() + pairs - 1) / pairs;
   // every split ends with 128 x nb fp32 atomics per tap: keep at least 8 stages (1024 pixels) of work behind them
-  if (splits > stages_total / 8) splits = stages_total / 8;
+  const int min_stages = knob(KNOB_WGRAD_MIN_STAGES, 8);
+  if (splits > stages_total / min_stages) splits = stages_total / min_stages;
   if (splits < 1) splits = 1;
   int64_t per = (stages_total + splits - 1) / splits;      // stages per split
   splits = (stages_total + per - 1) / per;
@@ -275,7 +276,7 @@ static int wgrad_tc_launch(int B, int H, int W, int N, const accx_operand_t* op,
   prm.px_per_split = per * WG_PX;
   const size_t stage_bytes = (size_t)(prm.dy_blocks + n_taps * a_blocks) * WG_BLK;
   const size_t fixed = 1024 + 2 * (size_t)a_blocks * 64 * 4 + 24 * 4 + 64;
-  int S = (int)((227 * 1024 - fixed) / stage_bytes);
+  int S = (int)((knob(KNOB_WGRAD_SMEM_KB, 227) * 1024 - fixed) / stage_bytes);
   if (S > 4) S = 4;
   if (S > per) S = (int)per;
   ACCX_REQUIRE(S >= 1, "pw_wgrad_tc: one pipeline stage (%zu bytes) does not fit in shared memory", stage_bytes);

@@ -19,7 +19,7 @@ DEV = "cuda"
 KNOBS = {n: i for i, n in enumerate(
     ["SE_SQUEEZE_BLOCKS", "SE_SQUEEZE_U", "SE_APPLY_BLOCKS", "SE_APPLY_STATS_BLOCKS", "SE_APPLY_U", "SE_BWD_REDUCE_BLOCKS",
      "SE_BWD_REDUCE_U", "SE_BWD_APPLY_BLOCKS", "SE_BWD_APPLY_BN_BLOCKS", "SE_BWD_APPLY_U", "BN_REDUCE_BLOCKS", "EW_BLOCKS",
-     "POOL_BLOCKS", "SPARE0", "SPARE1", "SPARE2"])}
+     "POOL_BLOCKS", "TC_SMEM_KB", "TC_MAX_STAGES", "WGRAD_MIN_STAGES", "WGRAD_SMEM_KB"])}
 SHAPES = [(16, 50176, 32), (16, 12544, 64), (16, 3136, 128), (16, 784, 256)]
 ROT = 4
 
