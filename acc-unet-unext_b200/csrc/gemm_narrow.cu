@@ -69,17 +69,38 @@ __global__ void __launch_bounds__(NAR_THREADS) pw_fwd_narrow_kernel(const __grid
 #pragma unroll
   for (int n = 0; n < NT; ++n) s1[n] = s2[n] = 0.f;
   const int HWp = prm.H * prm.W;
+  const bool vec_in = prm.n_ops == 1 && Kt % (16 / (int)sizeof(T)) == 0 && (prm.op[0].ld * sizeof(T)) % 16 == 0 &&
+                      (reinterpret_cast<uintptr_t>(prm.op[0].data) & 15) == 0;
+  const bool vec_out = N % (16 / (int)sizeof(TO)) == 0 && (prm.ldy * sizeof(TO)) % 16 == 0 &&
+                       (reinterpret_cast<uintptr_t>(prm.y) & 15) == 0;
   for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < prm.P; p += (int64_t)gridDim.x * blockDim.x) {
     float a[KT];
+    constexpr int IPV = 16 / sizeof(T);                  // input elements per 16-byte load
+    if (KT % IPV == 0 && vec_in) {                       // one operand, contiguous channels: 16-byte loads
+      const T* arow = kptr[0] + p * kld[0];
 #pragma unroll
-    for (int kk = 0; kk < KT; ++kk) {
-      float v = 0.f;
-      if (kk < Kt) {
-        v = to_f(kptr[kk][p * kld[kk]]);
-        v = fmaf(v, sc[kk], sh[kk]);
-        v = fmaxf(v, v * slope[kk]);
+      for (int k0 = 0; k0 < KT; k0 += IPV) {
+        float t[IPV];
+#pragma unroll
+        for (int e = 0; e < IPV; ++e) t[e] = 0.f;
+        if (k0 < Kt) ldv<T, IPV>(arow + k0, t);
+#pragma unroll
+        for (int e = 0; e < IPV; ++e) {
+          float v = fmaf(t[e], sc[k0 + e], sh[k0 + e]);
+          a[k0 + e] = (k0 + e < Kt) ? fmaxf(v, v * slope[k0 + e]) : 0.f;
+        }
       }
-      a[kk] = v;
+    } else {
+#pragma unroll
+      for (int kk = 0; kk < KT; ++kk) {
+        float v = 0.f;
+        if (kk < Kt) {
+          v = to_f(kptr[kk][p * kld[kk]]);
+          v = fmaf(v, sc[kk], sh[kk]);
+          v = fmaxf(v, v * slope[kk]);
+        }
+        a[kk] = v;
+      }
     }
     float y[NT];
 #pragma unroll
@@ -101,10 +122,24 @@ __global__ void __launch_bounds__(NAR_THREADS) pw_fwd_narrow_kernel(const __grid
       }
     }
     TO* dst = (TO*)prm.y + p * prm.ldy;
+    constexpr int EPV = 16 / sizeof(TO);                 // output elements per 16-byte store
+    if constexpr (NT % EPV == 0) {
+      if (vec_out) {                                     // a pixel's outputs as 16-byte stores (scalar 2-byte stores at a
+#pragma unroll                                           // 64-byte pitch cost one LSU transaction per element)
+        for (int n0 = 0; n0 < NT; n0 += EPV) {
+          if (n0 < N) {
+            float t[EPV];
+#pragma unroll
+            for (int e = 0; e < EPV; ++e) t[e] = y[n0 + e];
+            stv<TO, EPV>(dst + n0, t);
+          }
+        }
+      }
+    }
 #pragma unroll
     for (int n = 0; n < NT; ++n) {
       if (n < N) {
-        dst[n] = from_f<TO>(y[n]);
+        if (!(NT % EPV == 0 && vec_out)) dst[n] = from_f<TO>(y[n]);
         s1[n] += y[n];
         s2[n] = fmaf(y[n], y[n], s2[n]);
       }
@@ -138,24 +173,57 @@ __global__ void __launch_bounds__(NAR_THREADS) pw_wgrad_narrow_kernel(accx_opera
   }
   __syncthreads();
   const float slope = op.act == 2 ? ACCX_LRELU : 1.f;
+  const bool vec_a = K % (16 / (int)sizeof(T)) == 0 && (op.ld * sizeof(T)) % 16 == 0 &&
+                     (reinterpret_cast<uintptr_t>(op.data) & 15) == 0 && op.dy == 0 && op.dx == 0;
+  const bool vec_g = N % (16 / (int)sizeof(TG)) == 0 && (ldy * sizeof(TG)) % 16 == 0 &&
+                     (reinterpret_cast<uintptr_t>(dy) & 15) == 0;
   float acc[NT * KT];
 #pragma unroll
   for (int i = 0; i < NT * KT; ++i) acc[i] = 0.f;
   for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (int64_t)gridDim.x * blockDim.x) {
     float a[KT], g[NT];
     const T* arow = (const T*)op.data + p * op.ld;
+    constexpr int IPV = 16 / sizeof(T);
+    if (KT % IPV == 0 && vec_a) {
 #pragma unroll
-    for (int k = 0; k < KT; ++k) {
-      float v = 0.f;
-      if (k < K) {
-        v = fmaf(to_f(arow[k]), sc[k], sh[k]);
-        v = fmaxf(v, v * slope);
+      for (int k0 = 0; k0 < KT; k0 += IPV) {
+        float t[IPV];
+#pragma unroll
+        for (int e = 0; e < IPV; ++e) t[e] = 0.f;
+        if (k0 < K) ldv<T, IPV>(arow + k0, t);
+#pragma unroll
+        for (int e = 0; e < IPV; ++e) {
+          float v = fmaf(t[e], sc[k0 + e], sh[k0 + e]);
+          a[k0 + e] = (k0 + e < K) ? fmaxf(v, v * slope) : 0.f;
+        }
       }
-      a[k] = v;
+    } else {
+#pragma unroll
+      for (int k = 0; k < KT; ++k) {
+        float v = 0.f;
+        if (k < K) {
+          v = fmaf(to_f(arow[k]), sc[k], sh[k]);
+          v = fmaxf(v, v * slope);
+        }
+        a[k] = v;
+      }
     }
     const TG* grow = dy + p * ldy;
+    constexpr int GPV = 16 / sizeof(TG);                 // dY elements per 16-byte load
+    if (NT % GPV == 0 && vec_g) {
 #pragma unroll
-    for (int n = 0; n < NT; ++n) g[n] = n < N ? to_f(grow[n]) : 0.f;
+      for (int n0 = 0; n0 < NT; n0 += GPV) {
+        float t[GPV];
+#pragma unroll
+        for (int e = 0; e < GPV; ++e) t[e] = 0.f;
+        if (n0 < N) ldv<TG, GPV>(grow + n0, t);
+#pragma unroll
+        for (int e = 0; e < GPV; ++e) g[n0 + e] = t[e];
+      }
+    } else {
+#pragma unroll
+      for (int n = 0; n < NT; ++n) g[n] = n < N ? to_f(grow[n]) : 0.f;
+    }
 #pragma unroll
     for (int n = 0; n < NT; ++n)
 #pragma unroll
