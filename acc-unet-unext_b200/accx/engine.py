@@ -725,3 +725,21 @@ def adam_step(param, grad, exp_avg, exp_avg_sq, state, lr, beta1=0.9, beta2=0.99
     LAUNCHES += 1                      # the step-count tick
     _call("accx_adam_step", n, ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), ptr(state), float(lr), float(beta1),
           float(beta2), float(eps), float(weight_decay), float(grad_scale), stream(), cost=(7 * 4 * n, 0))
+
+
+def upshuffle(temp: torch.Tensor, bias, out: torch.Tensor, Co: int, forward: bool):
+    """temp [B,H,W,4*Co] <-> the left Co columns of out [B,2H,2W,ld] (see accx_upshuffle in include/accx.h)"""
+    B, H, W, _ = temp.shape
+    assert temp.dtype == out.dtype and temp.is_contiguous() and out.is_contiguous()
+    _call("accx_upshuffle", dt(temp), 1 if forward else 0, B, H, W, Co, ptr(temp), ptr(bias), ptr(out), out.shape[-1],
+          stream(), cost=(2 * nb(temp), 0), tag=f"{B}x{H}x{W}x{Co} fwd={int(forward)}")
+
+
+def copy_cols(src: torch.Tensor, src_coff: int, dst: torch.Tensor, dst_coff: int, C: int):
+    """dst[..., dst_coff:dst_coff+C] = src[..., src_coff:src_coff+C] for contiguous [.., ld] matrices of one dtype"""
+    assert src.dtype == dst.dtype and src.is_contiguous() and dst.is_contiguous()
+    P = src.numel() // src.shape[-1]
+    assert P == dst.numel() // dst.shape[-1]
+    es = src.element_size()
+    _call("accx_copy_cols", dt(src), P, C, src.data_ptr() + src_coff * es, src.shape[-1], dst.data_ptr() + dst_coff * es,
+          dst.shape[-1], stream(), cost=(2 * P * C * es, 0), tag=f"P={P} C={C}")

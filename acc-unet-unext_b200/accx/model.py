@@ -1,9 +1,8 @@
 """ACC-UNet assembled from the accx drop-in blocks (caller glue of ACC_UNet.py:530-659).
 
-The five hot-path module types run the accx kernels, and so do MaxPool2d(2) and the final 1x1 conv
-(SURVEY.md section 8, row f1).  ConvTranspose2d(2, 2, stride 2), the skip torch.cat and the optional
-sigmoid stay on torch as in the reference (row a8), operating on channels_last tensors so no layout
-change happens between blocks.
+The five hot-path module types run the accx kernels, and so does the glue between them (SURVEY.md
+section 8, rows a8 / f1): MaxPool2d(2), ConvTranspose2d(2, 2, stride 2) + the skip concat (one
+contraction + an interleave), the final 1x1 conv.  Only the optional final sigmoid is a torch op.
 
 `compute_dtype=torch.bfloat16` stores activations in bf16 (fp32 accumulation, statistics and
 parameters); default None follows the input's dtype (fp32 = the reference's arithmetic).
@@ -14,7 +13,7 @@ import torch
 from torch import nn
 
 from . import engine as E
-from .modules import HANCBlock, MLFC, ResPath, maxpool2, out_conv, run_parallel
+from .modules import HANCBlock, MLFC, ResPath, maxpool2, out_conv, run_parallel, up_cat
 
 
 class _ACCUNetBase(nn.Module):
@@ -81,10 +80,10 @@ class _ACCUNetBase(nn.Module):
             x2, x3, x4, x5 = self.mlfc1(x2, x3, x4, x5)
             x2, x3, x4, x5 = self.mlfc2(x2, x3, x4, x5)
             x2, x3, x4, x5 = self.mlfc3(x2, x3, x4, x5)
-            x7 = self.cnv62(self.cnv61(torch.cat([self.up6(x6), x5], dim=1)))
-            x8 = self.cnv72(self.cnv71(torch.cat([self.up7(x7), x4], dim=1)))
-            x9 = self.cnv82(self.cnv81(torch.cat([self.up8(x8), x3], dim=1)))
-            x10 = self.cnv92(self.cnv91(torch.cat([self.up9(x9), x2], dim=1)))
+            x7 = self.cnv62(self.cnv61(up_cat(x6, x5, self.up6)))
+            x8 = self.cnv72(self.cnv71(up_cat(x7, x4, self.up7)))
+            x9 = self.cnv82(self.cnv81(up_cat(x8, x3, self.up8)))
+            x10 = self.cnv92(self.cnv91(up_cat(x9, x2, self.up9)))
             logits = out_conv(x10, self.out)                       # fp32 logits
         if self.last_activation is not None:
             logits = self.last_activation(logits)

@@ -217,6 +217,64 @@ def out_conv(x, conv: nn.Conv2d):
     return _OutConvFn.apply(x, conv.weight, conv.bias)
 
 
+class _UpCatFn(torch.autograd.Function):
+    """torch.cat([ConvTranspose2d(Cin, Co, 2, stride 2)(x), skip], dim=1) of the decoder (ACC_UNet.py:578-599,620-631)
+    on accx kernels: the transposed conv is one pointwise contraction [P, Cin] x [Cin, 4*Co] (weight [Cin, Co, 2, 2]
+    through a strided view), interleaved into the left half of the concat buffer; the skip is copied into the right."""
+
+    @staticmethod
+    def forward(ctx, x, skip, weight, bias):
+        E.require_cuda(x)
+        xn, sn = E.to_nhwc(x.detach()), E.to_nhwc(skip.detach())
+        B, H, W, Cin = xn.shape
+        Co, Cs = weight.shape[1], sn.shape[3]
+        if tuple(weight.shape) != (Cin, Co, 2, 2) or tuple(sn.shape[:3]) != (B, 2 * H, 2 * W) or Co % 2 or sn.dtype != xn.dtype:
+            raise ValueError(f"accx up+cat: x {tuple(x.shape)}, skip {tuple(skip.shape)}, weight {tuple(weight.shape)}")
+        w = E.f32(weight)
+        temp = E.conv([Op(Lazy(xn), Cin, WV(w, 0, 1, 4 * Co))], 4 * Co, (B, H, W))
+        out = torch.empty((B, 2 * H, 2 * W, Co + Cs), dtype=xn.dtype, device=xn.device)
+        E.upshuffle(temp, E.f32(bias), out, Co, forward=True)
+        E.copy_cols(sn, 0, out, Co, Cs)
+        ctx.xn, ctx.weight, ctx.bias, ctx.dims = xn, weight, bias, (B, H, W, Cin, Co, Cs)
+        return E.to_nchw_view(out)
+
+    @staticmethod
+    def backward(ctx, dout):
+        xn, weight, bias = ctx.xn, ctx.weight, ctx.bias
+        ctx.xn = None
+        B, H, W, Cin, Co, Cs = ctx.dims
+        dn = E.to_nhwc(dout if dout.dtype == xn.dtype else dout.to(xn.dtype))
+        w = E.f32(weight)
+        dtemp = torch.empty((B, H, W, 4 * Co), dtype=xn.dtype, device=xn.device)
+        E.upshuffle(dtemp, None, dn, Co, forward=False)
+        dskip = None
+        if ctx.needs_input_grad[1]:
+            dskip = torch.empty((B, 2 * H, 2 * W, Cs), dtype=xn.dtype, device=xn.device)
+            E.copy_cols(dn, Co, dskip, 0, Cs)
+            dskip = E.to_nchw_view(dskip)
+        grads = E.GradPool([weight] + ([bias] if bias is not None else []))
+        gw = gb = None
+        if ctx.needs_input_grad[2]:
+            gw = E.grad_buf(grads, weight)
+            # dW[ci, n'] = sum_p x[p, ci] * dtemp[p, n']: dtemp as the operand, x as "dY", so that the accumulated
+            # rows are contiguous in the reference's [Cin, Co*4] layout (vector atomics)
+            E.wgrad(Op(Lazy(dtemp), 4 * Co, WV(w, 0, 4 * Co, 1)), xn, Cin, (B, H, W), gw)
+        if bias is not None and ctx.needs_input_grad[3]:
+            gb = E.grad_buf(grads, bias)
+            torch.sum(dtemp.view(-1, Co, 4), dim=(0, 2), dtype=torch.float32, out=gb)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = E.to_nchw_view(E.conv([Op(Lazy(dtemp), 4 * Co, WV(w, 0, 4 * Co, 1))], Cin, (B, H, W)))
+        return dx, dskip, gw, gb
+
+
+def up_cat(x, skip, up: nn.ConvTranspose2d):
+    """cat([up(x), skip], dim=1) for up = ConvTranspose2d(Cin, Co, kernel_size=2, stride=2)"""
+    if tuple(up.kernel_size) != (2, 2) or tuple(up.stride) != (2, 2) or tuple(up.padding) != (0, 0) or up.groups != 1:
+        raise NotImplementedError("accx up_cat implements ConvTranspose2d(kernel_size=2, stride=2) (all the reference builds)")
+    return _UpCatFn.apply(x, skip, up.weight, up.bias)
+
+
 class _AccxModule(nn.Module):
     def _run(self, *xs):
         params = [p for p in self.parameters()]

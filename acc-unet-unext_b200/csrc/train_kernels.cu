@@ -259,6 +259,92 @@ __global__ void __launch_bounds__(256) adam_flat_kernel(int64_t n4, float4* __re
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// ConvTranspose2d(kernel 2, stride 2) + skip concat (ACC_UNet.py:578-599,620-631).  The transposed conv is ONE
+// pointwise contraction [P, Cin] x [Cin, 4*Co] whose column co*4 + (ky*2+kx) is output pixel (2h+ky, 2w+kx),
+// channel co (the reference's weight layout [Cin, Co, 2, 2] IS that matrix, so the contraction reads it through a
+// strided view); these kernels interleave its result into the left Co columns of the [B, 2H, 2W, ld_out] concat
+// buffer (+ bias) and back, and copy column ranges (the skip half of the concat, its gradient).
+//   thread = one input pixel x 2 channels: a 16-byte load of (2 channels x 4 taps), four 4-byte stores (bf16) --
+//   consecutive threads write consecutive channel pairs of the same output pixel.
+template <typename T, bool FWD>
+__global__ void __launch_bounds__(256) upshuffle_kernel(int B, int H, int W, int Co, T* __restrict__ temp,
+                                                        const float* __restrict__ bias, T* __restrict__ out,
+                                                        int64_t ld_out) {
+  pdl_sync();
+  const int pairs = Co >> 1;
+  const int cp = blockIdx.y * blockDim.x + threadIdx.x;
+  if (cp >= pairs) return;
+  const int co = cp * 2;
+  const float b0 = (FWD && bias) ? bias[co] : 0.f, b1 = (FWD && bias) ? bias[co + 1] : 0.f;
+  const int64_t P = (int64_t)B * H * W;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.y + threadIdx.y; q < P; q += (int64_t)gridDim.x * blockDim.y) {
+    const int w = (int)(q % W);
+    const int64_t t = q / W;
+    const int h = (int)(t % H);
+    const int64_t b = t / H;
+    T* trow = temp + q * (4 * (int64_t)Co) + co * 4;
+    T* o00 = out + (((b * 2 * H + 2 * h) * 2 * W) + 2 * w) * ld_out + co;
+    const int64_t dnx = ld_out, dny = 2 * (int64_t)W * ld_out;
+    if constexpr (FWD) {
+      float v[8];
+      if constexpr (sizeof(T) == 2) {
+        ldv<T, 8>(trow, v);
+      } else {
+        ldv<T, 4>(trow, *reinterpret_cast<float(*)[4]>(v));
+        ldv<T, 4>(trow + 4, *reinterpret_cast<float(*)[4]>(v + 4));
+      }
+#pragma unroll
+      for (int tap = 0; tap < 4; ++tap) {
+        T* o = o00 + (tap >> 1) * dny + (tap & 1) * dnx;        // ld_out and co are even: one 4 / 8-byte store
+        if constexpr (sizeof(T) == 2) *reinterpret_cast<__nv_bfloat162*>(o) = __floats2bfloat162_rn(v[tap] + b0, v[4 + tap] + b1);
+        else *reinterpret_cast<float2*>(o) = make_float2(v[tap] + b0, v[4 + tap] + b1);
+      }
+    } else {
+      float v[8];
+#pragma unroll
+      for (int tap = 0; tap < 4; ++tap) {
+        const T* o = o00 + (tap >> 1) * dny + (tap & 1) * dnx;
+        if constexpr (sizeof(T) == 2) {
+          const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(o));
+          v[tap] = f.x;
+          v[4 + tap] = f.y;
+        } else {
+          const float2 f = *reinterpret_cast<const float2*>(o);
+          v[tap] = f.x;
+          v[4 + tap] = f.y;
+        }
+      }
+      if constexpr (sizeof(T) == 2) {
+        stv<T, 8>(trow, v);
+      } else {
+        stv<T, 4>(trow, *reinterpret_cast<float(*)[4]>(v));
+        stv<T, 4>(trow + 4, *reinterpret_cast<float(*)[4]>(v + 4));
+      }
+    }
+  }
+}
+
+// dst[p, 0..C) = src[p, 0..C) for row pitches ld_src / ld_dst (column ranges of wider matrices)
+template <typename T, int VEC>
+__global__ void copy_cols_kernel(int64_t P, int C, const T* __restrict__ src, int64_t ld_src, T* __restrict__ dst,
+                                 int64_t ld_dst) {
+  pdl_sync();
+  const int cv = blockIdx.y * blockDim.x + threadIdx.x;
+  if (cv * VEC >= C) return;
+  const int c0 = cv * VEC;
+  constexpr int U = 4;
+  RawVec<T, VEC> r[U];
+  pixel_loop<U>((int64_t)blockIdx.x * blockDim.y + threadIdx.y, P, (int64_t)gridDim.x * blockDim.y,
+      [&](int u, int64_t p) { r[u].load(src + p * ld_src + c0); },
+      [&](int u, int64_t p) {
+        float v[VEC];
+        r[u].unpack(v);
+        stv<T, VEC>(dst + p * ld_dst + c0, v);
+      });
+}
+
 }  // namespace accx
 
 using namespace accx;
@@ -344,6 +430,41 @@ int accx_adam_step(int64_t n, float* param, const float* grad, float* exp_avg, f
   launch_k(adam_flat_kernel, grid, 256, 0, st, n4, (float4*)param, (const float4*)grad, (float4*)exp_avg, (float4*)exp_avg_sq,
                                          state, lr, beta1, beta2, eps, weight_decay, grad_scale);
   return check_launch("adam_step");
+}
+
+
+int accx_upshuffle(int dtype, int forward, int B, int H, int W, int Co, void* temp, const float* bias, void* out,
+                   int64_t ld_out, void* stream) {
+  ACCX_REQUIRE(B > 0 && H > 0 && W > 0 && Co > 0 && Co % 2 == 0 && temp && out && ld_out >= Co,
+               "upshuffle: bad arguments (Co = %d must be even)", Co);
+  ACCX_REQUIRE(aligned16(temp) && aligned16(out) && ld_out % 2 == 0, "upshuffle: buffers must be 16-byte aligned");
+  const int pairs = Co / 2;
+  const int tx = pairs < 128 ? pairs : 128;
+  int ty = 256 / tx;
+  if (ty < 1) ty = 1;
+  const int64_t P = (int64_t)B * H * W;
+  dim3 block(tx, ty), grid(grid_x_for(P, ty * 2, 148 * 16), (pairs + tx - 1) / tx);
+  cudaStream_t st = (cudaStream_t)stream;
+  ACCX_DISPATCH_T(dtype, {
+    if (forward) launch_k(upshuffle_kernel<T, true>, grid, block, 0, st, B, H, W, Co, (T*)temp, bias, (T*)out, ld_out);
+    else launch_k(upshuffle_kernel<T, false>, grid, block, 0, st, B, H, W, Co, (T*)temp, bias, (T*)out, ld_out);
+  });
+  return check_launch("upshuffle");
+}
+
+int accx_copy_cols(int dtype, int64_t P, int C, const void* src, int64_t ld_src, void* dst, int64_t ld_dst,
+                   void* stream) {
+  ACCX_REQUIRE(P > 0 && C > 0 && src && dst && ld_src >= C && ld_dst >= C, "copy_cols: bad arguments");
+  ACCX_DISPATCH_T(dtype, {
+    const int esz = (int)sizeof(T);
+    const bool al = aligned16(src) && aligned16(dst) && (ld_src * esz) % 16 == 0 && (ld_dst * esz) % 16 == 0;
+    Lanes l = make_lanes(C, DT<T>::VEC, al);
+    dim3 block(l.tx, l.ty), grid(grid_x_for(P, l.ty * 4, 148 * 16), l.gy);
+    ACCX_DISPATCH_VEC(l, {
+      launch_k(copy_cols_kernel<T, VEC>, grid, block, 0, (cudaStream_t)stream, P, C, (const T*)src, ld_src, (T*)dst, ld_dst);
+    });
+  });
+  return check_launch("copy_cols");
 }
 
 }  // extern "C"

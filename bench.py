@@ -135,6 +135,9 @@ def main():
     ap.add_argument("--impl", default="accx", choices=["accx", "reference"])
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH)
+    ap.add_argument("--variant", default="base", choices=["base", "w", "lite"],
+                    help="ACC_UNet / ACC_UNet_W / ACC_UNet_Lite (BASELINE configs[3]; the headline is base)")
+    ap.add_argument("--hw", type=int, default=HW, help="image side (BASELINE configs[4] uses 512)")
     ap.add_argument("--graph", type=int, default=1, help="capture the whole step in a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kernel-table", default="", help="write the per-kernel timing table (JSON) here")
@@ -167,12 +170,14 @@ def main():
     cd = torch.bfloat16 if args.dtype == "bf16" else torch.float32
 
     torch.manual_seed(2)                                   # same weights on every rank
-    model = accx.ACC_UNet(3, 1, 32, compute_dtype=cd).to(dev).train()
+    cls = {"base": accx.ACC_UNet, "w": accx.ACC_UNet_W, "lite": accx.ACC_UNet_Lite}[args.variant]
+    hw = args.hw
+    model = cls(3, 1, 32, compute_dtype=cd).to(dev).train()
     model.last_activation = None                           # logits for the logit-based loss (ACC_UNet.py:653-657)
     step = TrainStep(model, lr=1e-3, graph=bool(args.graph))
     g = torch.Generator().manual_seed(100 + rank)          # rank-offset data
-    x_host = torch.randn(B, 3, HW, HW, generator=g).pin_memory()
-    m_host = (torch.rand(B, 1, HW, HW, generator=g) > 0.5).float().pin_memory()
+    x_host = torch.randn(B, 3, hw, hw, generator=g).pin_memory()
+    m_host = (torch.rand(B, 1, hw, hw, generator=g) > 0.5).float().pin_memory()
     x_dev, m_dev = x_host.to(dev), m_host.to(dev)
 
     def barrier():
@@ -303,8 +308,8 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.dtype if args.dtype == "bf16" else "f32", "data": "synthetic",
-            "config": {"workload": f"ACC_UNet(3,1,32) full train step (fwd + Dice/BCE + bwd + Adam), "
-                                   f"{B}x3x{HW}x{HW} per GPU, GlaS-shaped synthetic",
+            "config": {"workload": f"{cls.__name__}(3,1,32) full train step (fwd + Dice/BCE + bwd + Adam), "
+                                   f"{B}x3x{hw}x{hw} per GPU, GlaS-shaped synthetic",
                        "global_batch": B * world, "parallelism": f"dp{world}",
                        "cuda_graph": bool(args.graph),
                        "l2_policy": "per-step working set (several GB of activations) >> 126 MB L2; no flush needed"},

@@ -225,6 +225,17 @@ int accx_nhwc_to_nchw(int in_dtype, int out_dtype, int B, int C, int HW, const v
 int accx_maxpool2_fwd(int dtype, int B, int H, int W, int C, const void* x, void* out, void* stream);
 int accx_maxpool2_bwd(int dtype, int B, int H, int W, int C, const void* x, const void* dy, void* dx, void* stream);
 
+/* ConvTranspose2d(2, 2, stride 2) + the skip torch.cat of the decoder (ACC_UNet.py:578-599,620-631).  The
+ * transposed conv itself is ONE accx_pw_fwd contraction [P, Cin] x [Cin, 4*Co] (the weight [Cin, Co, 2, 2] read
+ * through a strided view; column co*4 + ky*2 + kx = output pixel (2h+ky, 2w+kx), channel co) into `temp`
+ * [B, H, W, 4*Co].  forward = 1: out[b, 2h+ky, 2w+kx, co] = temp[b, h, w, co*4+ky*2+kx] + bias[co], out is the
+ * [B, 2H, 2W, ld_out] concat buffer (left Co columns); forward = 0: the inverse gather of the gradient into temp.
+ * accx_copy_cols copies C columns between matrices of different row pitch (skip half of the concat, its gradient). */
+int accx_upshuffle(int dtype, int forward, int B, int H, int W, int Co, void* temp, const float* bias, void* out,
+                   int64_t ld_out, void* stream);
+int accx_copy_cols(int dtype, int64_t P, int C, const void* src, int64_t ld_src, void* dst, int64_t ld_dst,
+                   void* stream);
+
 /* WeightedDiceBCE(dice_weight, BCE_weight) on one-class logits (Experiments/utils.py:21-74 BCE normalised over
  * positives / negatives, :109-138 soft Dice on sigmoid(logit) with class weights [0.5, 0.5], :140-171 the sum).
  * logit [B, N] (dtype), truth [B, N] fp32.  sums: float[8*B + 8], ZEROED by the caller (per-image partial sums

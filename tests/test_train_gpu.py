@@ -75,6 +75,34 @@ def test_out_conv_matches_torch(dtype, C, N):
 
 
 # ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+@pytest.mark.parametrize("Cin,Co,Cs,H,W", [(16, 8, 8, 6, 10), (64, 32, 32, 14, 14), (512, 256, 256, 7, 7), (24, 6, 10, 5, 3)])
+def test_up_cat_matches_torch(dtype, Cin, Co, Cs, H, W):
+    """cat([ConvTranspose2d(Cin, Co, 2, 2)(x), skip], dim=1) forward + all gradients vs ATen"""
+    from accx.modules import up_cat
+    torch.manual_seed(4)
+    up = torch.nn.ConvTranspose2d(Cin, Co, kernel_size=(2, 2), stride=2).to(DEV)
+    ref = copy.deepcopy(up)
+    x = torch.randn(2, Cin, H, W, device=DEV).to(dtype)
+    sk = torch.randn(2, Cs, 2 * H, 2 * W, device=DEV).to(dtype)
+    xa, sa = x.clone().requires_grad_(True), sk.clone().requires_grad_(True)
+    xb, sb = x.float().clone().requires_grad_(True), sk.float().clone().requires_grad_(True)
+    ya = up_cat(xa, sa, up)
+    yb = torch.cat([ref(xb), sb], dim=1)
+    assert ya.shape == yb.shape and ya.dtype == dtype
+    rt, at = (1e-3, 1e-5) if dtype == torch.float32 else (2e-2, 1e-2)
+    close(ya.float(), yb, rt, at, "up_cat")
+    assert torch.equal(ya[:, Co:], sk)                       # the skip half is a copy
+    cot = torch.randn_like(yb)
+    ya.backward(cot.to(dtype))
+    yb.backward(cot.to(dtype).float())
+    close(xa.grad.float(), xb.grad, rt, at, "up_cat dx")
+    assert torch.equal(sa.grad, cot.to(dtype)[:, Co:])
+    close(up.weight.grad, ref.weight.grad, rt, at * 10, "up_cat dW")
+    close(up.bias.grad, ref.bias.grad, 1e-3 if dtype == torch.float32 else 2e-2, 1e-3, "up_cat db")
+
+
+# ---------------------------------------------------------------------------------------------------
 def _loss_inputs(B, H, W, seed, dtype=torch.float32, soft=False):
     g = torch.Generator().manual_seed(seed)
     lg = (torch.randn(B, 1, H, W, generator=g) * 3).to(DEV).to(dtype)
