@@ -727,12 +727,12 @@ def adam_step(param, grad, exp_avg, exp_avg_sq, state, lr, beta1=0.9, beta2=0.99
           float(beta2), float(eps), float(weight_decay), float(grad_scale), stream(), cost=(7 * 4 * n, 0))
 
 
-def upshuffle(temp: torch.Tensor, bias, out: torch.Tensor, Co: int, forward: bool):
+def upshuffle(temp: torch.Tensor, bias, out: torch.Tensor, Co: int, forward: bool, dbias=None):
     """temp [B,H,W,4*Co] <-> the left Co columns of out [B,2H,2W,ld] (see accx_upshuffle in include/accx.h)"""
     B, H, W, _ = temp.shape
     assert temp.dtype == out.dtype and temp.is_contiguous() and out.is_contiguous()
     _call("accx_upshuffle", dt(temp), 1 if forward else 0, B, H, W, Co, ptr(temp), ptr(bias), ptr(out), out.shape[-1],
-          stream(), cost=(2 * nb(temp), 0), tag=f"{B}x{H}x{W}x{Co} fwd={int(forward)}")
+          ptr(dbias), stream(), cost=(2 * nb(temp), 0), tag=f"{B}x{H}x{W}x{Co} fwd={int(forward)}")
 
 
 def copy_cols(src: torch.Tensor, src_coff: int, dst: torch.Tensor, dst_coff: int, C: int):

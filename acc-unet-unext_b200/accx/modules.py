@@ -245,23 +245,22 @@ class _UpCatFn(torch.autograd.Function):
         B, H, W, Cin, Co, Cs = ctx.dims
         dn = E.to_nhwc(dout if dout.dtype == xn.dtype else dout.to(xn.dtype))
         w = E.f32(weight)
+        grads = E.GradPool([weight] + ([bias] if bias is not None else []))
+        gw = gb = None
+        if bias is not None and ctx.needs_input_grad[3]:
+            gb = E.grad_buf(grads, bias)
         dtemp = torch.empty((B, H, W, 4 * Co), dtype=xn.dtype, device=xn.device)
-        E.upshuffle(dtemp, None, dn, Co, forward=False)
+        E.upshuffle(dtemp, None, dn, Co, forward=False, dbias=gb)         # + the bias gradient, in the same pass
         dskip = None
         if ctx.needs_input_grad[1]:
             dskip = torch.empty((B, 2 * H, 2 * W, Cs), dtype=xn.dtype, device=xn.device)
             E.copy_cols(dn, Co, dskip, 0, Cs)
             dskip = E.to_nchw_view(dskip)
-        grads = E.GradPool([weight] + ([bias] if bias is not None else []))
-        gw = gb = None
         if ctx.needs_input_grad[2]:
             gw = E.grad_buf(grads, weight)
             # dW[ci, n'] = sum_p x[p, ci] * dtemp[p, n']: dtemp as the operand, x as "dY", so that the accumulated
             # rows are contiguous in the reference's [Cin, Co*4] layout (vector atomics)
             E.wgrad(Op(Lazy(dtemp), 4 * Co, WV(w, 0, 4 * Co, 1)), xn, Cin, (B, H, W), gw)
-        if bias is not None and ctx.needs_input_grad[3]:
-            gb = E.grad_buf(grads, bias)
-            torch.sum(dtemp.view(-1, Co, 4), dim=(0, 2), dtype=torch.float32, out=gb)
         dx = None
         if ctx.needs_input_grad[0]:
             dx = E.to_nchw_view(E.conv([Op(Lazy(dtemp), 4 * Co, WV(w, 0, 4 * Co, 1))], Cin, (B, H, W)))

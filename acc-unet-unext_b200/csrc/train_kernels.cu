@@ -271,15 +271,17 @@ __global__ void __launch_bounds__(256) adam_flat_kernel(int64_t n4, float4* __re
 template <typename T, bool FWD>
 __global__ void __launch_bounds__(256) upshuffle_kernel(int B, int H, int W, int Co, T* __restrict__ temp,
                                                         const float* __restrict__ bias, T* __restrict__ out,
-                                                        int64_t ld_out) {
+                                                        int64_t ld_out, float* dbias) {
   pdl_sync();
+  extern __shared__ float smem[];
   const int pairs = Co >> 1;
   const int cp = blockIdx.y * blockDim.x + threadIdx.x;
-  if (cp >= pairs) return;
-  const int co = cp * 2;
+  const bool active = cp < pairs;
+  const int co = active ? cp * 2 : 0;
+  float bacc[1][2] = {{0.f, 0.f}};                     // backward: the transposed conv's bias gradient
   const float b0 = (FWD && bias) ? bias[co] : 0.f, b1 = (FWD && bias) ? bias[co + 1] : 0.f;
   const int64_t P = (int64_t)B * H * W;
-  for (int64_t q = (int64_t)blockIdx.x * blockDim.y + threadIdx.y; q < P; q += (int64_t)gridDim.x * blockDim.y) {
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.y + threadIdx.y; active && q < P; q += (int64_t)gridDim.x * blockDim.y) {
     const int w = (int)(q % W);
     const int64_t t = q / W;
     const int h = (int)(t % H);
@@ -322,7 +324,12 @@ __global__ void __launch_bounds__(256) upshuffle_kernel(int B, int H, int W, int
         stv<T, 4>(trow, *reinterpret_cast<float(*)[4]>(v));
         stv<T, 4>(trow + 4, *reinterpret_cast<float(*)[4]>(v + 4));
       }
+      bacc[0][0] += (v[0] + v[1]) + (v[2] + v[3]);
+      bacc[0][1] += (v[4] + v[5]) + (v[6] + v[7]);
     }
+  }
+  if constexpr (!FWD) {
+    if (dbias) reduce_lanes_atomic<1, 2>(bacc, smem, dbias, 0, Co);
   }
 }
 
@@ -434,7 +441,7 @@ int accx_adam_step(int64_t n, float* param, const float* grad, float* exp_avg, f
 
 
 int accx_upshuffle(int dtype, int forward, int B, int H, int W, int Co, void* temp, const float* bias, void* out,
-                   int64_t ld_out, void* stream) {
+                   int64_t ld_out, float* dbias, void* stream) {
   ACCX_REQUIRE(B > 0 && H > 0 && W > 0 && Co > 0 && Co % 2 == 0 && temp && out && ld_out >= Co,
                "upshuffle: bad arguments (Co = %d must be even)", Co);
   ACCX_REQUIRE(aligned16(temp) && aligned16(out) && ld_out % 2 == 0, "upshuffle: buffers must be 16-byte aligned");
@@ -443,11 +450,15 @@ int accx_upshuffle(int dtype, int forward, int B, int H, int W, int Co, void* te
   int ty = 256 / tx;
   if (ty < 1) ty = 1;
   const int64_t P = (int64_t)B * H * W;
-  dim3 block(tx, ty), grid(grid_x_for(P, ty * 2, 148 * 16), (pairs + tx - 1) / tx);
+  // the backward variant also reduces the bias gradient: few long-lived blocks (one atomic per block and channel)
+  dim3 block(tx, ty), grid(grid_x_for(P, ty * 2, forward || !dbias ? 148 * 16 : 148 * 4), (pairs + tx - 1) / tx);
+  const size_t sm = (forward || !dbias) ? 0 : (size_t)tx * ty * 2 * sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;
   ACCX_DISPATCH_T(dtype, {
-    if (forward) launch_k(upshuffle_kernel<T, true>, grid, block, 0, st, B, H, W, Co, (T*)temp, bias, (T*)out, ld_out);
-    else launch_k(upshuffle_kernel<T, false>, grid, block, 0, st, B, H, W, Co, (T*)temp, bias, (T*)out, ld_out);
+    if (forward)
+      launch_k(upshuffle_kernel<T, true>, grid, block, sm, st, B, H, W, Co, (T*)temp, bias, (T*)out, ld_out, (float*)nullptr);
+    else
+      launch_k(upshuffle_kernel<T, false>, grid, block, sm, st, B, H, W, Co, (T*)temp, bias, (T*)out, ld_out, dbias);
   });
   return check_launch("upshuffle");
 }

@@ -229,10 +229,11 @@ int accx_maxpool2_bwd(int dtype, int B, int H, int W, int C, const void* x, cons
  * transposed conv itself is ONE accx_pw_fwd contraction [P, Cin] x [Cin, 4*Co] (the weight [Cin, Co, 2, 2] read
  * through a strided view; column co*4 + ky*2 + kx = output pixel (2h+ky, 2w+kx), channel co) into `temp`
  * [B, H, W, 4*Co].  forward = 1: out[b, 2h+ky, 2w+kx, co] = temp[b, h, w, co*4+ky*2+kx] + bias[co], out is the
- * [B, 2H, 2W, ld_out] concat buffer (left Co columns); forward = 0: the inverse gather of the gradient into temp.
+ * [B, 2H, 2W, ld_out] concat buffer (left Co columns); forward = 0: the inverse gather of the gradient into temp,
+ * and dbias[co] += sum of that gradient over pixels and taps (the bias gradient; may be NULL).
  * accx_copy_cols copies C columns between matrices of different row pitch (skip half of the concat, its gradient). */
 int accx_upshuffle(int dtype, int forward, int B, int H, int W, int Co, void* temp, const float* bias, void* out,
-                   int64_t ld_out, void* stream);
+                   int64_t ld_out, float* dbias, void* stream);
 int accx_copy_cols(int dtype, int64_t P, int C, const void* src, int64_t ld_src, void* dst, int64_t ld_dst,
                    void* stream);
 
