@@ -426,6 +426,24 @@ __global__ void se_bwd_apply_kernel(int B, int HW, int C, int chunks, const T* _
     else { constexpr int U = 4; __VA_ARGS__ }           \
   } while (0)
 
+// channel-vector width: 1 (scalar fallback), the full 16-byte vector, or -- bf16 only, for the register-heavy
+// backward kernels -- half of it (8-byte accesses, half the per-channel constants per thread: 126 instead of
+// 203-239 registers, two blocks per SM instead of one; B200, 51 MB tensors: se_bwd_reduce 45 -> 37 us,
+// se_bwd_apply 61 -> 46 us; KNOB_SE_BWD_VEC = 8 restores the full vector)
+#define ACCX_DISPATCH_VEC_H(lanes, ...)                                  \
+  do {                                                                   \
+    if ((lanes).vec == 1) {                                              \
+      constexpr int VEC = 1;                                             \
+      __VA_ARGS__                                                        \
+    } else if ((lanes).vec == 4) {                                       \
+      constexpr int VEC = 4;                                             \
+      __VA_ARGS__                                                        \
+    } else {                                                             \
+      constexpr int VEC = accx::DT<T>::VEC;                              \
+      __VA_ARGS__                                                        \
+    }                                                                    \
+  } while (0)
+
 static inline int se_chunks(int B, int HW, int ty, int target_blocks = 148 * 4) {
   // enough blocks to fill the machine, but keep the number of atomics per (b,c) small
   int per_img = (HW + ty * 8 - 1) / (ty * 8);
@@ -499,12 +517,13 @@ int accx_se_bwd_reduce(int dtype, int B, int HW, int C, const void* x, const flo
   ACCX_REQUIRE(B > 0 && HW > 0 && C > 0 && x && gate && dout && G, "se_bwd_reduce: bad arguments");
   ACCX_REQUIRE(!dmix || (mix && residual), "se_bwd_reduce: dmix needs mix and residual");
   ACCX_DISPATCH_T(dtype, {
-    Lanes l = make_lanes(C, DT<T>::VEC, aligned16(x) && aligned16(dout) && (!residual || aligned16(residual)));
+    const int fv = knob(KNOB_SE_BWD_VEC, 4) == 4 ? 4 : DT<T>::VEC;
+    Lanes l = make_lanes(C, fv, aligned16(x) && aligned16(dout) && (!residual || aligned16(residual)));
     int chunks = se_chunks(B, HW, l.ty, 148 * knob(KNOB_SE_BWD_REDUCE_BLOCKS, 4));
     dim3 block(l.tx, l.ty), grid(B * chunks, l.gy);
     size_t sm = (size_t)l.tx * l.ty * l.vec * sizeof(float);
     const int u = knob(KNOB_SE_BWD_REDUCE_U, 8);
-    ACCX_DISPATCH_VEC(l, {
+    ACCX_DISPATCH_VEC_H(l, {
       ACCX_DISPATCH_U(u, {
         launch_k(se_bwd_reduce_kernel<T, VEC, U>, grid, block, sm, (cudaStream_t)stream, 
             B, HW, C, chunks, (const T*)x, scale, shift, act, gate, se_scale, se_shift, (const T*)dout, mix,
@@ -534,13 +553,14 @@ int accx_se_bwd_apply(int dtype, int B, int HW, int C, const void* x, const floa
   ACCX_REQUIRE(B > 0 && HW > 0 && C > 0 && x && gate && dout && PQR && da, "se_bwd_apply: bad arguments");
   ACCX_REQUIRE(!bn_sums || (bn_mean && bn_rstd), "se_bwd_apply: bn_sums needs bn_mean and bn_rstd");
   ACCX_DISPATCH_T(dtype, {
-    Lanes l = make_lanes(C, DT<T>::VEC, aligned16(x) && aligned16(dout) && aligned16(da));
+    const int fv = knob(KNOB_SE_BWD_VEC, 4) == 4 ? 4 : DT<T>::VEC;
+    Lanes l = make_lanes(C, fv, aligned16(x) && aligned16(dout) && aligned16(da));
     // reducing variant: few blocks (atomics)
     const int chunks = se_chunks(B, HW, l.ty, 148 * (bn_sums ? knob(KNOB_SE_BWD_APPLY_BN_BLOCKS, 4) : knob(KNOB_SE_BWD_APPLY_BLOCKS, 8)));
     dim3 block(l.tx, l.ty), grid(B * chunks, l.gy);
     const size_t sm = bn_sums ? (size_t)l.tx * l.ty * l.vec * sizeof(float) : 0;
     const int u = knob(KNOB_SE_BWD_APPLY_U, 8);
-    ACCX_DISPATCH_VEC(l, {
+    ACCX_DISPATCH_VEC_H(l, {
       ACCX_DISPATCH_U(u, {
         launch_k(se_bwd_apply_kernel<T, VEC, U>, grid, block, sm, (cudaStream_t)stream, 
             B, HW, C, chunks, (const T*)x, scale, shift, act, gate, se_scale, se_shift, (const T*)dout, mix, PQR, (T*)da,

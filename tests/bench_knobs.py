@@ -19,7 +19,7 @@ DEV = "cuda"
 KNOBS = {n: i for i, n in enumerate(
     ["SE_SQUEEZE_BLOCKS", "SE_SQUEEZE_U", "SE_APPLY_BLOCKS", "SE_APPLY_STATS_BLOCKS", "SE_APPLY_U", "SE_BWD_REDUCE_BLOCKS",
      "SE_BWD_REDUCE_U", "SE_BWD_APPLY_BLOCKS", "SE_BWD_APPLY_BN_BLOCKS", "SE_BWD_APPLY_U", "BN_REDUCE_BLOCKS", "EW_BLOCKS",
-     "POOL_BLOCKS", "TC_SMEM_KB", "TC_MAX_STAGES", "WGRAD_MIN_STAGES", "WGRAD_SMEM_KB"])}
+     "POOL_BLOCKS", "TC_SMEM_KB", "TC_MAX_STAGES", "WGRAD_MIN_STAGES", "WGRAD_SMEM_KB", "SE_BWD_VEC"])}
 SHAPES = [(16, 50176, 32), (16, 12544, 64), (16, 3136, 128), (16, 784, 256)]
 ROT = 4
 
@@ -99,6 +99,8 @@ SWEEPS = {
 
 def main():
     _lib.load()
+    if os.environ.get("SE_BWD_VEC"):
+        set_knob("SE_BWD_VEC", int(os.environ["SE_BWD_VEC"]))
     kernels = sys.argv[1:] or list(SWEEPS)
     for k in kernels:
         kb, ku = SWEEPS[k]
