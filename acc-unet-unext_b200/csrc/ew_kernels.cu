@@ -63,7 +63,7 @@ __global__ void bn_finalize_kernel(int C, double count, const float* __restrict_
 
 // --------------------------------------------------------------------------------------
 template <typename T, int VEC>
-__global__ void act_apply_kernel(int64_t P, int C, const T* __restrict__ x, const float* scale, const float* shift,
+__global__ void __launch_bounds__(256, 2) act_apply_kernel(int64_t P, int C, const T* __restrict__ x, const float* scale, const float* shift,
                                  int act, const float* scale2, const float* shift2, const T* __restrict__ residual,
                                  T* __restrict__ out, float* stats) {
   pdl_sync();
@@ -110,7 +110,7 @@ __global__ void act_apply_kernel(int64_t P, int C, const T* __restrict__ x, cons
 
 // z = act(a) + r
 template <typename T, int VEC>
-__global__ void add_fwd_kernel(int64_t P, int C, const T* __restrict__ a, const float* scale, const float* shift,
+__global__ void __launch_bounds__(256, 2) add_fwd_kernel(int64_t P, int C, const T* __restrict__ a, const float* scale, const float* shift,
                                int act, const T* __restrict__ r, T* __restrict__ z, float* stats) {
   pdl_sync();
   extern __shared__ float smem[];
