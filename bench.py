@@ -105,7 +105,7 @@ def run_reference(args, rank):
     steps, warm = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
     ips, spstep = cpu_oracle_images_per_s(steps, warm, cores)
     sample = f"{CPU_SAMPLE_BATCH}x3x{HW}x{HW} fp32 train step (fwd+Dice/BCE+bwd+Adam), {steps} timed steps after {warm} warm-up"
-    print(json.dumps({
+    emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warm, "ms_per_step": spstep * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
@@ -113,6 +113,18 @@ def run_reference(args, rank):
         "cpu_baseline": {"value": ips, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
+
+
+_RESULT_FD = None
+
+
+def emit(line: str):
+    """the one result line -> the process's original stdout"""
+    sys.stdout.flush()
+    if _RESULT_FD is None:
+        print(line, flush=True)
+    else:
+        os.write(_RESULT_FD, (line + "\n").encode())
 
 
 def kernel_table(profile):
@@ -146,6 +158,13 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    # stdout carries exactly ONE line, the JSON result: file descriptor 1 is pointed at stderr for the whole run
+    # (NCCL prints its version banner with a C-level printf that no Python-side redirection catches) and the
+    # result line is written to the saved descriptor at the end
+    sys.stdout.flush()
+    global _RESULT_FD
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args, rank)
         return
@@ -318,7 +337,7 @@ def main():
             "gpu_launches": launches_per_step * K,
             "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "loss": float(loss_host),
         }
-        print(json.dumps(out), flush=True)
+        emit(json.dumps(out))
     if world > 1:
         # Leave without tearing NCCL down: destroying a communicator whose collectives were captured into a
         # still-alive CUDA graph can block at exit.  Everything that matters (the JSON line) is already out.
