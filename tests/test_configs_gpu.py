@@ -43,6 +43,7 @@ def test_c1_forward_1x3x224x224_fp32_matches_cpu_oracle():
     # 220 BatchNorms over a single image: compare in relative L2 and in the worst element against the output range
     for got, want, what in ((got_train, want_train, "train"), (got_eval, want_eval, "eval")):
         scale = float(want.abs().max())
+        print(f"c1 {what}: rel-l2 {rel_l2(got, want):.2e}, max abs err {float((got - want).abs().max()):.2e} of {scale:.2e}")
         assert rel_l2(got, want) < 2e-3, f"{what}: rel-l2 {rel_l2(got, want):.2e}"
         assert float((got - want).abs().max()) < 5e-3 * scale, f"{what}: max {float((got - want).abs().max()):.2e} / {scale:.2e}"
 
@@ -64,6 +65,7 @@ def test_c2_train_step_16x3x224x224_bf16_properties():
         yp = m(x[perm])
         l0, l1 = float(dice_bce_loss(y, msk)), float(dice_bce_loss(yp, msk[perm]))
     assert torch.isfinite(y).all()
+    print(f"c2 fp32 batch permutation: output rel-l2 {rel_l2(yp, y[perm]):.2e}, loss {l0:.7f} vs {l1:.7f}")
     assert rel_l2(yp, y[perm]) < 1e-2, rel_l2(yp, y[perm])
     assert abs(l0 - l1) < 1e-4 * max(1.0, abs(l0)), (l0, l1)
     m.compute_dtype = torch.bfloat16                     # the bench configuration: bf16 storage
@@ -94,6 +96,7 @@ def test_c4_variants_32x3x224x224_bf16_fwd_bwd(cls_name):
         y8p = m(x[:8][perm])
         m.compute_dtype = torch.bfloat16
     assert y.shape == (32, 1, 224, 224) and torch.isfinite(y).all()
+    print(f"c4 {cls_name} fp32 batch permutation (8 images): output rel-l2 {rel_l2(y8p, y8[perm]):.2e}")
     assert rel_l2(y8p, y8[perm]) < 1e-2, rel_l2(y8p, y8[perm])
     xg = x.clone().requires_grad_(True)
     out = m(xg)

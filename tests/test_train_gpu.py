@@ -285,18 +285,22 @@ def test_train_step_whole_model_variants(variant):
     before = {n: p.detach().clone() for n, p in ma.named_parameters()}
     for it in range(3):
         la, lb = float(step(x, m)), float(_loose_step(mb, opt, x, m))
+        print(f"{variant} step {it}: flat {la:.6f} loose {lb:.6f}")
         tol = 1e-4 if it == 0 else 1e-2
         assert abs(la - lb) < tol * max(1.0, abs(lb)), (it, la, lb)
     fs = step.flat
     idle = 0
+    gmax = max(float(q.grad.abs().max()) for q in mb.parameters() if q.grad is not None)
     for (n, p), (_, q) in zip(ma.named_parameters(), mb.named_parameters()):
         assert p.data_ptr() == fs._view(fs.param, p).data_ptr()
         assert p.grad is None or p.grad.data_ptr() == fs._view(fs.grad, p).data_ptr()
         if q.grad is None:
             idle += 1
             assert torch.equal(p.detach(), before[n]), f"{n}: parameter without a gradient moved"
-        else:
-            assert not torch.equal(p.detach(), before[n]) or float(q.grad.abs().max()) == 0.0, f"{n} did not move"
+        elif float(q.grad.abs().max()) > 1e-6 * gmax:
+            # (a gradient at rounding level -- |g| << Adam's eps -- gives an update below the fp32 resolution of the
+            # parameter: seen on `out.bias`, whose gradient is a sum of +- terms that cancel to ~1e-13)
+            assert not torch.equal(p.detach(), before[n]), f"{n} did not move"
     assert (idle > 0) == (variant == "lite")
 
 
@@ -317,6 +321,7 @@ def test_train_step_graph_equals_eager_and_loss_decreases():
         la.append(float(sa(x, m)))
         lb.append(float(sb(x, m)))
     assert sa.graph is not None
+    print("graph vs eager losses:", [f"{a:.5f}/{b:.5f}" for a, b in zip(la, lb)])
     # same weights, bf16 storage: two bf16 evaluations differ by rounding-level noise in the statistics that the
     # BatchNorm stack amplifies (see the note above), so even the first loss only agrees to ~1e-3
     assert abs(la[0] - lb[0]) < 1e-2 * max(1.0, abs(lb[0])), (la, lb)
@@ -344,5 +349,6 @@ def test_train_step_matches_cpu_oracle_step():
     for it in range(3):
         lo, opt = O.train_step(sd, x, m, opt)
         la = float(step(x.to(DEV), m.to(DEV)))
+        print(f"oracle step {it}: accx {la:.6f} oracle {lo:.6f}")
         tol = 1e-4 if it == 0 else 1e-2          # see the note on conditioning above
         assert abs(la - lo) < tol * max(1.0, abs(lo)), (it, la, lo)
