@@ -116,3 +116,42 @@ def test_flat_state_layout_cpu():
     assert float(fs.grad.sum()) == p0.numel() * 1.0 + params[1].numel() * 2.0   # padding stays zero
     fs.begin_step()
     assert float(fs.grad.abs().sum()) == 0.0 and all(p.grad is None for p in params) and fs.serves(p0)
+
+
+def test_grad_arena_hands_flat_views_to_module_backward_cpu():
+    """engine.GRAD_ARENA protocol (host logic, no kernels): while a FlatState is the arena, GradPool leaves the
+    parameters it serves to the arena, grad_buf returns the arena's view once per step, and a foreign parameter
+    (not in the flat buffers) still gets its own zeroed accumulator."""
+    for p in (ROOT, os.path.join(ROOT, "acc-unet-unext_b200")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    from accx import engine as E
+    from accx.train import FlatState
+    net = torch.nn.Sequential(torch.nn.Conv2d(3, 4, 1), torch.nn.BatchNorm2d(4))
+    params = list(net.parameters())
+    foreign = torch.nn.Parameter(torch.ones(3))
+    fs = FlatState(params)
+    fs.begin_step()
+    old, E.GRAD_ARENA = E.GRAD_ARENA, fs
+    try:
+        pool = E.GradPool(params + [foreign])
+        assert set(pool.spare) == {id(foreign)}                       # only the foreign parameter gets a loose buffer
+        g0 = E.grad_buf(pool, params[0])
+        assert g0.data_ptr() == fs._view(fs.grad, params[0]).data_ptr() and float(g0.abs().sum()) == 0.0
+        assert E.grad_buf(pool, params[0]) is g0                      # same accumulator within one module backward
+        gf = E.grad_buf(pool, foreign)
+        assert gf.data_ptr() != fs.grad.data_ptr() and float(gf.abs().sum()) == 0.0
+        # a second module backward in the same step asking for the same parameter does NOT get the slice again
+        pool2 = E.GradPool([params[0]])
+        g1 = E.grad_buf(pool2, params[0])
+        assert g1.data_ptr() != g0.data_ptr() and float(g1.abs().sum()) == 0.0
+        frozen = torch.nn.Parameter(torch.ones(2), requires_grad=False)
+        assert E.grad_buf(pool, frozen) is None
+    finally:
+        E.GRAD_ARENA = old
+    fs.begin_step()                                                   # next step: the slices are handed out again
+    E.GRAD_ARENA = fs
+    try:
+        assert E.grad_buf(E.GradPool(params), params[0]).data_ptr() == fs._view(fs.grad, params[0]).data_ptr()
+    finally:
+        E.GRAD_ARENA = old
