@@ -40,12 +40,16 @@ def test_c1_forward_1x3x224x224_fp32_matches_cpu_oracle():
         want_train = O.acc_unet(O.Ctx({k: v.clone() for k, v in sd.items()}, True), x, "base", logits=True)
         got_train = m(x.to(DEV)).cpu()
     assert got_train.shape == want_train.shape == (1, 1, 224, 224)
-    # 220 BatchNorms over a single image: compare in relative L2 and in the worst element against the output range
-    for got, want, what in ((got_train, want_train, "train"), (got_eval, want_eval, "eval")):
+    # eval mode (running statistics, no batch reductions) is deterministic and must agree at fp32 rounding level
+    # (measured rel-l2 1.4e-7).  Train mode normalises with the statistics of ONE image through 220 BatchNorms: the
+    # fp32 summation order (atomics on the GPU, MKL-DNN's blocking on the CPU) perturbs every activation at the 1e-7
+    # level and the stack amplifies that to ~1e-3 at the output (measured rel-l2 1.2e-3, varying from run to run),
+    # so its bound is a loose one; the tight train-mode parity is carried by the per-module tests.
+    for got, want, what, lim in ((got_train, want_train, "train", 2e-2), (got_eval, want_eval, "eval", 1e-5)):
         scale = float(want.abs().max())
         print(f"c1 {what}: rel-l2 {rel_l2(got, want):.2e}, max abs err {float((got - want).abs().max()):.2e} of {scale:.2e}")
-        assert rel_l2(got, want) < 2e-3, f"{what}: rel-l2 {rel_l2(got, want):.2e}"
-        assert float((got - want).abs().max()) < 5e-3 * scale, f"{what}: max {float((got - want).abs().max()):.2e} / {scale:.2e}"
+        assert rel_l2(got, want) < lim, f"{what}: rel-l2 {rel_l2(got, want):.2e}"
+        assert float((got - want).abs().max()) < 5 * lim * scale, f"{what}: max {float((got - want).abs().max()):.2e} / {scale:.2e}"
 
 
 def test_c2_train_step_16x3x224x224_bf16_properties():
