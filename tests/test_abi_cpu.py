@@ -32,6 +32,30 @@ def test_invalid_arguments_return_error_codes_not_crashes():
         _lib.call("accx_pool_sum", 0, 0, 1, 3, 3, 8, 1, 1.0, 1, 1, 8, None)     # 3x3 not divisible by 2
 
 
+def test_train_step_entry_points_validate_arguments():
+    """rows f1 / f2 of the scope table: bad arguments come back as error codes before anything touches the GPU"""
+    from accx import _lib
+    lib = _lib.load()
+    err = lambda: lib.accx_last_error().decode()
+    assert lib.accx_adam_step(3, None, None, None, None, None, 1e-3, 0.9, 0.999, 1e-8, 0.0, 1.0, None) == -1
+    assert "adam_step" in err()
+    assert lib.accx_maxpool2_bwd(1, 1, 7, 8, 8, 1, 1, 1, None) == -1 and "even" in err()          # odd height
+    assert lib.accx_maxpool2_fwd(1, 1, 8, 8, 8, None, None, None) == -1 and "maxpool2_fwd" in err()
+    assert lib.accx_upshuffle(1, 1, 1, 4, 4, 7, 16, None, 16, 14, None, None) == -1 and "even" in err()   # odd Co
+    assert lib.accx_copy_cols(1, 4, 8, 16, 4, 16, 8, None) == -1 and "copy_cols" in err()            # ld_src < C
+    assert lib.accx_dice_bce_fwd(1, 2, 16, None, None, 0.5, 0.5, None, None, None) == -1 and "dice_bce_fwd" in err()
+    assert lib.accx_dice_bce_bwd(1, 7, 2, 16, 16, 16, 16, 0.5, 0.5, None, None, None) == -1 or "dice_bce_bwd" in err()
+    assert lib.accx_set_knob(999, 1) == -1 and "out of range" in err()
+    assert lib.accx_set_knob(0, 0) == 0
+
+
+def test_every_entry_point_is_mapped_to_the_reference_in_integration_md():
+    from accx import _lib
+    doc = open(os.path.join(_lib.ROOT, "INTEGRATION.md")).read()
+    missing = [n for n in _lib.parse_header() if f"`{n}`" not in doc]
+    assert not missing, f"INTEGRATION.md does not say which reference call these replace: {missing}"
+
+
 def test_reference_signatures_are_kept():
     import accx
     sig = lambda c: list(inspect.signature(c.__init__).parameters)[1:]

@@ -155,3 +155,22 @@ def test_grad_arena_hands_flat_views_to_module_backward_cpu():
         assert E.grad_buf(E.GradPool(params), params[0]).data_ptr() == fs._view(fs.grad, params[0]).data_ptr()
     finally:
         E.GRAD_ARENA = old
+
+
+@pytest.mark.timeout(600)
+def test_reference_arm_prints_one_json_line_with_the_contract_keys():
+    """`bench.py --impl reference` (the reference's CPU path on the host cores): stdout is exactly one JSON line
+    carrying the keys the driver reads; anything else the process prints goes to stderr."""
+    import json
+    import subprocess
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=580)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout[:500]
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"].startswith("ACC-UNet train images/sec") and d["unit"] == "images/s"
+    assert d["value"] > 0 and d["higher_is_better"] is True and d["n_gpus"] == 1
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["gpu_launches"] == 0
