@@ -86,7 +86,8 @@ def dice_bce_loss(logit: torch.Tensor, truth: torch.Tensor, dice_weight: float =
 
 class FlatState:
     """Parameters, gradients and Adam moments of a model as four flat fp32 buffers (see the module docstring).
-    While `active()` the accx backward kernels write parameter gradients into the flat gradient buffer."""
+    While it is installed as `engine.GRAD_ARENA` (TrainStep does that around forward + backward) the accx backward
+    kernels accumulate parameter gradients straight into the flat gradient buffer."""
 
     ALIGN = 64          # elements: every slice starts 256-byte aligned (vector loads, TMA-able weight views)
 
