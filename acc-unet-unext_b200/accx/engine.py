@@ -61,6 +61,8 @@ BWD_DEPTH = [0]
 _SIDE = {}
 _SIDE_DIRTY = set()
 _KEEP = []
+_KEEP_BYTES = [0]
+KEEP_LIMIT = int(float(os.environ.get("ACCX_SIDE_KEEP_GB", "12")) * (1 << 30))
 
 
 class side_stream:
@@ -86,7 +88,10 @@ class side_stream:
         _SIDE_DIRTY.add(dev)
         # whatever the side stream reads must outlive the join: a temporary the caller drops right after this
         # call would otherwise go back to the allocator and be handed to the next kernel on the caller's stream
-        _KEEP.extend(t for t in self.keep if t is not None)
+        for t in self.keep:
+            if t is not None:
+                _KEEP.append(t)
+                _KEEP_BYTES[0] += t.numel() * t.element_size()
         self.ctx = torch.cuda.stream(s)
         self.ctx.__enter__()
         return self
@@ -94,6 +99,11 @@ class side_stream:
     def __exit__(self, *exc):
         if self.ctx is not None:
             self.ctx.__exit__(*exc)
+            # deferred join (mode 2): everything the side stream reads stays allocated until the join; past
+            # KEEP_LIMIT bytes the caller's stream waits for the side stream here and the tensors are released
+            # (bounds the peak memory of the 512^2 / large-batch configurations; never reached at 16 x 224^2)
+            if _KEEP_BYTES[0] > KEEP_LIMIT:
+                join_side()
         return False
 
 
@@ -106,11 +116,37 @@ def join_side():
         torch.cuda.current_stream().wait_event(ev)
         _SIDE_DIRTY.discard(dev)
     _KEEP.clear()
+    _KEEP_BYTES[0] = 0
 
 
 def module_backward_end():
-    if SIDE_MODE == 1:
+    # mode 2 defers the join to the train step, which owns every gradient through its flat buffer (GRAD_ARENA);
+    # without an arena the gradients go to autograd right after this call, so the side stream is joined here
+    if SIDE_MODE == 1 or (SIDE_MODE == 2 and GRAD_ARENA is None):
         join_side()
+
+
+def param_grads(params, grads: dict):
+    """What a module backward returns to autograd for `params`.  A gradient that was accumulated in place in the
+    train step's flat gradient buffer (GRAD_ARENA) is NOT handed to autograd: AccumulateGrad would steal or -- when
+    anything else still references the tensor -- CLONE it on the caller's stream while the side stream may not
+    have finished (or started) adding to it, and the stale copy would later overwrite the slice.  FlatState.collect()
+    points p.grad at the slice after the join instead.  Any other gradient (a parameter the arena does not serve, or
+    a second use of a served one) is returned; in deferred-join mode the side stream is joined first."""
+    ga = GRAD_ARENA
+    out, loose = [], False
+    for p in params:
+        g = grads.get(id(p))
+        if g is not None and ga is not None and ga.owns(p, g):
+            g = None
+        elif g is not None:
+            loose = True
+            if g.dtype != p.dtype:
+                g = g.to(p.dtype)
+        out.append(g)
+    if loose and SIDE_MODE == 2:
+        join_side()
+    return out
 
 
 # ---- independent chains on parallel streams --------------------------------------------------------
@@ -347,7 +383,7 @@ def wgrad(op: Op, dy: torch.Tensor, N: int, dims, gw: torch.Tensor, dy_coff: int
     tag = f"P={P} N={N} K={op.K} shift={bool(op.dy or op.dx)}"
     dwp = gw.data_ptr() + op.wv.off * 4
     dyp = dy.data_ptr() + dy_coff * dy.element_size()
-    with side_stream(keep=(op.src.y, op.src.scale, op.src.shift, dy, gw)):
+    with side_stream(keep=(op.src.y, op.src.scale, op.src.shift, dy)):
         if (TC and in_dt == BF16 and not dy_f32 and op.K % 8 == 0 and N % 8 == 0 and o.ld % 8 == 0
                 and dy.shape[-1] % 8 == 0 and o.data % 16 == 0 and dyp % 16 == 0):
             _call("accx_pw_wgrad_tc", B, H, W, N, ctypes.byref(o), dwp, dyp, dy.shape[-1], stream(), cost=cost, tag=tag)
@@ -375,7 +411,7 @@ def wgrad_conv3x3(X: Lazy, C_in: int, w: torch.Tensor, dy: torch.Tensor, N: int,
     o = Operand()
     _fill(o, Op(X, C_in, WV(w, 0, C_in * 9, 9)), gw)
     P = B * H * W
-    with side_stream(keep=(y, X.scale, X.shift, dy, gw)):
+    with side_stream(keep=(y, X.scale, X.shift, dy)):
         for g0 in range(0, 9, per):
             grp = taps[g0:g0 + per]
             n = len(grp)
@@ -517,7 +553,7 @@ def dw_dgrad_bnred(L: Lazy, dy: torch.Tensor, w, arena: Arena):
 def dw_wgrad(L: Lazy, dy: torch.Tensor, gw: torch.Tensor):
     y = L.y
     B, H, W, C = y.shape
-    with side_stream(keep=(y, L.scale, L.shift, dy, gw)):
+    with side_stream(keep=(y, L.scale, L.shift, dy)):
         _call("accx_dw3x3_wgrad", dt(y), B, H, W, C, ptr(y), ptr(L.scale), ptr(L.shift), L.act, ptr(dy), ptr(gw),
               stream(), cost=(nb(y, dy), 18 * y.numel()), tag=f"{B}x{H}x{W}x{C}")
 

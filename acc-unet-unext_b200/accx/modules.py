@@ -65,12 +65,7 @@ class _ModuleFn(torch.autograd.Function):
         finally:
             E.BWD_DEPTH[0] -= 1
             E.module_backward_end()      # weight gradients run on a side stream (engine.side_stream)
-        gp = []
-        for p in ctx.params:
-            g = grads.get(id(p))
-            if g is not None and g.dtype != p.dtype:
-                g = g.to(p.dtype)
-            gp.append(g)
+        gp = E.param_grads(ctx.params, grads)
         gx = [None if dx is None else E.to_nchw_view(dx) for dx in dxs]
         return (None, None, *gx, *gp)
 
@@ -137,10 +132,7 @@ class _GroupFn(torch.autograd.Function):
         for chain_pools in pools:
             for gp in chain_pools:
                 grads.update(gp)
-        gp_all = []
-        for p in ctx.params:
-            g = grads.get(id(p))
-            gp_all.append(g if g is None or g.dtype == p.dtype else g.to(p.dtype))
+        gp_all = E.param_grads(ctx.params, grads)
         return (None, *[None if g is None else E.to_nchw_view(g) for g in gx], *gp_all)
 
 
@@ -210,6 +202,7 @@ class _OutConvFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dl = dn if dn.dtype == xn.dtype else dn.to(xn.dtype)
             dx = E.to_nchw_view(E.conv([Op(Lazy(dl), N, WV(w, 0, 1, C))], C, dims))
+        gw, gb = E.param_grads([weight, bias], grads)
         return dx, gw, gb
 
 
@@ -264,6 +257,7 @@ class _UpCatFn(torch.autograd.Function):
         dx = None
         if ctx.needs_input_grad[0]:
             dx = E.to_nchw_view(E.conv([Op(Lazy(dtemp), 4 * Co, WV(w, 0, 4 * Co, 1))], Cin, (B, H, W)))
+        gw, gb = E.param_grads([weight, bias], grads)
         return dx, dskip, gw, gb
 
 

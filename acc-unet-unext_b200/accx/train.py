@@ -132,6 +132,11 @@ class FlatState:
         self.taken.add(id(p))
         return self._view(self.grad, p)
 
+    def owns(self, p, g) -> bool:
+        """is `g` the slice of the flat gradient buffer that take(p) handed out?"""
+        o = self.offsets.get(id(p))
+        return o is not None and id(p) in self.taken and g.data_ptr() == self.grad.data_ptr() + 4 * o
+
     def begin_step(self):
         """zero the flat gradients (one memset) and drop the p.grad views of the previous step"""
         for p in self.params:
@@ -140,16 +145,23 @@ class FlatState:
         self.taken.clear()
 
     def collect(self):
-        """after backward: gradients that autograd produced outside the flat buffer (parameters of torch-native
-        layers such as ConvTranspose2d) are copied into their slices, and p.grad is pointed at the slice"""
+        """after backward (and after the side stream has been joined): p.grad of every parameter whose gradient was
+        accumulated in place is pointed at its slice -- those gradients never pass through autograd (see
+        engine.param_grads), so nothing is copied.  Gradients that autograd produced outside the flat buffer
+        (parameters of torch-native layers mixed into the model, a second use of a parameter) are added / copied
+        into the slice."""
         for p in self.params:
             g = p.grad
-            if g is None:
-                continue
+            mine = id(p) in self.taken
+            if g is None and not mine:
+                continue                              # no gradient this step (ACC_UNet_Lite's idle MLFC convs)
             v = self._view(self.grad, p)
-            if g.data_ptr() != v.data_ptr():
-                v.copy_(g)
-                p.grad = v
+            if g is not None and g.data_ptr() != v.data_ptr():
+                if mine:
+                    v.add_(g)
+                else:
+                    v.copy_(g)
+            p.grad = v
 
     def adam(self, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
         E.adam_step(self.param, self.grad, self.exp_avg, self.exp_avg_sq, self.step_state, lr, betas[0], betas[1], eps,

@@ -157,6 +157,48 @@ def test_grad_arena_hands_flat_views_to_module_backward_cpu():
         E.GRAD_ARENA = old
 
 
+def test_arena_gradients_never_pass_through_autograd_cpu():
+    """Regression for the stale-gradient race (round-1 advisor finding): a gradient accumulated in place in the flat
+    buffer must not be returned to autograd -- AccumulateGrad clones a tensor that anything else still references,
+    and under TrainStep's deferred side-stream join that clone could be taken before the weight-gradient kernels
+    have run.  engine.param_grads returns None for arena-owned gradients; FlatState.collect points p.grad at the
+    slice without a copy; a second, loose gradient of a served parameter is ADDED to the slice."""
+    for p in (ROOT, os.path.join(ROOT, "acc-unet-unext_b200")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    from accx import engine as E
+    from accx.train import FlatState
+    net = torch.nn.Sequential(torch.nn.Conv2d(3, 4, 1), torch.nn.BatchNorm2d(4))
+    params = list(net.parameters())
+    foreign = torch.nn.Parameter(torch.ones(3))
+    fs = FlatState(params)
+    fs.begin_step()
+    old, E.GRAD_ARENA = E.GRAD_ARENA, fs
+    try:
+        pool = E.GradPool(params + [foreign])
+        g0 = E.grad_buf(pool, params[0])
+        gf = E.grad_buf(pool, foreign)
+        out = E.param_grads(params + [foreign, None], pool)
+        assert out[0] is None                                  # lives in the flat buffer: autograd never sees it
+        assert out[1] is None and out[2] is None               # never touched by the module: grad stays None
+        assert out[len(params)] is gf and out[-1] is None      # the foreign parameter's loose buffer is returned
+        assert fs.owns(params[0], g0) and not fs.owns(foreign, gf) and not fs.owns(params[1], g0)
+        g0.add_(1.0)                                           # "the weight-gradient kernel" writes late ...
+        pool2 = E.GradPool([params[0]])                        # ... and a second use yields a loose gradient
+        g1 = E.grad_buf(pool2, params[0])
+        assert E.param_grads([params[0]], pool2)[0] is g1
+        g1.add_(0.5)
+        params[0].grad = g1
+    finally:
+        E.GRAD_ARENA = old
+    assert params[1].grad is None
+    fs.collect()
+    v = fs._view(fs.grad, params[0])
+    assert params[0].grad.data_ptr() == v.data_ptr()           # p.grad IS the slice, no copy-back of a snapshot
+    assert torch.all(v == 1.5)                                 # in-place part + the loose second use
+    assert params[1].grad is None                              # untouched parameters keep grad=None
+
+
 @pytest.mark.timeout(600)
 def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     """`bench.py --impl reference` (the reference's CPU path on the host cores): stdout is exactly one JSON line

@@ -332,6 +332,59 @@ def test_train_step_graph_equals_eager_and_loss_decreases():
     assert float(sa.flat.step_state[0]) == 10.0 and float(sb.flat.step_state[0]) == 10.0
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+def test_graph_replay_gradients_are_complete(dtype, monkeypatch):
+    """Regression for the stale-gradient race: under TrainStep the weight gradients run on a low-priority side stream
+    that is joined once before the optimiser.  The gradients left in the flat buffer by a GRAPH REPLAY must equal the
+    ones of a single-stream eager step on the same weights (lr = 0 keeps them fixed), conv weights included, and no
+    arena-served gradient may pass through autograd (p.grad is still None when backward returns)."""
+    import accx
+    from accx import train as T
+    from accx.train import TrainStep
+    torch.manual_seed(2)
+    ma = accx.ACC_UNet(3, 1, 8, compute_dtype=dtype).to(DEV).train()
+    ma.last_activation = None
+    mb = copy.deepcopy(ma)
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(4, 3, 64, 64, generator=g).to(DEV)
+    m = (torch.rand(4, 1, 64, 64, generator=g) > 0.5).float().to(DEV)
+    seen = []
+    orig = T.FlatState.collect
+
+    def spy(self):
+        seen.append(sum(p.grad is not None for p in self.params if id(p) in self.taken))
+        return orig(self)
+
+    monkeypatch.setattr(T.FlatState, "collect", spy)
+    sa = TrainStep(ma, lr=0.0, graph=True, graph_warmup=1)
+    for _ in range(4):
+        sa(x, m)
+    torch.cuda.synchronize()
+    assert sa.graph is not None
+    assert seen and all(n == 0 for n in seen), f"arena-served gradients went through autograd: {seen}"
+    eng = E()
+    mode, lanes = eng.SIDE_MODE, eng.LANES
+    eng.SIDE_MODE, eng.LANES = 0, 0                      # reference: everything on one stream
+    try:
+        sb = TrainStep(mb, lr=0.0, graph=False)
+        sb(x, m)
+        torch.cuda.synchronize()
+    finally:
+        eng.SIDE_MODE, eng.LANES = mode, lanes
+    tol = 2e-3 if dtype == torch.float32 else 6e-2
+    worst = ("", 0.0)
+    for (n, p), (_, q) in zip(ma.named_parameters(), mb.named_parameters()):
+        ga, gb = sa.flat._view(sa.flat.grad, p), sb.flat._view(sb.flat.grad, q)
+        if p.dim() < 2 or float(gb.abs().max()) == 0.0:
+            continue                                     # weight matrices: the ones the side stream produces
+        e = rel_l2(ga, gb)
+        if e > worst[1]:
+            worst = (n, e)
+        assert e < tol, f"{n}: replayed gradient differs from the single-stream one (rel L2 {e:.3e})"
+    print(f"graph-replay vs single-stream gradients: worst {worst[0]} rel L2 {worst[1]:.2e}")
+
+
+
 def test_train_step_matches_cpu_oracle_step():
     """optimisation steps of the accx TrainStep (fp32 storage) vs oracle.train_step on the CPU"""
     import accx
