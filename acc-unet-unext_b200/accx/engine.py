@@ -23,6 +23,12 @@ PROFILE = None        # list -> every launch is bracketed by CUDA events on the 
                       # appended as (kernel, start, end, algorithmic_bytes, flops); see bench.py
 
 
+RECORD = None         # dict -> every forward notes the operands that carry the path's discrete decisions (LeakyReLU signs,
+                      # max-pool arg-maxes), keyed by the torch module that owns them: ("bn", id(BatchNorm2d)) -> Lazy,
+                      # ("se", id(ChannelSELayer)) -> SECtx, ("hanc", id(HANCLayer)) -> Lazy input of the pyramid,
+                      # "pool" -> [inputs of MaxPool2d(2)].  tests/ replay them in the CPU restatement (flip-free gradient parity).
+
+
 PROFILE_LEAD = None   # (every, cycles): while profiling, a spin kernel of `cycles` SM clocks is queued before every
                       # `every`-th launch (outside the event pairs).  Eager launching is CPU-bound (~45 us per launch vs
                       # ~25 us per kernel); without the lead the GPU idles between an event and the kernel that follows,
@@ -211,6 +217,38 @@ class _NullCtx:
         return False
 
 
+# ---- deterministic reduction mode ------------------------------------------------------------------
+_DET = {}
+
+
+def set_deterministic(on: bool, workspace_mb: int = 256, device=None):
+    """Fixed-order reductions in every accx kernel (include/accx.h: accx_set_deterministic): two runs on the same
+    inputs are bit-identical.  The kernels share one workspace, so every launch goes to the caller's stream: the
+    weight-gradient side stream and the parallel lanes are switched off while the mode is on.  Parity / debugging
+    mode (slower); mandatory for the tight fp32 parity bounds in tests/."""
+    global SIDE_MODE, LANES
+    lib = _lib.load()
+    if not on:
+        if _DET:
+            _lib.call("accx_set_deterministic", 0, 0, 0, 0)
+            SIDE_MODE, LANES = _DET["modes"]
+            _DET.clear()
+        return
+    if _DET:
+        return
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    ws = torch.empty(workspace_mb << 20, dtype=torch.uint8, device=dev)
+    ctr = torch.zeros(1 << 16, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize(dev)
+    _lib.call("accx_set_deterministic", ws.data_ptr(), ws.numel(), ctr.data_ptr(), ctr.numel())
+    _DET.update(ws=ws, ctr=ctr, modes=(SIDE_MODE, LANES))
+    SIDE_MODE, LANES = 0, 0
+
+
+def deterministic() -> bool:
+    return bool(_DET)
+
+
 def nb(*ts) -> int:
     """bytes of the given tensors (algorithmic traffic accounting: each tensor once)"""
     return sum(t.numel() * t.element_size() for t in ts if t is not None)
@@ -275,11 +313,12 @@ class Arena:
 
 class Lazy:
     """raw NHWC tensor + pending per-channel affine/activation (see include/accx.h)."""
-    __slots__ = ("y", "scale", "shift", "act", "mean", "rstd", "bn")
+    __slots__ = ("y", "scale", "shift", "act", "mean", "rstd", "bn", "train")
 
-    def __init__(self, y, scale=None, shift=None, act=0, mean=None, rstd=None, bn=None):
+    def __init__(self, y, scale=None, shift=None, act=0, mean=None, rstd=None, bn=None, train=True):
         self.y, self.scale, self.shift, self.act = y, scale, shift, act
         self.mean, self.rstd, self.bn = mean, rstd, bn
+        self.train = train        # False: the BatchNorm ran on its running statistics (a fixed affine in backward)
 
     @property
     def dims(self):
@@ -440,7 +479,10 @@ def bn_lazy(y: torch.Tensor, stats, bn, act: int, arena: Arena, training: bool, 
     """conv_bias: bias of the conv that produced y and was NOT added to it (folded into the BN here)"""
     count = y.numel() // y.shape[-1]
     scale, shift, mean, rstd = bn_affine(bn, stats, count, arena, training, conv_bias)
-    return Lazy(y, scale, shift, act, mean, rstd, bn)
+    L = Lazy(y, scale, shift, act, mean, rstd, bn, train=training)
+    if RECORD is not None and act == 2:
+        RECORD[("bn", id(bn))] = L
+    return L
 
 
 def materialize(L: Lazy, scale2=None, shift2=None, residual=None, stats=None, out=None, stats_only=False):
@@ -461,10 +503,13 @@ def add_fwd(L: Lazy, r: torch.Tensor, stats):
 
 
 def bn_bwd(L: Lazy, da: torch.Tensor, grads: dict, arena: Arena, out: Optional[torch.Tensor] = None,
-           sums: Optional[torch.Tensor] = None) -> torch.Tensor:
+           sums: Optional[torch.Tensor] = None, conv=None) -> torch.Tensor:
     """gradient w.r.t. the raw tensor L.y given the gradient w.r.t. act(BN(L.y)); accumulates
     dgamma/dbeta into grads[bn.weight]/grads[bn.bias].  In place on `da` unless `out` is given.
-    `sums`: the (sum g, sum g*xhat) reduction if the producer of `da` already made it (hanc_unpool_bnred)."""
+    `sums`: the (sum g, sum g*xhat) reduction if the producer of `da` already made it (hanc_unpool_bnred).
+    `conv`: the convolution that produced L.y with its bias folded into this BatchNorm: its bias gradient is
+    analytically zero in training mode (the mean subtraction cancels a per-channel constant) and
+    sum_p dy = gamma * rstd * sum g in eval mode, where the BatchNorm is a fixed affine of the running statistics."""
     y = L.y
     C = y.shape[-1]
     P = y.numel() // C
@@ -477,9 +522,14 @@ def bn_bwd(L: Lazy, da: torch.Tensor, grads: dict, arena: Arena, out: Optional[t
     dy = da if out is None else out
     gg = grad_buf(grads, L.bn.weight)
     gb = grad_buf(grads, L.bn.bias)
+    # eval mode: 1 / count = 0 removes the batch-statistics terms, dy = gamma * rstd * g
     _call("accx_bn_bwd_apply", dtc, P, C, ptr(y), ptr(L.scale), ptr(L.shift), L.act, ptr(L.mean), ptr(L.rstd),
-          ptr(f32(L.bn.weight)), ptr(da), ptr(sums), float(P), ptr(dy), ptr(gg), ptr(gb), stream(),
-          cost=(nb(y, da, dy), 0), tag=f"P={P} C={C}")
+          ptr(f32(L.bn.weight)), ptr(da), ptr(sums), float(P) if L.train else float("inf"), ptr(dy), ptr(gg), ptr(gb),
+          stream(), cost=(nb(y, da, dy), 0), tag=f"P={P} C={C}")
+    if conv is not None and conv.bias is not None:
+        cb = grad_buf(grads, conv.bias)           # training: stays zero
+        if cb is not None and not L.train:
+            cb.add_(f32(L.bn.weight) * L.rstd * sums[:C])
     return dy
 
 
@@ -622,7 +672,7 @@ def add_inplace(dst: torch.Tensor, other: torch.Tensor):
 
 
 class SECtx:
-    __slots__ = ("L", "S", "gate", "hidden", "scale", "shift", "mean", "rstd", "mod", "residual", "mix", "mix_param")
+    __slots__ = ("L", "S", "gate", "hidden", "scale", "shift", "mean", "rstd", "mod", "residual", "mix", "mix_param", "train")
 
 
 def se_fwd(L: Lazy, se, arena: Arena, training: bool, residual=None, mix=None, stats=None, mix_param=None):
@@ -634,6 +684,9 @@ def se_fwd(L: Lazy, se, arena: Arena, training: bool, residual=None, mix=None, s
         raise _lib.AccxError(f"ChannelSELayer({C}): num_channels // 8 must be >= 1")
     c = SECtx()
     c.L, c.mod, c.residual, c.mix, c.mix_param = L, se, residual, mix, mix_param
+    c.train = training
+    if RECORD is not None:
+        RECORD[("se", id(se))] = c
     c.S = arena.take(2 * B * C)
     c.gate, c.hidden = arena.take(B * C), arena.take(B * Cr)      # every slice 256-byte aligned
     c.scale, c.shift, c.mean, c.rstd = arena.take(C), arena.take(C), arena.take(C), arena.take(C)
@@ -676,7 +729,7 @@ def se_bwd(c: SECtx, dout: torch.Tensor, grads: dict, arena: Arena, da: Optional
           ptr(f32(se.fc1.weight)), ptr(f32(se.fc2.weight)), ptr(f32(se.bn.weight)), ptr(c.mean), ptr(c.rstd),
           ptr(grad_buf(grads, se.fc1.weight)), ptr(grad_buf(grads, se.fc1.bias)), ptr(grad_buf(grads, se.fc2.weight)),
           ptr(grad_buf(grads, se.fc2.bias)), ptr(grad_buf(grads, se.bn.weight)), ptr(grad_buf(grads, se.bn.bias)),
-          ptr(PQR), stream())
+          ptr(PQR), 1 if c.train else 0, stream())
     if da is None:
         da = torch.empty_like(y)
         accumulate = False
@@ -720,6 +773,8 @@ def input_to_nhwc(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
 def maxpool2(x: torch.Tensor) -> torch.Tensor:
     """MaxPool2d(2) on a contiguous [B,H,W,C] tensor"""
     B, H, W, C = x.shape
+    if RECORD is not None:
+        RECORD.setdefault("pool", []).append(x)
     out = torch.empty((B, H // 2, W // 2, C), dtype=x.dtype, device=x.device)
     _call("accx_maxpool2_fwd", dt(x), B, H, W, C, ptr(x), ptr(out), stream(), cost=(nb(x, out), 0),
           tag=f"{B}x{H}x{W}x{C}")
@@ -751,6 +806,15 @@ def dice_bce_bwd(logit, truth, sums, dice_w, bce_w, gscale: Optional[torch.Tenso
     _call("accx_dice_bce_bwd", dt(logit), dt(d), B, N, ptr(logit), ptr(truth), ptr(sums), float(dice_w), float(bce_w),
           ptr(gscale), ptr(d), stream(), cost=(nb(logit, truth, d), 0))
     return d
+
+
+def seg_metrics(logit: torch.Tensor, truth: torch.Tensor) -> torch.Tensor:
+    """logit [B, N] (fp32 / bf16), truth [B, N] fp32 -> device tensor [mean IoU, mean hard Dice] (accx_seg_metrics)"""
+    B, N = logit.shape
+    counts = torch.zeros(4 * B + 1, dtype=torch.int32, device=logit.device)
+    out = torch.empty(2, dtype=torch.float32, device=logit.device)
+    _call("accx_seg_metrics", dt(logit), B, N, ptr(logit), ptr(truth), ptr(counts), ptr(out), stream(), cost=(nb(logit, truth), 0))
+    return out
 
 
 def adam_step(param, grad, exp_avg, exp_avg_sq, state, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0,

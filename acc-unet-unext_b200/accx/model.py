@@ -18,6 +18,8 @@ from .modules import HANCBlock, MLFC, ResPath, maxpool2, out_conv, run_parallel,
 
 class _ACCUNetBase(nn.Module):
     variant = "base"
+    cnv72_inv_fctr = 34        # ACC_UNet/ACC_UNet.py:584; the training harness's copy builds cnv72 with 3 (ACC_UNet_Harness)
+    sigmoid_out = True         # ACC_UNet/ACC_UNet.py:594-599: sigmoid on the one-class output
 
     def __init__(self, n_channels, n_classes, n_filts=32, compute_dtype=None):
         super().__init__()
@@ -48,7 +50,7 @@ class _ACCUNetBase(nn.Module):
         self.cnv62 = HANCBlock(f * 8, f * 8, k=2, inv_fctr=3)
         self.up7 = nn.ConvTranspose2d(f * 8, f * 4, kernel_size=(2, 2), stride=2)
         self.cnv71 = HANCBlock(f * 4 + f * 4, f * 4, k=3, inv_fctr=3)
-        self.cnv72 = HANCBlock(f * 4, f * 4, k=3, inv_fctr=34)
+        self.cnv72 = HANCBlock(f * 4, f * 4, k=3, inv_fctr=self.cnv72_inv_fctr)
         self.up8 = nn.ConvTranspose2d(f * 4, f * 2, kernel_size=(2, 2), stride=2)
         self.cnv81 = HANCBlock(f * 2 + f * 2, f * 2, k=3, inv_fctr=3)
         self.cnv82 = HANCBlock(f * 2, f * 2, k=3, inv_fctr=3)
@@ -57,7 +59,7 @@ class _ACCUNetBase(nn.Module):
         self.cnv92 = HANCBlock(f, f, k=3, inv_fctr=3)
         if n_classes == 1:
             self.out = nn.Conv2d(f, n_classes, kernel_size=(1, 1))
-            self.last_activation = nn.Sigmoid()
+            self.last_activation = nn.Sigmoid() if self.sigmoid_out else None
         else:
             self.out = nn.Conv2d(f, n_classes + 1, kernel_size=(1, 1))
             self.last_activation = None
@@ -103,3 +105,14 @@ class ACC_UNet_W(_ACCUNetBase):
 class ACC_UNet_Lite(_ACCUNetBase):
     """ACC_UNet/ACC_UNet_lite.py: MLFC reduced to its four SE layers (its conv parameters stay unused)"""
     variant = "lite"
+
+
+class ACC_UNet_Harness(_ACCUNetBase):
+    """The flavour the reference's TRAINING HARNESS builds (`from nets.ACC_UNet import ACC_UNet`,
+    Experiments/train_model.py:24): Experiments/nets/ACC_UNet.py differs from the canonical model file in two
+    places -- cnv72 is built with inv_fctr=3 (:584; conv1.weight [384, 128, 1, 1] instead of [4352, 128, 1, 1]) and
+    forward returns LOGITS (:596-597,655; the harness loss is logit based).  Checkpoints written by train_model.py
+    load into this class, not into ACC_UNet."""
+    variant = "base"
+    cnv72_inv_fctr = 3
+    sigmoid_out = False

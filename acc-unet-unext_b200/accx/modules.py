@@ -47,8 +47,6 @@ class _ModuleFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, *douts):
-        if not ctx.training:
-            raise E._lib.AccxError("accx backward implements training-mode BatchNorm only (call .train())")
         saved, mod = ctx.saved, ctx.mod
         ctx.saved = None
         ref = saved["out_like"]
@@ -99,8 +97,6 @@ class _GroupFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, *douts):
-        if not ctx.training:
-            raise E._lib.AccxError("accx backward implements training-mode BatchNorm only (call .train())")
         chains, saved, n = ctx.chains, ctx.saved, len(ctx.chains)
         ctx.saved = None
         dn = []
@@ -293,12 +289,6 @@ def _pw_bn(ops: List[Op], N, dims, conv: nn.Conv2d, bn: nn.BatchNorm2d, act, ar:
     return E.bn_lazy(y, st, bn, act, ar, training, conv_bias=conv.bias)
 
 
-def _zero_bias_grad(grads, conv):
-    # a conv bias feeding a training-mode BatchNorm has an analytically zero gradient
-    if conv.bias is not None:
-        E.grad_buf(grads, conv.bias)
-
-
 def _hanc_core_fwd(hnc, L2: Lazy, ar: Arena, training):
     """HANCLayer on a lazy input.  Split form: pooled maps get their own low-resolution
     contraction, results are nearest-upsample-added in the main contraction's epilogue."""
@@ -309,6 +299,8 @@ def _hanc_core_fwd(hnc, L2: Lazy, ar: Arena, training):
     if H % (1 << (k - 1)) or W % (1 << (k - 1)):
         raise ValueError(f"HANCLayer(k={k}) needs H, W divisible by {1 << (k - 1)}, got {H}x{W}")
     wh = _w(hnc.cnv.weight)            # [C, J*Ein] with K index e*J + j
+    if E.RECORD is not None:
+        E.RECORD[("hanc", id(hnc))] = L2
     pools = E.hanc_pools(L2, k)
     adds = []
     for l in range(1, k):
@@ -329,7 +321,6 @@ def _hanc_core_bwd(hnc, L2: Lazy, pools, dy3: torch.Tensor, grads, ar: Arena, ne
     C = hnc.cnv.out_channels
     wh = _w(hnc.cnv.weight)
     gw = E.grad_buf(grads, hnc.cnv.weight)
-    _zero_bias_grad(grads, hnc.cnv)
     if gw is not None:
         E.wgrad(Op(L2, Ein, WV(wh, 0, J * Ein, J)), dy3, C, (B, H, W), gw)
     da2 = None
@@ -416,7 +407,7 @@ class HANCLayer(_AccxModule):
     def _bwd(self, s, douts, in_need):
         grads = E.GradPool(self.parameters())
         ar = Arena(douts[0].device)
-        dy3 = E.bn_bwd(s["L3"], douts[0], grads, ar, out=torch.empty_like(s["L3"].y))
+        dy3 = E.bn_bwd(s["L3"], douts[0], grads, ar, out=torch.empty_like(s["L3"].y), conv=self.cnv)
         da = _hanc_core_bwd(self, s["L2"], s["pools"], dy3, grads, ar, need_da=in_need[0])
         return [da], grads
 
@@ -449,8 +440,7 @@ class Conv2d_batchnorm(_AccxModule):
         """-> gradient w.r.t. the raw conv output"""
         L, c = saved
         da, sums = E.se_bwd(c, dout, grads, ar, bn_sums=True)
-        _zero_bias_grad(grads, self.conv1)
-        return E.bn_bwd(L, da, grads, ar, sums=sums)
+        return E.bn_bwd(L, da, grads, ar, sums=sums, conv=self.conv1)
 
     def _fwd(self, xs, training, need):
         x = xs[0]
@@ -534,19 +524,17 @@ class HANCBlock(_AccxModule):
         w1, w3 = _w(self.conv1.weight), _w(self.conv3.weight)
         # SE -> norm3 -> conv3
         da5, sums5 = E.se_bwd(s["se"], dout, grads, ar, bn_sums=True)
-        dy5 = E.bn_bwd(L5, da5, grads, ar, sums=sums5)
-        _zero_bias_grad(grads, self.conv3)
+        dy5 = E.bn_bwd(L5, da5, grads, ar, sums=sums5, conv=self.conv3)
         g3 = E.grad_buf(grads, self.conv3.weight)
         if g3 is not None:
             E.wgrad(Op(L4, C, WV(w3, 0, C, 1)), dy5, Cout, dims, g3)
         da4 = E.conv([Op(Lazy(dy5), Cout, WV(w3, 0, 1, C))], C, dims)
         # norm(x + inp): dz feeds both the HANC branch and the residual
         dz = E.bn_bwd(L4, da4, grads, ar)
-        dy3 = E.bn_bwd(L3, dz, grads, ar, out=torch.empty_like(dz))
+        dy3 = E.bn_bwd(L3, dz, grads, ar, out=torch.empty_like(dz), conv=self.hnc.cnv)
         da2, sums2 = _hanc_core_bwd(self.hnc, L2, s["pools"], dy3, grads, ar, fuse_bn=True)
-        dy2 = E.bn_bwd(L2, da2, grads, ar, sums=sums2)
+        dy2 = E.bn_bwd(L2, da2, grads, ar, sums=sums2, conv=self.conv2)
         # depthwise
-        _zero_bias_grad(grads, self.conv2)
         g2 = E.grad_buf(grads, self.conv2.weight)
         if g2 is not None:
             E.dw_wgrad(L1, dy2, g2)
@@ -554,9 +542,8 @@ class HANCBlock(_AccxModule):
             da1, sums1 = E.dw_dgrad_bnred(L1, dy2, _w(self.conv2.weight), ar)
         else:
             da1, sums1 = E.dw_fwd(Lazy(dy2), _w(self.conv2.weight), None, None, flip=True), None
-        dy1 = E.bn_bwd(L1, da1, grads, ar, sums=sums1)
+        dy1 = E.bn_bwd(L1, da1, grads, ar, sums=sums1, conv=self.conv1)
         # conv1
-        _zero_bias_grad(grads, self.conv1)
         g1 = E.grad_buf(grads, self.conv1.weight)
         if g1 is not None:
             E.wgrad(Op(X, C, WV(w1, 0, C, 1)), dy1, Ex, dims, g1)
@@ -637,8 +624,7 @@ class ResPath(_AccxModule):
             X, L, sec = s["levels"][i]
             w = _w(self.convs[i].weight)
             da, sums = E.se_bwd(sec, dx, grads, ar, bn_sums=True)
-            dy = E.bn_bwd(L, da, grads, ar, sums=sums)
-            _zero_bias_grad(grads, self.convs[i])
+            dy = E.bn_bwd(L, da, grads, ar, sums=sums, conv=self.convs[i])
             gw = E.grad_buf(grads, self.convs[i].weight)
             if gw is not None:
                 E.wgrad_conv3x3(X, C, w, dy, C, dims, gw)

@@ -84,6 +84,22 @@ def dice_bce_loss(logit: torch.Tensor, truth: torch.Tensor, dice_weight: float =
     return _DiceBCEFn.apply(logit, truth, float(dice_weight), float(bce_weight))
 
 
+def seg_metrics(logit: torch.Tensor, truth: torch.Tensor) -> torch.Tensor:
+    """Per-batch training metrics WITHOUT a device-to-host sync: returns a device tensor [iou, dice] where
+    iou = iou_on_batch(masks, preds) (Experiments/utils.py:478-494: sigmoid, 0.5 threshold, sklearn's binary Jaccard
+    per image, batch mean) and dice = WeightedDiceBCE._show_dice(preds, masks) (utils.py:148-157).  The reference
+    computes both on the host every step (Train_one_epoch.py:134-135); read the tensor only when you log."""
+    E.require_cuda(logit)
+    B = logit.shape[0]
+    lg = logit.detach().reshape(B, -1)
+    if lg.dtype not in (torch.float32, torch.bfloat16):
+        lg = lg.float()
+    tr = truth.detach().reshape(B, -1).float().contiguous()
+    if tr.shape != lg.shape:
+        raise ValueError(f"seg_metrics: logits {tuple(logit.shape)} vs masks {tuple(truth.shape)}")
+    return E.seg_metrics(lg.contiguous(), tr)
+
+
 class FlatState:
     """Parameters, gradients and Adam moments of a model as four flat fp32 buffers (see the module docstring).
     While it is installed as `engine.GRAD_ARENA` (TrainStep does that around forward + backward) the accx backward
@@ -164,6 +180,7 @@ class FlatState:
             p.grad = v
 
     def adam(self, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        """lr < 0: the kernel reads the learning rate from step_state[1] (TrainStep.set_lr)"""
         E.adam_step(self.param, self.grad, self.exp_avg, self.exp_avg_sq, self.step_state, lr, betas[0], betas[1], eps,
                     weight_decay)
 
@@ -209,13 +226,24 @@ class TrainStep:
     `graph_warmup` eager steps; inputs are then copied into static buffers each step."""
 
     def __init__(self, model: torch.nn.Module, lr: float = 1e-3, graph: bool = False, graph_warmup: int = 3,
-                 betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0):
+                 betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0, metrics: bool = False):
         self.model = model
         self.params = [p for p in model.parameters() if p.requires_grad]
         E.require_cuda(self.params[0])
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
         self.flat = FlatState(self.params)
+        self.flat.step_state[1] = lr               # the Adam kernel reads the learning rate from the device
         self.avg = GradAverager(self.params, flat=self.flat)
+        # metrics=True: IoU / Dice of every step's predictions are computed on the device inside the step (and the
+        # step's CUDA graph) and left in `last_metrics` -- no per-step device-to-host sync (Train_one_epoch.py:134-135)
+        self.metrics = metrics
+        self.last_metrics: Optional[torch.Tensor] = None
+        if self.avg.world > 1:
+            # replicas must start identical whatever each rank's seed or checkpoint: rank 0's parameters and module
+            # buffers (BatchNorm running statistics) go to everyone; the statistics stay rank-local afterwards
+            dist.broadcast(self.flat.param, src=0)
+            for b in model.buffers():
+                dist.broadcast(b, src=0)
         self.use_graph = graph
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.graph_warmup = max(1, graph_warmup)
@@ -230,6 +258,8 @@ class TrainStep:
         try:
             logits = self.model(x)
             loss = dice_bce_loss(logits, m)
+            if self.metrics:
+                self.last_metrics = seg_metrics(logits, m)
             E.SIDE_MODE = 2 if mode else 0             # weight gradients overlap the whole backward ...
             try:
                 loss.backward()
@@ -240,8 +270,69 @@ class TrainStep:
             E.GRAD_ARENA = arena
         flat.collect()
         self.avg()
-        flat.adam(self.lr, self.betas, self.eps, self.weight_decay)
+        idle = None
+        if self.weight_decay != 0.0:
+            # torch.optim.Adam skips parameters whose grad is None (ACC_UNet_Lite's idle MLFC convs); the flat kernel
+            # would still decay them, so their values are put back after the update (their moments stay zero)
+            idle = [p for p in self.params if p.grad is None]
+            keep = [p.detach().clone() for p in idle]
+        flat.adam(-1.0, self.betas, self.eps, self.weight_decay)
+        if idle:
+            torch._foreach_copy_([p.data for p in idle], keep)
+            for p in idle:
+                flat._view(flat.exp_avg, p).zero_()
+                flat._view(flat.exp_avg_sq, p).zero_()
         return loss.detach()
+
+    def set_lr(self, lr: float):
+        """new learning rate from the next step on (lr_scheduler.step() of the harness, Train_one_epoch.py:187-188);
+        a device-side scalar, so the captured step graph stays valid"""
+        self.lr = float(lr)
+        self.flat.step_state[1] = self.lr
+
+    # ---- optimiser checkpointing (Experiments/train_model.py:125-145 saves optimizer.state_dict(), :677-689 and
+    # :815-818 restore it on resume) in torch.optim.Adam's own format, so reference checkpoints load and vice versa
+    def state_dict(self) -> dict:
+        step = self.flat.step_state[0].detach().cpu().clone()
+        state = {}
+        for i, p in enumerate(self.params):
+            state[i] = {"step": step.clone(), "exp_avg": self.flat._view(self.flat.exp_avg, p).detach().clone(),
+                        "exp_avg_sq": self.flat._view(self.flat.exp_avg_sq, p).detach().clone()}
+        group = {"lr": self.lr, "betas": tuple(self.betas), "eps": self.eps, "weight_decay": self.weight_decay,
+                 "amsgrad": False, "maximize": False, "foreach": None, "capturable": False, "differentiable": False,
+                 "fused": None, "decoupled_weight_decay": False, "params": list(range(len(self.params)))}
+        return {"state": state, "param_groups": [group]}
+
+    def load_state_dict(self, sd: dict):
+        """in place (the captured CUDA graph keeps pointing at the same buffers).  Parameters without an entry in
+        sd["state"] (never stepped: torch only creates state for parameters that had a gradient) get zero moments."""
+        groups = sd["param_groups"]
+        ids = [i for g in groups for i in g["params"]]
+        if len(ids) != len(self.params):
+            raise ValueError(f"optimizer state has {len(ids)} parameters, the model {len(self.params)}")
+        g0 = groups[0]
+        hyper = (tuple(self.betas), self.eps, self.weight_decay)
+        self.betas = tuple(g0.get("betas", self.betas))
+        self.eps, self.weight_decay = g0.get("eps", self.eps), g0.get("weight_decay", self.weight_decay)
+        if hyper != (tuple(self.betas), self.eps, self.weight_decay):
+            self.graph = None                       # baked into the captured launch: capture again on the next call
+        self.set_lr(g0.get("lr", self.lr))
+        steps = set()
+        with torch.no_grad():
+            self.flat.exp_avg.zero_()
+            self.flat.exp_avg_sq.zero_()
+            for p, i in zip(self.params, ids):
+                st = sd["state"].get(i)
+                if st is None:
+                    continue
+                if tuple(st["exp_avg"].shape) != tuple(p.shape):
+                    raise ValueError(f"optimizer state {i}: shape {tuple(st['exp_avg'].shape)} vs parameter {tuple(p.shape)}")
+                self.flat._view(self.flat.exp_avg, p).copy_(st["exp_avg"])
+                self.flat._view(self.flat.exp_avg_sq, p).copy_(st["exp_avg_sq"])
+                steps.add(float(st["step"]))
+            if len(steps) > 1:
+                raise ValueError(f"per-parameter step counts differ ({sorted(steps)}): the flat Adam kernel keeps one")
+            self.flat.step_state[0] = steps.pop() if steps else 0.0
 
     def __call__(self, x: torch.Tensor, m: torch.Tensor) -> torch.Tensor:
         self.calls += 1

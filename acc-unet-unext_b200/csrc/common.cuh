@@ -276,51 +276,127 @@ inline int grid_x_for(int64_t items, int per_block, int max_blocks) {
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+// ---- deterministic reduction mode (accx_set_deterministic) ------------------------------------------------------
+// By default the cross-block part of every reduction (BatchNorm statistics, SE sums, weight gradients) ends in fp32
+// atomics, so results depend on block scheduling at rounding level -- and 220 stacked BatchNorms amplify that.
+// With a workspace installed, every reducing kernel becomes order-fixed instead:
+//   * channel-lane kernels: each block stores its partial sums into its own slot of the workspace; the LAST block of
+//     the group to arrive (ticket counter) adds the slots in block order and emits the totals (det_commit);
+//   * kernels whose partials are whole tiles (weight gradients, the persistent tcgen05 / TMA-tiled kernels) are
+//     launched so that every destination address receives exactly one contribution (one split / one CTA per channel
+//     chunk), accumulated in a fixed order inside the CTA.
+// The workspace is shared by all launches: the mode requires that all accx calls are issued on ONE stream.
+struct Det {
+  float* ws;            // nullptr: atomics (default mode)
+  unsigned int* ctr;    // one zero-initialised ticket counter per group (re-armed by the last block)
+};
+extern Det g_det;
+extern int64_t g_det_floats;
+extern int g_det_ctrs;
+inline bool det_on() { return g_det.ws != nullptr; }
+// the handle a launcher passes to its kernel; fails (-> error code) when the workspace is too small
+inline bool det_handle(int64_t floats, int64_t groups, Det& out) {
+  out.ws = nullptr;
+  out.ctr = nullptr;
+  if (!det_on()) return true;
+  if (floats > g_det_floats || groups > g_det_ctrs) {
+    set_error("deterministic mode: workspace too small (%lld floats / %lld counters needed, %lld / %d installed)",
+              (long long)floats, (long long)groups, (long long)g_det_floats, g_det_ctrs);
+    return false;
+  }
+  out = g_det;
+  return true;
+}
+
+// Block-collective.  store(slot): every thread writes the partial sums it owns into slot[0 .. n_vals);
+// emit(i, total): called by the last block of the group for every i with the sum over members 0 .. n_members-1.
+template <typename StoreF, typename EmitF>
+__device__ __forceinline__ void det_commit(const Det& det, int group, int member, int n_members, int n_vals,
+                                           StoreF&& store, EmitF&& emit) {
+  __shared__ bool det_last;
+  const int tid = (threadIdx.z * blockDim.y + threadIdx.y) * blockDim.x + threadIdx.x;
+  const int nth = blockDim.x * blockDim.y * blockDim.z;
+  float* base = det.ws + (int64_t)group * n_members * n_vals;
+  store(base + (int64_t)member * n_vals);
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned int t = atomicAdd(det.ctr + group, 1u);
+    det_last = t == (unsigned)(n_members - 1);
+    if (det_last) det.ctr[group] = 0u;
+  }
+  __syncthreads();
+  if (!det_last) return;
+  __threadfence();
+  for (int i = tid; i < n_vals; i += nth) {
+    float total = 0.f;
+    for (int m = 0; m < n_members; ++m) total += __ldcg(base + (int64_t)m * n_vals + i);
+    emit(i, total);
+  }
+}
+
 // Block-level reduction of NS per-channel statistics held as acc[NS][VEC] by every thread
 // of a (TX, TY) block, then one atomicAdd per (stat, channel) into out[s * stride + c].
 // smem must hold blockDim.x * blockDim.y * VEC floats.  Two-stage tree through shared memory that keeps
 // every thread busy: (column, part) partial sums over TY / nparts rows, then nparts values per column.
+// Deterministic mode (det.ws != nullptr): the blocks that share destination addresses form `group`, this block is
+// its `member` of `n_members`; the per-block sums go through det_commit instead of atomics.
 template <int NS, int VEC>
 __device__ __forceinline__ void reduce_lanes_atomic(float (&acc)[NS][VEC], float* smem, float* out,
-                                                    int64_t stride, int C) {
+                                                    int64_t stride, int C, const Det det = Det{nullptr, nullptr},
+                                                    int group = 0, int member = 0, int n_members = 1) {
   const int tx = threadIdx.x, ty = threadIdx.y, TX = blockDim.x, TY = blockDim.y;
   const int ncol = TX * VEC, t = ty * TX + tx;
+  const bool det_mode = det.ws != nullptr;
+  float* slot = det_mode ? det.ws + ((int64_t)group * n_members + member) * (NS * ncol) : nullptr;
   if (TY == 1) {
     const int c0 = (blockIdx.y * TX + tx) * VEC;
 #pragma unroll
     for (int s = 0; s < NS; ++s)
 #pragma unroll
-      for (int i = 0; i < VEC; ++i)
-        if (c0 + i < C) atomicAdd(out + s * stride + c0 + i, acc[s][i]);
-    return;
+      for (int i = 0; i < VEC; ++i) {
+        if (det_mode) slot[s * ncol + i * TX + tx] = acc[s][i];
+        else if (c0 + i < C) atomicAdd(out + s * stride + c0 + i, acc[s][i]);
+      }
+  } else {
+    int nparts = (TX * TY) / ncol;          // = TY / VEC
+    if (nparts < 1) nparts = 1;
+    if (nparts > TY) nparts = TY;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      __syncthreads();
+      // row ty of the [TY][ncol] matrix; column index = i * TX + tx
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) smem[(ty * VEC + i) * TX + tx] = acc[s][i];
+      __syncthreads();
+      const int nth = TX * TY;
+      if (nparts > 1) {          // nth >= 2 * ncol: every thread owns exactly one (part, column) pair
+        float part = 0.f;
+        const int j = t % ncol, q = t / ncol;
+        if (q < nparts)
+          for (int r = q; r < TY; r += nparts) part += smem[r * ncol + j];
+        __syncthreads();
+        if (q < nparts) smem[q * ncol + j] = part;
+        __syncthreads();
+      }
+      const int rows = nparts > 1 ? nparts : TY;
+      for (int col = t; col < ncol; col += nth) {
+        float sum = 0.f;
+        for (int r = 0; r < rows; ++r) sum += smem[r * ncol + col];
+        const int c = (blockIdx.y * TX + (col % TX)) * VEC + col / TX;
+        if (det_mode) slot[s * ncol + col] = sum;
+        else if (c < C) atomicAdd(out + s * stride + c, sum);
+      }
+    }
   }
-  int nparts = (TX * TY) / ncol;          // = TY / VEC
-  if (nparts < 1) nparts = 1;
-  if (nparts > TY) nparts = TY;
-#pragma unroll
-  for (int s = 0; s < NS; ++s) {
-    __syncthreads();
-    // row ty of the [TY][ncol] matrix; column index = i * TX + tx
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) smem[(ty * VEC + i) * TX + tx] = acc[s][i];
-    __syncthreads();
-    const int nth = TX * TY;
-    if (nparts > 1) {          // nth >= 2 * ncol: every thread owns exactly one (part, column) pair
-      float part = 0.f;
-      const int j = t % ncol, q = t / ncol;
-      if (q < nparts)
-        for (int r = q; r < TY; r += nparts) part += smem[r * ncol + j];
-      __syncthreads();
-      if (q < nparts) smem[q * ncol + j] = part;
-      __syncthreads();
-    }
-    const int rows = nparts > 1 ? nparts : TY;
-    for (int col = t; col < ncol; col += nth) {
-      float sum = 0.f;
-      for (int r = 0; r < rows; ++r) sum += smem[r * ncol + col];
-      const int c = (blockIdx.y * TX + (col % TX)) * VEC + col / TX;
-      if (c < C) atomicAdd(out + s * stride + c, sum);
-    }
+  if (det_mode) {
+    const int by = blockIdx.y;
+    det_commit(det, group, member, n_members, NS * ncol, [](float*) {},
+               [&](int i, float total) {
+                 const int s = i / ncol, col = i - s * ncol;
+                 const int c = (by * TX + (col % TX)) * VEC + col / TX;
+                 if (c < C) atomicAdd(out + s * stride + c, total);   // the only contribution of this launch
+               });
   }
 }
 

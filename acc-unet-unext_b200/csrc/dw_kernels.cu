@@ -216,7 +216,7 @@ int accx_dw3x3_fwd(int dtype, int B, int H, int W, int C, const void* x, const f
     // 4 channels per thread for both dtypes: 9 taps x 4 weights + 4 x 4 accumulators stay under ~80 registers,
     // so three 256-thread CTAs fit on an SM (8-wide bf16 lanes needed 179 registers: one CTA per SM)
     Lanes l = make_lanes(C, 4, aligned16(x) && aligned16(y));
-    dim3 block(l.tx, l.ty), grid(grid_x_for(n_strips, l.ty * 2, 148 * 12), l.gy);
+    dim3 block(l.tx, l.ty), grid((stats && det_on()) ? 1 : grid_x_for(n_strips, l.ty * 2, 148 * 12), l.gy);   // det: one add per address
     size_t sm = (size_t)l.tx * l.ty * l.vec * sizeof(float);
     if (l.vec == 1)
       launch_k(dw3x3_fwd_kernel<T, 1>, grid, block, sm, (cudaStream_t)stream, B, H, W, C, (const T*)x, scale, shift, act, w,
@@ -237,7 +237,7 @@ int accx_dw3x3_wgrad(int dtype, int B, int H, int W, int C, const void* x, const
   const int64_t n_strips = (int64_t)B * H * ((W + STRIP - 1) / STRIP);
   ACCX_DISPATCH_T(dtype, {
     Lanes l = make_lanes(C, 4, aligned16(x) && aligned16(dy));
-    dim3 block(l.tx, l.ty), grid(grid_x_for(n_strips, l.ty * 4, 148 * 3), l.gy);
+    dim3 block(l.tx, l.ty), grid(det_on() ? 1 : grid_x_for(n_strips, l.ty * 4, 148 * 3), l.gy);   // det: one add per address
     size_t sm = (size_t)l.tx * l.ty * l.vec * sizeof(float);
     if (l.vec == 1)
       launch_k(dw3x3_wgrad_kernel<T, 1>, grid, block, sm, (cudaStream_t)stream, B, H, W, C, (const T*)x, scale, shift, act,

@@ -44,6 +44,7 @@ struct alignas(64) DwParams {
   const float* bn_mean;
   const float* bn_rstd;
   int bn_act;
+  int det;                      // deterministic mode: one CTA per channel chunk (see common.cuh)
 };
 
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
@@ -210,7 +211,11 @@ __global__ void __launch_bounds__(DW_THREADS, 2) dw3x3_tiled_kernel(const __grid
     if (BOX2) tma_load_4d(dst + x_bytes_al, &prm.map_dy, chunk * CC, w0, h0, b, bar);
   };
 
-  if (tid == 0 && (int64_t)blockIdx.x < total) issue(blockIdx.x, 0);
+  // tile walk: round-robin over all tiles, or -- deterministic mode -- CTA i owns every tile of channel chunk i, so
+  // each (channel, statistic) receives exactly one flush, accumulated in tile order
+  int64_t tile0 = blockIdx.x, tile_end = total, tstep = gridDim.x;
+  if (prm.det) { tile0 = (int64_t)blockIdx.x * prm.n_spatial; tile_end = tile0 + prm.n_spatial; tstep = 1; }
+  if (tid == 0 && tile0 < tile_end) issue(tile0, 0);
 
   // per-thread state that lives across tiles of one channel chunk
   f32x2 wt[9][2];                      // forward: the nine taps of this thread's 4 channels
@@ -229,11 +234,11 @@ __global__ void __launch_bounds__(DW_THREADS, 2) dw3x3_tiled_kernel(const __grid
   for (int i = 0; i < 4; ++i) { bn_s[i] = 1.f; bn_t[i] = 0.f; bn_mu[i] = 0.f; bn_rs[i] = 0.f; }
   int cur_chunk = -1;
   int it = 0;
-  for (int64_t tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+  for (int64_t tile = tile0; tile < tile_end; tile += tstep, ++it) {
     const int stage = it & 1;
-    const int64_t next = tile + gridDim.x;
+    const int64_t next = tile + tstep;
     // the other stage was last read by iteration it-1, which ended with __syncthreads
-    if (tid == 0 && next < total) issue(next, stage ^ 1);
+    if (tid == 0 && next < tile_end) issue(next, stage ^ 1);
     int chunk, b, h0, w0;
     decode(tile, chunk, b, h0, w0);
     const int c0 = chunk * CC;
@@ -438,6 +443,8 @@ static int dw_launch(DwParams& prm, const void* x, const void* dy, cudaStream_t 
   const int64_t total = prm.n_spatial * prm.n_chunks;
   int64_t grid = 2 * (int64_t)sm_count();
   if (grid > total) grid = total;
+  prm.det = det_on() ? 1 : 0;
+  if (prm.det) grid = prm.n_chunks;
   launch_k(kern, (unsigned)grid, DW_THREADS, smem, st, prm);
   return ACCX_OK;
 }

@@ -9,6 +9,9 @@ namespace accx {
 
 static thread_local char g_err[512] = "";
 int g_knobs[KNOB_COUNT] = {0};
+Det g_det = {nullptr, nullptr};
+int64_t g_det_floats = 0;
+int g_det_ctrs = 0;
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -65,7 +68,7 @@ __global__ void bn_finalize_kernel(int C, double count, const float* __restrict_
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256, 2) act_apply_kernel(int64_t P, int C, const T* __restrict__ x, const float* scale, const float* shift,
                                  int act, const float* scale2, const float* shift2, const T* __restrict__ residual,
-                                 T* __restrict__ out, float* stats) {
+                                 T* __restrict__ out, float* stats, Det det) {
   pdl_sync();
   extern __shared__ float smem[];
   const int cv = blockIdx.y * blockDim.x + threadIdx.x;
@@ -105,13 +108,13 @@ __global__ void __launch_bounds__(256, 2) act_apply_kernel(int64_t P, int C, con
           if (out) stv<T, VEC>(out + p * C + c0, v);
         });
   }
-  if (stats) reduce_lanes_atomic<2, VEC>(acc, smem, stats, C, C);
+  if (stats) reduce_lanes_atomic<2, VEC>(acc, smem, stats, C, C, det, blockIdx.y, blockIdx.x, gridDim.x);
 }
 
 // z = act(a) + r
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256, 2) add_fwd_kernel(int64_t P, int C, const T* __restrict__ a, const float* scale, const float* shift,
-                               int act, const T* __restrict__ r, T* __restrict__ z, float* stats) {
+                               int act, const T* __restrict__ r, T* __restrict__ z, float* stats, Det det) {
   pdl_sync();
   extern __shared__ float smem[];
   const int cv = blockIdx.y * blockDim.x + threadIdx.x;
@@ -144,14 +147,14 @@ __global__ void __launch_bounds__(256, 2) add_fwd_kernel(int64_t P, int C, const
           stv<T, VEC>(z + p * C + c0, v);
         });
   }
-  if (stats) reduce_lanes_atomic<2, VEC>(acc, smem, stats, C, C);
+  if (stats) reduce_lanes_atomic<2, VEC>(acc, smem, stats, C, C, det, blockIdx.y, blockIdx.x, gridDim.x);
 }
 
 // --------------------------------------------------------------------------------------
 template <typename T, int VEC>
 __global__ void bn_bwd_reduce_kernel(int64_t P, int C, const T* __restrict__ y, const float* scale,
                                      const float* shift, int act, const float* mean, const float* rstd,
-                                     const T* __restrict__ da, float* sums) {
+                                     const T* __restrict__ da, float* sums, Det det) {
   pdl_sync();
   extern __shared__ float smem[];
   const int cv = blockIdx.y * blockDim.x + threadIdx.x;
@@ -185,7 +188,7 @@ __global__ void bn_bwd_reduce_kernel(int64_t P, int C, const T* __restrict__ y, 
           }
         });
   }
-  reduce_lanes_atomic<2, VEC>(acc, smem, sums, C, C);
+  reduce_lanes_atomic<2, VEC>(acc, smem, sums, C, C, det, blockIdx.y, blockIdx.x, gridDim.x);
 }
 
 template <typename T, int VEC>
@@ -393,6 +396,23 @@ int accx_set_knob(int index, int value) {
   return ACCX_OK;
 }
 
+int accx_set_deterministic(void* workspace, int64_t workspace_bytes, unsigned int* counters, int n_counters) {
+  if (!workspace) {           // back to the default (atomics)
+    g_det.ws = nullptr;
+    g_det.ctr = nullptr;
+    g_det_floats = 0;
+    g_det_ctrs = 0;
+    return ACCX_OK;
+  }
+  ACCX_REQUIRE(workspace_bytes >= (1 << 20) && counters && n_counters >= 1024 && aligned16(workspace),
+               "set_deterministic: needs a 16-byte aligned workspace of >= 1 MiB and >= 1024 zeroed counters");
+  g_det.ws = (float*)workspace;
+  g_det.ctr = counters;
+  g_det_floats = workspace_bytes / 4;
+  g_det_ctrs = n_counters;
+  return ACCX_OK;
+}
+
 const char* accx_last_error(void) { return g_err; }
 int accx_version(void) { return 100; }
 
@@ -419,9 +439,11 @@ int accx_act_apply(int dtype, int64_t P, int C, const void* x, const float* scal
     // so the reducing variants run few, long-lived blocks (8 pixels in flight per thread keep HBM busy)
     dim3 block(l.tx, l.ty), grid(grid_x_for(P, l.ty * 8, stats ? 148 * 2 : 148 * 8), l.gy);
     size_t sm = (size_t)l.tx * l.ty * l.vec * sizeof(float);
+    Det det;
+    if (!det_handle(stats ? (int64_t)grid.x * grid.y * 2 * l.tx * l.vec : 0, grid.y, det)) return ACCX_ERR_INVALID;
     ACCX_DISPATCH_VEC(l, {
       launch_k(act_apply_kernel<T, VEC>, grid, block, sm, (cudaStream_t)stream, 
-          P, C, (const T*)x, scale, shift, act, scale2, shift2, (const T*)residual, (T*)out, stats);
+          P, C, (const T*)x, scale, shift, act, scale2, shift2, (const T*)residual, (T*)out, stats, det);
     });
   });
   return check_launch("act_apply");
@@ -434,9 +456,11 @@ int accx_add_fwd(int dtype, int64_t P, int C, const void* a, const float* scale,
     Lanes l = make_lanes(C, DT<T>::VEC, aligned16(a) && aligned16(r) && aligned16(z));
     dim3 block(l.tx, l.ty), grid(grid_x_for(P, l.ty * 8, stats ? 148 * 2 : 148 * 8), l.gy);
     size_t sm = (size_t)l.tx * l.ty * l.vec * sizeof(float);
+    Det det;
+    if (!det_handle(stats ? (int64_t)grid.x * grid.y * 2 * l.tx * l.vec : 0, grid.y, det)) return ACCX_ERR_INVALID;
     ACCX_DISPATCH_VEC(l, {
       launch_k(add_fwd_kernel<T, VEC>, grid, block, sm, (cudaStream_t)stream, P, C, (const T*)a, scale, shift, act,
-                                                                        (const T*)r, (T*)z, stats);
+                                                                        (const T*)r, (T*)z, stats, det);
     });
   });
   return check_launch("add_fwd");
@@ -449,9 +473,11 @@ int accx_bn_bwd_reduce(int dtype, int64_t P, int C, const void* y, const float* 
     Lanes l = make_lanes(C, DT<T>::VEC, aligned16(y) && aligned16(da));
     dim3 block(l.tx, l.ty), grid(grid_x_for(P, l.ty * 8, 148 * knob(KNOB_BN_REDUCE_BLOCKS, 2)), l.gy);
     size_t sm = (size_t)l.tx * l.ty * l.vec * sizeof(float);
+    Det det;
+    if (!det_handle((int64_t)grid.x * grid.y * 2 * l.tx * l.vec, grid.y, det)) return ACCX_ERR_INVALID;
     ACCX_DISPATCH_VEC(l, {
       launch_k(bn_bwd_reduce_kernel<T, VEC>, grid, block, sm, (cudaStream_t)stream, P, C, (const T*)y, scale, shift, act,
-                                                                              mean, rstd, (const T*)da, sums);
+                                                                              mean, rstd, (const T*)da, sums, det);
     });
   });
   return check_launch("bn_bwd_reduce");

@@ -236,7 +236,8 @@ template <typename T, typename TO>
 static int launch_fwd_narrow(const NarrowParams& prm, cudaStream_t st) {
   const int64_t blocks64 = (prm.P + NAR_THREADS - 1) / NAR_THREADS;
   const int cap = prm.stats ? 148 * 2 : 148 * 8;          // reducing variant: few blocks (same-address atomics)
-  const int blocks = (int)(blocks64 < cap ? blocks64 : cap);
+  int blocks = (int)(blocks64 < cap ? blocks64 : cap);
+  if (prm.stats && det_on()) blocks = 1;                  // deterministic mode: one contribution per statistic
   const int K = prm.k_total, N = prm.N;
 #define ACCX_NARROW_FWD(KT, NT)                                                        \
   if (K <= KT && N <= NT) {                                                            \
@@ -276,7 +277,8 @@ template <typename T, typename TG>
 static int launch_wgrad_narrow(const accx_operand_t& op, int N, int64_t P, const void* dy, int64_t ldy, float* dw,
                                cudaStream_t st) {
   const int64_t blocks64 = (P + NAR_THREADS - 1) / NAR_THREADS;
-  const int blocks = (int)(blocks64 < 148 * 2 ? blocks64 : 148 * 2);
+  int blocks = (int)(blocks64 < 148 * 2 ? blocks64 : 148 * 2);
+  if (det_on()) blocks = 1;                               // deterministic mode: one contribution per dW element
   const int K = op.K;
 #define ACCX_NARROW_WG(KT, NT)                                                                               \
   if (K <= KT && N <= NT) {                                                                                  \

@@ -24,6 +24,7 @@ struct PwParams {
   void* y;
   int64_t ldy;
   float* stats;
+  Det det;
 };
 
 template <typename T>
@@ -178,12 +179,22 @@ __global__ void __launch_bounds__(NTHREADS) pw_fwd_kernel(const __grid_constant_
       red[1][ty][tx * TN + j] = s2[j];
     }
     __syncthreads();
+    float s = 0.f;
+    const int which = tid / BN, n = tid % BN;
     if (tid < 2 * BN) {
-      const int which = tid / BN, n = tid % BN;
-      float s = 0.f;
 #pragma unroll
       for (int q = 0; q < 16; ++q) s += red[which][q][n];
-      if (n0 + n < prm.N) atomicAdd(prm.stats + (int64_t)which * prm.N + n0 + n, s);
+    }
+    if (prm.det.ws == nullptr) {
+      if (tid < 2 * BN && n0 + n < prm.N) atomicAdd(prm.stats + (int64_t)which * prm.N + n0 + n, s);
+    } else {
+      // deterministic mode: the pixel tiles of one column block are added in tile order by the last one to arrive
+      det_commit(prm.det, blockIdx.y, blockIdx.x, gridDim.x, 2 * BN,
+                 [&](float* slot) { if (tid < 2 * BN) slot[tid] = s; },
+                 [&](int i, float total) {
+                   const int wh = i / BN, nn = i % BN;
+                   if (n0 + nn < prm.N) atomicAdd(prm.stats + (int64_t)wh * prm.N + n0 + nn, total);
+                 });
     }
   }
 }
@@ -280,8 +291,13 @@ __global__ void __launch_bounds__(NTHREADS) pw_wgrad_kernel(accx_operand_t op, i
 }
 
 template <typename T, typename TO>
-static int launch_pw(const PwParams& prm, cudaStream_t st) {
+static int launch_pw(PwParams& prm, cudaStream_t st) {
   const int gx = (int)((prm.P + BM - 1) / BM);
+  {
+    const int bn = prm.N <= 32 ? 32 : ((prm.N <= 64 || prm.N % 128 != 0) ? 64 : 128);
+    const int gy = (prm.N + bn - 1) / bn;
+    if (!det_handle(prm.stats ? (int64_t)gx * gy * 2 * bn : 0, gy, prm.det)) return ACCX_ERR_INVALID;
+  }
   if (prm.N <= 32) {
     dim3 grid(gx, (prm.N + 31) / 32);
     launch_k(pw_fwd_kernel<T, TO, 2>, grid, NTHREADS, 0, st, prm);
@@ -363,6 +379,7 @@ int accx_pw_wgrad(int dtype, int B, int H, int W, int N, const accx_operand_t* o
     return pw_wgrad_narrow(dtype, dy_f32, *op, N, P, dy, ldy, dw, (cudaStream_t)stream);
   const int gx = (op->K + WG_T - 1) / WG_T, gy = (N + WG_T - 1) / WG_T;
   int64_t splits = (148 * 4 + gx * gy - 1) / (gx * gy);
+  if (det_on()) splits = 1;          // deterministic mode: one contribution per dW element, pixels in order
   const int64_t max_splits = (P + 255) / 256;
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;

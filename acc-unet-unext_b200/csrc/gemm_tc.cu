@@ -49,6 +49,7 @@ struct alignas(64) TcParams {
   int add_log2s[ACCX_MAX_ADDENDS];
   int n_add;
   float* stats;
+  int det;      // deterministic mode (common.cuh): ONE CTA walks all tiles, shared-memory statistics added in row order
 };
 
 // ---------------------------------------------------------------- weight packing
@@ -343,12 +344,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_fwd_tc_kernel(const __grid_c
     int cur_nt = -1;
 
     auto flush_stats = [&](int nt_flush) {
-      if (st_active) {
+      if (!prm.det) {
+        if (st_active) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          atomicAdd(&sstat[tx * 8 + j], s1[j]);
-          atomicAdd(&sstat[bn + tx * 8 + j], s2[j]);
-          s1[j] = s2[j] = 0.f;
+          for (int j = 0; j < 8; ++j) {
+            atomicAdd(&sstat[tx * 8 + j], s1[j]);
+            atomicAdd(&sstat[bn + tx * 8 + j], s2[j]);
+            s1[j] = s2[j] = 0.f;
+          }
+        }
+      } else {
+        // fixed order: the TY row-groups of a column add one after the other
+        for (int t = 0; t < TY; ++t) {
+          if (st_active && ty == t) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              sstat[tx * 8 + j] += s1[j];
+              sstat[bn + tx * 8 + j] += s2[j];
+              s1[j] = s2[j] = 0.f;
+            }
+          }
+          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
         }
       }
       asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
@@ -642,6 +658,8 @@ int accx_pw_fwd_tc(int dtype, int out_dtype, int B, int H, int W, int N, const a
   const int64_t total = (int64_t)prm.m_tiles * prm.n_tiles;
   int64_t grid = sm_count();
   if (grid > total) grid = total;
+  prm.det = (det_on() && stats) ? 1 : 0;
+  if (prm.det) grid = 1;      // each statistic then receives one contribution per epilogue group: a + b is order-free
   launch_k(pw_fwd_tc_kernel, (unsigned)grid, TC_THREADS, smem, st, prm);
   return check_launch("pw_fwd_tc");
 }

@@ -269,7 +269,7 @@ static int wgrad_tc_launch(int B, int H, int W, int N, const accx_operand_t* op,
   // every split ends with 128 x nb fp32 atomics per tap: keep at least 8 stages (1024 pixels) of work behind them
   const int min_stages = knob(KNOB_WGRAD_MIN_STAGES, 8);
   if (splits > stages_total / min_stages) splits = stages_total / min_stages;
-  if (splits < 1) splits = 1;
+  if (splits < 1 || det_on()) splits = 1;     // deterministic mode: one contribution per dW element, pixels in order
   int64_t per = (stages_total + splits - 1) / splits;      // stages per split
   splits = (stages_total + per - 1) / per;
   prm.splits = (int)splits;

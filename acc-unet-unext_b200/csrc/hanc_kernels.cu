@@ -163,7 +163,8 @@ __global__ void __launch_bounds__(128) hanc_unpool_bnred_kernel(int B, int H, in
                                                                 const float* scale, const float* shift, int act,
                                                                 const float* __restrict__ dp1,
                                                                 const float* __restrict__ dp2, bf16* __restrict__ da,
-                                                                const float* mean, const float* rstd, float* sums) {
+                                                                const float* mean, const float* rstd, float* sums,
+                                                                Det det) {
   pdl_sync();
   constexpr int S = 1 << LEVELS, NPX = S * S, VEC = 4;
   extern __shared__ float smem[];
@@ -261,7 +262,7 @@ __global__ void __launch_bounds__(128) hanc_unpool_bnred_kernel(int B, int H, in
   ldf<VEC>(rstd + c0, rs);
 #pragma unroll
   for (int e = 0; e < VEC; ++e) acc[1][e] *= rs[e];
-  reduce_lanes_atomic<2, VEC>(acc, smem, sums, C, C);
+  reduce_lanes_atomic<2, VEC>(acc, smem, sums, C, C, det, blockIdx.y, blockIdx.x, gridDim.x);
 }
 
 }  // namespace accx
@@ -333,12 +334,14 @@ int accx_hanc_unpool_bnred(int dtype, int B, int H, int W, int C, int levels, co
   l.gy = (l.cvn + l.tx - 1) / l.tx;
   dim3 block(l.tx, l.ty), grid(grid_x_for(n_win, l.ty, 148 * 3), l.gy);
   const size_t sm = (size_t)l.tx * l.ty * l.vec * sizeof(float);
+  Det det;
+  if (!det_handle((int64_t)grid.x * grid.y * 2 * l.tx * l.vec, grid.y, det)) return ACCX_ERR_INVALID;
   if (levels == 1)
     launch_k(hanc_unpool_bnred_kernel<1>, grid, block, sm, (cudaStream_t)stream, B, H, W, C, (const bf16*)y, scale, shift, act,
-                                                                            dpool1, dpool2, (bf16*)da, mean, rstd, sums);
+                                                                            dpool1, dpool2, (bf16*)da, mean, rstd, sums, det);
   else
     launch_k(hanc_unpool_bnred_kernel<2>, grid, block, sm, (cudaStream_t)stream, B, H, W, C, (const bf16*)y, scale, shift, act,
-                                                                            dpool1, dpool2, (bf16*)da, mean, rstd, sums);
+                                                                            dpool1, dpool2, (bf16*)da, mean, rstd, sums, det);
   return check_launch("hanc_unpool_bnred");
 }
 

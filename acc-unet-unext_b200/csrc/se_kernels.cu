@@ -11,7 +11,7 @@ namespace accx {
 // grid.x = B * chunks; each block reduces a slice of one image
 template <typename T, int VEC, int U>
 __global__ void se_squeeze_kernel(int B, int HW, int C, int chunks, const T* __restrict__ x, const float* scale,
-                                  const float* shift, int act, float* S) {
+                                  const float* shift, int act, float* S, Det det) {
   pdl_sync();
   extern __shared__ float smem[];
   const int cv = blockIdx.y * blockDim.x + threadIdx.x;
@@ -36,7 +36,8 @@ __global__ void se_squeeze_kernel(int B, int HW, int C, int chunks, const T* __r
           for (int i = 0; i < VEC; ++i) { acc[0][i] += v[i]; acc[1][i] += v[i] * v[i]; }
         });
   }
-  reduce_lanes_atomic<2, VEC>(acc, smem, S + (int64_t)b * C, (int64_t)B * C, C);
+  reduce_lanes_atomic<2, VEC>(acc, smem, S + (int64_t)b * C, (int64_t)B * C, C, det, b * gridDim.y + blockIdx.y, chunk,
+                              chunks);
 }
 
 // The two per-batch kernels are chains of dependent L2 round trips over tiny matrices (one image per block); wider
@@ -143,7 +144,7 @@ template <typename T, int VEC, int U>
 __global__ void se_apply_kernel(int B, int HW, int C, int chunks, const T* __restrict__ x, const float* scale,
                                 const float* shift, int act, const float* __restrict__ gate, const float* se_scale,
                                 const float* se_shift, const T* __restrict__ residual, const float* mix,
-                                T* __restrict__ out, float* stats) {
+                                T* __restrict__ out, float* stats, Det det) {
   pdl_sync();
   extern __shared__ float smem[];
   const int cv = blockIdx.y * blockDim.x + threadIdx.x;
@@ -190,7 +191,7 @@ __global__ void se_apply_kernel(int B, int HW, int C, int chunks, const T* __res
           stv<T, VEC>(out + off + p * C, v);
         });
   }
-  if (stats) reduce_lanes_atomic<2, VEC>(acc, smem, stats, C, C);
+  if (stats) reduce_lanes_atomic<2, VEC>(acc, smem, stats, C, C, det, blockIdx.y, blockIdx.x, gridDim.x);
 }
 
 // G[0,b,c] += sum_hw g', G[1,b,c] += sum_hw g'*a;  g' = dout*mix*lrelu'(v);  dmix += sum dout*(v_act - r)
@@ -198,7 +199,8 @@ template <typename T, int VEC, int U>
 __global__ void se_bwd_reduce_kernel(int B, int HW, int C, int chunks, const T* __restrict__ x, const float* scale,
                                      const float* shift, int act, const float* __restrict__ gate,
                                      const float* se_scale, const float* se_shift, const T* __restrict__ dout,
-                                     const float* mix, const T* __restrict__ residual, float* dmix, float* G) {
+                                     const float* mix, const T* __restrict__ residual, float* dmix, float* G,
+                                     Det det, float* dmix_part) {
   pdl_sync();
   extern __shared__ float smem[];
   const int cv = blockIdx.y * blockDim.x + threadIdx.x;
@@ -241,7 +243,8 @@ __global__ void se_bwd_reduce_kernel(int B, int HW, int C, int chunks, const T* 
           }
         });
   }
-  reduce_lanes_atomic<2, VEC>(acc, smem, G + (int64_t)b * C, (int64_t)B * C, C);
+  reduce_lanes_atomic<2, VEC>(acc, smem, G + (int64_t)b * C, (int64_t)B * C, C, det, b * gridDim.y + blockIdx.y, chunk,
+                              chunks);
   if (dmix) {   // block size need not be a multiple of 32: reduce through shared memory
     const int tid = threadIdx.y * blockDim.x + threadIdx.x, nth = blockDim.x * blockDim.y;
     __syncthreads();
@@ -250,7 +253,9 @@ __global__ void se_bwd_reduce_kernel(int B, int HW, int C, int chunks, const T* 
     if (tid == 0) {
       float s = 0.f;
       for (int i = 0; i < nth; ++i) s += smem[i];
-      atomicAdd(dmix, s);
+      // deterministic mode: one partial per block, added in block order by se_dmix_fold_kernel
+      if (dmix_part) dmix_part[blockIdx.y * gridDim.x + blockIdx.x] = s;
+      else atomicAdd(dmix, s);
     }
   }
 }
@@ -263,14 +268,15 @@ __global__ void __launch_bounds__(SE_GATE_THREADS) se_bwd_gate_kernel(int B, int
                                    const float* __restrict__ hidden, const float* __restrict__ w1,
                                    const float* __restrict__ w2, const float* __restrict__ gamma,
                                    const float* __restrict__ mean, const float* __restrict__ rstd, float* dw1,
-                                   float* db1, float* dw2, float* db2, float* dgamma, float* dbeta, float* PQR) {
+                                   float* db1, float* dw2, float* db2, float* dgamma, float* dbeta, float* PQR,
+                                   int training, int b_off) {
   pdl_sync();
   extern __shared__ float sm[];
   float* dpre2 = sm;            // [C]
   float* m = sm + C;            // [C]
   float* hact = sm + 2 * C;     // [Cr]
   float* dpre1 = hact + Cr;     // [Cr]
-  const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  const int b = blockIdx.x + b_off, tid = threadIdx.x, nt = blockDim.x;   // b_off: deterministic mode, one image per launch
   const double n = HW * (double)B;
   const float inv_hw = (float)(1.0 / HW);
   const int64_t BC = (int64_t)B * C;
@@ -288,7 +294,8 @@ __global__ void __launch_bounds__(SE_GATE_THREADS) se_bwd_gate_kernel(int B, int
       if (dbeta) atomicAdd(dbeta + c, (float)a1);
       if (dgamma) atomicAdd(dgamma + c, (float)a2);
     }
-    const float c1 = (float)(a1 / n), c2 = (float)(a2 / n);
+    // eval mode: the BatchNorm is a fixed affine of the running statistics, no batch-mean terms in its backward
+    const float c1 = training ? (float)(a1 / n) : 0.f, c2 = training ? (float)(a2 / n) : 0.f;
     const float g = gate[(int64_t)b * C + c];
     const float s1 = S[(int64_t)b * C + c], s2 = S[BC + (int64_t)b * C + c];
     const float g2 = G[BC + (int64_t)b * C + c];
@@ -341,7 +348,8 @@ __global__ void se_bwd_apply_kernel(int B, int HW, int C, int chunks, const T* _
                                     const float* shift, int act, const float* __restrict__ gate,
                                     const float* se_scale, const float* se_shift, const T* __restrict__ dout,
                                     const float* mix, const float* __restrict__ PQR, T* __restrict__ da,
-                                    int accumulate, const float* bn_mean, const float* bn_rstd, float* bn_sums) {
+                                    int accumulate, const float* bn_mean, const float* bn_rstd, float* bn_sums,
+                                    Det det) {
   pdl_sync();
   // bn_sums != NULL: also the BatchNorm-backward reduction of the lazy input's own BatchNorm on the gradient
   // just produced (sum g, sum g*xhat with g = da*act'(x)) -- saves the separate accx_bn_bwd_reduce pass
@@ -414,7 +422,7 @@ __global__ void se_bwd_apply_kernel(int B, int HW, int C, int chunks, const T* _
     ldf<VEC>(bn_rstd + c0, rs);
 #pragma unroll
     for (int i = 0; i < VEC; ++i) bacc[1][i] *= rs[i];
-    reduce_lanes_atomic<2, VEC>(bacc, smem, bn_sums, C, C);
+    reduce_lanes_atomic<2, VEC>(bacc, smem, bn_sums, C, C, det, blockIdx.y, blockIdx.x, gridDim.x);
   }
 }
 
@@ -444,6 +452,16 @@ __global__ void se_bwd_apply_kernel(int B, int HW, int C, int chunks, const T* _
     }                                                                    \
   } while (0)
 
+// deterministic mode: dmix += partial[0] + partial[1] + ..  in block order
+__global__ void se_dmix_fold_kernel(const float* __restrict__ part, int n, float* dmix) {
+  pdl_sync();
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < n; ++i) s += part[i];
+    *dmix += s;
+  }
+}
+
 static inline int se_chunks(int B, int HW, int ty, int target_blocks = 148 * 4) {
   // enough blocks to fill the machine, but keep the number of atomics per (b,c) small
   int per_img = (HW + ty * 8 - 1) / (ty * 8);
@@ -467,10 +485,12 @@ int accx_se_squeeze(int dtype, int B, int HW, int C, const void* x, const float*
     dim3 block(l.tx, l.ty), grid(B * chunks, l.gy);
     size_t sm = (size_t)l.tx * l.ty * l.vec * sizeof(float);
     const int u = knob(KNOB_SE_SQUEEZE_U, 4);
+    Det det;
+    if (!det_handle((int64_t)grid.x * grid.y * 2 * l.tx * l.vec, (int64_t)B * grid.y, det)) return ACCX_ERR_INVALID;
     ACCX_DISPATCH_VEC(l, {
       ACCX_DISPATCH_U(u, {
         launch_k(se_squeeze_kernel<T, VEC, U>, grid, block, sm, (cudaStream_t)stream, B, HW, C, chunks, (const T*)x, scale,
-                                                                                shift, act, S);
+                                                                                shift, act, S, det);
       });
     });
   });
@@ -500,11 +520,13 @@ int accx_se_apply(int dtype, int B, int HW, int C, const void* x, const float* s
     dim3 block(l.tx, l.ty), grid(B * chunks, l.gy);
     size_t sm = (size_t)l.tx * l.ty * l.vec * sizeof(float);
     const int u = knob(KNOB_SE_APPLY_U, 4);
+    Det det;
+    if (!det_handle(stats ? (int64_t)grid.x * grid.y * 2 * l.tx * l.vec : 0, grid.y, det)) return ACCX_ERR_INVALID;
     ACCX_DISPATCH_VEC(l, {
       ACCX_DISPATCH_U(u, {
         launch_k(se_apply_kernel<T, VEC, U>, grid, block, sm, (cudaStream_t)stream, B, HW, C, chunks, (const T*)x, scale, shift, act,
                                                                               gate, se_scale, se_shift, (const T*)residual,
-                                                                              mix, (T*)out, stats);
+                                                                              mix, (T*)out, stats, det);
       });
     });
   });
@@ -523,13 +545,19 @@ int accx_se_bwd_reduce(int dtype, int B, int HW, int C, const void* x, const flo
     dim3 block(l.tx, l.ty), grid(B * chunks, l.gy);
     size_t sm = (size_t)l.tx * l.ty * l.vec * sizeof(float);
     const int u = knob(KNOB_SE_BWD_REDUCE_U, 8);
+    Det det;
+    const int64_t lanes_floats = (int64_t)grid.x * grid.y * 2 * l.tx * l.vec;
+    const int n_blocks = (int)(grid.x * grid.y);
+    if (!det_handle(lanes_floats + (dmix ? n_blocks : 0), (int64_t)B * grid.y, det)) return ACCX_ERR_INVALID;
+    float* dmix_part = (det.ws && dmix) ? det.ws + lanes_floats : nullptr;
     ACCX_DISPATCH_VEC_H(l, {
       ACCX_DISPATCH_U(u, {
         launch_k(se_bwd_reduce_kernel<T, VEC, U>, grid, block, sm, (cudaStream_t)stream, 
             B, HW, C, chunks, (const T*)x, scale, shift, act, gate, se_scale, se_shift, (const T*)dout, mix,
-            (const T*)residual, dmix, G);
+            (const T*)residual, dmix, G, det, dmix_part);
       });
     });
+    if (dmix_part) launch_k(se_dmix_fold_kernel, 1, 32, 0, (cudaStream_t)stream, (const float*)dmix_part, n_blocks, dmix);
   });
   return check_launch("se_bwd_reduce");
 }
@@ -537,12 +565,19 @@ int accx_se_bwd_reduce(int dtype, int B, int HW, int C, const void* x, const flo
 int accx_se_bwd_gate(int B, int C, int Cr, double HW, const float* S, const float* G, const float* gate,
                      const float* hidden, const float* w1, const float* w2, const float* gamma, const float* mean,
                      const float* rstd, float* dw1, float* db1, float* dw2, float* db2, float* dgamma, float* dbeta,
-                     float* PQR, void* stream) {
+                     float* PQR, int training, void* stream) {
   ACCX_REQUIRE(B > 0 && C > 0 && Cr > 0 && S && G && gate && hidden && w1 && w2 && gamma && mean && rstd && PQR,
                "se_bwd_gate: bad arguments");
   size_t sm = (size_t)(2 * C + 2 * Cr) * sizeof(float);
+  if (det_on()) {
+    // the per-image blocks add into the shared FC gradients: one single-block launch per image, in image order
+    for (int b = 0; b < B; ++b)
+      launch_k(se_bwd_gate_kernel, 1, SE_GATE_THREADS, sm, (cudaStream_t)stream, B, C, Cr, HW, S, G, gate, hidden, w1, w2, gamma,
+               mean, rstd, dw1, db1, dw2, db2, dgamma, dbeta, PQR, training, b);
+    return check_launch("se_bwd_gate");
+  }
   launch_k(se_bwd_gate_kernel, B, SE_GATE_THREADS, sm, (cudaStream_t)stream, B, C, Cr, HW, S, G, gate, hidden, w1, w2, gamma, mean, rstd,
-                                                           dw1, db1, dw2, db2, dgamma, dbeta, PQR);
+                                                           dw1, db1, dw2, db2, dgamma, dbeta, PQR, training, 0);
   return check_launch("se_bwd_gate");
 }
 
@@ -560,11 +595,13 @@ int accx_se_bwd_apply(int dtype, int B, int HW, int C, const void* x, const floa
     dim3 block(l.tx, l.ty), grid(B * chunks, l.gy);
     const size_t sm = bn_sums ? (size_t)l.tx * l.ty * l.vec * sizeof(float) : 0;
     const int u = knob(KNOB_SE_BWD_APPLY_U, 8);
+    Det det;
+    if (!det_handle(bn_sums ? (int64_t)grid.x * grid.y * 2 * l.tx * l.vec : 0, grid.y, det)) return ACCX_ERR_INVALID;
     ACCX_DISPATCH_VEC_H(l, {
       ACCX_DISPATCH_U(u, {
         launch_k(se_bwd_apply_kernel<T, VEC, U>, grid, block, sm, (cudaStream_t)stream, 
             B, HW, C, chunks, (const T*)x, scale, shift, act, gate, se_scale, se_shift, (const T*)dout, mix, PQR, (T*)da,
-            accumulate, bn_mean, bn_rstd, bn_sums);
+            accumulate, bn_mean, bn_rstd, bn_sums, det);
       });
     });
   });

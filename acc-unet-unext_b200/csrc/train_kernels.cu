@@ -182,6 +182,70 @@ __global__ void __launch_bounds__(256) dice_bce_fwd_kernel(int B, int64_t N, con
   }
 }
 
+// Per-step segmentation metrics of the training loop, left ON THE DEVICE (Experiments/Train_one_epoch.py:134-135 calls
+// iou_on_batch -> .cpu().numpy() + sklearn every step: a device-to-host sync per step).  One pass over logits and masks:
+//   pred = sigmoid(logit) >= 0.5, mask = truth > 0                                  (Experiments/utils.py:478-494)
+//   counts[b] = {TP, #pred, #mask} as integers (order-free, exact)
+//   iou_b  = TP / (#pred + #mask - TP)   (sklearn.metrics.jaccard_score, binary; 0 when the union is empty)
+//   dice_b = WeightedDiceBCE._show_dice (utils.py:148-157): 1 - WeightedDiceLoss(binarised pred, mask) -- which
+//            passes the 0/1 prediction through sigmoid AGAIN (utils.py:121), so p is 0.5*sigmoid(1) or 0.5*sigmoid(0)
+// out[0] = mean_b iou_b, out[1] = mean_b dice_b, written by the last block.
+template <typename T>
+__global__ void __launch_bounds__(256) seg_metrics_kernel(int B, int64_t N, const T* __restrict__ logit,
+                                                          const float* __restrict__ truth, unsigned int* counts,
+                                                          float* out) {
+  pdl_sync();
+  __shared__ unsigned int red[8][3];
+  __shared__ bool is_last;
+  const int b = blockIdx.y;
+  const T* x = logit + (int64_t)b * N;
+  const float* y = truth + (int64_t)b * N;
+  unsigned int tp = 0, np = 0, nm = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+    const bool p = 1.f / (1.f + expf(-to_f(x[i]))) >= 0.5f;
+    const bool m = y[i] > 0.f;
+    tp += (p && m) ? 1u : 0u;
+    np += p ? 1u : 0u;
+    nm += m ? 1u : 0u;
+  }
+  tp = __reduce_add_sync(0xffffffffu, tp);
+  np = __reduce_add_sync(0xffffffffu, np);
+  nm = __reduce_add_sync(0xffffffffu, nm);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { red[warp][0] = tp; red[warp][1] = np; red[warp][2] = nm; }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    unsigned int s = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w][threadIdx.x];
+    atomicAdd(counts + b * 4 + threadIdx.x, s);
+  }
+  __threadfence();
+  __syncthreads();
+  unsigned int* counter = counts + (int64_t)B * 4;
+  if (threadIdx.x == 0) {
+    const unsigned int total = gridDim.x * gridDim.y;
+    is_last = atomicAdd(counter, 1u) == total - 1;
+    if (is_last) *counter = 0;
+  }
+  __syncthreads();
+  if (is_last && threadIdx.x == 0) {
+    __threadfence();
+    const double s1 = 1.0 / (1.0 + exp(-1.0));       // sigmoid(1): the second sigmoid of _show_dice on a positive
+    double iou = 0, dice = 0;
+    for (int i = 0; i < B; ++i) {
+      const double TP = __ldcg(counts + i * 4), NP = __ldcg(counts + i * 4 + 1), NM = __ldcg(counts + i * 4 + 2);
+      const double uni = NP + NM - TP;
+      iou += uni > 0 ? TP / uni : 0.0;
+      const double FN = NM - TP, N0 = (double)N - NP;
+      const double inter = 0.25 * (s1 * TP + 0.5 * FN);
+      const double pp = 0.25 * (s1 * s1 * NP + 0.25 * N0), tt = 0.25 * NM;
+      dice += (2.0 * inter + 1e-5) / (pp + tt + 1e-5);
+    }
+    out[0] = (float)(iou / B);
+    out[1] = (float)(dice / B);
+  }
+}
+
 // dlogit = gscale * d loss / d logit (TG = gradient storage type); dbias += sum dlogit (the final 1x1 conv's bias)
 template <typename T, typename TG>
 __global__ void __launch_bounds__(256) dice_bce_bwd_kernel(int B, int64_t N, const T* __restrict__ logit,
@@ -227,7 +291,9 @@ __global__ void __launch_bounds__(256) adam_flat_kernel(int64_t n4, float4* __re
   const double t = (double)state[0];
   const float bc1 = (float)(1.0 - pow((double)b1, t));
   const float bc2s = (float)sqrt(1.0 - pow((double)b2, t));
-  const float step_size = lr / bc1;
+  // lr < 0: the learning rate lives on the device (state[1]) -- a captured step graph then follows an LR schedule
+  // (CosineAnnealingWarmRestarts, Experiments/train_model.py:738) without being re-captured
+  const float step_size = (lr >= 0.f ? lr : state[1]) / bc1;
   constexpr int U = 2;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n4; i0 += U * stride) {
@@ -395,13 +461,23 @@ static inline int loss_grid_x(int B, int64_t N) {
 int accx_dice_bce_fwd(int dtype, int B, int64_t N, const void* logit, const float* truth, float dice_w, float bce_w,
                       float* sums, float* loss, void* stream) {
   ACCX_REQUIRE(B > 0 && N > 0 && logit && truth && sums && loss, "dice_bce_fwd: bad arguments");
-  dim3 grid(loss_grid_x(B, N), B);
+  dim3 grid(det_on() ? 1 : loss_grid_x(B, N), B);       // deterministic mode: one block (= one contribution) per image
   unsigned int* counter = reinterpret_cast<unsigned int*>(sums + (int64_t)B * LOSS_STRIDE);
   ACCX_DISPATCH_T(dtype, {
     launch_k(dice_bce_fwd_kernel<T>, grid, 256, 0, (cudaStream_t)stream, B, N, (const T*)logit, truth, dice_w, bce_w, sums,
                                                                     counter, loss);
   });
   return check_launch("dice_bce_fwd");
+}
+
+int accx_seg_metrics(int dtype, int B, int64_t N, const void* logit, const float* truth, unsigned int* counts, float* out,
+                     void* stream) {
+  ACCX_REQUIRE(B > 0 && N > 0 && N < ((int64_t)1 << 31) && logit && truth && counts && out, "seg_metrics: bad arguments");
+  dim3 grid(loss_grid_x(B, N), B);
+  ACCX_DISPATCH_T(dtype, {
+    launch_k(seg_metrics_kernel<T>, grid, 256, 0, (cudaStream_t)stream, B, N, (const T*)logit, truth, counts, out);
+  });
+  return check_launch("seg_metrics");
 }
 
 int accx_dice_bce_bwd(int dtype, int grad_dtype, int B, int64_t N, const void* logit, const float* truth,
@@ -454,6 +530,7 @@ int accx_upshuffle(int dtype, int forward, int B, int H, int W, int Co, void* te
   dim3 block(tx, ty), grid(grid_x_for(P, ty * 2, forward || !dbias ? 148 * 16 : 148 * 4), (pairs + tx - 1) / tx);
   const size_t sm = (forward || !dbias) ? 0 : (size_t)tx * ty * 2 * sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;
+  if (!forward && dbias && det_on()) grid.x = 1;       // deterministic mode: one contribution per bias gradient
   ACCX_DISPATCH_T(dtype, {
     if (forward)
       launch_k(upshuffle_kernel<T, true>, grid, block, sm, st, B, H, W, Co, (T*)temp, bias, (T*)out, ld_out, (float*)nullptr);

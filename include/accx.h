@@ -42,6 +42,16 @@ int accx_version(void);
 /* Launch-geometry tuning knob `index` (see KNOB_* in csrc/common.cuh) := value; 0 restores the built-in default.
  * Process-global, meant for the sweeps in tests/bench_knobs.py -- results never depend on it. */
 int accx_set_knob(int index, int value);
+/* Deterministic reduction mode.  By default the cross-block part of every reduction (BatchNorm statistics, SE sums,
+ * weight gradients) ends in fp32 atomics: results vary at rounding level from run to run, and ACC-UNet's 220
+ * stacked BatchNorm2d layers (ACC_UNet.py:34,74,244-260,311-319,388-410) amplify that.  With a caller-owned
+ * workspace installed, every reducing kernel adds its per-block partial sums in a FIXED order instead (two-stage:
+ * per-block slots, folded in block order by the last block to arrive; tile-shaped partials -- weight gradients,
+ * the persistent tcgen05 / TMA-tiled kernels -- get exactly one contribution per address): two runs are then
+ * bit-identical.  `counters` = n_counters (>= 1024) zero-initialised 32-bit words.  The workspace is shared by all
+ * launches, so the mode requires that every accx call is issued on ONE stream.  workspace = NULL restores the
+ * default.  Process-global; slower (parity / debugging mode), same arithmetic per element. */
+int accx_set_deterministic(void* workspace, int64_t workspace_bytes, unsigned int* counters, int n_counters);
 
 /* One A-operand of a pointwise contraction together with its weight slice.
  *   value(p, k) = act(data[p'*ld + k]*scale[k] + shift[k]),  p' = pixel p shifted by (dy, dx)
@@ -196,14 +206,16 @@ int accx_se_apply(int dtype, int B, int HW, int C, const void* x, const float* s
  * the tiny gate kernel turns G into per-(b,c) coefficients PQR and all parameter gradients;
  * apply: da (+)= P*g' + Q*a + R.  With mix: g' carries the factor mix and
  * dmix += sum dout*(v - residual).  bn_sums != NULL (apply): the lazy input's own BatchNorm-backward reduction
- * (accx_bn_bwd_reduce on the da just written) is accumulated in the same pass. */
+ * (accx_bn_bwd_reduce on the da just written) is accumulated in the same pass.
+ * training = 0 (gate): the layer's BatchNorm ran on its running statistics (eval mode) -- a fixed affine, so the
+ * batch-mean terms of its backward are dropped (the reference differentiates eval-mode modules the same way). */
 int accx_se_bwd_reduce(int dtype, int B, int HW, int C, const void* x, const float* scale, const float* shift, int act,
                        const float* gate, const float* se_scale, const float* se_shift, const void* dout,
                        const float* mix, const void* residual, float* dmix, float* G, void* stream);
 int accx_se_bwd_gate(int B, int C, int Cr, double HW, const float* S, const float* G, const float* gate,
                      const float* hidden, const float* w1, const float* w2, const float* gamma, const float* mean,
                      const float* rstd, float* dw1, float* db1, float* dw2, float* db2, float* dgamma, float* dbeta,
-                     float* PQR, void* stream);
+                     float* PQR, int training, void* stream);
 int accx_se_bwd_apply(int dtype, int B, int HW, int C, const void* x, const float* scale, const float* shift, int act,
                       const float* gate, const float* se_scale, const float* se_shift, const void* dout,
                       const float* mix, const float* PQR, void* da, int accumulate, const float* bn_mean,
@@ -237,6 +249,15 @@ int accx_upshuffle(int dtype, int forward, int B, int H, int W, int Co, void* te
 int accx_copy_cols(int dtype, int64_t P, int C, const void* src, int64_t ld_src, void* dst, int64_t ld_dst,
                    void* stream);
 
+/* Per-step segmentation metrics left on the device (the reference syncs device -> host every step for them:
+ * Experiments/Train_one_epoch.py:134-135).  pred = sigmoid(logit) >= 0.5, mask = truth > 0;
+ * out[0] = mean over images of sklearn's binary jaccard_score (iou_on_batch, Experiments/utils.py:478-494; 0 for an
+ * empty union), out[1] = WeightedDiceBCE._show_dice (utils.py:148-157, including its second sigmoid on the binarised
+ * prediction).  logit [B, N] (dtype), truth [B, N] fp32; counts: uint32[4*B + 1] ZEROED by the caller
+ * (per image TP, #pred, #mask as exact integers + a block counter). */
+int accx_seg_metrics(int dtype, int B, int64_t N, const void* logit, const float* truth, unsigned int* counts, float* out,
+                     void* stream);
+
 /* WeightedDiceBCE(dice_weight, BCE_weight) on one-class logits (Experiments/utils.py:21-74 BCE normalised over
  * positives / negatives, :109-138 soft Dice on sigmoid(logit) with class weights [0.5, 0.5], :140-171 the sum).
  * logit [B, N] (dtype), truth [B, N] fp32.  sums: float[8*B + 8], ZEROED by the caller (per-image partial sums
@@ -249,7 +270,8 @@ int accx_dice_bce_bwd(int dtype, int grad_dtype, int B, int64_t N, const void* l
 
 /* torch.optim.Adam(lr) step (train_model.py:647) over ONE flat fp32 buffer holding all parameters back to
  * back (n a multiple of 4, 16-byte aligned buffers).  state[0] = step count, kept on the device and incremented
- * by the call (graph-capturable).  grad is multiplied by grad_scale first; weight_decay is torch's L2 form. */
+ * by the call (graph-capturable).  grad is multiplied by grad_scale first; weight_decay is torch's L2 form.
+ * lr < 0: the learning rate is read from state[1] on the device (LR schedules under a captured graph). */
 int accx_adam_step(int64_t n, float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* state,
                    float lr, float beta1, float beta2, float eps, float weight_decay, float grad_scale, void* stream);
 

@@ -28,6 +28,7 @@ Reference lines each function follows (relative to /root/reference):
                                                   Lite: ACC_UNet_lite.py:424-427)
   acc_unet        ACC_UNet/ACC_UNet.py:601-659
   dice_bce_loss   Experiments/utils.py:21-74,109-171
+  seg_metrics     Experiments/utils.py:478-494 (iou_on_batch), :148-157 (_show_dice)
 """
 from __future__ import annotations
 
@@ -44,19 +45,34 @@ BN_MOMENTUM = 0.1
 
 
 class Ctx:
-    """Carries the state dict, the train/eval switch and collects BN buffer updates."""
+    """Carries the state dict, the train/eval switch and collects BN buffer updates.
 
-    def __init__(self, state: State, training: bool = True):
+    forced / record: the path's only discrete decisions are the sign under every LeakyReLU and the arg-max of
+    every max-pool window.  `record` (a dict) collects this evaluation's decisions per site; `forced` replays
+    decisions recorded elsewhere (site -> bool mask / window index).  The bf16 parity tests use it to compare
+    gradients element-wise: a bf16 evaluation flips a fraction of these decisions at rounding-level near-ties, which
+    moves whole gradient contributions by a factor 100 and says nothing about the kernels; with the decisions of
+    the CUDA run replayed here, what is left is the smooth rounding error that north_star's rtol bounds."""
+
+    def __init__(self, state: State, training: bool = True, forced: Optional[dict] = None, record: Optional[dict] = None):
         self.sd = state
         self.training = training
         self.updates: State = {}
+        self.forced = forced
+        self.record = record
 
     def p(self, name: str) -> torch.Tensor:
         return self.sd[name]
 
 
-def lrelu(x):
-    return torch.where(x > 0, x, x * LRELU_SLOPE)
+def lrelu(x, cx: Optional[Ctx] = None, site: Optional[str] = None):
+    m = x > 0
+    if cx is not None and site is not None:
+        if cx.forced is not None and site in cx.forced:
+            m = cx.forced[site].to(x.device)
+        if cx.record is not None:
+            cx.record[site] = m
+    return torch.where(m, x, x * LRELU_SLOPE)
 
 
 def batchnorm(cx: Ctx, name: str, x: torch.Tensor) -> torch.Tensor:
@@ -85,13 +101,29 @@ def pointwise(cx: Ctx, name: str, x: torch.Tensor) -> torch.Tensor:
     return y + cx.p(name + ".bias")[None, :, None, None]
 
 
-def block_reduce(x: torch.Tensor, s: int, how: str) -> torch.Tensor:
+def first_argmax(win: torch.Tensor) -> torch.Tensor:
+    """index of the FIRST maximum along the last dim (row-major window order: ATen's max-pool tie rule)"""
+    n = win.shape[-1]
+    hit = win == win.amax(dim=-1, keepdim=True)
+    pos = torch.arange(n, device=win.device).expand_as(win)
+    return torch.where(hit, pos, torch.full_like(pos, n)).amin(dim=-1)
+
+
+def block_reduce(x: torch.Tensor, s: int, how: str, cx: Optional[Ctx] = None, site: Optional[str] = None) -> torch.Tensor:
     """Non-overlapping s x s pooling computed directly on x."""
     B, C, H, W = x.shape
     v = x.reshape(B, C, H // s, s, W // s, s)
     if how == "avg":
         return v.mean(dim=(3, 5))
-    return v.amax(dim=(3, 5))
+    if cx is None or site is None or (cx.forced is None and cx.record is None):
+        return v.amax(dim=(3, 5))
+    win = v.permute(0, 1, 2, 4, 3, 5).reshape(B, C, H // s, W // s, s * s)      # row-major inside the window
+    idx = first_argmax(win.detach())
+    if cx.forced is not None and site in cx.forced:
+        idx = cx.forced[site].to(x.device)
+    if cx.record is not None:
+        cx.record[site] = idx
+    return win.gather(-1, idx.unsqueeze(-1)).squeeze(-1)
 
 
 def replicate(x: torch.Tensor, s: int) -> torch.Tensor:
@@ -102,12 +134,12 @@ def replicate(x: torch.Tensor, s: int) -> torch.Tensor:
 def se_layer(cx: Ctx, name: str, x: torch.Tensor) -> torch.Tensor:
     """Squeeze-excite gate followed by BN and LeakyReLU (non-standard tail)."""
     m = x.mean(dim=(2, 3))
-    h = lrelu(m @ cx.p(name + ".fc1.weight").t() + cx.p(name + ".fc1.bias"))
+    h = lrelu(m @ cx.p(name + ".fc1.weight").t() + cx.p(name + ".fc1.bias"), cx, name + ".fc1")
     g = torch.sigmoid(h @ cx.p(name + ".fc2.weight").t() + cx.p(name + ".fc2.bias"))
-    return lrelu(batchnorm(cx, name + ".bn", x * g[:, :, None, None]))
+    return lrelu(batchnorm(cx, name + ".bn", x * g[:, :, None, None]), cx, name + ".bn")
 
 
-def hanc_pyramid(x: torch.Tensor, k: int) -> torch.Tensor:
+def hanc_pyramid(x: torch.Tensor, k: int, cx: Optional[Ctx] = None, name: str = "") -> torch.Tensor:
     """[x, avg2, avg4, .., max2, max4, ..] interleaved so channel index = c*(2k-1)+j."""
     if k == 1:
         return x
@@ -115,37 +147,37 @@ def hanc_pyramid(x: torch.Tensor, k: int) -> torch.Tensor:
     for j in range(1, k):
         maps.append(replicate(block_reduce(x, 2 ** j, "avg"), 2 ** j))
     for j in range(1, k):
-        maps.append(replicate(block_reduce(x, 2 ** j, "max"), 2 ** j))
+        maps.append(replicate(block_reduce(x, 2 ** j, "max", cx, f"{name}.max{j}"), 2 ** j))
     B, C, H, W = x.shape
     return torch.stack(maps, dim=2).reshape(B, C * (2 * k - 1), H, W)
 
 
 def hanc_layer(cx: Ctx, name: str, x: torch.Tensor, k: int) -> torch.Tensor:
-    return lrelu(batchnorm(cx, name + ".bn", pointwise(cx, name + ".cnv", hanc_pyramid(x, k))))
+    return lrelu(batchnorm(cx, name + ".bn", pointwise(cx, name + ".cnv", hanc_pyramid(x, k, cx, name))), cx, name + ".bn")
 
 
 def hanc_block(cx: Ctx, name: str, inp: torch.Tensor, k: int) -> torch.Tensor:
-    x = lrelu(batchnorm(cx, name + ".norm1", pointwise(cx, name + ".conv1", inp)))
+    x = lrelu(batchnorm(cx, name + ".norm1", pointwise(cx, name + ".conv1", inp)), cx, name + ".norm1")
     w2 = cx.p(name + ".conv2.weight")
     x = F.conv2d(x, w2, cx.p(name + ".conv2.bias"), padding=1, groups=w2.shape[0])
-    x = lrelu(batchnorm(cx, name + ".norm2", x))
+    x = lrelu(batchnorm(cx, name + ".norm2", x), cx, name + ".norm2")
     x = hanc_layer(cx, name + ".hnc", x, k)
     x = batchnorm(cx, name + ".norm", x + inp)
-    x = lrelu(batchnorm(cx, name + ".norm3", pointwise(cx, name + ".conv3", x)))
+    x = lrelu(batchnorm(cx, name + ".norm3", pointwise(cx, name + ".conv3", x)), cx, name + ".norm3")
     return se_layer(cx, name + ".sqe", x)
 
 
 def conv_bn_se(cx: Ctx, name: str, x: torch.Tensor) -> torch.Tensor:
-    x = lrelu(batchnorm(cx, name + ".batchnorm", pointwise(cx, name + ".conv1", x)))
+    x = lrelu(batchnorm(cx, name + ".batchnorm", pointwise(cx, name + ".conv1", x)), cx, name + ".batchnorm")
     return se_layer(cx, name + ".sqe", x)
 
 
 def respath(cx: Ctx, name: str, x: torch.Tensor, n_lvl: int) -> torch.Tensor:
     for i in range(n_lvl):
         y = F.conv2d(x, cx.p(f"{name}.convs.{i}.weight"), cx.p(f"{name}.convs.{i}.bias"), padding=1)
-        x = x + se_layer(cx, f"{name}.sqes.{i}", lrelu(batchnorm(cx, f"{name}.bns.{i}", y)))
+        x = x + se_layer(cx, f"{name}.sqes.{i}", lrelu(batchnorm(cx, f"{name}.bns.{i}", y), cx, f"{name}.bns.{i}"))
     # the module registered under the name 'sqe' is a BatchNorm2d
-    return batchnorm(cx, name + ".sqe", lrelu(batchnorm(cx, name + ".bn", x)))
+    return batchnorm(cx, name + ".sqe", lrelu(batchnorm(cx, name + ".bn", x), cx, name + ".bn"))
 
 
 def _to_level(x: torch.Tensor, src: int, dst: int) -> torch.Tensor:
@@ -167,7 +199,7 @@ def mlfc(cx: Ctx, name: str, xs: List[torch.Tensor], lenn: int = 1, variant: str
         for l in range(4):
             gathered = torch.cat([_to_level(xs[s], s, l) for s in range(4)], dim=1)
             t = conv_bn_se(cx, f"{name}.cnv_blks{l + 1}.{i}", gathered)
-            xc.append(lrelu(batchnorm(cx, f"{name}.bns{l + 1}.{i}", t)))
+            xc.append(lrelu(batchnorm(cx, f"{name}.bns{l + 1}.{i}", t), cx, f"{name}.bns{l + 1}.{i}"))
         for l in range(4):
             B, C, H, W = xs[l].shape
             merged = torch.stack([xc[l], xs[l]], dim=2).reshape(B, 2 * C, H, W)
@@ -177,7 +209,7 @@ def mlfc(cx: Ctx, name: str, xs: List[torch.Tensor], lenn: int = 1, variant: str
                 t = t * wmix + xs[l] * (1 - wmix)
             else:
                 t = t + xs[l]
-            xc[l] = lrelu(batchnorm(cx, f"{name}.bns_mrg{l + 1}.{i}", t))
+            xc[l] = lrelu(batchnorm(cx, f"{name}.bns_mrg{l + 1}.{i}", t), cx, f"{name}.bns_mrg{l + 1}.{i}")
     return tuple(se_layer(cx, f"{name}.sqe{l + 1}", xc[l]) for l in range(4))
 
 
@@ -196,7 +228,8 @@ def acc_unet(cx: Ctx, x: torch.Tensor, variant: str = "base", logits: bool = Fal
         x = hanc_block(cx, nm, x, k)
         if idx % 2 == 1 and idx < 9:
             skips.append(x)
-            x = F.max_pool2d(x, 2)
+            x = block_reduce(x, 2, "max", cx, f"pool{idx // 2 + 1}") if (cx.forced is not None or cx.record is not None) \
+                else F.max_pool2d(x, 2)
     for l, n_lvl in enumerate((4, 3, 2, 1)):
         skips[l] = respath(cx, f"rspth{l + 1}", skips[l], n_lvl)
     for m in ("mlfc1", "mlfc2", "mlfc3"):
@@ -227,6 +260,26 @@ def dice_bce_loss(logit: torch.Tensor, truth: torch.Tensor, dice_weight=0.5, bce
     neg = 1 - pos
     bce = (0.5 * pos * l / pos.sum().clamp(min=1.0) + 0.5 * neg * l / neg.sum().clamp(min=1.0)).sum()
     return dice_weight * dice + bce_weight * bce
+
+
+def seg_metrics(logit: torch.Tensor, truth: torch.Tensor) -> Tuple[float, float]:
+    """(iou_on_batch, WeightedDiceBCE._show_dice) of the reference's training loop
+    (Experiments/utils.py:478-494, :148-157; called every step at Train_one_epoch.py:134-135)."""
+    B = logit.shape[0]
+    pred = (torch.sigmoid(logit.reshape(B, -1).float()) >= 0.5)
+    mask = truth.reshape(B, -1) > 0
+    ious, dices = [], []
+    s1 = 1.0 / (1.0 + math.exp(-1.0))
+    for b in range(B):
+        tp = float((pred[b] & mask[b]).sum())
+        n_pred, n_mask, n = float(pred[b].sum()), float(mask[b].sum()), float(pred.shape[1])
+        union = n_pred + n_mask - tp
+        ious.append(tp / union if union > 0 else 0.0)                  # sklearn jaccard_score(zero_division -> 0)
+        # _show_dice feeds the 0/1 prediction to WeightedDiceLoss, which applies sigmoid once more (utils.py:121)
+        inter = 0.25 * (s1 * tp + 0.5 * (n_mask - tp))
+        pp, tt = 0.25 * (s1 * s1 * n_pred + 0.25 * (n - n_pred)), 0.25 * n_mask
+        dices.append((2 * inter + 1e-5) / (pp + tt + 1e-5))
+    return sum(ious) / B, sum(dices) / B
 
 
 # ---------------------------------------------------------------------------------

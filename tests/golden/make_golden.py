@@ -155,6 +155,49 @@ def main():
                         sums=np.array([float(sd[k].double().sum()) for k in allk]),
                         abssums=np.array([float(sd[k].double().abs().sum()) for k in allk]))
 
+    # the training harness's flavour of the model (Experiments/nets/ACC_UNet.py: cnv72 inv_fctr=3, logits out)
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_nets_ACC_UNet", os.path.join(REF, "Experiments", "nets", "ACC_UNet.py"))
+    RH = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(RH)
+    torch.manual_seed(2)
+    m = RH.ACC_UNet(3, 1, 8)
+    sd = m.state_dict()
+    allk = list(sd.keys())
+    x = torch.randn(1, 3, 32, 32, generator=torch.Generator().manual_seed(7))
+    m.eval()
+    with torch.no_grad():
+        y = m(x)
+    np.savez_compressed(os.path.join(HERE, "init_seed2_f8_harness.npz"), names=np.array(allk),
+                        shapes=np.array([str(tuple(sd[k].shape)) for k in allk]),
+                        sums=np.array([float(sd[k].double().sum()) for k in allk]), x=x.numpy(), eval_logits=y.numpy())
+
+    # per-step metrics known-answer vectors (Experiments/utils.py:478-494 iou_on_batch, :148-157 _show_dice)
+    import warnings
+    warnings.filterwarnings("ignore")
+    gm = torch.Generator().manual_seed(321)
+    cases = {}
+
+    def add(name, lg, tr):
+        iou = U.iou_on_batch(tr.clone(), lg.clone())
+        dice = float(U.WeightedDiceBCE(dice_weight=0.5, BCE_weight=0.5)._show_dice(lg.clone(), tr.clone().float()))
+        cases[name + "/logit"], cases[name + "/truth"] = lg.numpy(), tr.numpy()
+        cases[name + "/iou"], cases[name + "/dice"] = np.array(float(iou)), np.array(dice)
+
+    lg = torch.randn(4, 1, 32, 32, generator=gm) * 2
+    tr = (torch.rand(4, 1, 32, 32, generator=gm) > 0.6).float()
+    add("random", lg, tr)
+    lg2, tr2 = lg.clone(), tr.clone()
+    lg2[0, 0, :4] = 0.0            # exact zeros: sigmoid = 0.5 counts as positive
+    lg2[1] = -3.0                  # an image without a positive prediction ...
+    tr2[1] = 0.0                   # ... and without a positive mask pixel: empty union -> jaccard_score 0
+    tr2[2] = 1.0
+    add("edges", lg2, tr2)
+    lg3 = torch.randn(3, 1, 20, 28, generator=gm)
+    tr3 = (torch.rand(3, 1, 20, 28, generator=gm) * 255).round() * (torch.rand(3, 1, 20, 28, generator=gm) > 0.5)
+    add("graymask", lg3, tr3.float())
+    np.savez_compressed(os.path.join(HERE, "metrics_kat.npz"), **cases)
+
 
 if __name__ == "__main__":
     main()

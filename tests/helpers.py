@@ -106,3 +106,80 @@ def close_frac(a, b, rtol, atol_rel, what, max_frac):
 
 def flat_cat(tensors):
     return torch.cat([t.detach().double().cpu().reshape(-1) for t in tensors])
+
+
+class deterministic:
+    """with deterministic(on): accx runs with fixed-order reductions (engine.set_deterministic) -- the mode every
+    fp32 parity bound in tests/ is stated for: no run-to-run spread, so a miss is a bug and not a draw of the atomics"""
+
+    def __init__(self, on=True):
+        self.on = on
+
+    def __enter__(self):
+        if self.on:
+            from accx import engine
+            engine.set_deterministic(True)
+        return self
+
+    def __exit__(self, *exc):
+        if self.on:
+            from accx import engine
+            torch.cuda.synchronize()
+            engine.set_deterministic(False)
+        return False
+
+
+def accx_decisions(mod, rec, dotted=True):
+    """engine.RECORD of ONE accx forward of `mod` -> {oracle site: decision}: the sign under every LeakyReLU
+    (bool, NCHW) and the first-maximum index of every max-pool window, exactly as the CUDA run took them.
+    dotted: module-level oracle calls use the name "" + ".child" (sites start with a dot); acc_unet() does not."""
+    from oracle import acc_oracle as O
+
+    def activated(L):
+        y = L.y.float()
+        if L.act:
+            y = y * L.scale + L.shift
+            if L.act == 2:
+                y = torch.where(y > 0, y, 0.01 * y)
+        return y
+
+    def windows(a, s):                       # NCHW -> [B, C, H/s, W/s, s*s], row-major inside the window
+        B, C, H, W = a.shape
+        return a.reshape(B, C, H // s, s, W // s, s).permute(0, 1, 2, 4, 3, 5).reshape(B, C, H // s, W // s, s * s)
+
+    out = {}
+    for name, m in mod.named_modules():
+        pre = ("." + name if name else "") if dotted else name
+        L = rec.get(("bn", id(m)))
+        if L is not None:
+            out[pre] = ((L.y.float() * L.scale + L.shift) > 0).permute(0, 3, 1, 2)
+        c = rec.get(("se", id(m)))
+        if c is not None:
+            a = activated(c.L)
+            B, H, W, C = a.shape
+            z = a * (c.gate.view(B, 1, 1, C) * c.scale) + c.shift
+            out[pre + ".bn"] = (z > 0).permute(0, 3, 1, 2)
+            out[pre + ".fc1"] = c.hidden.view(B, -1) > 0
+        L2 = rec.get(("hanc", id(m)))
+        if L2 is not None:
+            a = activated(L2).permute(0, 3, 1, 2)
+            for j in range(1, m.k):
+                out[f"{pre}.max{j}"] = O.first_argmax(windows(a, 2 ** j))
+    for i, x in enumerate(rec.get("pool", [])):
+        out[f"pool{i + 1}"] = O.first_argmax(windows(x.float().permute(0, 3, 1, 2), 2))
+    return out
+
+
+class record_decisions:
+    """with record_decisions() as rec: accx forwards fill rec (see engine.RECORD)"""
+
+    def __enter__(self):
+        from accx import engine
+        self.engine = engine
+        self.old = engine.RECORD
+        engine.RECORD = {}
+        return engine.RECORD
+
+    def __exit__(self, *exc):
+        self.engine.RECORD = self.old
+        return False

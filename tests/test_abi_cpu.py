@@ -92,6 +92,32 @@ def test_default_init_reproduces_reference_weights():
         assert abs(float(sd[str(n)].double().sum()) - s) <= 1e-9 + 1e-9 * abs(s), n
 
 
+def test_harness_flavour_reproduces_the_training_harness_model():
+    """`from nets.ACC_UNet import ACC_UNet` (Experiments/train_model.py:24) is NOT the canonical model: cnv72 is built
+    with inv_fctr=3 and the forward returns logits (Experiments/nets/ACC_UNet.py:584,596-597,655).  The shim under
+    acc-unet-unext_b200/nets/ resolves to accx.ACC_UNet_Harness, whose state_dict (names, shapes, seed-2 weights)
+    is the harness model's -- so train_model.py checkpoints load -- while accx.ACC_UNet keeps the canonical layout."""
+    import accx
+    from nets.ACC_UNet import ACC_UNet as HarnessNet
+    assert HarnessNet is accx.ACC_UNet_Harness
+    z = load_case("init_seed2_f8_harness")["raw"]
+    torch.manual_seed(2)
+    m = HarnessNet(3, 1, 8)
+    sd = m.state_dict()
+    assert [str(n) for n in z["names"]] == list(sd.keys())
+    for n, shp, s in zip(z["names"], z["shapes"], z["sums"]):
+        assert str(tuple(sd[str(n)].shape)) == str(shp), n
+        assert abs(float(sd[str(n)].double().sum()) - s) <= 1e-9 + 1e-9 * abs(s), n
+    assert m.last_activation is None
+    assert tuple(sd["cnv72.conv1.weight"].shape) == (96, 32, 1, 1)
+    torch.manual_seed(2)
+    canon = accx.ACC_UNet(3, 1, 8)
+    assert tuple(canon.state_dict()["cnv72.conv1.weight"].shape) == (1088, 32, 1, 1)
+    assert isinstance(canon.last_activation, torch.nn.Sigmoid)
+    with pytest.raises(RuntimeError):
+        canon.load_state_dict(sd)                 # the two flavours are not interchangeable
+
+
 def test_dropin_module_names_importable():
     import ACC_UNet, ACC_UNet_lite, ACC_UNet_w   # noqa: E401
     assert ACC_UNet.MLFC(8, 8, 8, 8).variant == "base"

@@ -157,6 +157,38 @@ def test_dice_bce_bf16_logits():
 
 
 # ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", ["random", "edges", "graymask"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+def test_seg_metrics_match_reference_known_answers(case, dtype):
+    """accx_seg_metrics vs iou_on_batch / _show_dice of the reference (fixtures made by tests/golden/make_golden.py)"""
+    from accx.train import seg_metrics
+    from oracle import acc_oracle as O
+    from helpers import load_case
+    z = load_case("metrics_kat")["raw"]
+    lg, tr = torch.from_numpy(z[case + "/logit"]), torch.from_numpy(z[case + "/truth"])
+    lgd = lg.to(DEV).to(dtype)
+    out = seg_metrics(lgd, tr.to(DEV))
+    assert out.is_cuda and out.shape == (2,)
+    iou, dice = (float(v) for v in out.cpu())
+    if dtype == torch.float32:
+        want_iou, want_dice = float(z[case + "/iou"]), float(z[case + "/dice"])
+    else:       # bf16 logits: the rounding can move a logit across 0, so the truth is the restatement on the rounded values
+        want_iou, want_dice = O.seg_metrics(lgd.float().cpu(), tr)
+    assert abs(iou - want_iou) < 1e-6, (iou, want_iou)            # integer counts, ratios in double, one fp32 rounding
+    assert abs(dice - want_dice) < 2e-6, (dice, want_dice)
+
+
+def test_seg_metrics_large_batch_matches_restatement():
+    from accx.train import seg_metrics
+    from oracle import acc_oracle as O
+    g = torch.Generator().manual_seed(11)
+    lg = torch.randn(16, 1, 224, 224, generator=g)
+    tr = (torch.rand(16, 1, 224, 224, generator=g) > 0.5).float()
+    out = seg_metrics(lg.to(DEV), tr.to(DEV)).cpu()
+    iou, dice = O.seg_metrics(lg, tr)
+    assert abs(float(out[0]) - iou) < 1e-6 and abs(float(out[1]) - dice) < 2e-6, (out, iou, dice)
+
+
 @pytest.mark.parametrize("wd", [0.0, 1e-2])
 def test_adam_flat_matches_torch_adam(wd):
     e = E()
