@@ -221,17 +221,15 @@ class _NullCtx:
 _DET = {}
 
 
-def set_deterministic(on: bool, workspace_mb: int = 256, device=None):
+def set_deterministic(on: bool, workspace_mb: int = 512, device=None):
     """Fixed-order reductions in every accx kernel (include/accx.h: accx_set_deterministic): two runs on the same
-    inputs are bit-identical.  The kernels share one workspace, so every launch goes to the caller's stream: the
-    weight-gradient side stream and the parallel lanes are switched off while the mode is on.  Parity / debugging
-    mode (slower); mandatory for the tight fp32 parity bounds in tests/."""
-    global SIDE_MODE, LANES
-    lib = _lib.load()
+    inputs are bit-identical, whatever the stream configuration (side stream, lanes, CUDA graph).  Parity / debugging
+    mode (slower); the fp32 parity bounds in tests/ are stated for it."""
+    _lib.load()
     if not on:
         if _DET:
+            torch.cuda.synchronize()
             _lib.call("accx_set_deterministic", 0, 0, 0, 0)
-            SIDE_MODE, LANES = _DET["modes"]
             _DET.clear()
         return
     if _DET:
@@ -241,8 +239,7 @@ def set_deterministic(on: bool, workspace_mb: int = 256, device=None):
     ctr = torch.zeros(1 << 16, dtype=torch.int32, device=dev)
     torch.cuda.synchronize(dev)
     _lib.call("accx_set_deterministic", ws.data_ptr(), ws.numel(), ctr.data_ptr(), ctr.numel())
-    _DET.update(ws=ws, ctr=ctr, modes=(SIDE_MODE, LANES))
-    SIDE_MODE, LANES = 0, 0
+    _DET.update(ws=ws, ctr=ctr)
 
 
 def deterministic() -> bool:
@@ -708,7 +705,7 @@ def se_fwd(L: Lazy, se, arena: Arena, training: bool, residual=None, mix=None, s
 
 
 def se_bwd(c: SECtx, dout: torch.Tensor, grads: dict, arena: Arena, da: Optional[torch.Tensor] = None,
-           accumulate=False, bn_sums=False):
+           accumulate=False, bn_sums=False, gmix: Optional[torch.Tensor] = None):
     """gradient w.r.t. the activated SE input given d(out); parameter grads accumulate in `grads`.
     (The residual branch, if any, simply receives dout * (1 - mix) -- handled by the caller.)
     bn_sums=True: -> (da, sums) where sums is the BatchNorm-backward reduction of the SE input's own
@@ -721,7 +718,10 @@ def se_bwd(c: SECtx, dout: torch.Tensor, grads: dict, arena: Arena, da: Optional
     assert dout.dtype == y.dtype and dout.is_contiguous()
     G = arena.take(2 * B * C)
     PQR = arena.take(3 * B * C)
-    gmix = grad_buf(grads, c.mix_param) if c.mix_param is not None else None
+    # gmix: where the gradient of the blend scalar is accumulated (default: the parameter's own accumulator; MLFC hands
+    # every pyramid level its own slot and adds the four in level order, so concurrent lanes never race on one float)
+    if gmix is None and c.mix_param is not None:
+        gmix = grad_buf(grads, c.mix_param)
     _call("accx_se_bwd_reduce", d, B, H * W, C, ptr(y), ptr(L.scale), ptr(L.shift), L.act, ptr(c.gate), ptr(c.scale),
           ptr(c.shift), ptr(dout), ptr(c.mix), ptr(c.residual) if gmix is not None else 0, ptr(gmix), ptr(G), stream(),
           cost=(nb(y, dout), 0), tag=f"B={B} HW={H * W} C={C}")

@@ -436,10 +436,10 @@ class Conv2d_batchnorm(_AccxModule):
         out, c = E.se_fwd(L, self.sqe, ar, training, residual=residual, mix=mix, stats=stats, mix_param=mix_param)
         return out, (L, c)
 
-    def _core_bwd(self, saved, dout, grads, ar):
+    def _core_bwd(self, saved, dout, grads, ar, gmix=None):
         """-> gradient w.r.t. the raw conv output"""
         L, c = saved
-        da, sums = E.se_bwd(c, dout, grads, ar, bn_sums=True)
+        da, sums = E.se_bwd(c, dout, grads, ar, bn_sums=True, gmix=gmix)
         return E.bn_bwd(L, da, grads, ar, sums=sums, conv=self.conv1)
 
     def _fwd(self, xs, training, need):
@@ -760,6 +760,7 @@ class MLFC(_AccxModule):
         # phase A: the four level chains are independent (lane l only touches dxs[l]) -> parallel lanes
         dys_blk = [None] * 4
         ars = [ar] + [Arena(douts[0].device) for _ in range(3)]
+        gmix4 = ar.take(4) if (mix is not None and self.W.requires_grad) else None     # one slot per level (W variant)
         with E.fork_lanes(4) as lanes:
             for l in range(4):
                 with lanes.lane(l):
@@ -774,7 +775,8 @@ class MLFC(_AccxModule):
                         acc(l, dt_)          # aliasing is safe: dt_ is only read by the launches queued below
                     else:
                         acc(l, self._scaled(dt_, mix, one_minus=True))
-                    dy = cm._core_bwd(mrg[l], dt_, grads, arl)                      # through SE(mix inside) + BN
+                    dy = cm._core_bwd(mrg[l], dt_, grads, arl,                      # through SE(mix inside) + BN
+                                      gmix=None if gmix4 is None else gmix4[l:l + 1])
                     gw = E.grad_buf(grads, cm.conv1.weight)
                     if gw is not None:
                         E.wgrad(Op(Lc[l], C, WV(wm, 0, 2 * C, 2)), dy, C, dims[l], gw)
@@ -784,6 +786,8 @@ class MLFC(_AccxModule):
                     dtc = E.bn_bwd(Lc[l], dac, grads, arl)                                    # bns
                     cb = getattr(self, f"cnv_blks{l + 1}")[i]
                     dys_blk[l] = cb._core_bwd(blk[l], dtc, grads, arl)
+        if gmix4 is not None:
+            E.grad_buf(grads, self.W).add_(gmix4.sum())        # the four levels, in level order
         # phase B: gather conv backward; lane `src` owns dxs[src] and collects the contributions of every target level
         gws = [E.grad_buf(grads, getattr(self, f"cnv_blks{l + 1}")[i].conv1.weight) for l in range(4)]
         with E.fork_lanes(4) as lanes:

@@ -285,7 +285,6 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 //   * kernels whose partials are whole tiles (weight gradients, the persistent tcgen05 / TMA-tiled kernels) are
 //     launched so that every destination address receives exactly one contribution (one split / one CTA per channel
 //     chunk), accumulated in a fixed order inside the CTA.
-// The workspace is shared by all launches: the mode requires that all accx calls are issued on ONE stream.
 struct Det {
   float* ws;            // nullptr: atomics (default mode)
   unsigned int* ctr;    // one zero-initialised ticket counter per group (re-armed by the last block)
@@ -294,17 +293,26 @@ extern Det g_det;
 extern int64_t g_det_floats;
 extern int g_det_ctrs;
 inline bool det_on() { return g_det.ws != nullptr; }
+// The workspace is divided into DET_SLOTS equal slices, one per CUDA stream that launches reducing kernels (the
+// caller's stream, the weight-gradient side stream, the parallel lanes, a graph-capture stream): launches of one
+// stream are ordered and may share a slice, launches of different streams may overlap and must not.
+constexpr int DET_SLOTS = 16;
+int det_slot(cudaStream_t st);      // ew_kernels.cu: slice index of `st` (assigned on first use), -1 if all are taken
 // the handle a launcher passes to its kernel; fails (-> error code) when the workspace is too small
-inline bool det_handle(int64_t floats, int64_t groups, Det& out) {
+inline bool det_handle(int64_t floats, int64_t groups, cudaStream_t st, Det& out) {
   out.ws = nullptr;
   out.ctr = nullptr;
   if (!det_on()) return true;
-  if (floats > g_det_floats || groups > g_det_ctrs) {
-    set_error("deterministic mode: workspace too small (%lld floats / %lld counters needed, %lld / %d installed)",
-              (long long)floats, (long long)groups, (long long)g_det_floats, g_det_ctrs);
+  const int slot = det_slot(st);
+  const int64_t slot_floats = g_det_floats / DET_SLOTS / 4 * 4;
+  const int slot_ctrs = g_det_ctrs / DET_SLOTS;
+  if (slot < 0 || floats > slot_floats || groups > slot_ctrs) {
+    set_error("deterministic mode: workspace too small (%lld floats / %lld counters needed, %lld / %d per stream slice, "
+              "slice %d)", (long long)floats, (long long)groups, (long long)slot_floats, slot_ctrs, slot);
     return false;
   }
-  out = g_det;
+  out.ws = g_det.ws + (int64_t)slot * slot_floats;
+  out.ctr = g_det.ctr + (int64_t)slot * slot_ctrs;
   return true;
 }
 

@@ -12,6 +12,16 @@ int g_knobs[KNOB_COUNT] = {0};
 Det g_det = {nullptr, nullptr};
 int64_t g_det_floats = 0;
 int g_det_ctrs = 0;
+static cudaStream_t g_det_streams[DET_SLOTS];
+static int g_det_n_streams = 0;
+
+int det_slot(cudaStream_t st) {
+  for (int i = 0; i < g_det_n_streams; ++i)
+    if (g_det_streams[i] == st) return i;
+  if (g_det_n_streams >= DET_SLOTS) return -1;
+  g_det_streams[g_det_n_streams] = st;
+  return g_det_n_streams++;
+}
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -397,6 +407,7 @@ int accx_set_knob(int index, int value) {
 }
 
 int accx_set_deterministic(void* workspace, int64_t workspace_bytes, unsigned int* counters, int n_counters) {
+  g_det_n_streams = 0;
   if (!workspace) {           // back to the default (atomics)
     g_det.ws = nullptr;
     g_det.ctr = nullptr;
@@ -404,8 +415,8 @@ int accx_set_deterministic(void* workspace, int64_t workspace_bytes, unsigned in
     g_det_ctrs = 0;
     return ACCX_OK;
   }
-  ACCX_REQUIRE(workspace_bytes >= (1 << 20) && counters && n_counters >= 1024 && aligned16(workspace),
-               "set_deterministic: needs a 16-byte aligned workspace of >= 1 MiB and >= 1024 zeroed counters");
+  ACCX_REQUIRE(workspace_bytes >= (16 << 20) && counters && n_counters >= 16384 && aligned16(workspace),
+               "set_deterministic: needs a 16-byte aligned workspace of >= 16 MiB and >= 16384 zeroed counters");
   g_det.ws = (float*)workspace;
   g_det.ctr = counters;
   g_det_floats = workspace_bytes / 4;
@@ -440,7 +451,7 @@ int accx_act_apply(int dtype, int64_t P, int C, const void* x, const float* scal
     dim3 block(l.tx, l.ty), grid(grid_x_for(P, l.ty * 8, stats ? 148 * 2 : 148 * 8), l.gy);
     size_t sm = (size_t)l.tx * l.ty * l.vec * sizeof(float);
     Det det;
-    if (!det_handle(stats ? (int64_t)grid.x * grid.y * 2 * l.tx * l.vec : 0, grid.y, det)) return ACCX_ERR_INVALID;
+    if (!det_handle(stats ? (int64_t)grid.x * grid.y * 2 * l.tx * l.vec : 0, grid.y, (cudaStream_t)stream, det)) return ACCX_ERR_INVALID;
     ACCX_DISPATCH_VEC(l, {
       launch_k(act_apply_kernel<T, VEC>, grid, block, sm, (cudaStream_t)stream, 
           P, C, (const T*)x, scale, shift, act, scale2, shift2, (const T*)residual, (T*)out, stats, det);
@@ -457,7 +468,7 @@ int accx_add_fwd(int dtype, int64_t P, int C, const void* a, const float* scale,
     dim3 block(l.tx, l.ty), grid(grid_x_for(P, l.ty * 8, stats ? 148 * 2 : 148 * 8), l.gy);
     size_t sm = (size_t)l.tx * l.ty * l.vec * sizeof(float);
     Det det;
-    if (!det_handle(stats ? (int64_t)grid.x * grid.y * 2 * l.tx * l.vec : 0, grid.y, det)) return ACCX_ERR_INVALID;
+    if (!det_handle(stats ? (int64_t)grid.x * grid.y * 2 * l.tx * l.vec : 0, grid.y, (cudaStream_t)stream, det)) return ACCX_ERR_INVALID;
     ACCX_DISPATCH_VEC(l, {
       launch_k(add_fwd_kernel<T, VEC>, grid, block, sm, (cudaStream_t)stream, P, C, (const T*)a, scale, shift, act,
                                                                         (const T*)r, (T*)z, stats, det);
@@ -474,7 +485,7 @@ int accx_bn_bwd_reduce(int dtype, int64_t P, int C, const void* y, const float* 
     dim3 block(l.tx, l.ty), grid(grid_x_for(P, l.ty * 8, 148 * knob(KNOB_BN_REDUCE_BLOCKS, 2)), l.gy);
     size_t sm = (size_t)l.tx * l.ty * l.vec * sizeof(float);
     Det det;
-    if (!det_handle((int64_t)grid.x * grid.y * 2 * l.tx * l.vec, grid.y, det)) return ACCX_ERR_INVALID;
+    if (!det_handle((int64_t)grid.x * grid.y * 2 * l.tx * l.vec, grid.y, (cudaStream_t)stream, det)) return ACCX_ERR_INVALID;
     ACCX_DISPATCH_VEC(l, {
       launch_k(bn_bwd_reduce_kernel<T, VEC>, grid, block, sm, (cudaStream_t)stream, P, C, (const T*)y, scale, shift, act,
                                                                               mean, rstd, (const T*)da, sums, det);

@@ -296,7 +296,7 @@ static int launch_pw(PwParams& prm, cudaStream_t st) {
   {
     const int bn = prm.N <= 32 ? 32 : ((prm.N <= 64 || prm.N % 128 != 0) ? 64 : 128);
     const int gy = (prm.N + bn - 1) / bn;
-    if (!det_handle(prm.stats ? (int64_t)gx * gy * 2 * bn : 0, gy, prm.det)) return ACCX_ERR_INVALID;
+    if (!det_handle(prm.stats ? (int64_t)gx * gy * 2 * bn : 0, gy, st, prm.det)) return ACCX_ERR_INVALID;
   }
   if (prm.N <= 32) {
     dim3 grid(gx, (prm.N + 31) / 32);

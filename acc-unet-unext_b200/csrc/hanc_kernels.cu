@@ -335,7 +335,7 @@ int accx_hanc_unpool_bnred(int dtype, int B, int H, int W, int C, int levels, co
   dim3 block(l.tx, l.ty), grid(grid_x_for(n_win, l.ty, 148 * 3), l.gy);
   const size_t sm = (size_t)l.tx * l.ty * l.vec * sizeof(float);
   Det det;
-  if (!det_handle((int64_t)grid.x * grid.y * 2 * l.tx * l.vec, grid.y, det)) return ACCX_ERR_INVALID;
+  if (!det_handle((int64_t)grid.x * grid.y * 2 * l.tx * l.vec, grid.y, (cudaStream_t)stream, det)) return ACCX_ERR_INVALID;
   if (levels == 1)
     launch_k(hanc_unpool_bnred_kernel<1>, grid, block, sm, (cudaStream_t)stream, B, H, W, C, (const bf16*)y, scale, shift, act,
                                                                             dpool1, dpool2, (bf16*)da, mean, rstd, sums, det);

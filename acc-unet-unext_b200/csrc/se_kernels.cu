@@ -486,7 +486,7 @@ int accx_se_squeeze(int dtype, int B, int HW, int C, const void* x, const float*
     size_t sm = (size_t)l.tx * l.ty * l.vec * sizeof(float);
     const int u = knob(KNOB_SE_SQUEEZE_U, 4);
     Det det;
-    if (!det_handle((int64_t)grid.x * grid.y * 2 * l.tx * l.vec, (int64_t)B * grid.y, det)) return ACCX_ERR_INVALID;
+    if (!det_handle((int64_t)grid.x * grid.y * 2 * l.tx * l.vec, (int64_t)B * grid.y, (cudaStream_t)stream, det)) return ACCX_ERR_INVALID;
     ACCX_DISPATCH_VEC(l, {
       ACCX_DISPATCH_U(u, {
         launch_k(se_squeeze_kernel<T, VEC, U>, grid, block, sm, (cudaStream_t)stream, B, HW, C, chunks, (const T*)x, scale,
@@ -521,7 +521,7 @@ int accx_se_apply(int dtype, int B, int HW, int C, const void* x, const float* s
     size_t sm = (size_t)l.tx * l.ty * l.vec * sizeof(float);
     const int u = knob(KNOB_SE_APPLY_U, 4);
     Det det;
-    if (!det_handle(stats ? (int64_t)grid.x * grid.y * 2 * l.tx * l.vec : 0, grid.y, det)) return ACCX_ERR_INVALID;
+    if (!det_handle(stats ? (int64_t)grid.x * grid.y * 2 * l.tx * l.vec : 0, grid.y, (cudaStream_t)stream, det)) return ACCX_ERR_INVALID;
     ACCX_DISPATCH_VEC(l, {
       ACCX_DISPATCH_U(u, {
         launch_k(se_apply_kernel<T, VEC, U>, grid, block, sm, (cudaStream_t)stream, B, HW, C, chunks, (const T*)x, scale, shift, act,
@@ -548,7 +548,7 @@ int accx_se_bwd_reduce(int dtype, int B, int HW, int C, const void* x, const flo
     Det det;
     const int64_t lanes_floats = (int64_t)grid.x * grid.y * 2 * l.tx * l.vec;
     const int n_blocks = (int)(grid.x * grid.y);
-    if (!det_handle(lanes_floats + (dmix ? n_blocks : 0), (int64_t)B * grid.y, det)) return ACCX_ERR_INVALID;
+    if (!det_handle(lanes_floats + (dmix ? n_blocks : 0), (int64_t)B * grid.y, (cudaStream_t)stream, det)) return ACCX_ERR_INVALID;
     float* dmix_part = (det.ws && dmix) ? det.ws + lanes_floats : nullptr;
     ACCX_DISPATCH_VEC_H(l, {
       ACCX_DISPATCH_U(u, {
@@ -596,7 +596,7 @@ int accx_se_bwd_apply(int dtype, int B, int HW, int C, const void* x, const floa
     const size_t sm = bn_sums ? (size_t)l.tx * l.ty * l.vec * sizeof(float) : 0;
     const int u = knob(KNOB_SE_BWD_APPLY_U, 8);
     Det det;
-    if (!det_handle(bn_sums ? (int64_t)grid.x * grid.y * 2 * l.tx * l.vec : 0, grid.y, det)) return ACCX_ERR_INVALID;
+    if (!det_handle(bn_sums ? (int64_t)grid.x * grid.y * 2 * l.tx * l.vec : 0, grid.y, (cudaStream_t)stream, det)) return ACCX_ERR_INVALID;
     ACCX_DISPATCH_VEC_H(l, {
       ACCX_DISPATCH_U(u, {
         launch_k(se_bwd_apply_kernel<T, VEC, U>, grid, block, sm, (cudaStream_t)stream, 

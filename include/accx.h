@@ -48,9 +48,11 @@ int accx_set_knob(int index, int value);
  * workspace installed, every reducing kernel adds its per-block partial sums in a FIXED order instead (two-stage:
  * per-block slots, folded in block order by the last block to arrive; tile-shaped partials -- weight gradients,
  * the persistent tcgen05 / TMA-tiled kernels -- get exactly one contribution per address): two runs are then
- * bit-identical.  `counters` = n_counters (>= 1024) zero-initialised 32-bit words.  The workspace is shared by all
- * launches, so the mode requires that every accx call is issued on ONE stream.  workspace = NULL restores the
- * default.  Process-global; slower (parity / debugging mode), same arithmetic per element. */
+ * bit-identical.  `counters` = n_counters (>= 16384) zero-initialised 32-bit words; workspace >= 16 MiB (512 MiB
+ * covers every shape of the 512 x 512 configuration).  Both are divided into 16 slices, one per CUDA stream that
+ * launches reducing kernels, so concurrent streams (and the branches of a captured graph) never share scratch.
+ * workspace = NULL restores the default.  Process-global; slower (parity / debugging mode), same arithmetic per
+ * element. */
 int accx_set_deterministic(void* workspace, int64_t workspace_bytes, unsigned int* counters, int n_counters);
 
 /* One A-operand of a pointwise contraction together with its weight slice.

@@ -127,6 +127,11 @@ def main():
     torch.manual_seed(2); run("mlfc_8_8_16_16_len2", R.MLFC(8, 8, 16, 16, lenn=2), ml_in((8, 8, 16, 16), 8, 60), 142)
     torch.manual_seed(2); run("mlfcw_8_16_32_64", RW.MLFC(8, 16, 32, 64, lenn=1), ml_in((8, 16, 32, 64), 16, 70), 143)
     torch.manual_seed(2); run("mlfclite_8_16_32_64", RL.MLFC(8, 16, 32, 64, lenn=1), ml_in((8, 16, 32, 64), 16, 80), 144)
+    # standalone Conv2d_batchnorm (ACC_UNet.py:146-186) and the channel set the fKAN consumer instantiates
+    # (Experiments/nets/archs/archs_InceptionNext_MLFC_fKAN.py:428)
+    torch.manual_seed(2); run("convbn_24_16", R.Conv2d_batchnorm(24, 16, (1, 1)), [g(2, 24, 8, 8, seed=35)], 135)
+    ml1 = lambda cs, hw, seed: [g(1, c, hw >> i, hw >> i, seed=seed + i) for i, c in enumerate(cs)]
+    torch.manual_seed(2); run("mlfc_80_128_160_160", R.MLFC(80, 128, 160, 160, lenn=1), ml1((80, 128, 160, 160), 16, 85), 145)
     # whole models, narrow (n_filts=8) so the fixture stays small
     for nm, cls in (("accunet_f8", R.ACC_UNet), ("accunetw_f8", RW.ACC_UNet_W), ("accunetlite_f8", RL.ACC_UNet_Lite)):
         torch.manual_seed(2)

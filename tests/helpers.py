@@ -25,7 +25,7 @@ def load_case(name):
 
 def module_cases():
     names = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz")))
-    return [n for n in names if n.startswith(("se_", "hanclayer_", "hancblock_", "respath_", "mlfc"))]
+    return [n for n in names if n.startswith(("se_", "hanclayer_", "hancblock_", "respath_", "mlfc", "convbn_"))]
 
 
 def close(a, b, rtol, atol_rel, what="", zero_scale=None):

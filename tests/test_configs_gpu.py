@@ -9,7 +9,7 @@ gradient; peak memory stays far below one B200's 180 GB.
 import pytest
 import torch
 
-from helpers import rel_l2
+from helpers import deterministic, rel_l2
 
 pytestmark = pytest.mark.gpu
 
@@ -32,24 +32,26 @@ def test_c1_forward_1x3x224x224_fp32_matches_cpu_oracle():
     m = _model("ACC_UNet")
     sd = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
     x = torch.randn(1, 3, 224, 224, generator=torch.Generator().manual_seed(2))
-    with torch.no_grad():
+    with torch.no_grad(), deterministic():
         m.eval()                                         # eval first: the train-mode forward moves the running statistics
         want_eval = O.acc_unet(O.Ctx({k: v.clone() for k, v in sd.items()}, False), x, "base", logits=True)
         got_eval = m(x.to(DEV)).cpu()
         m.train()
         want_train = O.acc_unet(O.Ctx({k: v.clone() for k, v in sd.items()}, True), x, "base", logits=True)
         got_train = m(x.to(DEV)).cpu()
+        again = m(x.to(DEV)).cpu()
+    assert torch.equal(got_train, again), "deterministic mode: two forwards of the same input differ"
     assert got_train.shape == want_train.shape == (1, 1, 224, 224)
-    # eval mode (running statistics, no batch reductions) is deterministic and must agree at fp32 rounding level
-    # (measured rel-l2 1.4e-7).  Train mode normalises with the statistics of ONE image through 220 BatchNorms: the
-    # fp32 summation order (atomics on the GPU, MKL-DNN's blocking on the CPU) perturbs every activation at the 1e-7
-    # level and the stack amplifies that to ~1e-3 at the output (measured rel-l2 1.2e-3, varying from run to run),
-    # so its bound is a loose one; the tight train-mode parity is carried by the per-module tests.
-    for got, want, what, lim in ((got_train, want_train, "train", 2e-2), (got_eval, want_eval, "eval", 1e-5)):
+    # eval mode (running statistics, no batch reductions) must agree at fp32 rounding level (measured rel-l2 1.4e-7).
+    # Train mode normalises with the statistics of ONE image through 220 BatchNorms, which amplifies the difference in
+    # fp32 summation order between the GPU kernels and MKL-DNN (the reference's own fp32 run is 3.6e-4 away from its fp64
+    # run at batch 2, tests/golden/full_accunet_224.npz): rel-l2 2e-3, every element within 5e-3 of the range.  The GPU
+    # side runs with deterministic reductions, so the figure does not move from run to run.
+    for got, want, what, lim in ((got_train, want_train, "train", 2e-3), (got_eval, want_eval, "eval", 1e-5)):
         scale = float(want.abs().max())
         print(f"c1 {what}: rel-l2 {rel_l2(got, want):.2e}, max abs err {float((got - want).abs().max()):.2e} of {scale:.2e}")
         assert rel_l2(got, want) < lim, f"{what}: rel-l2 {rel_l2(got, want):.2e}"
-        assert float((got - want).abs().max()) < 5 * lim * scale, f"{what}: max {float((got - want).abs().max()):.2e} / {scale:.2e}"
+        assert float((got - want).abs().max()) < 2.5 * lim * scale, f"{what}: max {float((got - want).abs().max()):.2e} / {scale:.2e}"
 
 
 def test_c2_train_step_16x3x224x224_bf16_properties():
@@ -64,13 +66,13 @@ def test_c2_train_step_16x3x224x224_bf16_properties():
     # rounding-level perturbation by ~1e3, so two bf16 evaluations that merely sum the statistics in another order
     # differ by tens of percent (the bf16 ORACLE does too, tests/test_modules_gpu.py) -- that says nothing about
     # batch-order dependence, the fp32 run does.
-    with torch.no_grad():
+    with torch.no_grad(), deterministic():
         y = m(x)
         yp = m(x[perm])
         l0, l1 = float(dice_bce_loss(y, msk)), float(dice_bce_loss(yp, msk[perm]))
     assert torch.isfinite(y).all()
     print(f"c2 fp32 batch permutation: output rel-l2 {rel_l2(yp, y[perm]):.2e}, loss {l0:.7f} vs {l1:.7f}")
-    assert rel_l2(yp, y[perm]) < 3e-2, rel_l2(yp, y[perm])        # measured 2.4e-3; a batch-order bug gives O(1)
+    assert rel_l2(yp, y[perm]) < 1e-2, rel_l2(yp, y[perm])        # measured 2.4e-3; a batch-order bug gives O(1)
     assert abs(l0 - l1) < 1e-4 * max(1.0, abs(l0)), (l0, l1)
     m.compute_dtype = torch.bfloat16                     # the bench configuration: bf16 storage
     with torch.no_grad():
@@ -96,12 +98,13 @@ def test_c4_variants_32x3x224x224_bf16_fwd_bwd(cls_name):
     with torch.no_grad():
         y = m(x)
         m.compute_dtype = None                           # batch-permutation property in fp32 storage (see c2), 8 images
-        y8 = m(x[:8])
-        y8p = m(x[:8][perm])
+        with deterministic():
+            y8 = m(x[:8])
+            y8p = m(x[:8][perm])
         m.compute_dtype = torch.bfloat16
     assert y.shape == (32, 1, 224, 224) and torch.isfinite(y).all()
     print(f"c4 {cls_name} fp32 batch permutation (8 images): output rel-l2 {rel_l2(y8p, y8[perm]):.2e}")
-    assert rel_l2(y8p, y8[perm]) < 3e-2, rel_l2(y8p, y8[perm])    # measured 1e-3
+    assert rel_l2(y8p, y8[perm]) < 1e-2, rel_l2(y8p, y8[perm])    # measured 1e-3
     xg = x.clone().requires_grad_(True)
     out = m(xg)
     out.square().mean().backward()

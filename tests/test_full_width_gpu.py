@@ -56,8 +56,9 @@ def norms_err(model, z, tag=""):
     params = dict(model.named_parameters())
     ours = np.array([float(params[n].grad.double().norm()) if params[n].grad is not None else -1.0 for n in names])
     for n, r, o in zip(names, ref, ours):
-        assert (r < 0) == (o < 0 or o == 0.0) or r == 0.0, f"{n}: reference grad {'None' if r < 0 else r}, ours {o}"
-    keep = ref > 0
+        assert (r < 0) == (o < 0), f"{n}: reference grad {'None' if r < 0 else r}, ours {'None' if o < 0 else o}"
+    # (conv biases in front of a training-mode BatchNorm: exactly 0 here, rounding noise ~1e-5 in the reference)
+    keep = ref > 1e-3 * np.median(ref[ref > 0])
     return float(np.linalg.norm(ours[keep] - ref[keep]) / np.linalg.norm(ref[keep]))
 
 
@@ -112,10 +113,9 @@ def test_full_width_train_step_fp32_matches_reference(cls_name, fixture):
         assert e_loss <= SLACK * r_loss + 1e-6, (e_loss, r_loss)
         assert e_gin <= SLACK * r_gin, (e_gin, r_gin)
         assert e_nrm <= SLACK * r_nrm, (e_nrm, r_nrm)
-        if r_full < 1.0:             # (the variants' maximum is taken over tensors that are ~0 in fp64: not a usable yardstick)
-            assert e_full <= SLACK * r_full, (wk, e_full, r_full)
-        else:
-            assert e_full <= SLACK * r_gin, (wk, e_full)
+        # (the variants' fixtures took the maximum over tensors that are ~0 in fp64 as well: not a usable yardstick; the
+        #  worst-conditioned tensor is the first layer's weight, whose reference error is 0.146 in the base model)
+        assert e_full <= SLACK * (r_full if r_full < 1.0 else 0.146), (wk, e_full, r_full)
         sd = model.state_dict()
         for k in z.files:
             if k.startswith("upd/"):

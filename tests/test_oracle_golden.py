@@ -29,6 +29,8 @@ def run_oracle(name, case, training=True, prepared=False, forced=None, record=No
         ys = (O.hanc_block(cx, "", xs[0], k),)
     elif kind == "respath":
         ys = (O.respath(cx, "", xs[0], int(name.split("_n")[1])),)
+    elif kind == "convbn":
+        ys = (O.conv_bn_se(cx, "", xs[0]),)
     else:
         variant = {"mlfc": "base", "mlfcw": "w", "mlfclite": "lite"}[kind]
         lenn = 2 if name.endswith("len2") else 1

@@ -358,7 +358,7 @@ def test_train_step_graph_equals_eager_and_loss_decreases():
     # BatchNorm stack amplifies (see the note above), so even the first loss only agrees to ~1e-3
     assert abs(la[0] - lb[0]) < 1e-2 * max(1.0, abs(lb[0])), (la, lb)
     for a, b in zip(la, lb):                                              # then within the run-to-run spread
-        assert abs(a - b) < 5e-2 * max(1.0, abs(b)), (la, lb)            # measured up to 1e-2 after 10 steps
+        assert abs(a - b) < 3e-2 * max(1.0, abs(b)), (la, lb)            # measured up to 1e-2 after 10 steps
     assert la[-1] < la[0] and lb[-1] < lb[0], (la, lb)        # memorising one batch: the loss must go down
     # one optimisation step per call, in eager, capture and replay alike
     assert float(sa.flat.step_state[0]) == 10.0 and float(sb.flat.step_state[0]) == 10.0
@@ -372,10 +372,31 @@ def test_graph_replay_gradients_are_complete(dtype, monkeypatch):
     arena-served gradient may pass through autograd (p.grad is still None when backward returns)."""
     import accx
     from accx import train as T
+    from accx.modules import maxpool2, out_conv, up_cat
     from accx.train import TrainStep
+
+    class Small(torch.nn.Module):
+        """two levels of the model's dataflow (HANC blocks, ResPath, MLFC-free skip, transposed conv + concat, final conv):
+        shallow enough to be well conditioned -- the whole ACC_UNet at random init amplifies the run-to-run rounding
+        noise of the fp32 atomics to ~10 % on its first layers, which would drown the comparison"""
+
+        def __init__(self):
+            super().__init__()
+            self.a = accx.HANCBlock(3, 16, k=3)
+            self.b = accx.HANCBlock(16, 32, k=2)
+            self.r = accx.ResPath(16, 2)
+            self.up = torch.nn.ConvTranspose2d(32, 16, kernel_size=(2, 2), stride=2)
+            self.c = accx.HANCBlock(32, 16, k=3)
+            self.out = torch.nn.Conv2d(16, 1, kernel_size=(1, 1))
+
+        def forward(self, x):
+            x = x.to(dtype).contiguous(memory_format=torch.channels_last)
+            e1 = self.a(x)
+            e2 = self.b(maxpool2(e1))
+            return out_conv(self.c(up_cat(e2, self.r(e1), self.up)), self.out)
+
     torch.manual_seed(2)
-    ma = accx.ACC_UNet(3, 1, 8, compute_dtype=dtype).to(DEV).train()
-    ma.last_activation = None
+    ma = Small().to(DEV).train()
     mb = copy.deepcopy(ma)
     g = torch.Generator().manual_seed(8)
     x = torch.randn(4, 3, 64, 64, generator=g).to(DEV)
@@ -388,33 +409,72 @@ def test_graph_replay_gradients_are_complete(dtype, monkeypatch):
         return orig(self)
 
     monkeypatch.setattr(T.FlatState, "collect", spy)
-    sa = TrainStep(ma, lr=0.0, graph=True, graph_warmup=1)
-    for _ in range(4):
-        sa(x, m)
-    torch.cuda.synchronize()
-    assert sa.graph is not None
-    assert seen and all(n == 0 for n in seen), f"arena-served gradients went through autograd: {seen}"
+    from helpers import deterministic
     eng = E()
-    mode, lanes = eng.SIDE_MODE, eng.LANES
-    eng.SIDE_MODE, eng.LANES = 0, 0                      # reference: everything on one stream
-    try:
-        sb = TrainStep(mb, lr=0.0, graph=False)
-        sb(x, m)
+    # deterministic reductions make the comparison exact: the replayed graph (weight gradients on the low-priority side
+    # stream, parallel lanes, one join before the optimiser) must reproduce the single-stream eager step BIT FOR BIT
+    with deterministic():
+        sa = TrainStep(ma, lr=0.0, graph=True, graph_warmup=1)
+        for _ in range(4):
+            sa(x, m)
         torch.cuda.synchronize()
-    finally:
-        eng.SIDE_MODE, eng.LANES = mode, lanes
-    tol = 2e-3 if dtype == torch.float32 else 6e-2
-    worst = ("", 0.0)
-    for (n, p), (_, q) in zip(ma.named_parameters(), mb.named_parameters()):
-        ga, gb = sa.flat._view(sa.flat.grad, p), sb.flat._view(sb.flat.grad, q)
-        if p.dim() < 2 or float(gb.abs().max()) == 0.0:
-            continue                                     # weight matrices: the ones the side stream produces
-        e = rel_l2(ga, gb)
-        if e > worst[1]:
-            worst = (n, e)
-        assert e < tol, f"{n}: replayed gradient differs from the single-stream one (rel L2 {e:.3e})"
-    print(f"graph-replay vs single-stream gradients: worst {worst[0]} rel L2 {worst[1]:.2e}")
+        assert sa.graph is not None
+        assert seen and all(n == 0 for n in seen), f"arena-served gradients went through autograd: {seen}"
+        mode, lanes = eng.SIDE_MODE, eng.LANES
+        eng.SIDE_MODE, eng.LANES = 0, 0                      # reference: everything on one stream
+        try:
+            sb = TrainStep(mb, lr=0.0, graph=False)
+            sb(x, m)
+            torch.cuda.synchronize()
+        finally:
+            eng.SIDE_MODE, eng.LANES = mode, lanes
+        n_w = 0
+        for (n, p), (_, q) in zip(ma.named_parameters(), mb.named_parameters()):
+            ga, gb = sa.flat._view(sa.flat.grad, p), sb.flat._view(sb.flat.grad, q)
+            assert torch.equal(ga, gb), (f"{n}: gradient left by the graph replay differs from the single-stream step "
+                                         f"(rel L2 {rel_l2(ga, gb):.3e})")
+            n_w += int(p.dim() >= 2 and float(gb.abs().max()) > 0)
+        assert n_w >= 20                                     # the conv / FC weights the side stream produces were compared
 
+
+def test_train_step_optimizer_state_roundtrips_through_torch_adam():
+    """TrainStep.state_dict() is torch.optim.Adam's format (the reference checkpoints optimizer.state_dict(),
+    Experiments/train_model.py:125-145, and restores it on resume, :677-689): it loads into torch.optim.Adam, comes back
+    through load_state_dict into a fresh TrainStep, and the resumed run continues bit-identically (deterministic mode);
+    set_lr changes the step size of an already captured graph."""
+    import accx
+    from accx.train import TrainStep
+    from helpers import deterministic
+    torch.manual_seed(2)
+    ma = accx.ACC_UNet(3, 1, 8).to(DEV).train()
+    ma.last_activation = None
+    g = torch.Generator().manual_seed(12)
+    x = torch.randn(2, 3, 32, 32, generator=g).to(DEV)
+    m = (torch.rand(2, 1, 32, 32, generator=g) > 0.5).float().to(DEV)
+    with deterministic():
+        sa = TrainStep(ma, lr=1e-3, metrics=True)
+        for _ in range(2):
+            sa(x, m)
+        assert sa.last_metrics is not None and sa.last_metrics.shape == (2,) and bool((sa.last_metrics >= 0).all())
+        mb = copy.deepcopy(ma)
+        sd = sa.state_dict()
+        opt = torch.optim.Adam([p for p in mb.parameters() if p.requires_grad], lr=5e-4)
+        opt.load_state_dict(sd)                                        # torch accepts the format
+        assert opt.param_groups[0]["lr"] == 1e-3
+        p0 = next(iter(mb.parameters()))
+        assert float(opt.state[p0]["step"]) == 2.0
+        assert torch.equal(opt.state[p0]["exp_avg"], sa.flat._view(sa.flat.exp_avg, sa.params[0]))
+        sb = TrainStep(mb, lr=123.0)
+        sb.load_state_dict(opt.state_dict())                           # and back
+        assert sb.lr == 1e-3 and float(sb.flat.step_state[0]) == 2.0 and float(sb.flat.step_state[1]) == pytest.approx(1e-3)
+        la, lb = float(sa(x, m)), float(sb(x, m))
+        assert la == lb
+        for p, q in zip(ma.parameters(), mb.parameters()):
+            assert torch.equal(p, q)
+        before = [p.detach().clone() for p in ma.parameters()]
+        sa.set_lr(0.0)                                                  # device-side scalar: no update at lr = 0
+        sa(x, m)
+        assert all(torch.equal(p, b) for p, b in zip(ma.parameters(), before))
 
 
 def test_train_step_matches_cpu_oracle_step():
