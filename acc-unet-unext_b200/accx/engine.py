@@ -808,6 +808,36 @@ def dice_bce_bwd(logit, truth, sums, dice_w, bce_w, gscale: Optional[torch.Tenso
     return d
 
 
+# ---- UNeXt shifted-MLP block pieces (include/accx.h, row f4) ------------------------------------------------
+def layernorm_fwd(x: torch.Tensor, gamma, beta, eps: float, y: torch.Tensor, mean, rstd):
+    """x, y: [.., C] contiguous; mean / rstd: fp32 [rows]"""
+    C = x.shape[-1]
+    R = x.numel() // C
+    _call("accx_layernorm_fwd", dt(x), R, C, ptr(x), ptr(gamma), ptr(beta), float(eps), ptr(y), ptr(mean), ptr(rstd), stream(),
+          cost=(nb(x, y), 0), tag=f"R={R} C={C}")
+
+
+def layernorm_bwd(x, gamma, mean, rstd, dy, dx, dgamma, dbeta):
+    C = x.shape[-1]
+    R = x.numel() // C
+    assert dy.dtype == x.dtype and dy.is_contiguous() and dx.dtype == x.dtype
+    _call("accx_layernorm_bwd", dt(x), R, C, ptr(x), ptr(gamma), ptr(mean), ptr(rstd), ptr(dy), ptr(dx), ptr(dgamma), ptr(dbeta),
+          stream(), cost=(nb(x, dy, dx), 0), tag=f"R={R} C={C}")
+
+
+def gelu(x: torch.Tensor) -> torch.Tensor:
+    y = torch.empty_like(x)
+    _call("accx_gelu_fwd", dt(x), x.numel(), ptr(x), ptr(y), stream(), cost=(nb(x, y), 0))
+    return y
+
+
+def gelu_bwd(x: torch.Tensor, dy: torch.Tensor) -> torch.Tensor:
+    assert dy.dtype == x.dtype and dy.is_contiguous() and x.is_contiguous()
+    dx = torch.empty_like(x)
+    _call("accx_gelu_bwd", dt(x), x.numel(), ptr(x), ptr(dy), ptr(dx), stream(), cost=(nb(x, dy, dx), 0))
+    return dx
+
+
 def seg_metrics(logit: torch.Tensor, truth: torch.Tensor) -> torch.Tensor:
     """logit [B, N] (fp32 / bf16), truth [B, N] fp32 -> device tensor [mean IoU, mean hard Dice] (accx_seg_metrics)"""
     B, N = logit.shape

@@ -251,6 +251,20 @@ int accx_upshuffle(int dtype, int forward, int B, int H, int W, int Co, void* te
 int accx_copy_cols(int dtype, int64_t P, int C, const void* src, int64_t ld_src, void* dst, int64_t ld_dst,
                    void* stream);
 
+/* UNeXt shifted tokenized-MLP block (Experiments/nets/UNext.py:38-160; BASELINE configs[2]).  Tokens [B, N, C] are an
+ * NHWC tensor: the shift (pad / chunk(5) / roll / narrow, :78-84,:97-103) is expressed as five shifted operands of
+ * accx_pw_fwd / accx_pw_wgrad, DWConv (:150-160) is accx_dw3x3_fwd with a bias, and these are the two remaining passes:
+ *   layernorm  nn.LayerNorm(C) over the channels of every row (shiftedBlock.norm2, :151,:156): y = (x-mean)*rstd*gamma + beta,
+ *              biased variance, mean / rstd [R] (fp32) saved for the backward (either may be NULL);
+ *              bwd: dx, and dgamma / dbeta ACCUMULATED (zero them first; either may be NULL).  C <= 1024.
+ *   gelu       nn.GELU, exact erf form (:47,:90); bwd: dx = dy * gelu'(x). */
+int accx_layernorm_fwd(int dtype, int64_t R, int C, const void* x, const float* gamma, const float* beta, float eps,
+                       void* y, float* mean, float* rstd, void* stream);
+int accx_layernorm_bwd(int dtype, int64_t R, int C, const void* x, const float* gamma, const float* mean,
+                       const float* rstd, const void* dy, void* dx, float* dgamma, float* dbeta, void* stream);
+int accx_gelu_fwd(int dtype, int64_t n, const void* x, void* y, void* stream);
+int accx_gelu_bwd(int dtype, int64_t n, const void* x, const void* dy, void* dx, void* stream);
+
 /* Per-step segmentation metrics left on the device (the reference syncs device -> host every step for them:
  * Experiments/Train_one_epoch.py:134-135).  pred = sigmoid(logit) >= 0.5, mask = truth > 0;
  * out[0] = mean over images of sklearn's binary jaccard_score (iou_on_batch, Experiments/utils.py:478-494; 0 for an

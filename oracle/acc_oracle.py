@@ -29,6 +29,7 @@ Reference lines each function follows (relative to /root/reference):
   acc_unet        ACC_UNet/ACC_UNet.py:601-659
   dice_bce_loss   Experiments/utils.py:21-74,109-171
   seg_metrics     Experiments/utils.py:478-494 (iou_on_batch), :148-157 (_show_dice)
+  token_shift / shiftmlp / shifted_block   Experiments/nets/UNext.py:38-113, :117-147, :150-160
 """
 from __future__ import annotations
 
@@ -260,6 +261,37 @@ def dice_bce_loss(logit: torch.Tensor, truth: torch.Tensor, dice_weight=0.5, bce
     neg = 1 - pos
     bce = (0.5 * pos * l / pos.sum().clamp(min=1.0) + 0.5 * neg * l / neg.sum().clamp(min=1.0)).sum()
     return dice_weight * dice + bce_weight * bce
+
+
+# ---- UNeXt shifted tokenized-MLP block (Experiments/nets/UNext.py:38-160) -------------------------------------
+def token_shift(x: torch.Tensor, H: int, W: int, axis: int, shift_size: int = 5) -> torch.Tensor:
+    """pad -> chunk(shift_size) over channels -> roll chunk g by g - pad along H (axis 2) or W (axis 3) -> narrow
+    (UNext.py:78-84, :97-103) on tokens [B, N, C]; equals: chunk g read at offset -(g - pad), zero outside the map."""
+    B, N, C = x.shape
+    pad = shift_size // 2
+    xn = x.transpose(1, 2).reshape(B, C, H, W)
+    xn = F.pad(xn, (pad, pad, pad, pad), "constant", 0)
+    xs = torch.chunk(xn, shift_size, 1)
+    xs = [torch.roll(c, s, axis) for c, s in zip(xs, range(-pad, pad + 1))]
+    xc = torch.cat(xs, 1)[:, :, pad:pad + H, pad:pad + W]
+    return xc.reshape(B, C, H * W).transpose(1, 2)
+
+
+def shiftmlp(cx: Ctx, name: str, x: torch.Tensor, H: int, W: int) -> torch.Tensor:
+    """shift_H -> fc1 -> DWConv (3x3 depthwise + bias) -> GELU -> shift_W -> fc2   (UNext.py:72-113, drop = 0)"""
+    B, N, C = x.shape
+    y = F.linear(token_shift(x, H, W, 2), cx.p(name + ".fc1.weight"), cx.p(name + ".fc1.bias"))
+    w = cx.p(name + ".dwconv.dwconv.weight")
+    y = F.conv2d(y.transpose(1, 2).reshape(B, -1, H, W), w, cx.p(name + ".dwconv.dwconv.bias"), padding=1, groups=w.shape[0])
+    y = F.gelu(y.flatten(2).transpose(1, 2))
+    return F.linear(token_shift(y, H, W, 3), cx.p(name + ".fc2.weight"), cx.p(name + ".fc2.bias"))
+
+
+def shifted_block(cx: Ctx, name: str, x: torch.Tensor, H: int, W: int) -> torch.Tensor:
+    """x + shiftmlp(LayerNorm(x))   (UNext.py:144-147, drop_path = 0)"""
+    C = x.shape[-1]
+    y = F.layer_norm(x, (C,), cx.p(name + ".norm2.weight"), cx.p(name + ".norm2.bias"), 1e-5)
+    return x + shiftmlp(cx, name + ".mlp", y, H, W)
 
 
 def seg_metrics(logit: torch.Tensor, truth: torch.Tensor) -> Tuple[float, float]:
