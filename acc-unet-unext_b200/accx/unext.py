@@ -288,8 +288,11 @@ class UNext(nn.Module):
     def __init__(self, n_channels=3, n_classes=1, deep_supervision=False, img_size=224, patch_size=16, in_chans=3,
                  embed_dims=[128, 160, 256], num_heads=[1, 2, 4, 8], mlp_ratios=[4, 4, 4, 4], qkv_bias=False, qk_scale=None,
                  drop_rate=0., attn_drop_rate=0., drop_path_rate=0., norm_layer=nn.LayerNorm, depths=[1, 1, 1],
-                 sr_ratios=[8, 4, 2, 1], **kwargs):
+                 sr_ratios=[8, 4, 2, 1], compute_dtype=None, **kwargs):
         super().__init__()
+        # storage dtype of the tokens inside the shiftedBlocks (None: whatever arrives; torch.bfloat16: throughput mode,
+        # the same switch ACC_UNet(compute_dtype=) has); the torch stem / decoder keep their own dtype
+        self.compute_dtype = compute_dtype
         self.encoder1 = nn.Conv2d(n_channels, 16, 3, stride=1, padding=1)
         self.encoder2 = nn.Conv2d(16, 32, 3, stride=1, padding=1)
         self.encoder3 = nn.Conv2d(32, 128, 3, stride=1, padding=1)
@@ -323,6 +326,14 @@ class UNext(nn.Module):
         self.final = nn.Conv2d(16, n_classes, kernel_size=1)
         self.soft = nn.Softmax(dim=1)
 
+    def _blocks(self, blocks, out, H, W):
+        dt0 = out.dtype
+        if self.compute_dtype is not None and dt0 != self.compute_dtype:
+            out = out.to(self.compute_dtype)
+        for blk in blocks:
+            out = blk(out, H, W)
+        return out if out.dtype == dt0 else out.to(dt0)
+
     @staticmethod
     def _tokens_to_map(out, B, H, W):
         return out.reshape(B, H, W, -1).permute(0, 3, 1, 2).contiguous()
@@ -337,13 +348,11 @@ class UNext(nn.Module):
         out = F.relu(F.max_pool2d(self.ebn3(self.encoder3(out)), 2, 2))
         t3 = out
         out, H, W = self.patch_embed3(out)
-        for blk in self.block1:
-            out = blk(out, H, W)
+        out = self._blocks(self.block1, out, H, W)
         out = self._tokens_to_map(self.norm3(out), B, H, W)
         t4 = out
         out, H, W = self.patch_embed4(out)
-        for blk in self.block2:
-            out = blk(out, H, W)
+        out = self._blocks(self.block2, out, H, W)
         out = self._tokens_to_map(self.norm4(out), B, H, W)
         out = F.relu(up(self.dbn1(self.decoder1(out))))
         if t4.shape[2:] != out.shape[2:]:
@@ -351,8 +360,7 @@ class UNext(nn.Module):
         out = torch.add(out, t4)
         _, _, H, W = out.shape
         out = out.flatten(2).transpose(1, 2)
-        for blk in self.dblock1:
-            out = blk(out, H, W)
+        out = self._blocks(self.dblock1, out, H, W)
         out = self._tokens_to_map(self.dnorm3(out), B, H, W)
         out = F.relu(up(self.dbn2(self.decoder2(out))))
         if t3.shape[2:] != out.shape[2:]:
@@ -360,8 +368,7 @@ class UNext(nn.Module):
         out = torch.add(out, t3)
         _, _, H, W = out.shape
         out = out.flatten(2).transpose(1, 2)
-        for blk in self.dblock2:
-            out = blk(out, H, W)
+        out = self._blocks(self.dblock2, out, H, W)
         out = self._tokens_to_map(self.dnorm4(out), B, H, W)
         out = F.relu(up(self.dbn3(self.decoder3(out))))
         if t2.shape[2:] != out.shape[2:]:

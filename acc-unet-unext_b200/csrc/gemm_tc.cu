@@ -160,35 +160,51 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_fwd_tc_kernel(const __grid_c
     // launch, no workspace traffic).  Every CTA reads the (small, L2-resident) weight matrix once.
     // one 16-byte chunk (8 consecutive k of one output row) per thread and step: eight independent loads in flight
     const int chunks_per_kb = bn * 8;
-    for (int ch = tid; ch < n_kb * chunks_per_kb; ch += TC_WARP_TMA * 32) {
-      const int kb = ch / chunks_per_kb, rem = ch - kb * chunks_per_kb;
-      const int nl = rem >> 3, c8 = rem & 7;
-      int o = 0;
-      while (o + 1 < prm.n_ops && kb >= prm.kb_start[o + 1]) ++o;
-      const accx_operand_t& op = prm.op[o];
-      const int k0 = (kb - prm.kb_start[o]) * TC_BK + c8 * 8;
-      float v[8];
+    const int n_chunks_w = n_kb * chunks_per_kb;
+    constexpr int WU = 4;                      // chunks in flight per thread: the loop is bound by L2 latency otherwise
+    for (int ch0 = tid; ch0 < n_chunks_w; ch0 += WU * TC_WARP_TMA * 32) {
+      float v[WU][8];
+      uint32_t addr[WU];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) v[e] = 0.f;
-      if (nl < prm.N && k0 < op.K) {
-        const float* src = op.w + (int64_t)nl * op.w_ld + (int64_t)k0 * op.w_ks;
-        if (op.w_ks == 1 && k0 + 8 <= op.K && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
-          const float4 a = __ldg(reinterpret_cast<const float4*>(src)), c = __ldg(reinterpret_cast<const float4*>(src) + 1);
-          v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
-        } else {
+      for (int u = 0; u < WU; ++u) {
+        const int ch = ch0 + u * TC_WARP_TMA * 32;
 #pragma unroll
-          for (int e = 0; e < 8; ++e)
-            if (k0 + e < op.K) v[e] = __ldg(src + (int64_t)e * op.w_ks);
+        for (int e = 0; e < 8; ++e) v[u][e] = 0.f;
+        addr[u] = 0;
+        if (ch < n_chunks_w) {
+          const int kb = ch / chunks_per_kb, rem = ch - kb * chunks_per_kb;
+          const int nl = rem >> 3, c8 = rem & 7;
+          int o = 0;
+          while (o + 1 < prm.n_ops && kb >= prm.kb_start[o + 1]) ++o;
+          const accx_operand_t& op = prm.op[o];
+          const int k0 = (kb - prm.kb_start[o]) * TC_BK + c8 * 8;
+          addr[u] = base + bres_off + kb * b_tile_bytes + nl * 128 + ((c8 ^ (nl & 7)) << 4);
+          if (nl < prm.N && k0 < op.K) {
+            const float* src = op.w + (int64_t)nl * op.w_ld + (int64_t)k0 * op.w_ks;
+            if (op.w_ks == 1 && k0 + 8 <= op.K && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+              const float4 a = __ldg(reinterpret_cast<const float4*>(src)), c = __ldg(reinterpret_cast<const float4*>(src) + 1);
+              v[u][0] = a.x; v[u][1] = a.y; v[u][2] = a.z; v[u][3] = a.w;
+              v[u][4] = c.x; v[u][5] = c.y; v[u][6] = c.z; v[u][7] = c.w;
+            } else {
+#pragma unroll
+              for (int e = 0; e < 8; ++e)
+                if (k0 + e < op.K) v[u][e] = __ldg(src + (int64_t)e * op.w_ks);
+            }
+          }
         }
       }
-      uint32_t w[4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * q], v[2 * q + 1]);
-        w[q] = *reinterpret_cast<uint32_t*>(&h2);
+      for (int u = 0; u < WU; ++u) {
+        if (addr[u] != 0) {
+          uint32_t w[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[u][2 * q], v[u][2 * q + 1]);
+            w[q] = *reinterpret_cast<uint32_t*>(&h2);
+          }
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr[u]), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+        }
       }
-      const uint32_t addr = base + bres_off + kb * b_tile_bytes + nl * 128 + ((c8 ^ (nl & 7)) << 4);
-      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
     }
     fence_async_smem();
     asm volatile("bar.sync 3, 512;" ::: "memory");

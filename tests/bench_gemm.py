@@ -67,8 +67,52 @@ def run_wgrad(i, reps=5):
           flush=True)
 
 
+SHAPES3 = [(16, 224, 224, 32), (16, 112, 112, 64), (16, 56, 56, 128), (16, 28, 28, 256)]
+SMALL = [(12544, 256, 256, 2, 1), (12544, 256, 768, 0, 1), (3136, 256, 768, 0, 1), (12544, 256, 128, 2, 1), (3136, 512, 1536, 0, 1),
+         (50176, 128, 128, 2, 1), (200704, 64, 64, 2, 1), (802816, 32, 32, 2, 1)]
+
+
+def run_taps(i, reps=5, wgrad=False):
+    """ResPath's dense 3x3 conv (ACC_UNet.py:316-318) at model level i: forward contraction / weight gradient"""
+    from accx.modules import ResPath
+    B, H, W, C = SHAPES3[i]
+    x = torch.randn(B, H, W, C, device="cuda").to(torch.bfloat16)
+    s = torch.rand(C, device="cuda") + 0.5
+    t = torch.randn(C, device="cuda") * 0.1
+    L = E.Lazy(x, s, t, 2)
+    w = torch.randn(C, C, 3, 3, device="cuda") / (9 * C) ** 0.5
+    stats = torch.zeros(2 * C, device="cuda")
+    dy = torch.randn(B, H, W, C, device="cuda").to(torch.bfloat16)
+    gw = torch.zeros_like(w)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    ts = []
+    for _ in range(reps + 2):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        if wgrad:
+            E.wgrad_conv3x3(L, C, w, dy, C, (B, H, W), gw)
+        else:
+            E.conv(ResPath._taps(L, w, C), C, (B, H, W), stats=stats)
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ms = sorted(ts[2:])[len(ts[2:]) // 2]
+    P = B * H * W
+    print(f"conv3x3{' wgrad' if wgrad else ''} {B}x{H}x{W}x{C}: {ms * 1e3:8.1f} us  {P * C * 4 / ms / 1e6:7.0f} GB/s  "
+          f"{2 * P * C * C * 9 / ms / 1e9:7.1f} TFLOP/s", flush=True)
+
+
 if __name__ == "__main__":
     args = sys.argv[1:]
+    if "taps" in args:
+        for i in range(len(SHAPES3)):
+            run_taps(i)
+            run_taps(i, wgrad=True)
+        sys.exit(0)
+    if "small" in args:
+        SHAPES[:] = SMALL
+        args.remove("small")
     wg = "wgrad" in args
     idx = [int(a) for a in args if a != "wgrad"] or range(len(SHAPES))
     for i in idx:
