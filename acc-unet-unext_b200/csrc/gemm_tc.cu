@@ -50,7 +50,17 @@ struct alignas(64) TcParams {
   int n_add;
   float* stats;
   int det;      // deterministic mode (common.cuh): ONE CTA walks all tiles, shared-memory statistics added in row order
+  // dense 3x3 convolution as ONE halo slab per filter row (ResPath, ACC_UNet.py:316-318): the nine operands are the
+  // nine taps of one tensor; per tile three slabs of TC_SLAB_ROWS pixels (rows m0 + dy*W - 1 ..) are landed and
+  // transformed once, the tap (dy, dx) reads its slab at a row offset of dx + 1, and the taps of each dx accumulate
+  // into their own TMEM accumulator so that the epilogue can leave out the dx = -1 / +1 sums of pixels in the first /
+  // last image column (zero padding).  tap_op[dy + 1][dx + 1] = operand (weight view) of that tap.
+  int conv3;
+  int tap_op[3][3];
 };
+
+constexpr int TC_SLAB_ROWS = 136;                    // 128 + 2 halo pixels, rounded up to the 8-row swizzle group
+constexpr int TC_SLAB_BYTES = TC_SLAB_ROWS * 128;
 
 // ---------------------------------------------------------------- weight packing
 // wpack[(n_tile * n_kb + kb) * bn * 64 + swizzled(n_local, kk)] = bf16(W_op[n, k0 + kk])
@@ -106,6 +116,8 @@ __device__ __forceinline__ void stage_chunk(const float (&v)[16], uint32_t stage
   }
 }
 
+// CONV3: the dense-3x3 halo-slab mode (see TcParams) -- its own instantiation, so that the plain contraction carries none of its code
+template <bool CONV3>
 __global__ void __launch_bounds__(TC_THREADS, 1) pw_fwd_tc_kernel(const __grid_constant__ TcParams prm) {
   pdl_sync();
   extern __shared__ uint8_t smem_raw[];
@@ -113,12 +125,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_fwd_tc_kernel(const __grid_c
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
   const int bn = prm.bn, S = prm.stages, n_kb = prm.n_kb;
   const uint32_t b_tile_bytes = bn * 128;
-  const uint32_t stage_bytes = TC_A_BYTES + (prm.b_resident ? 0 : b_tile_bytes);
+  const uint32_t stage_bytes = CONV3 ? (uint32_t)TC_SLAB_BYTES : TC_A_BYTES + (prm.b_resident ? 0 : b_tile_bytes);
   const uint32_t bres_off = S * stage_bytes;
   const uint32_t epi_off = bres_off + (prm.b_resident ? n_kb * b_tile_bytes : 0);      // 1024-aligned
   const uint32_t stat_off = epi_off + 2 * prm.out_boxes * TC_BOX_BYTES;                // float[2 groups][2 * bn]
   const uint32_t tab_off = (stat_off + 4 * bn * 4 + 15u) & ~15u;                       // float[n_kb][2][64] + int4[n_kb]
-  const uint32_t bar_off = tab_off + (prm.any_transform ? n_kb * (512 + 16) : 0);
+  const uint32_t htab_off = tab_off + (prm.any_transform ? n_kb * (512 + 16) : 0);     // int16[2][TC_SLAB_ROWS] (conv3)
+  const uint32_t bar_off = htab_off + (CONV3 ? 2 * TC_SLAB_ROWS * 2 : 0);
   const uint32_t landed_bar = base + bar_off;            // S x 8 bytes
   const uint32_t full_bar = landed_bar + 8 * S;
   const uint32_t empty_bar = full_bar + 8 * S;
@@ -214,15 +227,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_fwd_tc_kernel(const __grid_c
   if (warp == TC_WARP_TMA) {
     // ============================== TMA producer ==============================
     if (lane == 0) {
-      int it = 0;
+      int stage = 0;
+      uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int nt = tile / prm.m_tiles;
         const int64_t m0 = (int64_t)(tile % prm.m_tiles) * TC_BM;
+        if (CONV3) {
+          for (int dyi = 0; dyi < 3; ++dyi) {
+            mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+            const uint32_t bar = landed_bar + 8 * stage;
+            mbar_expect_tx(bar, TC_SLAB_BYTES);
+            // rows m0 + dy*W - 1 .. + 135 of the tensor (negative / past-the-end rows are zero-filled)
+            tma_load_2d(base + stage * stage_bytes, &prm.tmap[0], 0, (int)(m0 + (int64_t)(dyi - 1) * prm.W - 1), bar);
+            if (++stage == S) { stage = 0; phase ^= 1; }
+          }
+          continue;
+        }
         int o = 0;
-        for (int kb = 0; kb < n_kb; ++kb, ++it) {
+        for (int kb = 0; kb < n_kb; ++kb) {
           while (o + 1 < prm.n_ops && kb >= prm.kb_start[o + 1]) ++o;
-          const int stage = it % S;
-          const uint32_t phase = (it / S) & 1;
           mbar_wait(empty_bar + 8 * stage, phase ^ 1);
           const uint32_t a_smem = base + stage * stage_bytes;
           const uint32_t bar = landed_bar + 8 * stage;
@@ -232,6 +255,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_fwd_tc_kernel(const __grid_c
           tma_load_2d(a_smem, &prm.tmap[o], (kb - prm.kb_start[o]) * TC_BK, (int)row0, bar);
           if (!prm.b_resident)
             bulk_g2s(a_smem + TC_A_BYTES, prm.wpack + ((int64_t)nt * n_kb + kb) * bn * TC_BK, b_tile_bytes, bar);
+          if (++stage == S) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -243,25 +267,55 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_fwd_tc_kernel(const __grid_c
           (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       const uint32_t ready_bar = prm.any_transform ? full_bar : landed_bar;
       if (prm.b_resident) mbar_wait(bres_bar, 0);
-      int it = 0, tl = 0;
+      int stage = 0, tl = 0;
+      uint32_t phase = 0;
+      const int acc_stride = CONV3 ? 3 * bn : bn;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
         const int acc = tl & 1;
         mbar_wait(tempty_bar + 8 * acc, ((tl >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * bn;
-        for (int kb = 0; kb < n_kb; ++kb, ++it) {
-          const int stage = it % S;
-          const uint32_t phase = (it / S) & 1;
+        const uint32_t tmem_d = tmem_base + acc * acc_stride;
+        if (CONV3) {
+          const int nm = prm.op[0].K >= TC_BK ? TC_BK / 16 : (prm.op[0].K + 15) / 16;
+          for (int dyi = 0; dyi < 3; ++dyi) {
+            mbar_wait(ready_bar + 8 * stage, phase);
+            tc_fence_after();
+            const uint32_t a_smem = base + stage * stage_bytes;
+#pragma unroll
+            for (int dxi = 0; dxi < 3; ++dxi) {
+              // the tap's A operand = the slab read from row dx + 1 on: a start address inside the 8-row swizzle group
+              const uint32_t a_addr = a_smem + dxi * 128;
+              // (measured on B200: the 128B swizzle is a function of the absolute shared-memory address, so the
+              //  descriptor's base-offset field stays 0 -- setting it to (address >> 7) & 7 gives wrong sums)
+              const uint64_t adesc = make_desc_k_sw128(a_addr);
+              const uint64_t bdesc = make_desc_k_sw128(base + bres_off + prm.tap_op[dyi][dxi] * b_tile_bytes);
+#pragma unroll
+              for (int k = 0; k < TC_BK / 16; ++k)
+                if (k < nm) tc_mma(tmem_d + dxi * bn, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (dyi | k) ? 1u : 0u);
+            }
+            tc_commit(empty_bar + 8 * stage);
+            if (++stage == S) { stage = 0; phase ^= 1; }
+          }
+          tc_commit(tfull_bar + 8 * acc);
+          continue;
+        }
+        int o = 0;
+        for (int kb = 0; kb < n_kb; ++kb) {
+          while (o + 1 < prm.n_ops && kb >= prm.kb_start[o + 1]) ++o;
           mbar_wait(ready_bar + 8 * stage, phase);
           tc_fence_after();
           const uint32_t a_smem = base + stage * stage_bytes;
           const uint64_t adesc = make_desc_k_sw128(a_smem);
           const uint64_t bdesc =
               make_desc_k_sw128(prm.b_resident ? base + bres_off + kb * b_tile_bytes : a_smem + TC_A_BYTES);
+          // the last k-block of an operand may hold fewer than 64 channels (the rest is zero fill): skip those MMAs
+          const int krem = prm.op[o].K - (kb - prm.kb_start[o]) * TC_BK;
+          const int nm = krem >= TC_BK ? TC_BK / 16 : (krem + 15) / 16;
 #pragma unroll
           for (int k = 0; k < TC_BK / 16; ++k)
-            tc_mma(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+            if (k < nm) tc_mma(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
           tc_commit(empty_bar + 8 * stage);
+          if (++stage == S) { stage = 0; phase ^= 1; }
         }
         tc_commit(tfull_bar + 8 * acc);
       }
@@ -271,7 +325,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_fwd_tc_kernel(const __grid_c
     if (prm.any_transform) {
       const int t = tid - TC_WARP_XF0 * 32;
       const int c = t & 7, r0 = t >> 3;                       // rows r0, r0 + 32, r0 + 64, r0 + 96
-      // per-k-block tables in shared memory: scale[64] | shift[64] (zeros beyond K) and {act, dy, dx, -}
+      // per-k-block tables in shared memory: scale[64] | shift[64] (zeros beyond K) and {act, dy, dx, 16-byte chunks}
       float* tab = reinterpret_cast<float*>(smem + tab_off);
       int4* meta = reinterpret_cast<int4*>(smem + tab_off + n_kb * 512);
       for (int idx = t; idx < n_kb * 64; idx += TC_XF_THREADS) {
@@ -283,11 +337,75 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_fwd_tc_kernel(const __grid_c
         const bool on = op.act != 0 && k < op.K;
         tab[kb * 128 + j] = on ? __ldg(op.scale + k) : 0.f;
         tab[kb * 128 + 64 + j] = on ? __ldg(op.shift + k) : 0.f;
-        if (j == 0) meta[kb] = make_int4(op.act, op.dy, op.dx, 0);
+        if (j == 0) {
+          const int krem = op.K - k;
+          meta[kb] = make_int4(op.act, op.dy, op.dx, krem >= TC_BK ? 8 : (krem + 7) >> 3);
+        }
       }
-      asm volatile("bar.sync 2, 256;" ::: "memory");
+      asm volatile("bar.sync 4, 256;" ::: "memory");
       const int HWp = prm.H * prm.W;
-      int it = 0;
+      int stage = 0;
+      uint32_t phase = 0;
+      if (CONV3) {
+        // ---- dense 3x3: three slabs per tile, each transformed ONCE for its three taps ----
+        int16_t* htab = reinterpret_cast<int16_t*>(smem + htab_off);
+        const int act = prm.op[0].act;
+        const int kc_raw = (prm.op[0].K + 7) >> 3;                              // 16-byte chunks holding real channels
+        const int kc = kc_raw <= 2 ? 2 : (kc_raw <= 4 ? 4 : 8), kc_log = kc == 2 ? 1 : (kc == 4 ? 2 : 3);
+        // rows 0..127 of the slab: thread -> chunk cc of rows row_first + i * (128 / NR), NR = kc / 2 rows per thread
+        // (every lane busy); rows 128, 129 (the last halo pixels): the first 2 * kc threads.  Rows 130..135 are padding.
+        const int cc = t & (kc - 1), row_first = t >> kc_log, nr = kc >> 1, rs = TC_XF_THREADS >> kc_log;
+        const bool has_tail = t < 2 * kc;
+        const int tail_row = TC_BM + (t >> kc_log);
+        float sc[8], sh[8];
+        {
+          const float4* sp = reinterpret_cast<const float4*>(tab + cc * 8);
+          const float4 a0 = sp[0], a1 = sp[1], b0 = sp[16], b1 = sp[17];
+          sc[0] = a0.x; sc[1] = a0.y; sc[2] = a0.z; sc[3] = a0.w; sc[4] = a1.x; sc[5] = a1.y; sc[6] = a1.z; sc[7] = a1.w;
+          sh[0] = b0.x; sh[1] = b0.y; sh[2] = b0.z; sh[3] = b0.w; sh[4] = b1.x; sh[5] = b1.y; sh[6] = b1.z; sh[7] = b1.w;
+        }
+        int tl = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
+          const int m0 = (tile % prm.m_tiles) * TC_BM;
+          int16_t* ht = htab + (tl & 1) * TC_SLAB_ROWS;
+          if (t < TC_SLAB_ROWS) {           // image row of slab row t in the dy = 0 slab (pixel m0 - 1 + t); < 0: no pixel
+            const int q0 = m0 - 1 + t;
+            ht[t] = (q0 < 0 || q0 >= (int)prm.P) ? (int16_t)-16384 : (int16_t)((q0 % HWp) / prm.W);
+          }
+          asm volatile("bar.sync 4, 256;" ::: "memory");
+          int hrow[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) hrow[i] = i < nr ? (int)ht[row_first + i * rs] : 0;
+          const int htail = has_tail ? (int)ht[tail_row] : 0;
+          for (int dyi = 0; dyi < 3; ++dyi) {
+            const int dy = dyi - 1;
+            // a slab row is zero when it is no pixel or when the tap row dy falls outside that pixel's image
+            uint32_t zm = 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int hh = hrow[i] + dy;
+              if (i < nr && (hh < 0 || hh >= prm.H)) zm |= 1u << i;
+            }
+            const int hht = htail + dy;
+            const bool zt = hht < 0 || hht >= prm.H;
+            mbar_wait(landed_bar + 8 * stage, phase);
+            const uint32_t blk = base + stage * stage_bytes;
+            if (act != 0 || zm != 0) {
+              if (nr == 2) transform_block<2, 64>(blk, cc, row_first, act, sc, sh, zm);
+              else if (nr == 4) transform_block<4, 32>(blk, cc, row_first, act, sc, sh, zm);
+              else transform_block<1, 128>(blk, cc, row_first, act, sc, sh, zm);
+            }
+            if (has_tail && (act != 0 || zt)) transform_block<1, 128>(blk, cc, tail_row, act, sc, sh, zt ? 1u : 0u);
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full_bar + 8 * stage);
+            if (++stage == S) { stage = 0; phase ^= 1; }
+          }
+        }
+      } else {
+      // narrow operands (K = 32 / 16 in a 64-channel box: the rest is TMA zero fill and stays zero): only the chunks
+      // that hold channels are touched -- thread -> (chunk c4 of rows r4, r4 + 64) resp. (chunk c2 of row r2)
+      const int c4 = t & 3, r4 = t >> 2, c2 = t & 1, r2 = t >> 1;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int m0 = (tile % prm.m_tiles) * TC_BM;
         int ph[4], pw[4];
@@ -302,11 +420,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_fwd_tc_kernel(const __grid_c
             pw[i] = p < (int)prm.P ? rem - ph[i] * prm.W : -4;   // rows past the end count as outside the image
           }
         }
-        for (int kb = 0; kb < n_kb; ++kb, ++it) {
+        for (int kb = 0; kb < n_kb; ++kb) {
           const int4 mt = meta[kb];
+          const int kcw = prm.any_shift ? 8 : mt.w;
+          const int cx = kcw == 4 ? c4 : (kcw == 2 ? c2 : c);
           float s[8], sh[8];
           if (mt.x != 0) {
-            const float4* sp = reinterpret_cast<const float4*>(tab + kb * 128 + c * 8);
+            const float4* sp = reinterpret_cast<const float4*>(tab + kb * 128 + cx * 8);
             const float4 a0 = sp[0], a1 = sp[1], b0 = sp[16], b1 = sp[17];
             s[0] = a0.x; s[1] = a0.y; s[2] = a0.z; s[3] = a0.w; s[4] = a1.x; s[5] = a1.y; s[6] = a1.z; s[7] = a1.w;
             sh[0] = b0.x; sh[1] = b0.y; sh[2] = b0.z; sh[3] = b0.w; sh[4] = b1.x; sh[5] = b1.y; sh[6] = b1.z; sh[7] = b1.w;
@@ -322,14 +442,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_fwd_tc_kernel(const __grid_c
               if (hh < 0 || hh >= prm.H || ww < 0 || ww >= prm.W || pw[i] < 0) zero_mask |= 1u << i;
             }
           }
-          const int stage = it % S;
-          const uint32_t phase = (it / S) & 1;
           mbar_wait(landed_bar + 8 * stage, phase);
-          if (mt.x != 0 || zero_mask != 0) transform_block<4, 32>(base + stage * stage_bytes, c, r0, mt.x, s, sh, zero_mask);
+          const uint32_t blk = base + stage * stage_bytes;
+          if (mt.x != 0 || zero_mask != 0) {
+            if (kcw == 4) transform_block<2, 64>(blk, c4, r4, mt.x, s, sh, 0u);
+            else if (kcw == 2) transform_block<1, 64>(blk, c2, r2, mt.x, s, sh, 0u);
+            else transform_block<4, 32>(blk, c, r0, mt.x, s, sh, zero_mask);
+          }
           fence_async_smem();
           __syncwarp();
           if (lane == 0) mbar_arrive(full_bar + 8 * stage);
+          if (++stage == S) { stage = 0; phase ^= 1; }
         }
+      }
       }
     }
   } else {
@@ -425,17 +550,38 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_fwd_tc_kernel(const __grid_c
       // finished its statistics pass
       if (gtid == 0) bulk_wait_read0();
       asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-      const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * bn;
+      const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * (CONV3 ? 3 * bn : bn);
+      // dense 3x3: the dx = -1 / +1 accumulators do not count for pixels in the first / last image column
+      bool use_m = true, use_p = true;
+      if (CONV3) {
+        const int wcol = (int)p % prm.W;
+        use_m = wcol != 0;
+        use_p = wcol != prm.W - 1;
+      }
       for (int ch = 0; ch < n_chunks; ++ch) {
         uint32_t r[1][16];
-        tc_ld16_issue(trow + ch * 16, r[0]);
-        tc_ld_wait();
-        {
-          constexpr int u = 0;
-          const int c0 = ch * 16;
-          float v[16];
+        float v[16];
+        if (CONV3) {
+          uint32_t rm[16], rp[16];
+          tc_ld16_issue(trow + ch * 16, rm);
+          tc_ld16_issue(trow + bn + ch * 16, r[0]);
+          tc_ld16_issue(trow + 2 * bn + ch * 16, rp);
+          tc_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = rvalid ? __uint_as_float(r[u][j]) : 0.f;
+          for (int j = 0; j < 16; ++j) {
+            float a = __uint_as_float(r[0][j]);
+            if (use_m) a += __uint_as_float(rm[j]);
+            if (use_p) a += __uint_as_float(rp[j]);
+            v[j] = rvalid ? a : 0.f;
+          }
+        } else {
+          tc_ld16_issue(trow + ch * 16, r[0]);
+          tc_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = rvalid ? __uint_as_float(r[0][j]) : 0.f;
+        }
+        {
+          const int c0 = ch * 16;
           if (rvalid && (bias != nullptr || n_add > 0)) {
             if (n0 + c0 + 16 <= N && (N & 3) == 0) {
               if (bias) {
@@ -565,18 +711,20 @@ static size_t tc_geometry(int N, int64_t P, const accx_operand_t* ops, int n_ops
     }
     n_tiles = best_nt;
   }
+  if (prm.conv3) n_tiles = 1;          // one column tile of N <= 64 channels, three accumulators per TMEM buffer
   prm.bn = bn_for(n_tiles);
   prm.n_tiles = (N + prm.bn - 1) / prm.bn;
   int cols = 32;
-  while (cols < 2 * prm.bn) cols <<= 1;
+  while (cols < (prm.conv3 ? 6 : 2) * prm.bn) cols <<= 1;
   prm.tmem_cols = cols;
   prm.out_boxes = (prm.bn + box_cols - 1) / box_cols;
   const size_t b_tile = (size_t)prm.bn * 128;
   const size_t fixed = 1024 + 2 * (size_t)prm.out_boxes * TC_BOX_BYTES + 4 * prm.bn * 4 + 512 +
-                       (prm.any_transform ? (size_t)kb * (512 + 16) : 0);
+                       (prm.any_transform ? (size_t)kb * (512 + 16) : 0) + (prm.conv3 ? 2 * TC_SLAB_ROWS * 2 : 0);
   prm.b_resident = (prm.n_tiles == 1 && fixed + (size_t)kb * b_tile + 3 * TC_A_BYTES <= (size_t)TC_SMEM_MAX) ? 1 : 0;
+  if (prm.conv3) prm.b_resident = 1;   // nine tiles of <= 8 KB (checked by the caller)
   const size_t resident = prm.b_resident ? (size_t)kb * b_tile : 0;
-  const size_t stage = TC_A_BYTES + (prm.b_resident ? 0 : b_tile);
+  const size_t stage = prm.conv3 ? (size_t)TC_SLAB_BYTES : TC_A_BYTES + (prm.b_resident ? 0 : b_tile);
   // pipeline depth: as many stages as fit under the cap, at most 8.  The cap (160 KB, whole-step sweep on B200:
   // 227 KB 38.29 ms, 160 KB 37.82 ms, 112 KB 38.44 ms) leaves room for kernels of the other stream lanes on the SM
   size_t cap = (size_t)knob(KNOB_TC_SMEM_KB, 160) * 1024;
@@ -626,6 +774,21 @@ int accx_pw_fwd_tc(int dtype, int out_dtype, int B, int H, int W, int N, const a
   prm.any_shift = 0;
   const int64_t P = (int64_t)B * H * W;
   ACCX_REQUIRE(P < (int64_t)1 << 31, "pw_fwd_tc: too many pixels");
+  // dense 3x3 convolution (the nine taps of ONE tensor, <= 64 channels in and out): halo-slab mode, see TcParams
+  prm.conv3 = 0;
+  for (int a = 0; a < 3; ++a)
+    for (int b = 0; b < 3; ++b) prm.tap_op[a][b] = -1;
+  if (n_ops == 9 && N <= 64 && ops[0].K <= 64 && W >= 2 && knob(KNOB_TC_CONV3, 1) == 1) {
+    bool ok = true;
+    for (int i = 0; i < 9 && ok; ++i) {
+      const accx_operand_t& o = ops[i];
+      ok = o.data == ops[0].data && o.ld == ops[0].ld && o.K == ops[0].K && o.act == ops[0].act &&
+           o.scale == ops[0].scale && o.shift == ops[0].shift && o.dy >= -1 && o.dy <= 1 && o.dx >= -1 && o.dx <= 1 &&
+           prm.tap_op[o.dy + 1][o.dx + 1] < 0;
+      if (ok) prm.tap_op[o.dy + 1][o.dx + 1] = i;
+    }
+    prm.conv3 = ok ? 1 : 0;
+  }
   for (int i = 0; i < n_ops; ++i) {
     prm.op[i] = ops[i];
     ACCX_REQUIRE(ops[i].data && ops[i].w && ops[i].K > 0, "pw_fwd_tc: operand %d malformed", i);
@@ -635,7 +798,8 @@ int accx_pw_fwd_tc(int dtype, int out_dtype, int B, int H, int W, int N, const a
                  "pw_fwd_tc: operand %d scale/shift missing or misaligned", i);
     if (ops[i].dy || ops[i].dx || ops[i].act) prm.any_transform = 1;
     if (ops[i].dy || ops[i].dx) prm.any_shift = 1;
-    ACCX_REQUIRE(encode_2d_bf16(&prm.tmap[i], ops[i].data, ops[i].K, P, ops[i].ld, TC_BM),
+    if (prm.conv3 && i > 0) continue;       // one map: the slab box of the shared tensor
+    ACCX_REQUIRE(encode_2d_bf16(&prm.tmap[i], ops[i].data, ops[i].K, P, ops[i].ld, prm.conv3 ? TC_SLAB_ROWS : TC_BM),
                  "pw_fwd_tc: cuTensorMapEncodeTiled failed for operand %d", i);
   }
   ACCX_REQUIRE(encode_2d_out(&prm.tmap_y, y, N, P, ldy, esz, TC_BM), "pw_fwd_tc: cuTensorMapEncodeTiled failed for the output");
@@ -668,7 +832,8 @@ int accx_pw_fwd_tc(int dtype, int out_dtype, int B, int H, int W, int N, const a
   }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(pw_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX);
+    cudaFuncSetAttribute(pw_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX);
+    cudaFuncSetAttribute(pw_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX);
     attr_set = true;
   }
   const int64_t total = (int64_t)prm.m_tiles * prm.n_tiles;
@@ -676,7 +841,8 @@ int accx_pw_fwd_tc(int dtype, int out_dtype, int B, int H, int W, int N, const a
   if (grid > total) grid = total;
   prm.det = (det_on() && stats) ? 1 : 0;
   if (prm.det) grid = 1;      // each statistic then receives one contribution per epilogue group: a + b is order-free
-  launch_k(pw_fwd_tc_kernel, (unsigned)grid, TC_THREADS, smem, st, prm);
+  if (prm.conv3) launch_k(pw_fwd_tc_kernel<true>, (unsigned)grid, TC_THREADS, smem, st, prm);
+  else launch_k(pw_fwd_tc_kernel<false>, (unsigned)grid, TC_THREADS, smem, st, prm);
   return check_launch("pw_fwd_tc");
 }
 

@@ -100,6 +100,42 @@ def test_tc_dense3x3_nine_shifted_operands(C):
     close(y.float(), ref, RT, AT, "tc conv3x3")
 
 
+@pytest.mark.parametrize("shape", [(2, 9, 12), (3, 16, 28), (1, 1, 7), (2, 5, 2), (1, 40, 40), (2, 23, 3), (16, 56, 56)])
+@pytest.mark.parametrize("C,N,act", [(32, 32, 2), (64, 64, 2), (16, 48, 1), (8, 8, 0), (24, 64, 2)])
+def test_tc_dense3x3_slab_mode(shape, C, N, act):
+    """the halo-slab mode of accx_pw_fwd_tc (one landed slab per filter row, three TMEM accumulators, column masks in
+    the epilogue) against F.conv2d(padding=1) of the activated bf16 input: forward taps with statistics, and the
+    transposed taps of the input gradient; multi-tile maps, several tiles per CTA (16x56x56: 392 tiles), maps narrower than the halo, P not a multiple of 128.
+    Also against the nine-shifted-operand path it replaces (knob 18 = 2)."""
+    from accx import _lib
+    e = E()
+    B, H, W = shape
+    L, a = mk_lazy((B, H, W, C), torch.bfloat16, act, 21)
+    g = torch.Generator().manual_seed(22)
+    w = (torch.randn(N, C, 3, 3, generator=g) / (3 * C ** 0.5)).to(DEV)
+    ops = [e.Op(L, C, e.WV(w, ky * 3 + kx, C * 9, 9), 0, ky - 1, kx - 1) for ky in range(3) for kx in range(3)]
+    stats = torch.zeros(2 * N, device=DEV)
+    y = e.conv(ops, N, (B, H, W), stats=stats)
+    torch.backends.cudnn.allow_tf32 = False
+    ref = F.conv2d(bf(a).permute(0, 3, 1, 2), bf(w), None, padding=1).permute(0, 2, 3, 1)
+    close(y.float(), ref, RT, AT, "slab conv3x3")
+    yb = y.float()
+    close(stats[:N], yb.sum((0, 1, 2)), 1e-3, 1e-3, "slab conv3x3 sum")
+    close(stats[N:], (yb * yb).sum((0, 1, 2)), 1e-3, 1e-3, "slab conv3x3 sum of squares")
+    _lib.call("accx_set_knob", 18, 2)
+    try:
+        y9 = e.conv(ops, N, (B, H, W))
+    finally:
+        _lib.call("accx_set_knob", 18, 0)
+    close(y.float(), y9.float(), 1e-2, 1e-2, "slab vs nine operands")
+    if C == N:           # transposed taps (input gradient of the same conv), fp32 output
+        Ld, d = mk_lazy((B, H, W, N), torch.bfloat16, 0, 23)
+        opsT = [e.Op(Ld, N, e.WV(w, ky * 3 + kx, 9, C * 9), 0, 1 - ky, 1 - kx) for ky in range(3) for kx in range(3)]
+        dx = e.conv(opsT, C, (B, H, W), out_dtype=e.F32)
+        refT = F.conv_transpose2d(bf(d).permute(0, 3, 1, 2), bf(w), None, padding=1).permute(0, 2, 3, 1)
+        close(dx, refT, RT, AT, "slab conv3x3 transposed")
+
+
 def test_tc_large_tile_count_and_k_pipeline():
     """many M tiles, 17 N tiles (N=4352, the cnv72.conv1 shape) and a deep K loop (cnv72.hnc main: K=4352)"""
     e = E()
