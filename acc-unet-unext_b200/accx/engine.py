@@ -360,8 +360,11 @@ def _fill(o: Operand, op: Op, wt: Optional[torch.Tensor] = None):
 
 
 def conv(ops: Sequence[Op], N: int, dims: Tuple[int, int, int], bias=None, adds: Sequence[Tuple[torch.Tensor, int]] = (),
-         stats=None, out_dtype: Optional[int] = None, out: Optional[torch.Tensor] = None, out_coff: int = 0):
-    """accx_pw_fwd.  Returns the raw [B,H,W,N] output (or writes columns [out_coff, out_coff+N) of `out`)."""
+         stats=None, out_dtype: Optional[int] = None, out: Optional[torch.Tensor] = None, out_coff: int = 0,
+         residual: Optional[torch.Tensor] = None):
+    """accx_pw_fwd.  Returns the raw [B,H,W,N] output (or writes columns [out_coff, out_coff+N) of `out`).
+    residual: a [B,H,W,N] tensor in the output dtype added to the result (in the tcgen05 epilogue; otherwise as one
+    more pass); `out` may be the residual itself (accumulation in place)."""
     B, H, W = dims
     arr = (Operand * len(ops))()
     for i, op in enumerate(ops):
@@ -386,23 +389,43 @@ def conv(ops: Sequence[Op], N: int, dims: Tuple[int, int, int], bias=None, adds:
             seen.add(key)
             rd += P * op.K * op.src.y.element_size()
     rd += sum(t.numel() * 4 for t, _ in adds)
+    if residual is not None:
+        assert residual.dtype == out.dtype and tuple(residual.shape) == (B, H, W, N) and residual.is_contiguous()
+        rd += residual.numel() * residual.element_size()
     cost = (rd + P * N * out.element_size(), 2 * P * N * sum(op.K for op in ops))
     yptr = out.data_ptr() + out_coff * out.element_size()
     tc_ok = (TC and in_dt == BF16 and all(o.K % 8 == 0 and o.ld % 8 == 0 and o.data % 16 == 0 for o in arr)
              and yptr % 16 == 0 and (out.shape[-1] * out.element_size()) % 16 == 0       # TMA store of the output
              and not (stats is not None and odt == F32)
              and all(t.data_ptr() % 16 == 0 for t, _ in adds))
+    fuse = (residual is not None and tc_ok and N % 8 == 0 and residual.data_ptr() % 16 == 0)
+    if residual is not None and not fuse:
+        # no fused epilogue on this path: contract into a temporary, then one accx pass adds it
+        assert stats is None and out_coff == 0 and out.shape[-1] == N
+        tmp = conv(ops, N, dims, bias=bias, adds=adds, out_dtype=odt)
+        if residual.data_ptr() == out.data_ptr():
+            return add_inplace(out, tmp)
+        return _add_into(out, tmp, residual)
     if tc_ok:
         ws_bytes = _lib.load().accx_pw_tc_workspace_bytes(N, arr, len(ops))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=out.device)
         LAUNCHES_EXTRA[0] += 1          # the weight re-pack kernel
-        _call("accx_pw_fwd_tc", in_dt, odt, B, H, W, N, arr, len(ops), ptr(bias), ap, al, len(adds),
-              yptr, out.shape[-1], ptr(stats), ptr(ws), ws_bytes, stream(), cost=cost,
-              tag=f"P={P} N={N} K={[o.K for o in ops]} shift={any(o.dy or o.dx for o in ops)} adds={len(adds)}")
+        _call("accx_pw_fwd_tc_res", in_dt, odt, B, H, W, N, arr, len(ops), ptr(bias), ap, al, len(adds),
+              ptr(residual) if fuse else 0, N, yptr, out.shape[-1], ptr(stats), ptr(ws), ws_bytes, stream(), cost=cost,
+              tag=f"P={P} N={N} K={[o.K for o in ops]} shift={any(o.dy or o.dx for o in ops)} adds={len(adds)}"
+                  + (" res" if fuse else ""))
     else:
         _call("accx_pw_fwd", in_dt, odt, B, H, W, N, arr, len(ops), ptr(bias), ap, al, len(adds),
               yptr, out.shape[-1], ptr(stats), stream(), cost=cost,
               tag=f"P={P} N={N} K={[o.K for o in ops]} in={in_dt} out={odt}")
+    return out
+
+
+def _add_into(out: torch.Tensor, a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """out = a + b (one accx pass; `out` may be `a`)"""
+    C = out.shape[-1]
+    _call("accx_act_apply", dt(a), a.numel() // C, C, ptr(a), 0, 0, 0, 0, 0, ptr(b), ptr(out), 0, stream(),
+          cost=(3 * nb(out), 0))
     return out
 
 

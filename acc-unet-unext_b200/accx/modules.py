@@ -549,8 +549,7 @@ class HANCBlock(_AccxModule):
             E.wgrad(Op(X, C, WV(w1, 0, C, 1)), dy1, Ex, dims, g1)
         dx = None
         if in_need[0]:
-            dx = E.conv([Op(Lazy(dy1), Ex, WV(w1, 0, 1, C))], C, dims)
-            E.add_inplace(dx, dz)
+            dx = E.conv([Op(Lazy(dy1), Ex, WV(w1, 0, 1, C))], C, dims, residual=dz)      # + the skip branch, in the epilogue
         return [dx], grads
 
 
@@ -629,8 +628,7 @@ class ResPath(_AccxModule):
             if gw is not None:
                 E.wgrad_conv3x3(X, C, w, dy, C, dims, gw)
             if i > 0 or in_need[0]:
-                dxi = E.conv(self._taps(Lazy(dy), w, C, transpose=True), C, dims)
-                dx = E.add_inplace(dxi, dx)
+                dx = E.conv(self._taps(Lazy(dy), w, C, transpose=True), C, dims, residual=dx)
         return [dx if in_need[0] else None], grads
 
 
@@ -757,6 +755,13 @@ class MLFC(_AccxModule):
         def acc(l, g):
             dxs[l] = g if dxs[l] is None else E.add_inplace(dxs[l], g)
 
+        def acc_conv(l, ops, N, dims_, **kw):
+            """dxs[l] += contraction: accumulated in the contraction's own epilogue (in place)"""
+            if dxs[l] is None:
+                dxs[l] = E.conv(ops, N, dims_, **kw)
+            else:
+                E.conv(ops, N, dims_, out=dxs[l], residual=dxs[l])
+
         # phase A: the four level chains are independent (lane l only touches dxs[l]) -> parallel lanes
         dys_blk = [None] * 4
         ars = [ar] + [Arena(douts[0].device) for _ in range(3)]
@@ -781,7 +786,7 @@ class MLFC(_AccxModule):
                     if gw is not None:
                         E.wgrad(Op(Lc[l], C, WV(wm, 0, 2 * C, 2)), dy, C, dims[l], gw)
                         E.wgrad(Op(Lazy(xs[l]), C, WV(wm, 1, 2 * C, 2)), dy, C, dims[l], gw)
-                    acc(l, E.conv([Op(Lazy(dy), C, WV(wm, 1, 2, 2 * C))], C, dims[l]))       # d wrt x (odd K)
+                    acc_conv(l, [Op(Lazy(dy), C, WV(wm, 1, 2, 2 * C))], C, dims[l])          # d wrt x (odd K)
                     dac = E.conv([Op(Lazy(dy), C, WV(wm, 0, 2, 2 * C))], C, dims[l])         # d wrt x_c (even K)
                     dtc = E.bn_bwd(Lc[l], dac, grads, arl)                                    # bns
                     cb = getattr(self, f"cnv_blks{l + 1}")[i]
@@ -804,20 +809,19 @@ class MLFC(_AccxModule):
                             A = Lazy(pooled[(src, l)] if src < l else xs[l])
                             if gw is not None:
                                 E.wgrad(Op(A, Cs, wv), dy, C, dims[l], gw)
-                            g = E.conv([Op(Lazy(dy), C, wvt)], Cs, dims[l])
                             if src == l:
-                                acc(l, g)
-                            else:     # gradient of the average pool: broadcast / s^2
-                                first = dxs[src] is None
-                                if first:
-                                    dxs[src] = torch.empty_like(xs[src])
-                                E.upsample_add(g, dxs[src], l - src, 1.0 / float(4 ** (l - src)), accumulate=not first)
+                                acc_conv(l, [Op(Lazy(dy), C, wvt)], Cs, dims[l])
+                                continue
+                            g = E.conv([Op(Lazy(dy), C, wvt)], Cs, dims[l])
+                            first = dxs[src] is None           # gradient of the average pool: broadcast / s^2
+                            if first:
+                                dxs[src] = torch.empty_like(xs[src])
+                            E.upsample_add(g, dxs[src], l - src, 1.0 / float(4 ** (l - src)), accumulate=not first)
                         else:         # coarser source, contracted at its own resolution: block-sum dY first
                             dR = E.pool_sum(dy, src - l, 1.0)
                             if gw is not None:
                                 E.wgrad(Op(Lazy(xs[src]), Cs, wv), dR, C, dims[src], gw)
-                            g = E.conv([Op(Lazy(dR), C, wvt)], Cs, dims[src], out_dtype=E.dt(xs[src]))
-                            acc(src, g)
+                            acc_conv(src, [Op(Lazy(dR), C, wvt)], Cs, dims[src], out_dtype=E.dt(xs[src]))
         return dxs, grads
 
     @staticmethod

@@ -99,9 +99,8 @@ class _ShiftMlpFn(torch.autograd.Function):
         y1 = E.conv(_shift_ops(L0, w1, C, mlp.pad, True, mlp.shift_size), hidden, dims, bias=E.f32(mlp.fc1.bias))
         y2 = E.dw_fwd(Lazy(y1), wd, E.f32(mlp.dwconv.dwconv.bias), None)
         a = E.gelu(y2)
-        y3 = E.conv(_shift_ops(Lazy(a), w2, hidden, mlp.pad, False, mlp.shift_size), Cout, dims, bias=E.f32(mlp.fc2.bias))
-        if residual:
-            E.add_inplace(y3, xn)
+        y3 = E.conv(_shift_ops(Lazy(a), w2, hidden, mlp.pad, False, mlp.shift_size), Cout, dims, bias=E.f32(mlp.fc2.bias),
+                    residual=xn if residual else None)
         ctx.saved = (xn, y0, mean, rstd, y1, y2, a)
         ctx.mods = (mlp, norm, residual, dims)
         ctx.params = params

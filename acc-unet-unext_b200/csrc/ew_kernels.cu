@@ -267,7 +267,25 @@ __global__ void pool_sum_kernel(int B, int H, int W, int C, int log2s, float mul
     float acc[VEC];
 #pragma unroll
     for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
-    if constexpr (S > 0) {      // compile-time window: all S*S loads in flight before the first add
+    if constexpr (S == 8) {     // 8 x 8 window: one window row (8 loads) in flight at a time, two rows per step
+#pragma unroll 1
+      for (int i = 0; i < 8; i += 2) {
+        RawVec<TI, VEC> rx[16];
+        const TI* row = x + (((int64_t)b * H + (ho * 8 + i)) * W + (int64_t)wo * 8) * C + c0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          rx[j].load(row + (int64_t)j * C);
+          rx[8 + j].load(row + ((int64_t)W + j) * C);
+        }
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          float v[VEC];
+          rx[k].unpack(v);
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) acc[e] += v[e];
+        }
+      }
+    } else if constexpr (S > 0) {      // compile-time window: all S*S loads in flight before the first add
       RawVec<TI, VEC> rx[S * S];
 #pragma unroll
       for (int i = 0; i < S; ++i) {
@@ -377,7 +395,8 @@ static int launch_pool_sum(int B, int H, int W, int C, int log2s, float mul, con
   constexpr bool same = sizeof(TI) == sizeof(TO);
   const bool al = same && aligned16(x) && aligned16(out) && out_ld % 8 == 0 && C % 8 == 0;
   Lanes l = make_lanes(C, DT<TI>::VEC, al);
-  dim3 block(l.tx, l.ty), grid(grid_x_for(Po, l.ty * 4, 148 * 8), l.gy);
+  // large windows: few output pixels, many loads per pixel -> one output pixel per thread
+  dim3 block(l.tx, l.ty), grid(grid_x_for(Po, l.ty * (log2s >= 3 ? 1 : 4), 148 * 8), l.gy);
   if constexpr (same) {
     if (l.vec != 1) {
       constexpr int V = DT<TI>::VEC;
@@ -385,6 +404,8 @@ static int launch_pool_sum(int B, int H, int W, int C, int log2s, float mul, con
         launch_k(pool_sum_kernel<TI, TO, V, 2>, grid, block, 0, st, B, H, W, C, log2s, mul, (const TI*)x, (TO*)out, out_ld);
       else if (log2s == 2)
         launch_k(pool_sum_kernel<TI, TO, V, 4>, grid, block, 0, st, B, H, W, C, log2s, mul, (const TI*)x, (TO*)out, out_ld);
+      else if (log2s == 3)
+        launch_k(pool_sum_kernel<TI, TO, V, 8>, grid, block, 0, st, B, H, W, C, log2s, mul, (const TI*)x, (TO*)out, out_ld);
       else
         launch_k(pool_sum_kernel<TI, TO, V, 0>, grid, block, 0, st, B, H, W, C, log2s, mul, (const TI*)x, (TO*)out, out_ld);
       return check_launch("pool_sum");

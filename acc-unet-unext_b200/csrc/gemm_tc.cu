@@ -49,6 +49,8 @@ struct alignas(64) TcParams {
   int add_log2s[ACCX_MAX_ADDENDS];
   int n_add;
   float* stats;
+  const void* res;      // residual in the output dtype, added in the epilogue (may alias the output)
+  int64_t ld_res;
   int det;      // deterministic mode (common.cuh): ONE CTA walks all tiles, shared-memory statistics added in row order
   // dense 3x3 convolution as ONE halo slab per filter row (ResPath, ACC_UNet.py:316-318): the nine operands are the
   // nine taps of one tensor; per tile three slabs of TC_SLAB_ROWS pixels (rows m0 + dy*W - 1 ..) are landed and
@@ -616,6 +618,40 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_fwd_tc_kernel(const __grid_c
               }
             }
           }
+          if (prm.res != nullptr && rvalid) {
+            if (prm.out_f32) {
+              const float* rp = reinterpret_cast<const float*>(prm.res) + p * prm.ld_res + n0 + c0;
+              if (n0 + c0 + 16 <= N) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const float4 a4 = *reinterpret_cast<const float4*>(rp + 4 * q);
+                  v[4 * q] += a4.x; v[4 * q + 1] += a4.y; v[4 * q + 2] += a4.z; v[4 * q + 3] += a4.w;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                  if (n0 + c0 + j < N) v[j] += rp[j];
+              }
+            } else {
+              const bf16* rp = reinterpret_cast<const bf16*>(prm.res) + p * prm.ld_res + n0 + c0;
+              if (n0 + c0 + 16 <= N) {
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                  const uint4 a4 = *reinterpret_cast<const uint4*>(rp + 8 * q);
+                  const uint32_t w4[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    v[8 * q + 2 * e] += __uint_as_float(w4[e] << 16);
+                    v[8 * q + 2 * e + 1] += __uint_as_float(w4[e] & 0xffff0000u);
+                  }
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                  if (n0 + c0 + j < N) v[j] += __bfloat162float(rp[j]);
+              }
+            }
+          }
           if (prm.out_f32) stage_chunk<true>(v, stage, row, c0);
           else stage_chunk<false>(v, stage, row, c0);
         }
@@ -754,9 +790,10 @@ int64_t accx_pw_tc_workspace_bytes(int N, const accx_operand_t* ops, int n_ops) 
   return kb * TC_BK * 2 * n_pad;
 }
 
-int accx_pw_fwd_tc(int dtype, int out_dtype, int B, int H, int W, int N, const accx_operand_t* ops, int n_ops,
-                   const float* bias, const float* const* add, const int* add_log2s, int n_add, void* y, int64_t ldy,
-                   float* stats, void* workspace, int64_t workspace_bytes, void* stream) {
+int accx_pw_fwd_tc_res(int dtype, int out_dtype, int B, int H, int W, int N, const accx_operand_t* ops, int n_ops,
+                       const float* bias, const float* const* add, const int* add_log2s, int n_add, const void* residual,
+                       int64_t ld_res, void* y, int64_t ldy, float* stats, void* workspace, int64_t workspace_bytes,
+                       void* stream) {
   ACCX_REQUIRE(B > 0 && H > 0 && W > 0 && N > 0 && ops && y && workspace, "pw_fwd_tc: bad arguments");
   ACCX_REQUIRE(n_ops >= 1 && n_ops <= ACCX_MAX_OPERANDS, "pw_fwd_tc: n_ops %d out of range", n_ops);
   ACCX_REQUIRE(n_add >= 0 && n_add <= ACCX_MAX_ADDENDS, "pw_fwd_tc: n_add %d out of range", n_add);
@@ -824,6 +861,10 @@ int accx_pw_fwd_tc(int dtype, int out_dtype, int B, int H, int W, int N, const a
     ACCX_REQUIRE(aligned16(add[i]) || (N & 3) != 0, "pw_fwd_tc: addend %d must be 16-byte aligned", i);
   }
   prm.stats = stats;
+  prm.res = residual;
+  prm.ld_res = ld_res;
+  ACCX_REQUIRE(!residual || (aligned16(residual) && (ld_res * esz) % 16 == 0 && ld_res >= N && N % 8 == 0),
+               "pw_fwd_tc: residual needs a 16-byte aligned base and row pitch, ld_res >= N, N %% 8 == 0");
   cudaStream_t st = (cudaStream_t)stream;
   if (!prm.b_resident) {     // streamed weight tiles come from a bf16 re-pack in the workspace
     launch_k(tc_pack_weights_kernel, dim3(prm.n_kb, n_tiles, (prm.bn * TC_BK + 1023) / 1024), 256, 0, st, prm, (bf16*)workspace);
@@ -844,6 +885,13 @@ int accx_pw_fwd_tc(int dtype, int out_dtype, int B, int H, int W, int N, const a
   if (prm.conv3) launch_k(pw_fwd_tc_kernel<true>, (unsigned)grid, TC_THREADS, smem, st, prm);
   else launch_k(pw_fwd_tc_kernel<false>, (unsigned)grid, TC_THREADS, smem, st, prm);
   return check_launch("pw_fwd_tc");
+}
+
+int accx_pw_fwd_tc(int dtype, int out_dtype, int B, int H, int W, int N, const accx_operand_t* ops, int n_ops,
+                   const float* bias, const float* const* add, const int* add_log2s, int n_add, void* y, int64_t ldy,
+                   float* stats, void* workspace, int64_t workspace_bytes, void* stream) {
+  return accx_pw_fwd_tc_res(dtype, out_dtype, B, H, W, N, ops, n_ops, bias, add, add_log2s, n_add, nullptr, 0, y, ldy, stats,
+                            workspace, workspace_bytes, stream);
 }
 
 }  // extern "C"

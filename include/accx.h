@@ -98,6 +98,14 @@ int accx_pw_fwd_tc(int dtype, int out_dtype, int B, int H, int W, int N,
                    const accx_operand_t* ops, int n_ops, const float* bias,
                    const float* const* add, const int* add_log2s, int n_add,
                    void* y, int64_t ldy, float* stats, void* workspace, int64_t workspace_bytes, void* stream);
+/* accx_pw_fwd_tc with a residual: Y = contraction (+ bias + addends) + R, R a [P, ld_res] matrix in the OUTPUT dtype
+ * (16-byte aligned base and row pitch).  R may be Y itself (in-place accumulation: every tile is read before it is
+ * written).  Fuses the `x + inp` / gradient-accumulation passes that follow an input-gradient contraction
+ * (HANCBlock backward ACC_UNet.py:279, ResPath backward :325-326, MLFC's per-level sums :431-485). */
+int accx_pw_fwd_tc_res(int dtype, int out_dtype, int B, int H, int W, int N,
+                       const accx_operand_t* ops, int n_ops, const float* bias,
+                       const float* const* add, const int* add_log2s, int n_add, const void* residual, int64_t ld_res,
+                       void* y, int64_t ldy, float* stats, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* dW[n*w_ld + k*w_ks] += sum_p dY[p, n] * value(p, k)  for one operand (weight gradient of the
  * contraction above; fp32 atomics).  dy is a plain [P, ldy] matrix in `dtype` storage

@@ -136,6 +136,30 @@ def test_tc_dense3x3_slab_mode(shape, C, N, act):
         close(dx, refT, RT, AT, "slab conv3x3 transposed")
 
 
+@pytest.mark.parametrize("K,N", [(32, 32), (96, 40), (64, 272), (128, 4352)])
+@pytest.mark.parametrize("f32_out", [False, True])
+def test_tc_residual_in_epilogue(K, N, f32_out):
+    """accx_pw_fwd_tc_res: Y = A.W^T + R with R in the output dtype, added before the output is rounded; out-of-place
+    and in place (R is Y); several column tiles (N = 272, 4352) and a ragged last chunk (N = 40)"""
+    e = E()
+    B, H, W = 2, 12, 20
+    L, a = mk_lazy((B, H, W, K), torch.bfloat16, 2, 31)
+    g = torch.Generator().manual_seed(32)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV)
+    odt = torch.float32 if f32_out else torch.bfloat16
+    r = torch.randn(B, H, W, N, generator=g).to(DEV).to(odt)
+    ops = [e.Op(L, K, e.WV(w, 0, K, 1))]
+    l0 = e.LAUNCHES
+    y = e.conv(ops, N, (B, H, W), out_dtype=e.F32 if f32_out else None, residual=r)
+    assert e.LAUNCHES - l0 == 1, "the residual was not fused into the contraction"
+    ref = bf(a) @ bf(w).t() + r.float()
+    close(y.float(), ref, RT, AT, "residual")
+    y2 = r.clone()
+    e.conv(ops, N, (B, H, W), out=y2, residual=y2)
+    close(y2.float(), ref, RT, AT, "residual in place")
+    assert torch.equal(y2, y)
+
+
 def test_tc_large_tile_count_and_k_pipeline():
     """many M tiles, 17 N tiles (N=4352, the cnv72.conv1 shape) and a deep K loop (cnv72.hnc main: K=4352)"""
     e = E()
