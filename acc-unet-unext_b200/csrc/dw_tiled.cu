@@ -45,6 +45,10 @@ struct alignas(64) DwParams {
   const float* bn_rstd;
   int bn_act;
   int det;                      // deterministic mode: one CTA per channel chunk (see common.cuh)
+  // channel chunks narrower than a 128-byte line (C = 96 in bf16: 64-byte segments): CTA i owns chunk i % n_chunks and the
+  // CTAs of the n_chunks chunks walk the spatial tiles in step, so that the lines a chunk's box touches are still in L2
+  // when its neighbours fetch theirs (chunk-major order re-fetched every line once per chunk: 2x DRAM reads, ncu)
+  int interleave;
 };
 
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
@@ -90,11 +94,10 @@ __device__ __forceinline__ void lds4(uint32_t addr, f32x2& p0, f32x2& p1) {
 }
 
 // in-place activation of the landed halo tile; 16-byte vectors, thread t owns vector slots t, t+256, ..
-template <typename T>
-__device__ __forceinline__ void dw_activate_tile(const DwParams& prm, uint32_t tile, int n_pos, int halo_w, int h0,
-                                                 int w0, int c0) {
+template <typename T, int CC, int halo_w>
+__device__ __forceinline__ void dw_activate_tile(const DwParams& prm, uint32_t tile, int n_pos, int h0, int w0, int c0) {
   constexpr int EPV = 16 / sizeof(T);                 // elements per 16-byte vector
-  const int vpp = prm.CC / EPV;                       // vectors per pixel (divides 256)
+  constexpr int vpp = CC / EPV;                       // vectors per pixel (divides 256)
   const int sub = threadIdx.x % vpp;
   const int c = c0 + sub * EPV;
   float s[EPV], t[EPV];
@@ -105,15 +108,16 @@ __device__ __forceinline__ void dw_activate_tile(const DwParams& prm, uint32_t t
 #pragma unroll
     for (int e = 0; e < EPV; ++e) { s[e] = 0.f; t[e] = 0.f; }
   }
-  const int step = DW_THREADS / vpp;
+  constexpr int step = DW_THREADS / vpp;
   const bool lre = prm.act == 2;
+  const int H = prm.H, W = prm.W;
   int pos = threadIdx.x / vpp;
   int hy = pos / halo_w, hx = pos - hy * halo_w;          // advanced incrementally: no division in the loop
   for (; pos < n_pos; pos += step, hx += step) {
     while (hx >= halo_w) { hx -= halo_w; ++hy; }
     const int h = h0 - 1 + hy, w = w0 - 1 + hx;
-    const bool inside = h >= 0 && h < prm.H && w >= 0 && w < prm.W;
-    const uint32_t addr = tile + (uint32_t)(pos * prm.CC + sub * EPV) * sizeof(T);
+    const bool inside = h >= 0 && h < H && w >= 0 && w < W;
+    const uint32_t addr = tile + (uint32_t)(pos * CC + sub * EPV) * sizeof(T);
     uint32_t u[4];
     if (!inside) {
       u[0] = u[1] = u[2] = u[3] = 0u;
@@ -144,10 +148,10 @@ __device__ __forceinline__ void dw_activate_tile(const DwParams& prm, uint32_t t
 
 // block reduction over the tile columns of NV per-thread values (4 channels each), then one atomicAdd per
 // (value, channel): out[(c) * c_stride + v * v_stride].  `red` holds DW_THREADS floats.
-template <int NV>
+template <int NV, int TW>
 __device__ __forceinline__ void dw_flush(const DwParams& prm, float (&acc)[NV][4], float* red, int cl, int col, int c0,
                                          float* out, int c_stride, int v_stride) {
-  const int lanes_c = prm.lanes_c, TW = prm.TW;
+  constexpr int lanes_c = 256 / TW;
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
 #pragma unroll
@@ -167,18 +171,22 @@ __device__ __forceinline__ void dw_flush(const DwParams& prm, float (&acc)[NV][4
 }
 
 // MODE 0: forward / input gradient (flip);  1: weight gradient;  2: input gradient + BN-backward reduction
-template <typename T, int TH, int MODE>
+// (tile width TW -- hence CC = 1024 / TW channels per tile -- is a template parameter: every shared-memory offset of
+//  the unrolled row loop is then an immediate; with run-time pitches the kernel spent a third of its issue slots on
+//  integer address arithmetic, ncu profiles/r02_dw_fwd_4352_before.txt)
+template <typename T, int TH, int MODE, int TW>
 __global__ void __launch_bounds__(DW_THREADS, 2) dw3x3_tiled_kernel(const __grid_constant__ DwParams prm) {
   pdl_sync();
   constexpr bool WGRAD = MODE == 1, BOX2 = MODE != 0;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
-  const int TW = prm.TW, CC = prm.CC, lanes_c = prm.lanes_c;
-  const int halo_w = TW + 2, n_pos = (TH + 2) * halo_w;
-  const uint32_t x_bytes = (uint32_t)n_pos * CC * sizeof(T);
-  const uint32_t x_bytes_al = (x_bytes + 127u) & ~127u;
-  const uint32_t g_bytes = BOX2 ? (uint32_t)TH * TW * CC * sizeof(T) : 0u;      // multiple of 128
-  const uint32_t stage_bytes = x_bytes_al + g_bytes;
+  constexpr int CC = 1024 / TW, lanes_c = CC / 4;
+  constexpr int halo_w = TW + 2, n_pos = (TH + 2) * halo_w;
+  constexpr uint32_t x_bytes = (uint32_t)n_pos * CC * sizeof(T);
+  constexpr uint32_t x_bytes_al = (x_bytes + 127u) & ~127u;
+  constexpr uint32_t g_bytes = BOX2 ? (uint32_t)TH * TW * CC * sizeof(T) : 0u;      // multiple of 128
+  constexpr uint32_t stage_bytes = x_bytes_al + g_bytes;
+  const int H = prm.H, W = prm.W, C = prm.C;
   const uint32_t bar0 = base + 2 * stage_bytes;                                 // two mbarriers
   float* red = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw)) + 2 * stage_bytes + 16);
   const int tid = threadIdx.x;
@@ -215,6 +223,12 @@ __global__ void __launch_bounds__(DW_THREADS, 2) dw3x3_tiled_kernel(const __grid
   // each (channel, statistic) receives exactly one flush, accumulated in tile order
   int64_t tile0 = blockIdx.x, tile_end = total, tstep = gridDim.x;
   if (prm.det) { tile0 = (int64_t)blockIdx.x * prm.n_spatial; tile_end = tile0 + prm.n_spatial; tstep = 1; }
+  else if (prm.interleave) {
+    const int my_chunk = blockIdx.x % prm.n_chunks;
+    tile0 = (int64_t)my_chunk * prm.n_spatial + blockIdx.x / prm.n_chunks;
+    tile_end = (int64_t)(my_chunk + 1) * prm.n_spatial;
+    tstep = gridDim.x / prm.n_chunks;
+  }
   if (tid == 0 && tile0 < tile_end) issue(tile0, 0);
 
   // per-thread state that lives across tiles of one channel chunk
@@ -249,14 +263,14 @@ __global__ void __launch_bounds__(DW_THREADS, 2) dw3x3_tiled_kernel(const __grid
 #pragma unroll
           for (int i = 0; i < 4; ++i) acc_st[1][i] *= bn_rs[i];
         }
-        if (WGRAD) dw_flush<9>(prm, acc_w, red, cl, col, cur_chunk * CC, prm.dw, 9, 1);
-        else if (prm.stats) dw_flush<2>(prm, acc_st, red, cl, col, cur_chunk * CC, prm.stats, 1, prm.C);
+        if (WGRAD) dw_flush<9, TW>(prm, acc_w, red, cl, col, cur_chunk * CC, prm.dw, 9, 1);
+        else if (prm.stats) dw_flush<2, TW>(prm, acc_st, red, cl, col, cur_chunk * CC, prm.stats, 1, prm.C);
       }
       cur_chunk = chunk;
       if (MODE == 2) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const bool ok = c + i < prm.C;
+          const bool ok = c + i < C;
           bn_s[i] = (ok && prm.bn_act != 0) ? __ldg(prm.bn_scale + c + i) : 1.f;
           bn_t[i] = (ok && prm.bn_act != 0) ? __ldg(prm.bn_shift + c + i) : 0.f;
           bn_mu[i] = ok ? __ldg(prm.bn_mean + c + i) : 0.f;
@@ -269,8 +283,8 @@ __global__ void __launch_bounds__(DW_THREADS, 2) dw3x3_tiled_kernel(const __grid
         for (int i = 0; i < 4; ++i) {
 #pragma unroll
           for (int t = 0; t < 9; ++t)
-            wf[i][t] = (c + i < prm.C) ? __ldg(prm.w + (int64_t)(c + i) * 9 + (prm.flip ? 8 - t : t)) : 0.f;
-          bs[i] = (prm.bias != nullptr && c + i < prm.C) ? __ldg(prm.bias + c + i) : 0.f;
+            wf[i][t] = (c + i < C) ? __ldg(prm.w + (int64_t)(c + i) * 9 + (prm.flip ? 8 - t : t)) : 0.f;
+          bs[i] = (prm.bias != nullptr && c + i < C) ? __ldg(prm.bias + c + i) : 0.f;
         }
 #pragma unroll
         for (int t = 0; t < 9; ++t) {
@@ -282,15 +296,17 @@ __global__ void __launch_bounds__(DW_THREADS, 2) dw3x3_tiled_kernel(const __grid
     const uint32_t xt = base + stage * stage_bytes;
     mbar_wait(bar0 + 8 * stage, (it >> 1) & 1);
     if (prm.act != 0) {
-      dw_activate_tile<T>(prm, xt, n_pos, halo_w, h0, w0, c0);
+      dw_activate_tile<T, CC, halo_w>(prm, xt, n_pos, h0, w0, c0);
       __syncthreads();
     }
     // ---- sliding window down the tile column: halo row r feeds output rows r-2, r-1, r (tile-local) ----
     const uint32_t colb = xt + (uint32_t)(col * CC + cl * 4) * sizeof(T);
-    const uint32_t row_pitch = (uint32_t)halo_w * CC * sizeof(T), px_pitch = (uint32_t)CC * sizeof(T);
-    const bool col_ok = (w0 + col < prm.W) && (c < prm.C);
+    constexpr uint32_t row_pitch = (uint32_t)halo_w * CC * sizeof(T), px_pitch = (uint32_t)CC * sizeof(T);
+    const bool col_ok = (w0 + col < W) && (c < C);
     if (!WGRAD) {
       const f32x2 b01 = pack2(bs[0], bs[1]), b23 = pack2(bs[2], bs[3]);
+      T* const dst0 = (T*)prm.y + ((((int64_t)b * H + h0) * W + (w0 + col)) * C + c);    // output row h0 of this column
+      const int64_t dst_pitch = (int64_t)W * C;
       f32x2 o[3][2] = {{b01, b23}, {b01, b23}, {b01, b23}};     // o[k]: output row (r - k) under construction
 #pragma unroll
       for (int r = 0; r < TH + 2; ++r) {
@@ -315,7 +331,7 @@ __global__ void __launch_bounds__(DW_THREADS, 2) dw3x3_tiled_kernel(const __grid
           float v[4];
           unpack2(o[2][0], v[0], v[1]);
           unpack2(o[2][1], v[2], v[3]);
-          if (col_ok && h < prm.H) {
+          if (col_ok && h < H) {
             if constexpr (MODE == 2) {
               f32x2 y01, y23;
               lds4<T>(xt + x_bytes_al + (uint32_t)(((r - 2) * TW + col) * CC + cl * 4) * sizeof(T), y01, y23);
@@ -336,14 +352,13 @@ __global__ void __launch_bounds__(DW_THREADS, 2) dw3x3_tiled_kernel(const __grid
                 acc_st[1][i] = fmaf(v[i], v[i], acc_st[1][i]);
               }
             }
-            T* dst = (T*)prm.y + ((((int64_t)b * prm.H + h) * prm.W + (w0 + col)) * prm.C + c);
-            stv<T, 4>(dst, v);
+            stv<T, 4>(dst0 + (int64_t)(r - 2) * dst_pitch, v);
           }
         }
       }
     } else {
       const uint32_t gb = xt + x_bytes_al + (uint32_t)(col * CC + cl * 4) * sizeof(T);
-      const uint32_t g_row_pitch = (uint32_t)TW * CC * sizeof(T);
+      constexpr uint32_t g_row_pitch = (uint32_t)TW * CC * sizeof(T);
       f32x2 aw[9][2];
 #pragma unroll
       for (int t = 0; t < 9; ++t) aw[t][0] = aw[t][1] = pack2(0.f, 0.f);
@@ -382,8 +397,8 @@ __global__ void __launch_bounds__(DW_THREADS, 2) dw3x3_tiled_kernel(const __grid
 #pragma unroll
       for (int i = 0; i < 4; ++i) acc_st[1][i] *= bn_rs[i];
     }
-    if (WGRAD) dw_flush<9>(prm, acc_w, red, cl, col, cur_chunk * CC, prm.dw, 9, 1);
-    else if (prm.stats) dw_flush<2>(prm, acc_st, red, cl, col, cur_chunk * CC, prm.stats, 1, prm.C);
+    if (WGRAD) dw_flush<9, TW>(prm, acc_w, red, cl, col, cur_chunk * CC, prm.dw, 9, 1);
+    else if (prm.stats) dw_flush<2, TW>(prm, acc_st, red, cl, col, cur_chunk * CC, prm.stats, 1, prm.C);
   }
 }
 
@@ -418,11 +433,21 @@ static void dw_geometry(int B, int H, int W, int C, int TH, DwParams& prm) {
   prm.n_spatial = (int64_t)B * prm.tiles_h * prm.tiles_w;
 }
 
+template <typename T, int TH, int MODE, int TW>
+static int dw_launch_tw(DwParams& prm, const void* x, const void* dy, cudaStream_t st);
+
 template <typename T, int TH, int MODE>
 static int dw_launch(DwParams& prm, const void* x, const void* dy, cudaStream_t st) {
+  dw_geometry(prm.B, prm.H, prm.W, prm.C, TH, prm);
+  if (prm.TW == 32) return dw_launch_tw<T, TH, MODE, 32>(prm, x, dy, st);
+  if (prm.TW == 16) return dw_launch_tw<T, TH, MODE, 16>(prm, x, dy, st);
+  return dw_launch_tw<T, TH, MODE, 8>(prm, x, dy, st);
+}
+
+template <typename T, int TH, int MODE, int TW>
+static int dw_launch_tw(DwParams& prm, const void* x, const void* dy, cudaStream_t st) {
   constexpr bool BOX2 = MODE != 0;
   const int esz = sizeof(T);
-  dw_geometry(prm.B, prm.H, prm.W, prm.C, TH, prm);
   if (!encode_4d(&prm.map_x, x, esz, prm.B, prm.H, prm.W, prm.C, prm.CC, prm.TW + 2, TH + 2)) {
     set_error("dw3x3: cuTensorMapEncodeTiled failed for the input");
     return ACCX_ERR_CUDA;
@@ -434,7 +459,7 @@ static int dw_launch(DwParams& prm, const void* x, const void* dy, cudaStream_t 
   const size_t x_bytes = ((size_t)(TH + 2) * (prm.TW + 2) * prm.CC * esz + 127) & ~(size_t)127;
   const size_t g_bytes = BOX2 ? (size_t)TH * prm.TW * prm.CC * esz : 0;
   const size_t smem = 128 + 2 * (x_bytes + g_bytes) + 16 + DW_THREADS * sizeof(float);
-  auto kern = dw3x3_tiled_kernel<T, TH, MODE>;
+  auto kern = dw3x3_tiled_kernel<T, TH, MODE, TW>;
   static bool attr_set = false;       // one flag per template instantiation
   if (!attr_set) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -444,7 +469,12 @@ static int dw_launch(DwParams& prm, const void* x, const void* dy, cudaStream_t 
   int64_t grid = 2 * (int64_t)sm_count();
   if (grid > total) grid = total;
   prm.det = det_on() ? 1 : 0;
+  prm.interleave = 0;
   if (prm.det) grid = prm.n_chunks;
+  else if (prm.CC * esz < 128 && prm.n_chunks > 1 && prm.n_chunks <= grid) {
+    prm.interleave = 1;
+    grid = grid / prm.n_chunks * prm.n_chunks;
+  }
   launch_k(kern, (unsigned)grid, DW_THREADS, smem, st, prm);
   return ACCX_OK;
 }
