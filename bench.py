@@ -146,7 +146,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="accx", choices=["accx", "reference"])
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--batch", type=int, default=PER_GPU_BATCH)
+    ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="images per GPU (weak scaling)")
+    ap.add_argument("--global-batch", type=int, default=0,
+                    help="fixed total batch split over the GPUs (strong scaling; BASELINE configs[4]: 64 at --hw 512)")
     ap.add_argument("--variant", default="base", choices=["base", "w", "lite"],
                     help="ACC_UNet / ACC_UNet_W / ACC_UNet_Lite (BASELINE configs[3]; the headline is base)")
     ap.add_argument("--hw", type=int, default=HW, help="image side (BASELINE configs[4] uses 512)")
@@ -190,6 +192,9 @@ def main():
     W = max(args.warmup, 3)
     K = args.steps
     B = args.batch
+    if args.global_batch:
+        assert args.global_batch % world == 0, "--global-batch must be a multiple of the number of GPUs"
+        B = args.global_batch // world
     cd = torch.bfloat16 if args.dtype == "bf16" else torch.float32
 
     torch.manual_seed(2)                                   # same weights on every rank
@@ -375,8 +380,10 @@ def main():
 
     if rank == 0:
         out = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "metric": METRIC if hw == HW else f"ACC-UNet train images/sec @{hw}^2", "value": value, "unit": UNIT,
+            "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong" if args.global_batch else "weak",
+            "vs_baseline": None,
             "dtype": args.dtype if args.dtype == "bf16" else "f32", "data": "synthetic",
             "config": {"workload": f"{cls.__name__}(3,1,32) full train step (fwd + Dice/BCE + bwd + Adam), "
                                    f"{B}x3x{hw}x{hw} per GPU, GlaS-shaped synthetic",
