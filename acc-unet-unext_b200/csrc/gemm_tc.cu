@@ -58,6 +58,9 @@ struct alignas(64) TcParams {
   // into their own TMEM accumulator so that the epilogue can leave out the dx = -1 / +1 sums of pixels in the first /
   // last image column (zero padding).  tap_op[dy + 1][dx + 1] = operand (weight view) of that tap.
   int conv3;
+  int nacc_log;         // log2 of the TMEM accumulator ring (2 or 4 buffers): narrow tiles keep the MMA issuer up to four
+                        // tiles ahead of the epilogue groups, so neither waits out the other's latency every tile
+  int debug;            // KNOB_TC_DEBUG (timing diagnostics only: results are wrong when non-zero)
   int tap_op[3][3];
 };
 
@@ -137,10 +140,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_fwd_tc_kernel(const __grid_c
   const uint32_t landed_bar = base + bar_off;            // S x 8 bytes
   const uint32_t full_bar = landed_bar + 8 * S;
   const uint32_t empty_bar = full_bar + 8 * S;
-  const uint32_t tfull_bar = empty_bar + 8 * S;          // 2 x 8
-  const uint32_t tempty_bar = tfull_bar + 16;            // 2 x 8
-  const uint32_t bres_bar = tempty_bar + 16;             // 8
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + bar_off + 24 * S + 40);
+  const uint32_t tfull_bar = empty_bar + 8 * S;          // up to 4 x 8
+  const uint32_t tempty_bar = tfull_bar + 32;            // up to 4 x 8
+  const uint32_t bres_bar = tempty_bar + 32;             // 8
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + bar_off + 24 * S + 72);
+  const int nacc_log = prm.nacc_log, nacc_mask = (1 << nacc_log) - 1;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int total_tiles = prm.m_tiles * prm.n_tiles;
@@ -151,7 +155,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_fwd_tc_kernel(const __grid_c
       mbar_init(full_bar + 8 * s, 8);     // the eight transform warps
       mbar_init(empty_bar + 8 * s, 1);    // tcgen05.commit
     }
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a <= nacc_mask; ++a) {
       mbar_init(tfull_bar + 8 * a, 1);    // tcgen05.commit after the last k-block of a tile
       mbar_init(tempty_bar + 8 * a, 4);   // the four epilogue warps of group a have drained the accumulator
     }
@@ -273,8 +277,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_fwd_tc_kernel(const __grid_c
       uint32_t phase = 0;
       const int acc_stride = CONV3 ? 3 * bn : bn;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
-        const int acc = tl & 1;
-        mbar_wait(tempty_bar + 8 * acc, ((tl >> 1) & 1) ^ 1);
+        const int acc = tl & nacc_mask;
+        mbar_wait(tempty_bar + 8 * acc, ((tl >> nacc_log) & 1) ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * acc_stride;
         if (CONV3) {
@@ -446,7 +450,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_fwd_tc_kernel(const __grid_c
           }
           mbar_wait(landed_bar + 8 * stage, phase);
           const uint32_t blk = base + stage * stage_bytes;
-          if (mt.x != 0 || zero_mask != 0) {
+          if ((mt.x != 0 || zero_mask != 0) && !(prm.debug & 1)) {
             if (kcw == 4) transform_block<2, 64>(blk, c4, r4, mt.x, s, sh, 0u);
             else if (kcw == 2) transform_block<1, 64>(blk, c2, r2, mt.x, s, sh, 0u);
             else transform_block<4, 32>(blk, c, r0, mt.x, s, sh, zero_mask);
@@ -527,7 +531,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_fwd_tc_kernel(const __grid_c
       const int nt = tile / prm.m_tiles;
       const int n0 = nt * bn;
       const int64_t m0 = (int64_t)(tile % prm.m_tiles) * TC_BM;
-      const int acc = grp;
+      const int acc = tl & nacc_mask;       // (even ring sizes: an accumulator is always drained by the same group)
       if (st_on && nt != cur_nt && cur_nt >= 0) flush_stats(cur_nt);
       cur_nt = nt;
       const int64_t p = m0 + row;
@@ -546,7 +550,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_fwd_tc_kernel(const __grid_c
           }
         }
       }
-      mbar_wait(tfull_bar + 8 * acc, (tl >> 1) & 1);
+      mbar_wait(tfull_bar + 8 * acc, (tl >> nacc_log) & 1);
       tc_fence_after();
       // the staging boxes are free once the previous tile's TMA stores have read them and every thread has
       // finished its statistics pass
@@ -560,7 +564,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_fwd_tc_kernel(const __grid_c
         use_m = wcol != 0;
         use_p = wcol != prm.W - 1;
       }
-      for (int ch = 0; ch < n_chunks; ++ch) {
+      for (int ch = 0; ch < ((prm.debug & 8) ? 0 : n_chunks); ++ch) {
         uint32_t r[1][16];
         float v[16];
         if (CONV3) {
@@ -664,10 +668,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_fwd_tc_kernel(const __grid_c
       asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
       if (gtid == 0) {
         for (int b = 0; b < prm.out_boxes; ++b)
-          if (n0 + b * box_cols < N) tma_store_2d(&prm.tmap_y, stage + b * TC_BOX_BYTES, n0 + b * box_cols, (int)m0);
+          if (n0 + b * box_cols < N && !(prm.debug & 4)) tma_store_2d(&prm.tmap_y, stage + b * TC_BOX_BYTES, n0 + b * box_cols, (int)m0);
         bulk_commit();
       }
-      if (st_active) {
+      if (st_active && !(prm.debug & 2)) {
         // column-wise read-back of the staged bf16 tile: this thread's 8 columns over its rows
         for (int r = ty; r < TC_BM; r += 4 * TY) {
           uint4 u[4];
@@ -750,8 +754,13 @@ static size_t tc_geometry(int N, int64_t P, const accx_operand_t* ops, int n_ops
   if (prm.conv3) n_tiles = 1;          // one column tile of N <= 64 channels, three accumulators per TMEM buffer
   prm.bn = bn_for(n_tiles);
   prm.n_tiles = (N + prm.bn - 1) / prm.bn;
+  // accumulator ring: four buffers when they fit in 256 TMEM columns (the other half stays free for a weight-gradient
+  // CTA of the side stream on the same SM), else two
+  // (measured on B200, K = N = 32 at 16x224x224: a ring of four changes nothing, 51.4 vs 50.8 us -- the narrow-tile rate
+  //  is set by the per-row cost of the 128-row TMA boxes, tests/bench_gemm.py debug / stages -- so two it stays)
+  prm.nacc_log = 1;
   int cols = 32;
-  while (cols < (prm.conv3 ? 6 : 2) * prm.bn) cols <<= 1;
+  while (cols < (prm.conv3 ? 3 : 1) * (1 << prm.nacc_log) * prm.bn) cols <<= 1;
   prm.tmem_cols = cols;
   prm.out_boxes = (prm.bn + box_cols - 1) / box_cols;
   const size_t b_tile = (size_t)prm.bn * 128;
@@ -861,6 +870,7 @@ int accx_pw_fwd_tc_res(int dtype, int out_dtype, int B, int H, int W, int N, con
     ACCX_REQUIRE(aligned16(add[i]) || (N & 3) != 0, "pw_fwd_tc: addend %d must be 16-byte aligned", i);
   }
   prm.stats = stats;
+  prm.debug = g_knobs[KNOB_TC_DEBUG];
   prm.res = residual;
   prm.ld_res = ld_res;
   ACCX_REQUIRE(!residual || (aligned16(residual) && (ld_res * esz) % 16 == 0 && ld_res >= N && N % 8 == 0),

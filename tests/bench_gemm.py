@@ -17,6 +17,36 @@ SHAPES = [  # (P, K, N, act, stats)
 ]
 
 
+def run_graph(i, n=20):
+    """the same launch 20 times inside one CUDA graph (no launch-side CPU time between kernels), L2-warm inputs"""
+    P, K, N, act, st = SHAPES[i]
+    x = torch.randn(1, 1, P, K, device="cuda").to(torch.bfloat16)
+    s = torch.rand(K, device="cuda") + 0.5
+    t = torch.randn(K, device="cuda") * 0.1
+    L = E.Lazy(x, s, t, act) if act else E.Lazy(x)
+    w = torch.randn(N, K, device="cuda") / K ** 0.5
+    stats = torch.zeros(2 * N, device="cuda") if st else None
+    y = torch.empty(1, 1, P, N, device="cuda", dtype=torch.bfloat16)
+    ops = [E.Op(L, K, E.WV(w, 0, K, 1))]
+    for _ in range(3):
+        E.conv(ops, N, (1, 1, P), stats=stats, out=y)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(n):
+            E.conv(ops, N, (1, 1, P), stats=stats, out=y)
+    g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    byt = P * (K + N) * 2
+    print(f"graph P={P:8d} K={K:5d} N={N:5d} act={act}: {ms * 1e3:8.1f} us  {byt / ms / 1e6:7.0f} GB/s", flush=True)
+
+
 def run(i, reps=5):
     P, K, N, act, st = SHAPES[i]
     x = torch.randn(1, 1, P, K, device="cuda").to(torch.bfloat16)
@@ -109,6 +139,30 @@ if __name__ == "__main__":
         for i in range(len(SHAPES3)):
             run_taps(i)
             run_taps(i, wgrad=True)
+        sys.exit(0)
+    if "debug" in args:          # pw_fwd_tc with parts of the kernel switched off (knob 19): where does the tile time go?
+        from accx import _lib
+        SHAPES[:] = [(802816, 32, 32, 2, 1), (802816, 96, 32, 2, 1), (802816, 32, 96, 0, 1), (200704, 64, 64, 2, 1), (12544, 256, 256, 2, 1)]
+        for dbg, what in ((0, "full kernel"), (1, "no transform math"), (2, "no statistics pass"), (4, "no TMA store"),
+                          (8, "no TMEM drain / staging"), (15, "pipeline only")):
+            _lib.call("accx_set_knob", 19, dbg)
+            print(f"---- {what}")
+            for i in range(len(SHAPES)):
+                run_graph(i)
+        _lib.call("accx_set_knob", 19, 0)
+        sys.exit(0)
+    if "stages" in args:         # sensitivity of the narrow tile rate to the pipeline depth (knob 14 = TC_MAX_STAGES)
+        from accx import _lib
+        SHAPES[:] = [(802816, 32, 32, 2, 1), (802816, 64, 64, 2, 1), (802816, 128, 32, 2, 1)]
+        for dbg in (15, 0):
+            _lib.call("accx_set_knob", 19, dbg)
+            for S in (1, 2, 3, 4, 8):
+                _lib.call("accx_set_knob", 14, S)
+                print(f"---- debug {dbg} stages <= {S}")
+                for i in range(len(SHAPES)):
+                    run_graph(i)
+        _lib.call("accx_set_knob", 19, 0)
+        _lib.call("accx_set_knob", 14, 0)
         sys.exit(0)
     if "small" in args:
         SHAPES[:] = SMALL
