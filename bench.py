@@ -319,7 +319,9 @@ def main():
         roof.update({"kernel": name, "launches_per_step": n, "avg_launch_us": tms / n * 1e3,
                      "algorithmic_bytes_per_launch": nbytes / n,
                      "share_of_accx_time": tms / tot, "accx_kernel_ms_per_step": tot, "eager_step_ms": step_ms,
-                     "peak_source": which, "traffic": traffic_from_profiles(name)})
+                     "peak_source": which, "traffic": traffic_from_profiles(name),
+                     "traffic_source": "profiles/traffic.json: ncu dram__bytes of one eager step at the round-2 head "
+                                       "(not this run)"})
         table = {k: {"launches": a[0], "ms": a[1], "alg_gbytes": a[2] / 1e9, "gflop": a[3] / 1e9,
                      "gb_per_s": a[2] / max(a[1], 1e-9) / 1e6, "tflop_per_s": a[3] / max(a[1], 1e-9) / 1e9}
                  for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1])}
@@ -410,7 +412,9 @@ def main():
 
 
 def traffic_from_profiles(kernel):
-    """dram bytes per launch of `kernel` from the committed ncu --set full summary, if any"""
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, averaged over the launches of ONE training step
+    captured with ncu (profiles/r02_launches.md lists the same capture; profiles/traffic_from_ncu.py made the file).
+    It is a committed measurement of this code, not of this run: ncu cannot run inside the timed bench."""
     path = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(path):
         d = json.load(open(path)).get(kernel)

@@ -21,17 +21,23 @@ for n, r in enumerate(rows[2:2 + lim]):
     for k in KEYS:
         if k in ix:
             print(f"   {k:62s} {r[ix[k]]:>16s} {rows[1][ix[k]]}")
-for n in range(min(lim, len(rows) - 2)):
-    src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--launch-skip", str(n), "--launch-count", "1"],
-                         capture_output=True, text=True).stdout
-    sr = list(csv.reader(src.splitlines()))
+src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+tables, cur = [], None
+for line in src.splitlines():
+    if line.startswith('"Kernel Name"'):
+        cur = [line]
+        tables.append(cur)
+    elif cur is not None:
+        cur.append(line)
+for n, tab in enumerate(tables[:lim]):
+    sr = list(csv.reader(tab))
     try:
         hi = next(i for i, r in enumerate(sr) if "Source" in r and "Address" in r)
     except StopIteration:
         continue
     sh = sr[hi]
     sx = {k: i for i, k in enumerate(sh)}
-    body = sr[hi + 1:]
+    body = [r for r in sr[hi + 1:] if len(r) == len(sh)]
     E, S = sx["Instructions Executed"], sx["# Samples"]
     tot = sum(int(r[E] or 0) for r in body) or 1
     c = Counter()

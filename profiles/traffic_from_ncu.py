@@ -11,7 +11,7 @@ from collections import defaultdict
 
 UNIT = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 # C++ kernel name -> C ABI entry point that launches it
-ABI = [("pw_fwd_tc_kernel", "accx_pw_fwd_tc"), ("pw_wgrad_tc_kernel", "accx_pw_wgrad_tc"),
+ABI = [("pw_fwd_tc_kernel", "accx_pw_fwd_tc_res"), ("pw_wgrad_tc_kernel", "accx_pw_wgrad_tc"),
        ("dw3x3_tiled_kernel", "accx_dw3x3"), ("bn_bwd_apply_kernel", "accx_bn_bwd_apply"),
        ("bn_bwd_reduce_kernel", "accx_bn_bwd_reduce"), ("se_bwd_apply_kernel", "accx_se_bwd_apply"),
        ("se_apply_kernel", "accx_se_apply"), ("hanc_unpool_bnred_kernel", "accx_hanc_unpool_bnred")]

@@ -73,7 +73,24 @@ def main():
             O.shifted_block(O.Ctx(sd, True), "", x, H, H).backward(cot)
 
         ms_t = timed(run_torch, args.steps)
-        out["blocks"].append({"tokens": [B, N, C], "accx_ms": ms_a, "torch_ops_ms": ms_t, "accx_launches": launches})
+
+        def graphed(fn):
+            """the same fwd+bwd captured in a CUDA graph: GPU time without the launching CPU in the way"""
+            s_ = torch.cuda.Stream()
+            s_.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s_):
+                for _ in range(3):
+                    fn()
+            torch.cuda.current_stream().wait_stream(s_)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                fn()
+            return timed(g.replay, args.steps)
+
+        ms_ag, ms_tg = graphed(run_accx), graphed(run_torch)
+        out["blocks"].append({"tokens": [B, N, C], "accx_ms": ms_a, "torch_ops_ms": ms_t, "accx_graph_ms": ms_ag,
+                              "torch_ops_graph_ms": ms_tg, "accx_launches": launches})
 
     # ---- whole model ------------------------------------------------------------------------------------------
     torch.manual_seed(2)
