@@ -17,6 +17,8 @@ from ._lib import BF16, F32, Operand
 import os
 
 TC = os.environ.get("ACCX_TC", "1") != "0"   # tcgen05 tensor-core contraction for bf16 activations
+TC_F32 = os.environ.get("ACCX_TC_F32", "1") != "0"   # ... and for fp32 activations (3 x TF32, fp32 output)
+TC_F32_IN_DET = False   # tests: keep the 3 x TF32 contraction in deterministic mode too (default there: exact fp32 FMA)
 LAUNCHES = 0          # number of accx kernels launched by this process (bench.py reports it)
 LAUNCHES_EXTRA = [0]  # kernels launched inside an accx call beyond the first (weight re-pack)
 PROFILE = None        # list -> every launch is bracketed by CUDA events on the launching stream and
@@ -401,9 +403,12 @@ def conv(ops: Sequence[Op], N: int, dims: Tuple[int, int, int], bias=None, adds:
         rd += residual.numel() * residual.element_size()
     cost = (rd + P * N * out.element_size(), 2 * P * N * sum(op.K for op in ops))
     yptr = out.data_ptr() + out_coff * out.element_size()
-    tc_ok = (TC and in_dt == BF16 and all(o.K % 8 == 0 and o.ld % 8 == 0 and o.data % 16 == 0 for o in arr)
+    # fp32 storage: 3 x TF32 on the tensor cores by default; the deterministic parity mode keeps the exact fp32-FMA
+    # contraction (whole-model deviation from the reference 2-6x smaller: tests/test_full_width_gpu.py)
+    tc_ok = (TC and (in_dt == BF16 or (TC_F32 and in_dt == F32 and odt == F32 and (TC_F32_IN_DET or not deterministic())))
+             and all(o.K % 8 == 0 and o.ld % 8 == 0 and o.data % 16 == 0 for o in arr)
              and yptr % 16 == 0 and (out.shape[-1] * out.element_size()) % 16 == 0       # TMA store of the output
-             and not (stats is not None and odt == F32)
+             and not (stats is not None and odt == F32 and in_dt == BF16)
              and all(t.data_ptr() % 16 == 0 for t, _ in adds))
     fuse = (residual is not None and tc_ok and N % 8 == 0 and residual.data_ptr() % 16 == 0)
     if residual is not None and not fuse:

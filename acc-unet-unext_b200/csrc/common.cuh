@@ -33,6 +33,7 @@ enum {
   KNOB_SE_BWD_APPLY_U, KNOB_BN_REDUCE_BLOCKS, KNOB_EW_BLOCKS, KNOB_POOL_BLOCKS, KNOB_TC_SMEM_KB, KNOB_TC_MAX_STAGES, KNOB_WGRAD_MIN_STAGES, KNOB_WGRAD_SMEM_KB, KNOB_SE_BWD_VEC,
   KNOB_TC_CONV3,      // 18: dense-3x3 slab mode of pw_fwd_tc: 1 (default) on, 2 off (nine shifted operands)
   KNOB_TC_DEBUG,      // 19: timing diagnostics of pw_fwd_tc (bit 0 no transform math, 1 no statistics pass, 2 no TMA store, 3 no TMEM drain)
+  KNOB_TC_F32_TERMS,  // 20: products of the tf32 split in fp32-storage contractions: 3 (default) or 4
   KNOB_COUNT
 };
 extern int g_knobs[KNOB_COUNT];

@@ -58,6 +58,7 @@ struct alignas(64) TcParams {
   // into their own TMEM accumulator so that the epilogue can leave out the dx = -1 / +1 sums of pixels in the first /
   // last image column (zero padding).  tap_op[dy + 1][dx + 1] = operand (weight view) of that tap.
   int conv3;
+  int f32in;            // fp32 storage on the bf16 tensor cores (three-term split, see pw_fwd_tc_kernel MODE 2)
   int nacc_log;         // log2 of the TMEM accumulator ring (2 or 4 buffers): narrow tiles keep the MMA issuer up to four
                         // tiles ahead of the epilogue groups, so neither waits out the other's latency every tile
   int debug;            // KNOB_TC_DEBUG (timing diagnostics only: results are wrong when non-zero)
@@ -75,8 +76,22 @@ __global__ void tc_pack_weights_kernel(const __grid_constant__ TcParams prm, bf1
   int o = 0;
   while (o + 1 < prm.n_ops && kb >= prm.kb_start[o + 1]) ++o;
   const accx_operand_t& op = prm.op[o];
-  const int k0 = (kb - prm.kb_start[o]) * TC_BK;
-  bf16* tile = wpack + ((int64_t)nt * prm.n_kb + kb) * prm.bn * TC_BK;
+  const int wtiles = prm.f32in ? 2 : 1, bkc = prm.f32in ? 32 : TC_BK;
+  const int k0 = (kb - prm.kb_start[o]) * bkc;
+  bf16* tile = wpack + ((int64_t)nt * prm.n_kb + kb) * wtiles * prm.bn * TC_BK;
+  if (prm.f32in) {      // 3 x TF32: two fp32 tiles [bn rows][32 floats] per k-block, w_hi and w_lo (same 128-byte swizzle)
+    float* tf = reinterpret_cast<float*>(tile);
+    for (int idx = blockIdx.z * blockDim.x + threadIdx.x; idx < 2 * prm.bn * 32; idx += gridDim.z * blockDim.x) {
+      const int wt = idx / (prm.bn * 32), r = idx - wt * prm.bn * 32;
+      const int nl = r >> 5, kk = r & 31;
+      const int n = nt * prm.bn + nl, k = k0 + kk;
+      float v = 0.f;
+      if (n < prm.N && k < op.K) v = __ldg(op.w + (int64_t)n * op.w_ld + (int64_t)k * op.w_ks);
+      const float hi = to_tf32(v);
+      tf[wt * prm.bn * 32 + nl * 32 + ((((kk >> 2) ^ (nl & 7)) << 2) | (kk & 3))] = wt ? to_tf32(v - hi) : hi;
+    }
+    return;
+  }
   for (int idx = blockIdx.z * blockDim.x + threadIdx.x; idx < prm.bn * TC_BK; idx += gridDim.z * blockDim.x) {
     const int nl = idx / TC_BK, kk = idx % TC_BK;
     const int n = nt * prm.bn + nl, k = k0 + kk;
@@ -121,21 +136,31 @@ __device__ __forceinline__ void stage_chunk(const float (&v)[16], uint32_t stage
   }
 }
 
-// CONV3: the dense-3x3 halo-slab mode (see TcParams) -- its own instantiation, so that the plain contraction carries none of its code
-template <bool CONV3>
+// MODE 0: bf16 operands.  MODE 1: the dense-3x3 halo-slab mode (see TcParams).  MODE 2: fp32 STORAGE (the reference's
+// arithmetic, rtol 1e-3 parity mode) on the tensor cores as 3 x TF32: x_hi = tf32(x) (round to nearest),
+// x_lo = tf32(x - x_hi), a*w ~ a_hi*w_hi + a_lo*w_hi + a_hi*w_lo with kind::tf32 MMAs -- 21-22 significant bits, against
+// 24 of an fp32 FMA (a two-term bf16 split, 16 bits, was tried first: per-contraction error 1.5e-5, but the 220 stacked
+// BatchNorms amplify it to 7e-3 at the logits, 20x the reference's own fp32-vs-fp64 error).  A k-block is 32 fp32
+// channels: the landed 128 x 32 fp32 box becomes a_hi in place, a_lo goes to a second tile of the stage, and every
+// k-block has two weight tiles, w_hi and w_lo.  Separate instantiations: the bf16 contraction carries none of this code.
+template <int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1) pw_fwd_tc_kernel(const __grid_constant__ TcParams prm) {
+  constexpr bool CONV3 = MODE == 1, F32IN = MODE == 2;
+  constexpr int BKC = F32IN ? 32 : TC_BK;          // channels per k-block
   pdl_sync();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
   const int bn = prm.bn, S = prm.stages, n_kb = prm.n_kb;
-  const uint32_t b_tile_bytes = bn * 128;
-  const uint32_t stage_bytes = CONV3 ? (uint32_t)TC_SLAB_BYTES : TC_A_BYTES + (prm.b_resident ? 0 : b_tile_bytes);
+  const uint32_t b_tile_bytes = (F32IN ? 2 : 1) * bn * 128;      // fp32 split: two weight tiles per k-block
+  constexpr uint32_t A_STAGE = (F32IN ? 2 : 1) * TC_A_BYTES;       // fp32 split: a_hi | a_lo
+  const uint32_t stage_bytes = CONV3 ? (uint32_t)TC_SLAB_BYTES : A_STAGE + (prm.b_resident ? 0 : b_tile_bytes);
   const uint32_t bres_off = S * stage_bytes;
   const uint32_t epi_off = bres_off + (prm.b_resident ? n_kb * b_tile_bytes : 0);      // 1024-aligned
   const uint32_t stat_off = epi_off + 2 * prm.out_boxes * TC_BOX_BYTES;                // float[2 groups][2 * bn]
   const uint32_t tab_off = (stat_off + 4 * bn * 4 + 15u) & ~15u;                       // float[n_kb][2][64] + int4[n_kb]
-  const uint32_t htab_off = tab_off + (prm.any_transform ? n_kb * (512 + 16) : 0);     // int16[2][TC_SLAB_ROWS] (conv3)
+  constexpr int TS = 2 * BKC;                 // floats per k-block in the scale | shift table
+  const uint32_t htab_off = tab_off + ((prm.any_transform || F32IN) ? n_kb * (TS * 4 + 16) : 0);     // int16[2][TC_SLAB_ROWS] (conv3)
   const uint32_t bar_off = htab_off + (CONV3 ? 2 * TC_SLAB_ROWS * 2 : 0);
   const uint32_t landed_bar = base + bar_off;            // S x 8 bytes
   const uint32_t full_bar = landed_bar + 8 * S;
@@ -178,29 +203,39 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_fwd_tc_kernel(const __grid_c
     // fp32 strided view -> bf16, K-major 128B-swizzled [bn rows][64] tiles, one per k-block (no pre-pack
     // launch, no workspace traffic).  Every CTA reads the (small, L2-resident) weight matrix once.
     // one 16-byte chunk (8 consecutive k of one output row) per thread and step: eight independent loads in flight
-    const int chunks_per_kb = bn * 8;
+    const int chunks_per_kb = bn * (F32IN ? 16 : 8);
     const int n_chunks_w = n_kb * chunks_per_kb;
     constexpr int WU = 4;                      // chunks in flight per thread: the loop is bound by L2 latency otherwise
     for (int ch0 = tid; ch0 < n_chunks_w; ch0 += WU * TC_WARP_TMA * 32) {
       float v[WU][8];
       uint32_t addr[WU];
+      bool low[WU];                            // fp32 split: this chunk holds w_lo = bf16(w - w_hi)
 #pragma unroll
       for (int u = 0; u < WU; ++u) {
         const int ch = ch0 + u * TC_WARP_TMA * 32;
 #pragma unroll
         for (int e = 0; e < 8; ++e) v[u][e] = 0.f;
         addr[u] = 0;
+        low[u] = false;
         if (ch < n_chunks_w) {
-          const int kb = ch / chunks_per_kb, rem = ch - kb * chunks_per_kb;
+          const int kb = ch / chunks_per_kb;
+          int rem = ch - kb * chunks_per_kb;
+          int wt = 0;                          // weight tile of the k-block: 0 = [w_hi | w_hi], 1 = [w_lo | 0]
+          if (F32IN && rem >= bn * 8) { wt = 1; rem -= bn * 8; }
           const int nl = rem >> 3, c8 = rem & 7;
           int o = 0;
           while (o + 1 < prm.n_ops && kb >= prm.kb_start[o + 1]) ++o;
           const accx_operand_t& op = prm.op[o];
-          const int k0 = (kb - prm.kb_start[o]) * TC_BK + c8 * 8;
-          addr[u] = base + bres_off + kb * b_tile_bytes + nl * 128 + ((c8 ^ (nl & 7)) << 4);
+          const int k0 = (kb - prm.kb_start[o]) * BKC + c8 * (F32IN ? 4 : 8);
+          addr[u] = base + bres_off + kb * b_tile_bytes + wt * bn * 128 + nl * 128 + ((c8 ^ (nl & 7)) << 4);
+          low[u] = wt == 1;
           if (nl < prm.N && k0 < op.K) {
             const float* src = op.w + (int64_t)nl * op.w_ld + (int64_t)k0 * op.w_ks;
-            if (op.w_ks == 1 && k0 + 8 <= op.K && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+            if (F32IN) {           // four fp32 words per chunk
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if (k0 + e < op.K) v[u][e] = __ldg(src + (int64_t)e * op.w_ks);
+            } else if (op.w_ks == 1 && k0 + 8 <= op.K && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
               const float4 a = __ldg(reinterpret_cast<const float4*>(src)), c = __ldg(reinterpret_cast<const float4*>(src) + 1);
               v[u][0] = a.x; v[u][1] = a.y; v[u][2] = a.z; v[u][3] = a.w;
               v[u][4] = c.x; v[u][5] = c.y; v[u][6] = c.z; v[u][7] = c.w;
@@ -218,8 +253,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_fwd_tc_kernel(const __grid_c
           uint32_t w[4];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[u][2 * q], v[u][2 * q + 1]);
-            w[q] = *reinterpret_cast<uint32_t*>(&h2);
+            if constexpr (F32IN) {       // w_hi = the tf32 part of the word, w_lo = the exact remainder
+              const float hi = to_tf32(v[u][q]);
+              w[q] = __float_as_uint(low[u] ? to_tf32(v[u][q] - hi) : hi);
+            } else {
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(v[u][2 * q], v[u][2 * q + 1]);
+              w[q] = *reinterpret_cast<uint32_t*>(&h2);
+            }
           }
           asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr[u]), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
         }
@@ -258,9 +298,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_fwd_tc_kernel(const __grid_c
           mbar_expect_tx(bar, TC_A_BYTES + (prm.b_resident ? 0 : b_tile_bytes));
           const accx_operand_t& op = prm.op[o];
           const int64_t row0 = m0 + (int64_t)op.dy * prm.W + op.dx;   // may be negative: OOB rows are zero-filled
-          tma_load_2d(a_smem, &prm.tmap[o], (kb - prm.kb_start[o]) * TC_BK, (int)row0, bar);
+          tma_load_2d(a_smem, &prm.tmap[o], (kb - prm.kb_start[o]) * BKC, (int)row0, bar);
           if (!prm.b_resident)
-            bulk_g2s(a_smem + TC_A_BYTES, prm.wpack + ((int64_t)nt * n_kb + kb) * bn * TC_BK, b_tile_bytes, bar);
+            bulk_g2s(a_smem + A_STAGE, prm.wpack + ((int64_t)nt * n_kb + kb) * (b_tile_bytes / 2), b_tile_bytes, bar);
           if (++stage == S) { stage = 0; phase ^= 1; }
         }
       }
@@ -269,9 +309,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_fwd_tc_kernel(const __grid_c
     // ============================== MMA issuer ================================
     if (lane == 0) {
       // instruction descriptor: D fp32, A/B bf16, both K-major, N = bn, M = 128
-      const uint32_t idesc =
-          (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-      const uint32_t ready_bar = prm.any_transform ? full_bar : landed_bar;
+      // (a / b format field: 1 = bf16 for kind::f16, 2 = tf32 for kind::tf32)
+      const uint32_t idesc = (1u << 4) | ((F32IN ? 2u : 1u) << 7) | ((F32IN ? 2u : 1u) << 10) | ((uint32_t)(bn >> 3) << 17) |
+                             ((uint32_t)(TC_BM >> 4) << 24);
+      const uint32_t ready_bar = (prm.any_transform || F32IN) ? full_bar : landed_bar;
       if (prm.b_resident) mbar_wait(bres_bar, 0);
       int stage = 0, tl = 0;
       uint32_t phase = 0;
@@ -313,13 +354,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_fwd_tc_kernel(const __grid_c
           const uint32_t a_smem = base + stage * stage_bytes;
           const uint64_t adesc = make_desc_k_sw128(a_smem);
           const uint64_t bdesc =
-              make_desc_k_sw128(prm.b_resident ? base + bres_off + kb * b_tile_bytes : a_smem + TC_A_BYTES);
+              make_desc_k_sw128(prm.b_resident ? base + bres_off + kb * b_tile_bytes : a_smem + A_STAGE);
+          if constexpr (F32IN) {
+            // 3 x TF32: a_hi.w_hi + a_lo.w_hi + a_hi.w_lo, four K = 8 steps (32 bytes) each; small terms after the large one
+            const uint64_t adesc_lo = adesc + (uint64_t)(TC_A_BYTES >> 4), bdesc_lo = bdesc + (uint64_t)((bn * 128) >> 4);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              tc_mma_tf32(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) tc_mma_tf32(tmem_d, adesc_lo + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, 1u);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) tc_mma_tf32(tmem_d, adesc + (uint64_t)(k * 2), bdesc_lo + (uint64_t)(k * 2), idesc, 1u);
+            if (prm.f32in > 1) {       // fourth term a_lo.w_lo (2^-22 relative; measured: no effect on whole-model error)
+#pragma unroll
+              for (int k = 0; k < 4; ++k) tc_mma_tf32(tmem_d, adesc_lo + (uint64_t)(k * 2), bdesc_lo + (uint64_t)(k * 2), idesc, 1u);
+            }
+          } else {
           // the last k-block of an operand may hold fewer than 64 channels (the rest is zero fill): skip those MMAs
           const int krem = prm.op[o].K - (kb - prm.kb_start[o]) * TC_BK;
           const int nm = krem >= TC_BK ? TC_BK / 16 : (krem + 15) / 16;
 #pragma unroll
           for (int k = 0; k < TC_BK / 16; ++k)
             if (k < nm) tc_mma(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+          }
           tc_commit(empty_bar + 8 * stage);
           if (++stage == S) { stage = 0; phase ^= 1; }
         }
@@ -328,21 +385,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_fwd_tc_kernel(const __grid_c
     }
   } else if (warp >= TC_WARP_XF0) {
     // ============================== transform warps ===========================
-    if (prm.any_transform) {
+    if (prm.any_transform || F32IN) {
       const int t = tid - TC_WARP_XF0 * 32;
       const int c = t & 7, r0 = t >> 3;                       // rows r0, r0 + 32, r0 + 64, r0 + 96
       // per-k-block tables in shared memory: scale[64] | shift[64] (zeros beyond K) and {act, dy, dx, 16-byte chunks}
       float* tab = reinterpret_cast<float*>(smem + tab_off);
-      int4* meta = reinterpret_cast<int4*>(smem + tab_off + n_kb * 512);
-      for (int idx = t; idx < n_kb * 64; idx += TC_XF_THREADS) {
-        const int kb = idx >> 6, j = idx & 63;
+      int4* meta = reinterpret_cast<int4*>(smem + tab_off + n_kb * TS * 4);
+      for (int idx = t; idx < n_kb * BKC; idx += TC_XF_THREADS) {
+        const int kb = idx / BKC, j = idx % BKC;
         int o = 0;
         while (o + 1 < prm.n_ops && kb >= prm.kb_start[o + 1]) ++o;
         const accx_operand_t& op = prm.op[o];
-        const int k = (kb - prm.kb_start[o]) * TC_BK + j;
-        const bool on = op.act != 0 && k < op.K;
-        tab[kb * 128 + j] = on ? __ldg(op.scale + k) : 0.f;
-        tab[kb * 128 + 64 + j] = on ? __ldg(op.shift + k) : 0.f;
+        const int k = (kb - prm.kb_start[o]) * BKC + j;
+        const bool on = op.act != 0 && j < BKC && k < op.K;
+        tab[kb * TS + j] = on ? __ldg(op.scale + k) : 0.f;
+        tab[kb * TS + BKC + j] = on ? __ldg(op.shift + k) : 0.f;
         if (j == 0) {
           const int krem = op.K - k;
           meta[kb] = make_int4(op.act, op.dy, op.dx, krem >= TC_BK ? 8 : (krem + 7) >> 3);
@@ -352,7 +409,76 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_fwd_tc_kernel(const __grid_c
       const int HWp = prm.H * prm.W;
       int stage = 0;
       uint32_t phase = 0;
-      if (CONV3) {
+      if constexpr (F32IN) {
+        // ---- fp32 storage: activate in fp32, a_hi (tf32 part) in place, a_lo = a - a_hi into the second tile; two threads per row ----
+        const int row = t >> 1, half = t & 1;
+        const uint32_t rsw = (uint32_t)(row & 7);
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+          const int m0 = (tile % prm.m_tiles) * TC_BM;
+          int ph = 0, pw = 0;
+          if (prm.any_shift) {
+            const int p = m0 + row;
+            const int rem = p % HWp;
+            ph = rem / prm.W;
+            pw = p < (int)prm.P ? rem - ph * prm.W : -4;
+          }
+          for (int kb = 0; kb < n_kb; ++kb) {
+            const int4 mt = meta[kb];
+            bool zero = false;
+            if (mt.y != 0 || mt.z != 0) {
+              const int hh = ph + mt.y, ww = pw + mt.z;
+              zero = hh < 0 || hh >= prm.H || ww < 0 || ww >= prm.W || pw < 0;
+            }
+            mbar_wait(landed_bar + 8 * stage, phase);
+            const uint32_t rowb = base + stage * stage_bytes + row * 128;
+            float v[16];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint32_t addr = rowb + ((((uint32_t)(half * 4 + q)) ^ rsw) << 4);
+              uint32_t a0, a1, a2, a3;
+              asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(addr));
+              v[4 * q] = __uint_as_float(a0); v[4 * q + 1] = __uint_as_float(a1);
+              v[4 * q + 2] = __uint_as_float(a2); v[4 * q + 3] = __uint_as_float(a3);
+            }
+            if (zero) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = 0.f;
+            } else if (mt.x != 0) {
+              const float4* sp = reinterpret_cast<const float4*>(tab + kb * TS + half * 16);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float4 sc = sp[q], sf = sp[BKC / 4 + q];
+                v[4 * q] = fmaf(v[4 * q], sc.x, sf.x); v[4 * q + 1] = fmaf(v[4 * q + 1], sc.y, sf.y);
+                v[4 * q + 2] = fmaf(v[4 * q + 2], sc.z, sf.z); v[4 * q + 3] = fmaf(v[4 * q + 3], sc.w, sf.w);
+              }
+              if (mt.x == 2) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], v[i] * ACCX_LRELU);
+              }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint32_t addr = rowb + ((((uint32_t)(half * 4 + q)) ^ rsw) << 4);
+              float h[4], l[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                h[e] = to_tf32(v[4 * q + e]);                 // round to nearest: the remainder is symmetric, |a_lo| <= 2^-11 |a|
+                l[e] = to_tf32(v[4 * q + e] - h[e]);          // (the difference is exact; rounded here, not truncated by the MMA)
+              }
+              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(__float_as_uint(h[0])), "r"(__float_as_uint(h[1])),
+                           "r"(__float_as_uint(h[2])), "r"(__float_as_uint(h[3]))
+                           : "memory");
+              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr + TC_A_BYTES), "r"(__float_as_uint(l[0])),
+                           "r"(__float_as_uint(l[1])), "r"(__float_as_uint(l[2])), "r"(__float_as_uint(l[3]))
+                           : "memory");
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full_bar + 8 * stage);
+            if (++stage == S) { stage = 0; phase ^= 1; }
+          }
+        }
+      } else if (CONV3) {
         // ---- dense 3x3: three slabs per tile, each transformed ONCE for its three taps ----
         int16_t* htab = reinterpret_cast<int16_t*>(smem + htab_off);
         const int act = prm.op[0].act;
@@ -475,10 +601,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_fwd_tc_kernel(const __grid_c
     const int n_chunks = bn >> 4;
     const int bar_id = 1 + grp;
     // statistics role: chunk tx (8 columns) of rows ty, ty + TY, ..
-    const int cpr = bn >> 3;
+    constexpr int CW = F32IN ? 4 : 8;          // columns per 16-byte chunk of the staged tile (fp32 split mode stages fp32)
+    const int cpr = bn / CW;
     const int TY = 128 / cpr;
     const int tx = gtid % cpr, ty = gtid / cpr;
-    const bool st_on = prm.stats != nullptr && !prm.out_f32;
+    const bool st_on = prm.stats != nullptr && (F32IN || !prm.out_f32);
     const bool st_active = st_on && ty < TY;
     const uint32_t st_base = stage + (tx >> 3) * TC_BOX_BYTES;
     float s1[8], s2[8];
@@ -494,9 +621,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_fwd_tc_kernel(const __grid_c
       if (!prm.det) {
         if (st_active) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            atomicAdd(&sstat[tx * 8 + j], s1[j]);
-            atomicAdd(&sstat[bn + tx * 8 + j], s2[j]);
+          for (int j = 0; j < CW; ++j) {
+            atomicAdd(&sstat[tx * CW + j], s1[j]);
+            atomicAdd(&sstat[bn + tx * CW + j], s2[j]);
             s1[j] = s2[j] = 0.f;
           }
         }
@@ -505,9 +632,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_fwd_tc_kernel(const __grid_c
         for (int t = 0; t < TY; ++t) {
           if (st_active && ty == t) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              sstat[tx * 8 + j] += s1[j];
-              sstat[bn + tx * 8 + j] += s2[j];
+            for (int j = 0; j < CW; ++j) {
+              sstat[tx * CW + j] += s1[j];
+              sstat[bn + tx * CW + j] += s2[j];
               s1[j] = s2[j] = 0.f;
             }
           }
@@ -688,6 +815,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_fwd_tc_kernel(const __grid_c
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const uint32_t w[4] = {u[q].x, u[q].y, u[q].z, u[q].w};
+            if constexpr (F32IN) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float f = __uint_as_float(w[e]);
+                s1[e] += f;
+                s2[e] = fmaf(f, f, s2[e]);
+              }
+            } else {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const float lo = __uint_as_float(w[e] << 16), hi = __uint_as_float(w[e] & 0xffff0000u);
@@ -695,6 +830,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_fwd_tc_kernel(const __grid_c
               s2[2 * e] = fmaf(lo, lo, s2[2 * e]);
               s1[2 * e + 1] += hi;
               s2[2 * e + 1] = fmaf(hi, hi, s2[2 * e + 1]);
+            }
             }
           }
         }
@@ -717,9 +853,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_fwd_tc_kernel(const __grid_c
 // in shared memory when the whole matrix fits next to >= 3 pipeline stages.
 static size_t tc_geometry(int N, int64_t P, const accx_operand_t* ops, int n_ops, bool out_f32, TcParams& prm) {
   int kb = 0;
+  const int bkc = prm.f32in ? 32 : TC_BK;       // channels per k-block
   for (int i = 0; i < n_ops; ++i) {
     prm.kb_start[i] = kb;
-    kb += (ops[i].K + TC_BK - 1) / TC_BK;
+    kb += (ops[i].K + bkc - 1) / bkc;
   }
   prm.kb_start[n_ops] = kb;
   prm.n_kb = kb;
@@ -752,6 +889,8 @@ static size_t tc_geometry(int N, int64_t P, const accx_operand_t* ops, int n_ops
     n_tiles = best_nt;
   }
   if (prm.conv3) n_tiles = 1;          // one column tile of N <= 64 channels, three accumulators per TMEM buffer
+  size_t fixed = 0, resident = 0, stage = 0;
+  for (;; ++n_tiles) {                 // (narrower column tiles until two pipeline stages fit: fp32 outputs / fp32 split mode)
   prm.bn = bn_for(n_tiles);
   prm.n_tiles = (N + prm.bn - 1) / prm.bn;
   // accumulator ring: four buffers when they fit in 256 TMEM columns (the other half stays free for a weight-gradient
@@ -763,13 +902,15 @@ static size_t tc_geometry(int N, int64_t P, const accx_operand_t* ops, int n_ops
   while (cols < (prm.conv3 ? 3 : 1) * (1 << prm.nacc_log) * prm.bn) cols <<= 1;
   prm.tmem_cols = cols;
   prm.out_boxes = (prm.bn + box_cols - 1) / box_cols;
-  const size_t b_tile = (size_t)prm.bn * 128;
-  const size_t fixed = 1024 + 2 * (size_t)prm.out_boxes * TC_BOX_BYTES + 4 * prm.bn * 4 + 512 +
-                       (prm.any_transform ? (size_t)kb * (512 + 16) : 0) + (prm.conv3 ? 2 * TC_SLAB_ROWS * 2 : 0);
-  prm.b_resident = (prm.n_tiles == 1 && fixed + (size_t)kb * b_tile + 3 * TC_A_BYTES <= (size_t)TC_SMEM_MAX) ? 1 : 0;
+  const size_t b_tile = (size_t)(prm.f32in ? 2 : 1) * prm.bn * 128;
+  fixed = 1024 + 2 * (size_t)prm.out_boxes * TC_BOX_BYTES + 4 * prm.bn * 4 + 512 +
+          ((prm.any_transform || prm.f32in) ? (size_t)kb * (bkc * 8 + 16) : 0) + (prm.conv3 ? 2 * TC_SLAB_ROWS * 2 : 0);
+  prm.b_resident = (prm.n_tiles == 1 && fixed + (size_t)kb * b_tile + 3 * (size_t)(prm.f32in ? 2 : 1) * TC_A_BYTES <= (size_t)TC_SMEM_MAX) ? 1 : 0;
   if (prm.conv3) prm.b_resident = 1;   // nine tiles of <= 8 KB (checked by the caller)
-  const size_t resident = prm.b_resident ? (size_t)kb * b_tile : 0;
-  const size_t stage = prm.conv3 ? (size_t)TC_SLAB_BYTES : TC_A_BYTES + (prm.b_resident ? 0 : b_tile);
+  resident = prm.b_resident ? (size_t)kb * b_tile : 0;
+  stage = prm.conv3 ? (size_t)TC_SLAB_BYTES : (size_t)(prm.f32in ? 2 : 1) * TC_A_BYTES + (prm.b_resident ? 0 : b_tile);
+  if (fixed + resident + 2 * stage <= (size_t)TC_SMEM_MAX || prm.bn <= box_cols) break;
+  }
   // pipeline depth: as many stages as fit under the cap, at most 8.  The cap (160 KB, whole-step sweep on B200:
   // 227 KB 38.29 ms, 160 KB 37.82 ms, 112 KB 38.44 ms) leaves room for kernels of the other stream lanes on the SM
   size_t cap = (size_t)knob(KNOB_TC_SMEM_KB, 160) * 1024;
@@ -793,10 +934,11 @@ extern "C" {
 int64_t accx_pw_tc_workspace_bytes(int N, const accx_operand_t* ops, int n_ops) {
   if (!ops || n_ops < 1 || n_ops > ACCX_MAX_OPERANDS) return -1;
   // the packing geometry depends on the output dtype and on P only through BN: reserve for the finest split
+  // (sized for the fp32-split mode as well: 32-channel k-blocks with two bf16 tiles each)
   int64_t kb = 0;
-  for (int i = 0; i < n_ops; ++i) kb += (ops[i].K + TC_BK - 1) / TC_BK;
+  for (int i = 0; i < n_ops; ++i) kb += (ops[i].K + 31) / 32;
   const int64_t n_pad = 2 * (((int64_t)N + 15) / 16 * 16) + 64;
-  return kb * TC_BK * 2 * n_pad;
+  return kb * 2 * TC_BK * 2 * n_pad;
 }
 
 int accx_pw_fwd_tc_res(int dtype, int out_dtype, int B, int H, int W, int N, const accx_operand_t* ops, int n_ops,
@@ -806,13 +948,15 @@ int accx_pw_fwd_tc_res(int dtype, int out_dtype, int B, int H, int W, int N, con
   ACCX_REQUIRE(B > 0 && H > 0 && W > 0 && N > 0 && ops && y && workspace, "pw_fwd_tc: bad arguments");
   ACCX_REQUIRE(n_ops >= 1 && n_ops <= ACCX_MAX_OPERANDS, "pw_fwd_tc: n_ops %d out of range", n_ops);
   ACCX_REQUIRE(n_add >= 0 && n_add <= ACCX_MAX_ADDENDS, "pw_fwd_tc: n_add %d out of range", n_add);
-  ACCX_REQUIRE(dtype == ACCX_BF16, "pw_fwd_tc: operands must be bf16 (use accx_pw_fwd for fp32 storage)");
+  ACCX_REQUIRE(dtype == ACCX_BF16 || dtype == ACCX_F32, "pw_fwd_tc: operands must be bf16 or fp32");
+  ACCX_REQUIRE(dtype == ACCX_BF16 || out_dtype == ACCX_F32, "pw_fwd_tc: fp32 operands produce an fp32 output");
   ACCX_REQUIRE(ldy >= N, "pw_fwd_tc: ldy < N");
-  const bool out_f32 = out_dtype == ACCX_F32;
+  const bool out_f32 = out_dtype == ACCX_F32, in_f32 = dtype == ACCX_F32;
   const int esz = out_f32 ? 4 : 2;
   ACCX_REQUIRE(aligned16(y) && (ldy * esz) % 16 == 0,
                "pw_fwd_tc: output needs a 16-byte aligned base and row pitch (use accx_pw_fwd)");
-  ACCX_REQUIRE(!(stats && out_f32), "pw_fwd_tc: statistics are produced for bf16 outputs only (use accx_pw_fwd)");
+  ACCX_REQUIRE(!(stats && out_f32 && !in_f32),
+               "pw_fwd_tc: bf16 operands produce statistics for bf16 outputs only (use accx_pw_fwd)");
   ACCX_REQUIRE(get_encode() != nullptr, "pw_fwd_tc: cuTensorMapEncodeTiled not available from the driver");
   TcParams prm;
   prm.n_ops = n_ops;
@@ -822,9 +966,10 @@ int accx_pw_fwd_tc_res(int dtype, int out_dtype, int B, int H, int W, int N, con
   ACCX_REQUIRE(P < (int64_t)1 << 31, "pw_fwd_tc: too many pixels");
   // dense 3x3 convolution (the nine taps of ONE tensor, <= 64 channels in and out): halo-slab mode, see TcParams
   prm.conv3 = 0;
+  prm.f32in = in_f32 ? (knob(KNOB_TC_F32_TERMS, 3) == 4 ? 2 : 1) : 0;
   for (int a = 0; a < 3; ++a)
     for (int b = 0; b < 3; ++b) prm.tap_op[a][b] = -1;
-  if (n_ops == 9 && N <= 64 && ops[0].K <= 64 && W >= 2 && knob(KNOB_TC_CONV3, 1) == 1) {
+  if (!in_f32 && n_ops == 9 && N <= 64 && ops[0].K <= 64 && W >= 2 && knob(KNOB_TC_CONV3, 1) == 1) {
     bool ok = true;
     for (int i = 0; i < 9 && ok; ++i) {
       const accx_operand_t& o = ops[i];
@@ -845,13 +990,17 @@ int accx_pw_fwd_tc_res(int dtype, int out_dtype, int B, int H, int W, int N, con
     if (ops[i].dy || ops[i].dx || ops[i].act) prm.any_transform = 1;
     if (ops[i].dy || ops[i].dx) prm.any_shift = 1;
     if (prm.conv3 && i > 0) continue;       // one map: the slab box of the shared tensor
+    if (in_f32)       // 128 x 32 fp32 boxes (128-byte rows, the same swizzle): one k-block of the split mode
+      ACCX_REQUIRE(encode_2d_out(&prm.tmap[i], ops[i].data, ops[i].K, P, ops[i].ld, 4, TC_BM),
+                   "pw_fwd_tc: cuTensorMapEncodeTiled failed for operand %d", i);
+    else
     ACCX_REQUIRE(encode_2d_bf16(&prm.tmap[i], ops[i].data, ops[i].K, P, ops[i].ld, prm.conv3 ? TC_SLAB_ROWS : TC_BM),
                  "pw_fwd_tc: cuTensorMapEncodeTiled failed for operand %d", i);
   }
   ACCX_REQUIRE(encode_2d_out(&prm.tmap_y, y, N, P, ldy, esz, TC_BM), "pw_fwd_tc: cuTensorMapEncodeTiled failed for the output");
   const size_t smem = tc_geometry(N, P, ops, n_ops, out_f32, prm);
   const int n_tiles = prm.n_tiles;
-  const int64_t need = (int64_t)n_tiles * prm.n_kb * prm.bn * TC_BK * 2;
+  const int64_t need = (int64_t)n_tiles * prm.n_kb * (in_f32 ? 2 : 1) * prm.bn * TC_BK * 2;
   ACCX_REQUIRE(prm.b_resident || (workspace_bytes >= need && aligned16(workspace)),
                "pw_fwd_tc: workspace too small (%lld < %lld)", (long long)workspace_bytes, (long long)need);
   prm.B = B; prm.H = H; prm.W = W; prm.N = N;
@@ -877,14 +1026,16 @@ int accx_pw_fwd_tc_res(int dtype, int out_dtype, int B, int H, int W, int N, con
                "pw_fwd_tc: residual needs a 16-byte aligned base and row pitch, ld_res >= N, N %% 8 == 0");
   cudaStream_t st = (cudaStream_t)stream;
   if (!prm.b_resident) {     // streamed weight tiles come from a bf16 re-pack in the workspace
-    launch_k(tc_pack_weights_kernel, dim3(prm.n_kb, n_tiles, (prm.bn * TC_BK + 1023) / 1024), 256, 0, st, prm, (bf16*)workspace);
+    launch_k(tc_pack_weights_kernel, dim3(prm.n_kb, n_tiles, ((prm.f32in ? 2 : 1) * prm.bn * TC_BK + 1023) / 1024), 256, 0, st, prm,
+             (bf16*)workspace);
     int rc = check_launch("tc_pack_weights");
     if (rc) return rc;
   }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(pw_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX);
-    cudaFuncSetAttribute(pw_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX);
+    cudaFuncSetAttribute(pw_fwd_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX);
+    cudaFuncSetAttribute(pw_fwd_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX);
+    cudaFuncSetAttribute(pw_fwd_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX);
     attr_set = true;
   }
   const int64_t total = (int64_t)prm.m_tiles * prm.n_tiles;
@@ -892,8 +1043,9 @@ int accx_pw_fwd_tc_res(int dtype, int out_dtype, int B, int H, int W, int N, con
   if (grid > total) grid = total;
   prm.det = (det_on() && stats) ? 1 : 0;
   if (prm.det) grid = 1;      // each statistic then receives one contribution per epilogue group: a + b is order-free
-  if (prm.conv3) launch_k(pw_fwd_tc_kernel<true>, (unsigned)grid, TC_THREADS, smem, st, prm);
-  else launch_k(pw_fwd_tc_kernel<false>, (unsigned)grid, TC_THREADS, smem, st, prm);
+  if (prm.f32in) launch_k(pw_fwd_tc_kernel<2>, (unsigned)grid, TC_THREADS, smem, st, prm);
+  else if (prm.conv3) launch_k(pw_fwd_tc_kernel<1>, (unsigned)grid, TC_THREADS, smem, st, prm);
+  else launch_k(pw_fwd_tc_kernel<0>, (unsigned)grid, TC_THREADS, smem, st, prm);
   return check_launch("pw_fwd_tc");
 }
 

@@ -62,6 +62,23 @@ __device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
 }
+// fp32 -> tf32 (10 mantissa bits), round to nearest: the bit pattern is an fp32 word with the 13 low mantissa bits clear
+__device__ __forceinline__ float to_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, tf32 x tf32 -> fp32 (32-bit operands in shared memory, K = 8 per instruction)
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
 // K-major, 128B swizzle, 8-row groups 1024 B apart (SBO), sm100 descriptor version 1
 __device__ __forceinline__ uint64_t make_desc_k_sw128(uint32_t saddr) {
   uint64_t d = 0;

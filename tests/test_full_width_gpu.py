@@ -22,6 +22,25 @@ DEV = "cuda"
 torch.backends.cudnn.allow_tf32 = False
 torch.backends.cuda.matmul.allow_tf32 = False
 SLACK = 3.0
+# fp32 storage with 3 x TF32 tensor-core contractions (the free-running fp32 mode; ~2^-21 per product instead of 2^-24):
+# the whole-model deviation is 2-6x the reference's own fp32-vs-fp64 error (measured on B200, printed by the tests); the
+# exact fp32-FMA contractions of the deterministic parity mode stay within SLACK.  Module-level parity (rtol 1e-3) holds
+# for both (tests/test_modules_gpu.py::test_module_matches_reference_golden[fp32tc]).
+SLACK_TF32 = 8.0
+
+
+class _contractions:
+    def __init__(self, tf32):
+        self.tf32 = tf32
+
+    def __enter__(self):
+        from accx import engine
+        self.old, engine.TC_F32_IN_DET = engine.TC_F32_IN_DET, bool(self.tf32)
+
+    def __exit__(self, *exc):
+        from accx import engine
+        engine.TC_F32_IN_DET = self.old
+        return False
 
 
 def inputs(B, hw, seed):
@@ -85,12 +104,14 @@ def full_grads_err(model, z, tag=""):
     return worst
 
 
+@pytest.mark.parametrize("tf32", [False, True], ids=["fma", "tf32x3"])
 @pytest.mark.parametrize("cls_name,fixture", [("ACC_UNet", "full_accunet_224"), ("ACC_UNet_Lite", "full_accunetlite_224"),
                                               ("ACC_UNet_W", "full_accunetw_224")])
-def test_full_width_train_step_fp32_matches_reference(cls_name, fixture):
+def test_full_width_train_step_fp32_matches_reference(cls_name, fixture, tf32):
     z = load_case(fixture)["raw"]
     x, m = inputs(2, 224, 2024)
-    with deterministic():
+    SLACK = SLACK_TF32 if tf32 else globals()["SLACK"]
+    with deterministic(), _contractions(tf32):
         model = build(cls_name).train()
         logits, loss, gin = step(model, x, m)
         ref_logits = torch.from_numpy(z["logits"])
@@ -139,11 +160,13 @@ def _eval_model(z, dtype=None):
     return model.eval()
 
 
-def test_full_width_eval_mode_forward_backward_fp32_matches_reference():
+@pytest.mark.parametrize("tf32", [False, True], ids=["fma", "tf32x3"])
+def test_full_width_eval_mode_forward_backward_fp32_matches_reference(tf32):
     """eval(): BatchNorm on running statistics, differentiated as a fixed affine (the reference's modules do that too)"""
     z = load_case("full_accunet_224")["raw"]
     x2, m2 = inputs(2, 224, 2025)
-    with deterministic():
+    SLACK = SLACK_TF32 if tf32 else globals()["SLACK"]
+    with deterministic(), _contractions(tf32):
         model = _eval_model(z)
         logits, loss, gin = step(model, x2, m2)
     e_log, r_log = rel_l2(logits, torch.from_numpy(z["eval/logits"])), float(z["ref_err/eval_logits_rel_l2"])

@@ -160,6 +160,51 @@ def test_tc_residual_in_epilogue(K, N, f32_out):
     assert torch.equal(y2, y)
 
 
+@pytest.mark.parametrize("P_shape", [(2, 12, 20), (3, 7, 11), (4, 32, 32)])
+@pytest.mark.parametrize("K,N,act", [(32, 96, 0), (96, 32, 2), (480, 64, 1), (128, 136, 2), (16, 256, 2), (8, 8, 0),
+                                     (1088, 128, 2), (24, 40, 2), (128, 4352, 0)])
+def test_tc_fp32_storage_split(P_shape, K, N, act):
+    """fp32 storage on the bf16 tensor cores (three-term split, MODE 2 of pw_fwd_tc_kernel): the reference's own
+    arithmetic is fp32, so the bound is the fp32 parity bound -- rtol 1e-3, atol 1e-5 * max -- against an fp64 product
+    of the same fp32 inputs; statistics from the fp32 output"""
+    e = E()
+    B, H, W = P_shape
+    L, a = mk_lazy((B, H, W, K), torch.float32, act, 41)
+    w = (torch.randn(N, K, generator=torch.Generator().manual_seed(42)) / K ** 0.5).to(DEV)
+    stats = torch.zeros(2 * N, device=DEV)
+    from accx import _lib
+    names = []
+    orig = _lib.call
+    _lib.call = lambda n, *a_: (names.append(n), orig(n, *a_))[1]
+    try:
+        y = e.conv([e.Op(L, K, e.WV(w, 0, K, 1))], N, (B, H, W), stats=stats)
+    finally:
+        _lib.call = orig
+    assert names == ["accx_pw_fwd_tc_res"], names
+    assert y.dtype == torch.float32
+    ref = (a.double() @ w.double().t())
+    close(y, ref, 1e-3, 1e-5, "fp32 split")
+    assert float((y.double() - ref).abs().max() / ref.abs().max()) < 1e-5       # 3 x TF32: ~2^-21 per product
+    close(stats[:N], ref.sum((0, 1, 2)), 1e-3, 1e-4, "fp32 split sum")
+    close(stats[N:], (ref * ref).sum((0, 1, 2)), 1e-3, 1e-4, "fp32 split sum of squares")
+
+
+def test_tc_fp32_storage_split_dense3x3_and_residual():
+    """nine shifted fp32 operands (ResPath in fp32 storage), bias, residual in the epilogue"""
+    e = E()
+    B, H, W, C = 2, 9, 12, 32
+    L, a = mk_lazy((B, H, W, C), torch.float32, 2, 43)
+    g = torch.Generator().manual_seed(44)
+    w = (torch.randn(C, C, 3, 3, generator=g) / (3 * C ** 0.5)).to(DEV)
+    b = torch.randn(C, generator=g).to(DEV)
+    r = torch.randn(B, H, W, C, generator=g).to(DEV)
+    ops = [e.Op(L, C, e.WV(w, ky * 3 + kx, C * 9, 9), 0, ky - 1, kx - 1) for ky in range(3) for kx in range(3)]
+    y = e.conv(ops, C, (B, H, W), bias=b, residual=r)
+    torch.backends.cudnn.allow_tf32 = False
+    ref = F.conv2d(a.double().permute(0, 3, 1, 2), w.double(), b.double(), padding=1).permute(0, 2, 3, 1) + r.double()
+    close(y, ref, 1e-3, 1e-5, "fp32 split conv3x3 + residual")
+
+
 def test_tc_large_tile_count_and_k_pipeline():
     """many M tiles, 17 N tiles (N=4352, the cnv72.conv1 shape) and a deep K loop (cnv72.hnc main: K=4352)"""
     e = E()

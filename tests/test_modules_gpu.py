@@ -164,14 +164,34 @@ def run_accx(mod, xs_cpu, cots, dtype):
     return yg, xg, accx_decisions(m, rec)
 
 
-@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+class tf32_contractions:
+    """fp32 storage with the 3 x TF32 tensor-core contraction (the default of the free-running fp32 mode) inside the
+    deterministic reduction mode, so that the fp32 bounds below test the contraction and not the atomics"""
+
+    def __init__(self, on):
+        self.on = on
+
+    def __enter__(self):
+        from accx import engine
+        self.old, engine.TC_F32_IN_DET = engine.TC_F32_IN_DET, bool(self.on)
+
+    def __exit__(self, *exc):
+        from accx import engine
+        engine.TC_F32_IN_DET = self.old
+        return False
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16", "fp32tc"])
 @pytest.mark.parametrize("name", module_cases())
-def test_module_matches_reference_golden(name, dtype):
+def test_module_matches_reference_golden(name, mode):
+    """fp32: fp32 storage, exact fp32-FMA contractions; fp32tc: fp32 storage, 3 x TF32 tensor-core contractions -- the
+    SAME rtol 1e-3 bounds; bf16: bf16 storage, tcgen05 contractions"""
+    dtype = torch.bfloat16 if mode == "bf16" else torch.float32
     case = load_case(name)
     mod = build(name).to(DEV)
     mod.load_state_dict(case["sd"])
     sd_dot = {"." + k: v for k, v in case["sd"].items()}
-    with deterministic(dtype == torch.float32):
+    with deterministic(dtype == torch.float32), tf32_contractions(mode == "fp32tc"):
         ys, xs, decisions = run_accx(mod, case["in"], case["cot"], dtype)
         if dtype == torch.float32:
             ref_gin, ref_gp = case["gin"], case["gp"]      # the reference's own gradients, free-running
