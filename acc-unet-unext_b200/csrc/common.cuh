@@ -34,6 +34,7 @@ enum {
   KNOB_TC_CONV3,      // 18: dense-3x3 slab mode of pw_fwd_tc: 1 (default) on, 2 off (nine shifted operands)
   KNOB_TC_DEBUG,      // 19: timing diagnostics of pw_fwd_tc (bit 0 no transform math, 1 no statistics pass, 2 no TMA store, 3 no TMEM drain)
   KNOB_TC_F32_TERMS,  // 20: products of the tf32 split in fp32-storage contractions: 3 (default) or 4
+  KNOB_TC_NACC,       // 21: TMEM accumulator ring of pw_fwd_tc: 2 (default) or 4 buffers (when 4 * BN <= 512 columns)
   KNOB_COUNT
 };
 extern int g_knobs[KNOB_COUNT];

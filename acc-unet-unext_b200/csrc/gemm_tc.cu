@@ -68,6 +68,20 @@ struct alignas(64) TcParams {
 constexpr int TC_SLAB_ROWS = 136;                    // 128 + 2 halo pixels, rounded up to the 8-row swizzle group
 constexpr int TC_SLAB_BYTES = TC_SLAB_ROWS * 128;
 
+// ---------------------------------------------------------------- role timeline (diagnostics)
+// KNOB_TC_DEBUG bit 5: CTA 0 stamps %globaltimer at the hand-offs of its first 64 tiles (accx_debug_tc_trace reads them):
+// event * 64 + tile iteration; 0 TMA issued, 1 transform saw the tile land, 2 transform arrived on `full`, 3 MMA saw
+// `full`, 4 MMA committed the tile, 5 MMA got the accumulator, 6 epilogue saw `tfull`, 7 epilogue released the
+// accumulator, 8 store issued, 9 statistics pass done.
+__device__ unsigned long long g_tc_trace[10 * 64];
+__device__ __forceinline__ void tc_trace(const TcParams& prm, int ev, int it) {
+  if ((prm.debug & 32) && blockIdx.x == 0 && it < 64) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    g_tc_trace[ev * 64 + it] = t;
+  }
+}
+
 // ---------------------------------------------------------------- weight packing
 // wpack[(n_tile * n_kb + kb) * bn * 64 + swizzled(n_local, kk)] = bf16(W_op[n, k0 + kk])
 __global__ void tc_pack_weights_kernel(const __grid_constant__ TcParams prm, bf16* __restrict__ wpack) {
@@ -293,6 +307,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_fwd_tc_kernel(const __grid_c
         for (int kb = 0; kb < n_kb; ++kb) {
           while (o + 1 < prm.n_ops && kb >= prm.kb_start[o + 1]) ++o;
           mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+          if (kb == 0) tc_trace(prm, 0, (tile - (int)blockIdx.x) / (int)gridDim.x);
           const uint32_t a_smem = base + stage * stage_bytes;
           const uint32_t bar = landed_bar + 8 * stage;
           mbar_expect_tx(bar, TC_A_BYTES + (prm.b_resident ? 0 : b_tile_bytes));
@@ -320,6 +335,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_fwd_tc_kernel(const __grid_c
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
         const int acc = tl & nacc_mask;
         mbar_wait(tempty_bar + 8 * acc, ((tl >> nacc_log) & 1) ^ 1);
+        tc_trace(prm, 5, tl);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * acc_stride;
         if (CONV3) {
@@ -350,6 +366,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_fwd_tc_kernel(const __grid_c
         for (int kb = 0; kb < n_kb; ++kb) {
           while (o + 1 < prm.n_ops && kb >= prm.kb_start[o + 1]) ++o;
           mbar_wait(ready_bar + 8 * stage, phase);
+          if (kb == 0) tc_trace(prm, 3, tl);
           tc_fence_after();
           const uint32_t a_smem = base + stage * stage_bytes;
           const uint64_t adesc = make_desc_k_sw128(a_smem);
@@ -381,6 +398,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_fwd_tc_kernel(const __grid_c
           if (++stage == S) { stage = 0; phase ^= 1; }
         }
         tc_commit(tfull_bar + 8 * acc);
+        tc_trace(prm, 4, tl);
       }
     }
   } else if (warp >= TC_WARP_XF0) {
@@ -538,7 +556,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_fwd_tc_kernel(const __grid_c
       // narrow operands (K = 32 / 16 in a 64-channel box: the rest is TMA zero fill and stays zero): only the chunks
       // that hold channels are touched -- thread -> (chunk c4 of rows r4, r4 + 64) resp. (chunk c2 of row r2)
       const int c4 = t & 3, r4 = t >> 2, c2 = t & 1, r2 = t >> 1;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int tlx = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tlx) {
         const int m0 = (tile % prm.m_tiles) * TC_BM;
         int ph[4], pw[4];
 #pragma unroll
@@ -575,6 +594,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_fwd_tc_kernel(const __grid_c
             }
           }
           mbar_wait(landed_bar + 8 * stage, phase);
+          if (kb == 0 && t == 0) tc_trace(prm, 1, tlx);
           const uint32_t blk = base + stage * stage_bytes;
           if ((mt.x != 0 || zero_mask != 0) && !(prm.debug & 1)) {
             if (kcw == 4) transform_block<2, 64>(blk, c4, r4, mt.x, s, sh, 0u);
@@ -584,6 +604,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_fwd_tc_kernel(const __grid_c
           fence_async_smem();
           __syncwarp();
           if (lane == 0) mbar_arrive(full_bar + 8 * stage);
+          if (kb == n_kb - 1 && t == 0) tc_trace(prm, 2, tlx);
           if (++stage == S) { stage = 0; phase ^= 1; }
         }
       }
@@ -678,6 +699,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_fwd_tc_kernel(const __grid_c
         }
       }
       mbar_wait(tfull_bar + 8 * acc, (tl >> nacc_log) & 1);
+      if (gtid == 0) tc_trace(prm, 6, tl);
       tc_fence_after();
       // the staging boxes are free once the previous tile's TMA stores have read them and every thread has
       // finished its statistics pass
@@ -791,12 +813,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_fwd_tc_kernel(const __grid_c
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar + 8 * acc);
+      if (gtid == 0) tc_trace(prm, 7, tl);
       fence_async_smem();                                   // generic-proxy writes -> visible to the TMA store
       asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
       if (gtid == 0) {
         for (int b = 0; b < prm.out_boxes; ++b)
           if (n0 + b * box_cols < N && !(prm.debug & 4)) tma_store_2d(&prm.tmap_y, stage + b * TC_BOX_BYTES, n0 + b * box_cols, (int)m0);
         bulk_commit();
+        tc_trace(prm, 8, tl);
       }
       if (st_active && !(prm.debug & 2)) {
         // column-wise read-back of the staged bf16 tile: this thread's 8 columns over its rows
@@ -835,6 +859,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_fwd_tc_kernel(const __grid_c
           }
         }
       }
+      if (gtid == 0) tc_trace(prm, 9, tl);
     }
     if (st_on && cur_nt >= 0) flush_stats(cur_nt);
     if (gtid == 0) bulk_wait0();           // all stores complete before the CTA (and its shared memory) retires
@@ -897,7 +922,7 @@ static size_t tc_geometry(int N, int64_t P, const accx_operand_t* ops, int n_ops
   // CTA of the side stream on the same SM), else two
   // (measured on B200, K = N = 32 at 16x224x224: a ring of four changes nothing, 51.4 vs 50.8 us -- the narrow-tile rate
   //  is set by the per-row cost of the 128-row TMA boxes, tests/bench_gemm.py debug / stages -- so two it stays)
-  prm.nacc_log = 1;
+  prm.nacc_log = (knob(KNOB_TC_NACC, 2) == 4 && !prm.conv3 && 4 * prm.bn <= 512) ? 2 : 1;
   int cols = 32;
   while (cols < (prm.conv3 ? 3 : 1) * (1 << prm.nacc_log) * prm.bn) cols <<= 1;
   prm.tmem_cols = cols;
@@ -930,6 +955,13 @@ static size_t tc_geometry(int N, int64_t P, const accx_operand_t* ops, int n_ops
 using namespace accx;
 
 extern "C" {
+
+// diagnostics: the role timeline of the last pw_fwd_tc launch made with KNOB_TC_DEBUG bit 5 (640 x uint64 nanoseconds)
+int accx_debug_tc_trace(unsigned long long* dst, int n) {
+  ACCX_REQUIRE(dst && n > 0 && n <= 640, "debug_tc_trace: bad arguments");
+  cudaDeviceSynchronize();
+  return cudaMemcpyFromSymbol(dst, g_tc_trace, (size_t)n * 8) == cudaSuccess ? ACCX_OK : ACCX_ERR_CUDA;
+}
 
 int64_t accx_pw_tc_workspace_bytes(int N, const accx_operand_t* ops, int n_ops) {
   if (!ops || n_ops < 1 || n_ops > ACCX_MAX_OPERANDS) return -1;

@@ -98,6 +98,9 @@ int accx_pw_fwd_tc(int dtype, int out_dtype, int B, int H, int W, int N,
                    const accx_operand_t* ops, int n_ops, const float* bias,
                    const float* const* add, const int* add_log2s, int n_add,
                    void* y, int64_t ldy, float* stats, void* workspace, int64_t workspace_bytes, void* stream);
+/* Diagnostics: with knob 19 (KNOB_TC_DEBUG) bit 5 set, CTA 0 of accx_pw_fwd_tc stamps %globaltimer at the role hand-offs
+ * of its first 64 tiles; this copies the 10 x 64 nanosecond stamps out (event * 64 + tile; events in csrc/gemm_tc.cu). */
+int accx_debug_tc_trace(unsigned long long* dst, int n);
 /* accx_pw_fwd_tc with a residual: Y = contraction (+ bias + addends) + R, R a [P, ld_res] matrix in the OUTPUT dtype
  * (16-byte aligned base and row pitch).  R may be Y itself (in-place accumulation: every tile is read before it is
  * written).  Fuses the `x + inp` / gradient-accumulation passes that follow an input-gradient contraction

@@ -151,6 +151,44 @@ if __name__ == "__main__":
                 run_graph(i)
         _lib.call("accx_set_knob", 19, 0)
         sys.exit(0)
+    if "trace" in args:          # role timeline of CTA 0 (knob 19 bit 5): who waits for whom, tile by tile
+        import ctypes
+        from accx import _lib
+        SHAPES[:] = [(802816, 32, 32, 2, 1), (802816, 64, 64, 2, 1)]
+        names = ["tma_issue", "xf_landed", "xf_arrive", "mma_full", "mma_commit", "mma_acc", "epi_tfull", "epi_release",
+                 "epi_store", "epi_stats"]
+        for i in range(len(SHAPES)):
+            P, K, N, act, st = SHAPES[i]
+            x = torch.randn(1, 1, P, K, device="cuda").to(torch.bfloat16)
+            L = E.Lazy(x, torch.rand(K, device="cuda") + 0.5, torch.randn(K, device="cuda") * 0.1, act)
+            w = torch.randn(N, K, device="cuda") / K ** 0.5
+            stats = torch.zeros(2 * N, device="cuda")
+            ops = [E.Op(L, K, E.WV(w, 0, K, 1))]
+            for _ in range(3):
+                E.conv(ops, N, (1, 1, P), stats=stats)
+            _lib.call("accx_set_knob", 19, 32)
+            E.conv(ops, N, (1, 1, P), stats=stats)
+            _lib.call("accx_set_knob", 19, 0)
+            buf = (ctypes.c_ulonglong * 640)()
+            _lib.call("accx_debug_tc_trace", buf, 640)
+            t0 = min(v for v in buf if v)
+            print(f"==== K={K} N={N}: ns since the first stamp, tiles 0..13 of CTA 0 (then 30..33)")
+            for tl in list(range(14)) + list(range(30, 34)):
+                print(f"tile {tl:2d}: " + "  ".join(f"{names[e]} {buf[e * 64 + tl] - t0:6d}" for e in range(10)))
+        sys.exit(0)
+    if "ring" in args:           # accumulator ring (knob 21) x parts of the kernel off (knob 19)
+        from accx import _lib
+        SHAPES[:] = [(802816, 32, 32, 2, 1), (802816, 64, 64, 2, 1), (802816, 32, 96, 0, 1)]
+        for nacc in (2, 4):
+            _lib.call("accx_set_knob", 21, nacc)
+            for dbg in (0, 1, 2, 3, 8, 10, 11, 15):
+                _lib.call("accx_set_knob", 19, dbg)
+                print(f"---- ring {nacc} debug {dbg}")
+                for i in range(len(SHAPES)):
+                    run_graph(i)
+        _lib.call("accx_set_knob", 19, 0)
+        _lib.call("accx_set_knob", 21, 0)
+        sys.exit(0)
     if "stages" in args:         # sensitivity of the narrow tile rate to the pipeline depth (knob 14 = TC_MAX_STAGES)
         from accx import _lib
         SHAPES[:] = [(802816, 32, 32, 2, 1), (802816, 64, 64, 2, 1), (802816, 128, 32, 2, 1)]
