@@ -73,6 +73,9 @@ SIDE_MODE = int(os.environ.get("ACCX_WGRAD_STREAM", "1"))
 SIDE_PRIORITY = int(os.environ.get("ACCX_SIDE_PRIO", "0"))
 MAIN_PRIORITY = int(os.environ.get("ACCX_MAIN_PRIO", "-3"))
 BWD_DEPTH = [0]
+BWD_START_HOOK = None  # callable(obj) run when the backward of an accx module (obj) or of a group of chains (a list) starts:
+                       # every module whose backward ran before has all its parameter gradients queued (TrainStep overlaps
+                       # the gradient all-reduce of finished parts of the model with the rest of backward)
 _SIDE = {}
 _SIDE_DIRTY = set()
 _KEEP = []

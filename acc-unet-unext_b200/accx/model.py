@@ -64,6 +64,16 @@ class _ACCUNetBase(nn.Module):
             self.out = nn.Conv2d(f, n_classes + 1, kernel_size=(1, 1))
             self.last_activation = None
 
+    def allreduce_phases(self):
+        """Data-parallel training: [(trigger, modules)] -- when the backward of `trigger` (a module, or "group" = the first
+        group of parallel chains) starts, every parameter gradient of `modules` is final.  Backward runs decoder ->
+        MLFC -> (ResPaths || encoder), and the parameters of each part are contiguous in parameter order, so TrainStep
+        all-reduces the decoder's 60 % of the gradient buffer under the MLFC + encoder backward and MLFC's under the
+        encoder's (ACC_UNet.py:620-631 read backwards)."""
+        dec = [self.up6, self.cnv61, self.cnv62, self.up7, self.cnv71, self.cnv72, self.up8, self.cnv81, self.cnv82,
+               self.up9, self.cnv91, self.cnv92, self.out]
+        return [(self.mlfc3, dec), ("group", [self.mlfc1, self.mlfc2, self.mlfc3])]
+
     def forward(self, x):
         E.require_cuda(x)
         cd = self.compute_dtype or x.dtype

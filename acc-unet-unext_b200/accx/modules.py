@@ -49,6 +49,8 @@ class _ModuleFn(torch.autograd.Function):
     def backward(ctx, *douts):
         saved, mod = ctx.saved, ctx.mod
         ctx.saved = None
+        if E.BWD_START_HOOK is not None:
+            E.BWD_START_HOOK(mod)
         ref = saved["out_like"]
         dn = []
         for d, like in zip(douts, ref):
@@ -99,6 +101,8 @@ class _GroupFn(torch.autograd.Function):
     def backward(ctx, *douts):
         chains, saved, n = ctx.chains, ctx.saved, len(ctx.chains)
         ctx.saved = None
+        if E.BWD_START_HOOK is not None:
+            E.BWD_START_HOOK(chains)
         dn = []
         for d, sv in zip(douts, saved):
             like = sv[-1]["out_like"][0]

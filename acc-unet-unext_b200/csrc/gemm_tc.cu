@@ -62,6 +62,7 @@ struct alignas(64) TcParams {
   int nacc_log;         // log2 of the TMEM accumulator ring (2 or 4 buffers): narrow tiles keep the MMA issuer up to four
                         // tiles ahead of the epilogue groups, so neither waits out the other's latency every tile
   int debug;            // KNOB_TC_DEBUG (timing diagnostics only: results are wrong when non-zero)
+  int occ;              // CTAs per SM this launch is sized for (1 or 2; host side only)
   int tap_op[3][3];
 };
 
@@ -157,8 +158,8 @@ __device__ __forceinline__ void stage_chunk(const float (&v)[16], uint32_t stage
 // BatchNorms amplify it to 7e-3 at the logits, 20x the reference's own fp32-vs-fp64 error).  A k-block is 32 fp32
 // channels: the landed 128 x 32 fp32 box becomes a_hi in place, a_lo goes to a second tile of the stage, and every
 // k-block has two weight tiles, w_hi and w_lo.  Separate instantiations: the bf16 contraction carries none of this code.
-template <int MODE>
-__global__ void __launch_bounds__(TC_THREADS, 1) pw_fwd_tc_kernel(const __grid_constant__ TcParams prm) {
+template <int MODE, int OCC = 1>
+__global__ void __launch_bounds__(TC_THREADS, OCC) pw_fwd_tc_kernel(const __grid_constant__ TcParams prm) {
   constexpr bool CONV3 = MODE == 1, F32IN = MODE == 2;
   constexpr int BKC = F32IN ? 32 : TC_BK;          // channels per k-block
   pdl_sync();
@@ -946,6 +947,21 @@ static size_t tc_geometry(int N, int64_t P, const accx_operand_t* ops, int n_ops
   const int max_stages = knob(KNOB_TC_MAX_STAGES, 8);
   if (S > max_stages) S = max_stages;
   if (S < 1) S = 1;
+  // Two CTAs per SM for narrow tiles over many pixels: every role of this kernel is a chain of long-latency hand-offs
+  // (0.8 us per 128-pixel tile whatever the bytes), so a second, independent pipeline on the same SM
+  // hides them.  Needs both CTAs' shared memory (<= 112 KB each with >= 3 stages), TMEM (<= 256 columns each) and
+  // registers (the OCC = 2 instantiation is held to 56) to fit, and at least two tiles per CTA.
+  prm.occ = 1;
+  if (knob(KNOB_TC_OCC, 2) == 2 && !prm.f32in && !prm.conv3 && prm.tmem_cols <= 256 &&
+      (int64_t)prm.m_tiles * prm.n_tiles >= 4 * (int64_t)n_sm) {
+    const size_t cap2 = 112 * 1024;
+    if (fixed + resident + 3 * stage <= cap2) {
+      int S2 = (int)((cap2 - fixed - resident) / stage);
+      if (S2 > max_stages) S2 = max_stages;
+      S = S2;
+      prm.occ = 2;
+    }
+  }
   prm.stages = S;
   return fixed + resident + (size_t)S * stage;
 }
@@ -1066,17 +1082,19 @@ int accx_pw_fwd_tc_res(int dtype, int out_dtype, int B, int H, int W, int N, con
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(pw_fwd_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX);
+    cudaFuncSetAttribute(pw_fwd_tc_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
     cudaFuncSetAttribute(pw_fwd_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX);
     cudaFuncSetAttribute(pw_fwd_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX);
     attr_set = true;
   }
   const int64_t total = (int64_t)prm.m_tiles * prm.n_tiles;
-  int64_t grid = sm_count();
+  int64_t grid = (int64_t)prm.occ * sm_count();
   if (grid > total) grid = total;
   prm.det = (det_on() && stats) ? 1 : 0;
   if (prm.det) grid = 1;      // each statistic then receives one contribution per epilogue group: a + b is order-free
   if (prm.f32in) launch_k(pw_fwd_tc_kernel<2>, (unsigned)grid, TC_THREADS, smem, st, prm);
   else if (prm.conv3) launch_k(pw_fwd_tc_kernel<1>, (unsigned)grid, TC_THREADS, smem, st, prm);
+  else if (prm.occ == 2) launch_k(pw_fwd_tc_kernel<0, 2>, (unsigned)grid, TC_THREADS, smem, st, prm);
   else launch_k(pw_fwd_tc_kernel<0>, (unsigned)grid, TC_THREADS, smem, st, prm);
   return check_launch("pw_fwd_tc");
 }

@@ -14,8 +14,9 @@
 
 namespace accx {
 
-constexpr int WG_PX = 128;                 // pixels per pipeline stage (8 MMAs of K = 16)
-constexpr int WG_BLK = WG_PX * 64 * 2;     // bytes of one 128 px x 64 ch block
+// pixels per pipeline stage: 128 (8 MMAs of K = 16), or 256 for the narrow level-1 / level-2 contractions -- every stage
+// is a chain of hand-offs (TMA -> transform -> MMA issue -> commit) with ~1 us of fixed latency, so tiles of 16-32 KB are
+// bound by the number of hand-offs, not by bytes (the role timeline of the forward kernel)
 constexpr int WG_THREADS = 320;
 
 struct alignas(64) WgParams {
@@ -26,7 +27,7 @@ struct alignas(64) WgParams {
   int nb;                 // A-channel tile (multiple of 64, <= 256)
   int n_tiles, k_tiles;   // over dY channels (128 each) and A channels (nb each)
   int splits;
-  int64_t px_per_split;   // multiple of WG_PX
+  int64_t px_per_split;   // multiple of the stage size
   int stages, tmem_cols, any_transform;
   float* dw;
   // several filter taps of a dense 3x3 convolution in ONE pass over dY and the activation (ResPath): tap t reads
@@ -37,7 +38,10 @@ struct alignas(64) WgParams {
   int64_t tap_woff[9];
 };
 
+template <int WG_PX>
 __global__ void __launch_bounds__(WG_THREADS) pw_wgrad_tc_kernel(const __grid_constant__ WgParams prm) {
+  constexpr int WG_BLK = WG_PX * 64 * 2;     // bytes of one WG_PX px x 64 ch block
+  constexpr int NR = WG_PX / 32;             // rows per transform thread
   pdl_sync();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -130,7 +134,7 @@ __global__ void __launch_bounds__(WG_THREADS) pw_wgrad_tc_kernel(const __grid_co
   } else {
     // warps 0-7: transform during the pixel loop; warps 0-3 then drain the accumulator
     if (prm.any_transform) {
-      const int c = tid & 7, r0 = tid >> 3;                       // rows r0, r0 + 32, r0 + 64, r0 + 96
+      const int c = tid & 7, r0 = tid >> 3;                       // rows r0, r0 + 32, r0 + 64, ..
       float* tab = reinterpret_cast<float*>(smem + tab_off);
       for (int j = tid; j < nbp; j += 256) {
         const bool on = prm.op.act != 0 && j < nb && k0 + j < prm.op.K;
@@ -143,13 +147,13 @@ __global__ void __launch_bounds__(WG_THREADS) pw_wgrad_tc_kernel(const __grid_co
       const int HWp = prm.H * prm.W;
       for (int it = 0; it < n_it; ++it) {
         const int stage = it % S;
-        int ph[4], pw[4];
+        int ph[NR], pw[NR];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { ph[i] = 0; pw[i] = 0; }
+        for (int i = 0; i < NR; ++i) { ph[i] = 0; pw[i] = 0; }
         if (shifted) {
           const int p0 = (int)(pbeg + (int64_t)it * WG_PX);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
+          for (int i = 0; i < NR; ++i) {
             const int p = p0 + r0 + 32 * i;
             const int rem = p % HWp;
             ph[i] = rem / prm.W;
@@ -162,7 +166,7 @@ __global__ void __launch_bounds__(WG_THREADS) pw_wgrad_tc_kernel(const __grid_co
           uint32_t zero_mask = 0;
           if (prm.tap_dy[t] != 0 || prm.tap_dx[t] != 0) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < NR; ++i) {
               const int hh = ph[i] + prm.tap_dy[t], ww = pw[i] + prm.tap_dx[t];
               if (hh < 0 || hh >= prm.H || ww < 0 || ww >= prm.W || pw[i] < 0) zero_mask |= 1u << i;
             }
@@ -175,7 +179,7 @@ __global__ void __launch_bounds__(WG_THREADS) pw_wgrad_tc_kernel(const __grid_co
             const float4 a0 = sp[0], a1 = sp[1], b0 = tp[0], b1 = tp[1];
             sc[0] = a0.x; sc[1] = a0.y; sc[2] = a0.z; sc[3] = a0.w; sc[4] = a1.x; sc[5] = a1.y; sc[6] = a1.z; sc[7] = a1.w;
             sh[0] = b0.x; sh[1] = b0.y; sh[2] = b0.z; sh[3] = b0.w; sh[4] = b1.x; sh[5] = b1.y; sh[6] = b1.z; sh[7] = b1.w;
-            transform_block<4, 32>(st + (dyb + t * a_blocks + j) * WG_BLK, c, r0, prm.op.act, sc, sh, zero_mask);
+            transform_block<NR, 32>(st + (dyb + t * a_blocks + j) * WG_BLK, c, r0, prm.op.act, sc, sh, zero_mask);
           }
         }
         fence_async_smem();
@@ -264,10 +268,13 @@ static int wgrad_tc_launch(int B, int H, int W, int N, const accx_operand_t* op,
   while (cols < n_taps * prm.nb) cols <<= 1;
   prm.tmem_cols = cols;
   const int pairs = prm.n_tiles * prm.k_tiles;
+  // 256-pixel stages for single-tap contractions of at most three 64-channel blocks per stage and many pixels
+  const int WG_PX = (n_taps == 1 && prm.dy_blocks + a_blocks <= 3 && prm.P >= 100000 && knob(KNOB_WGRAD_PX, 256) == 256) ? 256 : 128;
+  const size_t WG_BLK = (size_t)WG_PX * 64 * 2;
   const int64_t stages_total = (prm.P + WG_PX - 1) / WG_PX;
   int64_t splits = (2 * (int64_t)sm_count() + pairs - 1) / pairs;
   // every split ends with 128 x nb fp32 atomics per tap: keep at least 8 stages (1024 pixels) of work behind them
-  const int min_stages = knob(KNOB_WGRAD_MIN_STAGES, 8);
+  const int min_stages = knob(KNOB_WGRAD_MIN_STAGES, 8) * 128 / WG_PX;
   if (splits > stages_total / min_stages) splits = stages_total / min_stages;
   if (splits < 1 || det_on()) splits = 1;     // deterministic mode: one contribution per dW element, pixels in order
   int64_t per = (stages_total + splits - 1) / splits;      // stages per split
@@ -286,10 +293,12 @@ static int wgrad_tc_launch(int B, int H, int W, int N, const accx_operand_t* op,
   const size_t smem = 1024 + S * stage_bytes + 2 * (size_t)a_blocks * 64 * 4 + 24 * S + 64;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(pw_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(pw_wgrad_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(pw_wgrad_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr_set = true;
   }
-  launch_k(pw_wgrad_tc_kernel, (unsigned)(pairs * splits), WG_THREADS, smem, (cudaStream_t)stream, prm);
+  if (WG_PX == 256) launch_k(pw_wgrad_tc_kernel<256>, (unsigned)(pairs * splits), WG_THREADS, smem, (cudaStream_t)stream, prm);
+  else launch_k(pw_wgrad_tc_kernel<128>, (unsigned)(pairs * splits), WG_THREADS, smem, (cudaStream_t)stream, prm);
   return check_launch("pw_wgrad_tc");
 }
 

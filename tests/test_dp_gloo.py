@@ -216,3 +216,69 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["gpu_launches"] == 0
+
+
+# ---- backward-overlapped exchange: ranges of the flat buffer reduced early + the final reduction of the rest ----------
+def test_allreduce_phase_plan_covers_contiguous_ranges():
+    """ACC_UNet.allreduce_phases -> slices of the flat gradient buffer: decoder (60 % of the parameters) and MLFC are
+    contiguous in parameter order, disjoint, and hold exactly their modules' parameters"""
+    for p in (ROOT, os.path.join(ROOT, "acc-unet-unext_b200")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import accx
+    from accx.train import FlatState, plan_ranges
+    model = accx.ACC_UNet(3, 1, 8)
+    flat = FlatState(list(model.parameters()))
+    plan = plan_ranges(flat, model.allreduce_phases())
+    assert [t if isinstance(t, str) else "mod" for t, *_ in plan] == ["mod", "group"]
+    (_, lo1, hi1, p1), (_, lo2, hi2, p2) = plan
+    assert hi1 == flat.n and lo1 == hi2 and 0 < lo2 < hi2                 # head | MLFC | decoder
+    names = {id(p): n for n, p in model.named_parameters()}
+    assert all(names[id(p)].split(".")[0].startswith(("up", "cnv6", "cnv7", "cnv8", "cnv9", "out")) for p in p1)
+    assert all(names[id(p)].startswith("mlfc") for p in p2)
+    frac = sum(p.numel() for p in p1) / sum(p.numel() for p in model.parameters())
+    assert 0.5 < frac < 0.7
+    # a phase whose parameters are not contiguous is refused
+    with pytest.raises(ValueError):
+        plan_ranges(flat, [("group", [model.cnv11, model.out])])
+
+
+def _worker_ranges(rank, world, port, out_dir):
+    for p in (ROOT, os.path.join(ROOT, "acc-unet-unext_b200")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from accx.train import FlatState, GradAverager
+    torch.manual_seed(2)
+    params = [torch.nn.Parameter(torch.randn(n)) for n in (70, 5, 130, 64, 9)]
+    flat = FlatState(params)
+    flat.grad.copy_(torch.randn(flat.n, generator=torch.Generator().manual_seed(7 + rank)))
+    ref = flat.grad.clone()
+    dist.all_reduce(ref)
+    ref /= world
+    avg = GradAverager(params, flat=flat)
+
+    class Done:                      # the early reductions' handle: already complete on this backend
+        def wait(self):
+            return True
+
+    # two ranges go out "early" (sum + divide here: gloo has no AVG), the final call covers head, gap and tail
+    for lo, hi in ((128, 192), (320, 384)):
+        v = flat.grad[lo:hi]
+        dist.all_reduce(v)
+        v /= world
+        avg.pending.append((lo, hi, Done()))
+    avg()
+    assert not avg.pending
+    torch.save({"got": flat.grad.clone(), "ref": ref}, os.path.join(out_dir, f"r{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_early_ranges_plus_final_reduction_equal_one_all_reduce(tmp_path):
+    port = _free_port()
+    mp.spawn(_worker_ranges, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = (torch.load(os.path.join(tmp_path, f"r{r}.pt")) for r in range(2))
+    assert torch.allclose(r0["got"], r0["ref"], rtol=0, atol=1e-6) and torch.equal(r0["got"], r1["got"])

@@ -238,6 +238,29 @@ def test_tc_wgrad(P_shape, K, N, act):
     close(gw, ref, RT, AT, "tc wgrad")
 
 
+@pytest.mark.parametrize("K,N,act", [(32, 32, 2), (64, 64, 2), (96, 32, 1), (32, 96, 0), (64, 128, 2)])
+def test_tc_wgrad_256_pixel_stages(K, N, act):
+    """narrow weight gradients over many pixels run 256-pixel pipeline stages (P >= 1e5, at most three 64-channel blocks per
+    stage); P not a multiple of 256; same result as the 128-pixel stages (knob 22) up to the order of the fp32 sums"""
+    from accx import _lib
+    e = E()
+    B, H, W = 3, 181, 187               # 101541 pixels: 396 stages + a ragged tail
+    L, a = mk_lazy((B, H, W, K), torch.bfloat16, act, 51)
+    dy = torch.randn(B, H, W, N, generator=torch.Generator().manual_seed(52)).to(DEV).to(torch.bfloat16)
+    w = torch.zeros(N, K, device=DEV)
+    gw = torch.zeros(N, K, device=DEV)
+    e.wgrad(e.Op(L, K, e.WV(w, 0, K, 1)), dy, N, (B, H, W), gw)
+    ref = torch.einsum("bhwn,bhwk->nk", dy.double(), bf(a).double())
+    close(gw, ref, 1e-3, 1e-4, "wgrad 256-pixel stages")
+    gw2 = torch.zeros(N, K, device=DEV)
+    _lib.call("accx_set_knob", 22, 128)
+    try:
+        e.wgrad(e.Op(L, K, e.WV(w, 0, K, 1)), dy, N, (B, H, W), gw2)
+    finally:
+        _lib.call("accx_set_knob", 22, 0)
+    close(gw, gw2, 1e-4, 1e-5, "256- vs 128-pixel stages")
+
+
 def test_tc_wgrad_strided_weight_view_and_column_slices():
     """HANC layout: dW[n, e*J + j] for the max half (columns E..2E) of the pooled buffer"""
     e = E()
