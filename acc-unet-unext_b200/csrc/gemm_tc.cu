@@ -62,7 +62,11 @@ struct alignas(64) TcParams {
   int nacc_log;         // log2 of the TMEM accumulator ring (2 or 4 buffers): narrow tiles keep the MMA issuer up to four
                         // tiles ahead of the epilogue groups, so neither waits out the other's latency every tile
   int debug;            // KNOB_TC_DEBUG (timing diagnostics only: results are wrong when non-zero)
-  int occ;              // CTAs per SM this launch is sized for (1 or 2; host side only)
+  // pixel folding (narrow contiguous tensors, see accx_pw_fwd_tc_res): row r of every operand / of the output holds the
+  // pixels 2r and 2r + 1 side by side, so op[].K, op[].ld, N, ld_res and P above are the FOLDED sizes (2K, 2ld, 2N, P/2)
+  // and the weights are block-diagonal: W'[n, k] = W[n % Nf, k % Kf] when n / Nf == k / Kf, else 0 (Nf = N/2, Kf = K/2);
+  // scale / shift / bias / statistics / addend columns are taken modulo the real channel counts
+  int fold;
   int tap_op[3][3];
 };
 
@@ -158,8 +162,10 @@ __device__ __forceinline__ void stage_chunk(const float (&v)[16], uint32_t stage
 // BatchNorms amplify it to 7e-3 at the logits, 20x the reference's own fp32-vs-fp64 error).  A k-block is 32 fp32
 // channels: the landed 128 x 32 fp32 box becomes a_hi in place, a_lo goes to a second tile of the stage, and every
 // k-block has two weight tiles, w_hi and w_lo.  Separate instantiations: the bf16 contraction carries none of this code.
-template <int MODE, int OCC = 1>
-__global__ void __launch_bounds__(TC_THREADS, OCC) pw_fwd_tc_kernel(const __grid_constant__ TcParams prm) {
+// (96 registers per thread: registers are allocated for 20 warps, so 112 x 576 threads does not launch.  With the next
+//  chunk's TMEM load in flight while the current one is staged, the epilogue spills ~600 bytes at 96: not kept.)
+template <int MODE>
+__global__ void __launch_bounds__(TC_THREADS, 1) pw_fwd_tc_kernel(const __grid_constant__ TcParams prm) {
   constexpr bool CONV3 = MODE == 1, F32IN = MODE == 2;
   constexpr int BKC = F32IN ? 32 : TC_BK;          // channels per k-block
   pdl_sync();
@@ -244,20 +250,30 @@ __global__ void __launch_bounds__(TC_THREADS, OCC) pw_fwd_tc_kernel(const __grid
           const int k0 = (kb - prm.kb_start[o]) * BKC + c8 * (F32IN ? 4 : 8);
           addr[u] = base + bres_off + kb * b_tile_bytes + wt * bn * 128 + nl * 128 + ((c8 ^ (nl & 7)) << 4);
           low[u] = wt == 1;
-          if (nl < prm.N && k0 < op.K) {
-            const float* src = op.w + (int64_t)nl * op.w_ld + (int64_t)k0 * op.w_ks;
+          // folded launch: the chunk (8 channels, never straddling the two pixels: Kf % 8 == 0) is non-zero on the
+          // block diagonal only
+          int nw = nl, kw = k0, Kw = op.K, Nw = prm.N;
+          bool diag = true;
+          if (prm.fold) {
+            Kw = op.K >> 1; Nw = prm.N >> 1;
+            const int hn = nl >= Nw ? 1 : 0, hk = k0 >= Kw ? 1 : 0;
+            diag = hn == hk;
+            nw = nl - hn * Nw; kw = k0 - hk * Kw;
+          }
+          if (diag && nw < Nw && kw < Kw) {
+            const float* src = op.w + (int64_t)nw * op.w_ld + (int64_t)kw * op.w_ks;
             if (F32IN) {           // four fp32 words per chunk
 #pragma unroll
               for (int e = 0; e < 4; ++e)
-                if (k0 + e < op.K) v[u][e] = __ldg(src + (int64_t)e * op.w_ks);
-            } else if (op.w_ks == 1 && k0 + 8 <= op.K && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+                if (kw + e < Kw) v[u][e] = __ldg(src + (int64_t)e * op.w_ks);
+            } else if (op.w_ks == 1 && kw + 8 <= Kw && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
               const float4 a = __ldg(reinterpret_cast<const float4*>(src)), c = __ldg(reinterpret_cast<const float4*>(src) + 1);
               v[u][0] = a.x; v[u][1] = a.y; v[u][2] = a.z; v[u][3] = a.w;
               v[u][4] = c.x; v[u][5] = c.y; v[u][6] = c.z; v[u][7] = c.w;
             } else {
 #pragma unroll
               for (int e = 0; e < 8; ++e)
-                if (k0 + e < op.K) v[u][e] = __ldg(src + (int64_t)e * op.w_ks);
+                if (kw + e < Kw) v[u][e] = __ldg(src + (int64_t)e * op.w_ks);
             }
           }
         }
@@ -417,8 +433,9 @@ __global__ void __launch_bounds__(TC_THREADS, OCC) pw_fwd_tc_kernel(const __grid
         const accx_operand_t& op = prm.op[o];
         const int k = (kb - prm.kb_start[o]) * BKC + j;
         const bool on = op.act != 0 && j < BKC && k < op.K;
-        tab[kb * TS + j] = on ? __ldg(op.scale + k) : 0.f;
-        tab[kb * TS + BKC + j] = on ? __ldg(op.shift + k) : 0.f;
+        const int kc = (prm.fold && k >= (op.K >> 1)) ? k - (op.K >> 1) : k;      // folded rows: channel of either pixel
+        tab[kb * TS + j] = on ? __ldg(op.scale + kc) : 0.f;
+        tab[kb * TS + BKC + j] = on ? __ldg(op.shift + kc) : 0.f;
         if (j == 0) {
           const int krem = op.K - k;
           meta[kb] = make_int4(op.act, op.dy, op.dx, krem >= TC_BK ? 8 : (krem + 7) >> 3);
@@ -634,6 +651,7 @@ __global__ void __launch_bounds__(TC_THREADS, OCC) pw_fwd_tc_kernel(const __grid
 #pragma unroll
     for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
     const int HWp = prm.H * prm.W, N = prm.N, n_add = prm.n_add;
+    const int Nc = prm.fold ? N >> 1 : N;      // real channel count (columns of bias / addends / statistics)
     const int64_t P = prm.P;
     const float* bias = prm.bias;
     const int box_cols = prm.out_f32 ? 32 : 64;
@@ -667,8 +685,9 @@ __global__ void __launch_bounds__(TC_THREADS, OCC) pw_fwd_tc_kernel(const __grid
       const int n0f = nt_flush * bn;
       for (int j = gtid; j < bn; j += 128) {
         if (n0f + j < N) {
-          atomicAdd(prm.stats + n0f + j, sstat[j]);
-          atomicAdd(prm.stats + N + n0f + j, sstat[bn + j]);
+          const int n = n0f + j, nc = n >= Nc ? n - Nc : n;       // folded rows: both pixels' columns add into one channel
+          atomicAdd(prm.stats + nc, sstat[j]);
+          atomicAdd(prm.stats + Nc + nc, sstat[bn + j]);
         }
         sstat[j] = 0.f;
         sstat[bn + j] = 0.f;
@@ -689,13 +708,15 @@ __global__ void __launch_bounds__(TC_THREADS, OCC) pw_fwd_tc_kernel(const __grid
 #pragma unroll
       for (int a = 0; a < ACCX_MAX_ADDENDS; ++a) ap[a] = nullptr;
       if (n_add > 0 && rvalid) {
-        const int b = (int)(p / HWp), rem = (int)(p % HWp);
+        // folded rows: pixels 2p and 2p + 1 share every addend pixel (W even, upsampling factor >= 2: checked by the launcher)
+        const int64_t pr = prm.fold ? 2 * p : p;
+        const int b = (int)(pr / HWp), rem = (int)(pr % HWp);
         const int h = rem / prm.W, w = rem % prm.W;
 #pragma unroll
         for (int a = 0; a < ACCX_MAX_ADDENDS; ++a) {
           if (a < n_add) {
             const int l = prm.add_log2s[a];
-            ap[a] = prm.add[a] + (((int64_t)b * (prm.H >> l) + (h >> l)) * (prm.W >> l) + (w >> l)) * N + n0;
+            ap[a] = prm.add[a] + (((int64_t)b * (prm.H >> l) + (h >> l)) * (prm.W >> l) + (w >> l)) * Nc;
           }
         }
       }
@@ -714,34 +735,16 @@ __global__ void __launch_bounds__(TC_THREADS, OCC) pw_fwd_tc_kernel(const __grid
         use_m = wcol != 0;
         use_p = wcol != prm.W - 1;
       }
-      for (int ch = 0; ch < ((prm.debug & 8) ? 0 : n_chunks); ++ch) {
-        uint32_t r[1][16];
-        float v[16];
-        if (CONV3) {
-          uint32_t rm[16], rp[16];
-          tc_ld16_issue(trow + ch * 16, rm);
-          tc_ld16_issue(trow + bn + ch * 16, r[0]);
-          tc_ld16_issue(trow + 2 * bn + ch * 16, rp);
-          tc_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float a = __uint_as_float(r[0][j]);
-            if (use_m) a += __uint_as_float(rm[j]);
-            if (use_p) a += __uint_as_float(rp[j]);
-            v[j] = rvalid ? a : 0.f;
-          }
-        } else {
-          tc_ld16_issue(trow + ch * 16, r[0]);
-          tc_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = rvalid ? __uint_as_float(r[0][j]) : 0.f;
-        }
+      // one 16-column chunk of this thread's row: (+ bias, addends, residual) -> staging boxes
+      auto finish_chunk = [&](const int ch, float (&v)[16]) {
         {
           const int c0 = ch * 16;
+          // column of this chunk in bias / addend rows (folded rows: Nc % 16 == 0, a chunk never straddles the two pixels)
+          const int cb = (n0 + c0 >= Nc && prm.fold) ? n0 + c0 - Nc : n0 + c0;
           if (rvalid && (bias != nullptr || n_add > 0)) {
             if (n0 + c0 + 16 <= N && (N & 3) == 0) {
               if (bias) {
-                const float4* bp = reinterpret_cast<const float4*>(bias + n0 + c0);
+                const float4* bp = reinterpret_cast<const float4*>(bias + cb);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                   const float4 b4 = __ldg(bp + q);
@@ -751,7 +754,7 @@ __global__ void __launch_bounds__(TC_THREADS, OCC) pw_fwd_tc_kernel(const __grid
 #pragma unroll
               for (int a = 0; a < ACCX_MAX_ADDENDS; ++a) {
                 if (a < n_add) {
-                  const float4* a4p = reinterpret_cast<const float4*>(ap[a] + c0);
+                  const float4* a4p = reinterpret_cast<const float4*>(ap[a] + cb);
 #pragma unroll
                   for (int q = 0; q < 4; ++q) {
                     const float4 a4 = __ldg(a4p + q);
@@ -764,10 +767,10 @@ __global__ void __launch_bounds__(TC_THREADS, OCC) pw_fwd_tc_kernel(const __grid
               for (int j = 0; j < 16; ++j) {
                 const int n = n0 + c0 + j;
                 if (n < N) {
-                  if (bias) v[j] += __ldg(bias + n);
+                  if (bias) v[j] += __ldg(bias + cb + j);
 #pragma unroll
                   for (int a = 0; a < ACCX_MAX_ADDENDS; ++a)
-                    if (a < n_add) v[j] += __ldg(ap[a] + c0 + j);
+                    if (a < n_add) v[j] += __ldg(ap[a] + cb + j);
                 }
               }
             }
@@ -808,6 +811,35 @@ __global__ void __launch_bounds__(TC_THREADS, OCC) pw_fwd_tc_kernel(const __grid
           }
           if (prm.out_f32) stage_chunk<true>(v, stage, row, c0);
           else stage_chunk<false>(v, stage, row, c0);
+        }
+      };
+      const int n_ch = (prm.debug & 8) ? 0 : n_chunks;
+      if (CONV3) {
+        for (int ch = 0; ch < n_ch; ++ch) {
+          uint32_t rm[16], r0[16], rp[16];
+          float v[16];
+          tc_ld16_issue(trow + ch * 16, rm);
+          tc_ld16_issue(trow + bn + ch * 16, r0);
+          tc_ld16_issue(trow + 2 * bn + ch * 16, rp);
+          tc_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float a = __uint_as_float(r0[j]);
+            if (use_m) a += __uint_as_float(rm[j]);
+            if (use_p) a += __uint_as_float(rp[j]);
+            v[j] = rvalid ? a : 0.f;
+          }
+          finish_chunk(ch, v);
+        }
+      } else {
+        for (int ch = 0; ch < n_ch; ++ch) {
+          uint32_t r0[16];
+          float v[16];
+          tc_ld16_issue(trow + ch * 16, r0);
+          tc_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = rvalid ? __uint_as_float(r0[j]) : 0.f;
+          finish_chunk(ch, v);
         }
       }
       // accumulator drained: hand the TMEM buffer back to the MMA warp
@@ -947,21 +979,11 @@ static size_t tc_geometry(int N, int64_t P, const accx_operand_t* ops, int n_ops
   const int max_stages = knob(KNOB_TC_MAX_STAGES, 8);
   if (S > max_stages) S = max_stages;
   if (S < 1) S = 1;
-  // Two CTAs per SM for narrow tiles over many pixels: every role of this kernel is a chain of long-latency hand-offs
-  // (0.8 us per 128-pixel tile whatever the bytes), so a second, independent pipeline on the same SM
-  // hides them.  Needs both CTAs' shared memory (<= 112 KB each with >= 3 stages), TMEM (<= 256 columns each) and
-  // registers (the OCC = 2 instantiation is held to 56) to fit, and at least two tiles per CTA.
-  prm.occ = 1;
-  if (knob(KNOB_TC_OCC, 2) == 2 && !prm.f32in && !prm.conv3 && prm.tmem_cols <= 256 &&
-      (int64_t)prm.m_tiles * prm.n_tiles >= 4 * (int64_t)n_sm) {
-    const size_t cap2 = 112 * 1024;
-    if (fixed + resident + 3 * stage <= cap2) {
-      int S2 = (int)((cap2 - fixed - resident) / stage);
-      if (S2 > max_stages) S2 = max_stages;
-      S = S2;
-      prm.occ = 2;
-    }
-  }
+  // (Two CTAs per SM -- a 56-register instantiation, <= 112 KB of shared memory and <= 256 TMEM columns each -- were built and
+  //  measured on the narrow many-tile shapes, profiles/r02_pw_fwd_tc_two_ctas_per_sm.txt: K = 96 / 192 -> N = 32 / 64 gain
+  //  9-10 %, K = N = 32 loses 4 %, K = 32 -> N = 64 18 %, K = N = 64 12 %, the step does not move (33.34 vs 33.29 ms).
+  //  The narrow tiles are bound by what the two CTAs share: the SM's TMA unit moves a 128-row box of 64-byte rows in
+  //  255 ns whatever the bytes (r02_tma_box_rate.txt), one load + one store per tile.  Removed.)
   prm.stages = S;
   return fixed + resident + (size_t)S * stage;
 }
@@ -1029,7 +1051,6 @@ int accx_pw_fwd_tc_res(int dtype, int out_dtype, int B, int H, int W, int N, con
     prm.conv3 = ok ? 1 : 0;
   }
   for (int i = 0; i < n_ops; ++i) {
-    prm.op[i] = ops[i];
     ACCX_REQUIRE(ops[i].data && ops[i].w && ops[i].K > 0, "pw_fwd_tc: operand %d malformed", i);
     ACCX_REQUIRE(ops[i].K % 8 == 0 && ops[i].ld % 8 == 0 && aligned16(ops[i].data),
                  "pw_fwd_tc: operand %d needs K, ld multiples of 8 and a 16-byte aligned base (use accx_pw_fwd)", i);
@@ -1037,22 +1058,63 @@ int accx_pw_fwd_tc_res(int dtype, int out_dtype, int B, int H, int W, int N, con
                  "pw_fwd_tc: operand %d scale/shift missing or misaligned", i);
     if (ops[i].dy || ops[i].dx || ops[i].act) prm.any_transform = 1;
     if (ops[i].dy || ops[i].dx) prm.any_shift = 1;
-    if (prm.conv3 && i > 0) continue;       // one map: the slab box of the shared tensor
-    if (in_f32)       // 128 x 32 fp32 boxes (128-byte rows, the same swizzle): one k-block of the split mode
-      ACCX_REQUIRE(encode_2d_out(&prm.tmap[i], ops[i].data, ops[i].K, P, ops[i].ld, 4, TC_BM),
-                   "pw_fwd_tc: cuTensorMapEncodeTiled failed for operand %d", i);
-    else
-    ACCX_REQUIRE(encode_2d_bf16(&prm.tmap[i], ops[i].data, ops[i].K, P, ops[i].ld, prm.conv3 ? TC_SLAB_ROWS : TC_BM),
-                 "pw_fwd_tc: cuTensorMapEncodeTiled failed for operand %d", i);
   }
-  ACCX_REQUIRE(encode_2d_out(&prm.tmap_y, y, N, P, ldy, esz, TC_BM), "pw_fwd_tc: cuTensorMapEncodeTiled failed for the output");
-  const size_t smem = tc_geometry(N, P, ops, n_ops, out_f32, prm);
+  ACCX_REQUIRE(!residual || (aligned16(residual) && (ld_res * esz) % 16 == 0 && ld_res >= N && N % 8 == 0),
+               "pw_fwd_tc: residual needs a 16-byte aligned base and row pitch, ld_res >= N, N %% 8 == 0");
+  for (int i = 0; i < n_add; ++i)
+    ACCX_REQUIRE(add && add_log2s && add[i] && add_log2s[i] >= 0 && (H >> add_log2s[i]) << add_log2s[i] == H &&
+                     (W >> add_log2s[i]) << add_log2s[i] == W,
+                 "pw_fwd_tc: addend %d does not tile %dx%d", i, H, W);
+  // Pixel folding: a contiguous [P, C] tensor with C <= 32 has rows of <= 64 bytes, and the SM's TMA unit moves a
+  // 128-row box in ~255 ns whatever the row length (profiles/r02_tma_box_rate.txt) -- one load and one store box per
+  // 128-pixel tile, so such contractions run at the BOX rate (~2 TB/s), not at the HBM rate.  When every operand, the
+  // output and the residual are contiguous and unshifted, the same memory is read as [P/2, 2C] (two pixels per row) and
+  // contracted with block-diagonal weights diag(W, W): full 128-byte rows, 256 pixels per tile and per role hand-off,
+  // the same bytes.  The MMAs do twice the arithmetic (the zero blocks), which a narrow contraction has to spare.
+  // Not in the deterministic mode (a statistic would receive four contributions per CTA), not with addends of
+  // upsampling factor 1 (the two pixels of a row would need different addend rows).
+  bool fold = knob(KNOB_TC_FOLD, 2) == 2 && !in_f32 && !out_f32 && !prm.conv3 && !prm.any_shift && !(det_on() && stats) &&
+              P % 2 == 0 && N % 16 == 0 && N <= 64 && ldy == N && (!residual || ld_res == N) && (n_add == 0 || W % 2 == 0);
+  if (fold) {
+    int ksum = 0;
+    bool narrow = N <= 32;
+    for (int i = 0; i < n_ops; ++i) {
+      fold = fold && ops[i].ld == ops[i].K;
+      narrow = narrow || ops[i].K <= 32;
+      ksum += ops[i].K;
+    }
+    for (int i = 0; i < n_add; ++i) fold = fold && add_log2s[i] >= 1;
+    fold = fold && narrow && ksum <= 128;
+  }
+  size_t smem = 0;
+  for (;;) {
+    const int f = fold ? 2 : 1;
+    prm.fold = fold ? 1 : 0;
+    for (int i = 0; i < n_ops; ++i) {
+      prm.op[i] = ops[i];
+      prm.op[i].K = ops[i].K * f;
+      prm.op[i].ld = ops[i].ld * f;
+      if (prm.conv3 && i > 0) continue;       // one map: the slab box of the shared tensor
+      if (in_f32)       // 128 x 32 fp32 boxes (128-byte rows, the same swizzle): one k-block of the split mode
+        ACCX_REQUIRE(encode_2d_out(&prm.tmap[i], ops[i].data, ops[i].K, P, ops[i].ld, 4, TC_BM),
+                     "pw_fwd_tc: cuTensorMapEncodeTiled failed for operand %d", i);
+      else
+        ACCX_REQUIRE(encode_2d_bf16(&prm.tmap[i], ops[i].data, prm.op[i].K, P / f, prm.op[i].ld, prm.conv3 ? TC_SLAB_ROWS : TC_BM),
+                     "pw_fwd_tc: cuTensorMapEncodeTiled failed for operand %d", i);
+    }
+    ACCX_REQUIRE(encode_2d_out(&prm.tmap_y, y, (int64_t)N * f, P / f, ldy * f, esz, TC_BM),
+                 "pw_fwd_tc: cuTensorMapEncodeTiled failed for the output");
+    smem = tc_geometry(N * f, P / f, prm.op, n_ops, out_f32, prm);
+    if (!fold || prm.b_resident) break;
+    fold = false;                             // folded weights are packed in shared memory only: back to plain rows
+  }
   const int n_tiles = prm.n_tiles;
   const int64_t need = (int64_t)n_tiles * prm.n_kb * (in_f32 ? 2 : 1) * prm.bn * TC_BK * 2;
   ACCX_REQUIRE(prm.b_resident || (workspace_bytes >= need && aligned16(workspace)),
                "pw_fwd_tc: workspace too small (%lld < %lld)", (long long)workspace_bytes, (long long)need);
-  prm.B = B; prm.H = H; prm.W = W; prm.N = N;
-  prm.P = P;
+  prm.B = B; prm.H = H; prm.W = W;
+  prm.N = fold ? 2 * N : N;
+  prm.P = fold ? P / 2 : P;
   prm.out_f32 = out_f32 ? 1 : 0;
   prm.wpack = (const bf16*)workspace;
   prm.bias = bias;
@@ -1061,17 +1123,12 @@ int accx_pw_fwd_tc_res(int dtype, int out_dtype, int B, int H, int W, int N, con
   for (int i = 0; i < n_add; ++i) {
     prm.add[i] = add[i];
     prm.add_log2s[i] = add_log2s[i];
-    ACCX_REQUIRE(add[i] && add_log2s[i] >= 0 && (H >> add_log2s[i]) << add_log2s[i] == H &&
-                     (W >> add_log2s[i]) << add_log2s[i] == W,
-                 "pw_fwd_tc: addend %d does not tile %dx%d", i, H, W);
     ACCX_REQUIRE(aligned16(add[i]) || (N & 3) != 0, "pw_fwd_tc: addend %d must be 16-byte aligned", i);
   }
   prm.stats = stats;
   prm.debug = g_knobs[KNOB_TC_DEBUG];
   prm.res = residual;
-  prm.ld_res = ld_res;
-  ACCX_REQUIRE(!residual || (aligned16(residual) && (ld_res * esz) % 16 == 0 && ld_res >= N && N % 8 == 0),
-               "pw_fwd_tc: residual needs a 16-byte aligned base and row pitch, ld_res >= N, N %% 8 == 0");
+  prm.ld_res = fold ? 2 * ld_res : ld_res;
   cudaStream_t st = (cudaStream_t)stream;
   if (!prm.b_resident) {     // streamed weight tiles come from a bf16 re-pack in the workspace
     launch_k(tc_pack_weights_kernel, dim3(prm.n_kb, n_tiles, ((prm.f32in ? 2 : 1) * prm.bn * TC_BK + 1023) / 1024), 256, 0, st, prm,
@@ -1082,19 +1139,17 @@ int accx_pw_fwd_tc_res(int dtype, int out_dtype, int B, int H, int W, int N, con
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(pw_fwd_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX);
-    cudaFuncSetAttribute(pw_fwd_tc_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
     cudaFuncSetAttribute(pw_fwd_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX);
     cudaFuncSetAttribute(pw_fwd_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX);
     attr_set = true;
   }
   const int64_t total = (int64_t)prm.m_tiles * prm.n_tiles;
-  int64_t grid = (int64_t)prm.occ * sm_count();
+  int64_t grid = sm_count();
   if (grid > total) grid = total;
   prm.det = (det_on() && stats) ? 1 : 0;
   if (prm.det) grid = 1;      // each statistic then receives one contribution per epilogue group: a + b is order-free
   if (prm.f32in) launch_k(pw_fwd_tc_kernel<2>, (unsigned)grid, TC_THREADS, smem, st, prm);
   else if (prm.conv3) launch_k(pw_fwd_tc_kernel<1>, (unsigned)grid, TC_THREADS, smem, st, prm);
-  else if (prm.occ == 2) launch_k(pw_fwd_tc_kernel<0, 2>, (unsigned)grid, TC_THREADS, smem, st, prm);
   else launch_k(pw_fwd_tc_kernel<0>, (unsigned)grid, TC_THREADS, smem, st, prm);
   return check_launch("pw_fwd_tc");
 }

@@ -158,8 +158,8 @@ __global__ void hanc_unpool_kernel(int B, int H, int W, int C, int log2s, const 
 // One thread owns a 2^LEVELS-square window of 4 channels: y and da are read ONCE (the per-level kernels read y
 // and read-modify-write da once per level, and the BN reduction reads both again), every load of the window is
 // in flight before the first compare.  bf16 storage.
-template <int LEVELS, int OCC>
-__global__ void __launch_bounds__(128, OCC) hanc_unpool_bnred_kernel(int B, int H, int W, int C, const bf16* __restrict__ y,
+template <int LEVELS>
+__global__ void __launch_bounds__(128) hanc_unpool_bnred_kernel(int B, int H, int W, int C, const bf16* __restrict__ y,
                                                                 const float* scale, const float* shift, int act,
                                                                 const float* __restrict__ dp1,
                                                                 const float* __restrict__ dp2, bf16* __restrict__ da,
@@ -332,20 +332,16 @@ int accx_hanc_unpool_bnred(int dtype, int B, int H, int W, int C, int levels, co
     if (l.cvn % d == 0) { l.tx = d; break; }
   l.ty = 128 / l.tx;
   l.gy = (l.cvn + l.tx - 1) / l.tx;
-  dim3 block(l.tx, l.ty), grid(grid_x_for(n_win, l.ty, 148 * (knob(KNOB_UNPOOL_OCC, 2) >= 3 ? 6 : 3)), l.gy);
+  dim3 block(l.tx, l.ty), grid(grid_x_for(n_win, l.ty, 148 * 3), l.gy);
   const size_t sm = (size_t)l.tx * l.ty * l.vec * sizeof(float);
   Det det;
   if (!det_handle((int64_t)grid.x * grid.y * 2 * l.tx * l.vec, grid.y, (cudaStream_t)stream, det)) return ACCX_ERR_INVALID;
-  const int occ = knob(KNOB_UNPOOL_OCC, 2);
-#define ACCX_UNPOOL_LAUNCH(LV, OC)                                                                                          \
-  launch_k(hanc_unpool_bnred_kernel<LV, OC>, grid, block, sm, (cudaStream_t)stream, B, H, W, C, (const bf16*)y, scale, shift, \
-           act, dpool1, dpool2, (bf16*)da, mean, rstd, sums, det)
-  if (levels == 1) {
-    if (occ == 3) ACCX_UNPOOL_LAUNCH(1, 3); else ACCX_UNPOOL_LAUNCH(1, 2);
-  } else {
-    if (occ == 3) ACCX_UNPOOL_LAUNCH(2, 3); else if (occ == 4) ACCX_UNPOOL_LAUNCH(2, 4); else ACCX_UNPOOL_LAUNCH(2, 2);
-  }
-#undef ACCX_UNPOOL_LAUNCH
+  if (levels == 1)
+    launch_k(hanc_unpool_bnred_kernel<1>, grid, block, sm, (cudaStream_t)stream, B, H, W, C, (const bf16*)y, scale, shift, act,
+                                                                            dpool1, dpool2, (bf16*)da, mean, rstd, sums, det);
+  else
+    launch_k(hanc_unpool_bnred_kernel<2>, grid, block, sm, (cudaStream_t)stream, B, H, W, C, (const bf16*)y, scale, shift, act,
+                                                                            dpool1, dpool2, (bf16*)da, mean, rstd, sums, det);
   return check_launch("hanc_unpool_bnred");
 }
 

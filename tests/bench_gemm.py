@@ -202,6 +202,18 @@ if __name__ == "__main__":
         _lib.call("accx_set_knob", 19, 0)
         _lib.call("accx_set_knob", 14, 0)
         sys.exit(0)
+    if "fold" in args:           # pixel folding of narrow contiguous contractions (knob 23: 1 = off, default on)
+        from accx import _lib
+        SHAPES[:] = [(802816, 32, 32, 2, 1), (802816, 32, 32, 0, 1), (802816, 96, 32, 2, 1), (802816, 32, 64, 0, 1),
+                     (802816, 64, 32, 2, 1), (802816, 32, 96, 0, 1), (200704, 32, 64, 2, 1), (200704, 64, 32, 2, 1),
+                     (200704, 64, 64, 2, 1)]
+        for f in (1, 2):
+            _lib.call("accx_set_knob", 23, f)
+            print(f"---- pixel folding {'off' if f == 1 else 'on'}")
+            for i in range(len(SHAPES)):
+                run_graph(i)
+        _lib.call("accx_set_knob", 23, 0)
+        sys.exit(0)
     if "small" in args:
         SHAPES[:] = SMALL
         args.remove("small")

@@ -261,6 +261,120 @@ def test_tc_wgrad_256_pixel_stages(K, N, act):
     close(gw, gw2, 1e-4, 1e-5, "256- vs 128-pixel stages")
 
 
+@pytest.mark.parametrize("ops_k,N,act,extra", [((32,), 32, 2, "res"), ((64,), 64, 2, "stats"), ((96,), 32, 1, "bias"),
+                                               ((192,), 64, 2, "stats"), ((32, 32), 32, 2, "stats"), ((32,), 64, 0, "shift"),
+                                               ((16,), 24, 2, "f32out")])
+def test_tc_many_tiles_per_cta(ops_k, N, act, extra):
+    """narrow contractions over many tiles (794: five or six per persistent CTA, so every pipeline stage, both TMEM
+    accumulators and both epilogue groups wrap around several times; ragged last tile) with statistics / bias / residual /
+    a shifted operand / fp32 output, against the torch restatement; two runs agree bit for bit in the outputs"""
+    e = E()
+    B, H, W = 3, 181, 187               # 101541 pixels: 794 tiles, a ragged last tile
+    g = torch.Generator().manual_seed(61)
+    Ls, As, ws = [], [], []
+    for i, K in enumerate(ops_k):
+        L, a = mk_lazy((B, H, W, K), torch.bfloat16, act, 62 + i)
+        Ls.append(L), As.append(a)
+    Kt = sum(ops_k)
+    w = (torch.randn(N, Kt, generator=g) / Kt ** 0.5).to(DEV)
+    bias = torch.randn(N, generator=g).to(DEV) if extra == "bias" else None
+    res = torch.randn(B, H, W, N, generator=g).to(DEV).to(torch.bfloat16) if extra == "res" else None
+    dy, dx = (1, -1) if extra == "shift" else (0, 0)
+    ops, k0 = [], 0
+    for L, K in zip(Ls, ops_k):
+        ops.append(e.Op(L, K, e.WV(w, k0, Kt, 1), 0, dy, dx))
+        k0 += K
+    kw = dict(bias=bias, out_dtype=e.F32 if extra == "f32out" else None)
+
+    def run():
+        stats = torch.zeros(2 * N, device=DEV) if extra in ("stats", "res") else None
+        out = res.clone() if res is not None else None
+        y = e.conv(ops, N, (B, H, W), stats=stats, residual=out, out=out, **kw) if res is not None else \
+            e.conv(ops, N, (B, H, W), stats=stats, **kw)
+        return y, stats
+
+    y1, st1 = run()
+    y2, st2 = run()
+    assert torch.equal(y1, y2), "outputs differ between two runs"
+    ref = torch.zeros(B, H, W, N, device=DEV)
+    k0 = 0
+    for a, K in zip(As, ops_k):
+        ab = bf(a)
+        if dy or dx:
+            ab = F.pad(ab, (0, 0, 1, 1, 1, 1))[:, 1 + dy:1 + dy + H, 1 + dx:1 + dx + W]
+        ref = ref + ab @ bf(w[:, k0:k0 + K]).t()
+        k0 += K
+    if bias is not None:
+        ref = ref + bias
+    if res is not None:
+        ref = ref + res.float()
+    close(y2.float(), ref, RT, AT, "many tiles per CTA")
+    if st2 is not None:
+        close(st2, st1, 1e-4, 1e-4, "statistics of two runs")
+        close(st2[:N], y2.float().sum((0, 1, 2)), 2e-2, 2e-2, "stats sum")
+
+
+@pytest.mark.parametrize("shape", [(3, 180, 188), (2, 12, 20), (1, 6, 6)])
+@pytest.mark.parametrize("ops_k,N,act,extra", [((32,), 32, 2, "res"), ((32,), 32, 1, "stats"), ((32, 32), 32, 2, "stats"),
+                                               ((32,), 64, 0, "bias"), ((96,), 32, 2, "adds"), ((64,), 32, 2, "stats"),
+                                               ((16,), 48, 2, "stats"), ((32, 64), 64, 2, "adds"), ((8,), 16, 0, "res")])
+def test_tc_pixel_folding(shape, ops_k, N, act, extra):
+    """narrow contiguous contractions read two pixels per row ([P/2, 2C] views, block-diagonal weights; accx_pw_fwd_tc_res):
+    outputs equal the unfolded launch (knob 23 = 1) bit for bit -- the extra products are exact zeros -- statistics agree up
+    to the order of the fp32 sums, and both match the torch restatement; with bias, residual, several operands, a
+    BatchNorm + LeakyReLU transform and nearest-upsampled addends (factor 2 and 4)"""
+    from accx import _lib
+    e = E()
+    B, H, W = shape
+    if extra == "adds" and (H % 4 or W % 4):
+        pytest.skip("addends need a map divisible by 4")
+    g = torch.Generator().manual_seed(71)
+    Ls, As = [], []
+    for i, K in enumerate(ops_k):
+        L, a = mk_lazy((B, H, W, K), torch.bfloat16, act, 72 + i)
+        Ls.append(L), As.append(a)
+    Kt = sum(ops_k)
+    w = (torch.randn(N, Kt, generator=g) / Kt ** 0.5).to(DEV)
+    bias = torch.randn(N, generator=g).to(DEV) if extra == "bias" else None
+    res = torch.randn(B, H, W, N, generator=g).to(DEV).to(torch.bfloat16) if extra == "res" else None
+    adds = [(torch.randn(B, H >> l, W >> l, N, generator=g).to(DEV), l) for l in (1, 2)] if extra == "adds" else []
+    ops, k0 = [], 0
+    for L, K in zip(Ls, ops_k):
+        ops.append(e.Op(L, K, e.WV(w, k0, Kt, 1)))
+        k0 += K
+
+    def run():
+        stats = torch.zeros(2 * N, device=DEV) if extra in ("stats", "res") else None
+        if res is not None:
+            out = res.clone()
+            return e.conv(ops, N, (B, H, W), stats=stats, residual=out, out=out), stats
+        return e.conv(ops, N, (B, H, W), bias=bias, adds=adds, stats=stats), stats
+
+    y2, st2 = run()
+    _lib.call("accx_set_knob", 23, 1)
+    try:
+        y1, st1 = run()
+    finally:
+        _lib.call("accx_set_knob", 23, 0)
+    assert torch.equal(y1, y2), "pixel folding changed the outputs"
+    ref = torch.zeros(B, H, W, N, device=DEV)
+    k0 = 0
+    for a, K in zip(As, ops_k):
+        ref = ref + bf(a) @ bf(w[:, k0:k0 + K]).t()
+        k0 += K
+    if bias is not None:
+        ref = ref + bias
+    for t, l in adds:
+        ref = ref + t.repeat_interleave(1 << l, 1).repeat_interleave(1 << l, 2)
+    if res is not None:
+        ref = ref + res.float()
+    close(y2.float(), ref, RT, AT, "pixel folding")
+    if st2 is not None:
+        close(st2, st1, 1e-4, 1e-3, "statistics, folded vs plain rows")
+        close(st2[:N], y2.float().sum((0, 1, 2)), 2e-2, 2e-2, "stats sum")
+        close(st2[N:], y2.float().square().sum((0, 1, 2)), 2e-2, 2e-2, "stats sumsq")
+
+
 def test_tc_wgrad_strided_weight_view_and_column_slices():
     """HANC layout: dW[n, e*J + j] for the max half (columns E..2E) of the pooled buffer"""
     e = E()
