@@ -36,7 +36,8 @@ enum {
   KNOB_TC_F32_TERMS,  // 20: products of the tf32 split in fp32-storage contractions: 3 (default) or 4
   KNOB_TC_NACC,       // 21: TMEM accumulator ring of pw_fwd_tc: 2 (default) or 4 buffers (when 4 * BN <= 512 columns)
   KNOB_WGRAD_PX,      // 22: pixels per stage of the narrow weight-gradient contractions: 256 (default) or 128
-  KNOB_TC_FOLD,       // 23: pixel folding of narrow contiguous contractions in pw_fwd_tc (two pixels per row): 2 (default) on, 1 off
+  KNOB_TC_FOLD,       // 23: pixel folding of narrow contiguous contractions (pw_fwd_tc, pw_wgrad_tc; two pixels per row): 2 (default) on
+                      //     when a side has <= 32 channels, 1 off, 3 on whenever legal
   KNOB_COUNT
 };
 extern int g_knobs[KNOB_COUNT];

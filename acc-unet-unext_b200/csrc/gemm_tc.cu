@@ -1073,11 +1073,12 @@ int accx_pw_fwd_tc_res(int dtype, int out_dtype, int B, int H, int W, int N, con
   // the same bytes.  The MMAs do twice the arithmetic (the zero blocks), which a narrow contraction has to spare.
   // Not in the deterministic mode (a statistic would receive four contributions per CTA), not with addends of
   // upsampling factor 1 (the two pixels of a row would need different addend rows).
-  bool fold = knob(KNOB_TC_FOLD, 2) == 2 && !in_f32 && !out_f32 && !prm.conv3 && !prm.any_shift && !(det_on() && stats) &&
-              P % 2 == 0 && N % 16 == 0 && N <= 64 && ldy == N && (!residual || ld_res == N) && (n_add == 0 || W % 2 == 0);
+  const int fold_knob = knob(KNOB_TC_FOLD, 2);      // 1 off, 2 on (default), 3 on also when no side is narrower than 64 channels
+  bool fold = fold_knob >= 2 && !in_f32 && !out_f32 && !prm.conv3 && !prm.any_shift && !(det_on() && stats) &&
+              P % 2 == 0 && N % 16 == 0 && N <= 128 && ldy == N && (!residual || ld_res == N) && (n_add == 0 || W % 2 == 0);
   if (fold) {
     int ksum = 0;
-    bool narrow = N <= 32;
+    bool narrow = N <= 32 || fold_knob == 3;
     for (int i = 0; i < n_ops; ++i) {
       fold = fold && ops[i].ld == ops[i].K;
       narrow = narrow || ops[i].K <= 32;

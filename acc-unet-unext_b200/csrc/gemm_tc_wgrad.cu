@@ -36,6 +36,10 @@ struct alignas(64) WgParams {
   int n_taps, dy_blocks;
   int tap_dy[9], tap_dx[9];
   int64_t tap_woff[9];
+  // pixel folding (see accx_pw_fwd_tc_res in gemm_tc.cu): dY and A are read as [P/2, 2N] / [P/2, 2K] (op.K, op.ld, N, P
+  // are the folded sizes) and only the two diagonal blocks of the [2N, 2K] product are weight gradients:
+  // dW[n, k] = D[n, k] + D[N + n, K + k]
+  int fold;
 };
 
 template <int WG_PX>
@@ -138,8 +142,9 @@ __global__ void __launch_bounds__(WG_THREADS) pw_wgrad_tc_kernel(const __grid_co
       float* tab = reinterpret_cast<float*>(smem + tab_off);
       for (int j = tid; j < nbp; j += 256) {
         const bool on = prm.op.act != 0 && j < nb && k0 + j < prm.op.K;
-        tab[j] = on ? __ldg(prm.op.scale + k0 + j) : 0.f;
-        tab[nbp + j] = on ? __ldg(prm.op.shift + k0 + j) : 0.f;
+        const int kc = (prm.fold && k0 + j >= (prm.op.K >> 1)) ? k0 + j - (prm.op.K >> 1) : k0 + j;
+        tab[j] = on ? __ldg(prm.op.scale + kc) : 0.f;
+        tab[nbp + j] = on ? __ldg(prm.op.shift + kc) : 0.f;
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
       bool shifted = false;
@@ -192,26 +197,30 @@ __global__ void __launch_bounds__(WG_THREADS) pw_wgrad_tc_kernel(const __grid_co
     // epilogue: partial dW tile -> global fp32 atomics (strided weight view)
     mbar_wait(done_bar, 0);
     tc_fence_after();
-    const int n = n0 + warp * 32 + lane;
+    const int nrow = n0 + warp * 32 + lane;
+    // folded: accumulator row nrow = channel nrow % Nc of pixel nrow / Nc; only the chunks of the same pixel's channels count
+    const int Nc = prm.fold ? prm.N >> 1 : prm.N, Kc = prm.fold ? prm.op.K >> 1 : prm.op.K;
+    const int hn = (prm.fold && nrow >= Nc) ? 1 : 0, n = nrow - hn * Nc;
     const bool vec_red = prm.op.w_ks == 1 && (prm.op.w_ld & 3) == 0 && ((reinterpret_cast<uintptr_t>(prm.dw) & 15) == 0);
     for (int t = 0; t < n_taps; ++t)
     for (int c0 = 0; c0 < nb; c0 += 16) {
       float v[16];
       tc_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + t * nb + c0, v);
-      if (n < prm.N) {
+      const int hk = (prm.fold && k0 + c0 >= Kc) ? 1 : 0, kc0 = k0 + c0 - hk * Kc;      // (Kc % 16 == 0 when folded)
+      if (nrow < prm.N && hn == hk) {
         float* rowp = prm.dw + prm.tap_woff[t] + (int64_t)n * prm.op.w_ld;
-        if (vec_red && k0 + c0 + 16 <= prm.op.K) {
+        if (vec_red && kc0 + 16 <= Kc) {
           // contiguous weight row: four 16-byte vector reductions instead of sixteen scalar atomics
 #pragma unroll
           for (int q = 0; q < 4; ++q)
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(rowp + k0 + c0 + 4 * q), "f"(v[4 * q]),
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(rowp + kc0 + 4 * q), "f"(v[4 * q]),
                          "f"(v[4 * q + 1]), "f"(v[4 * q + 2]), "f"(v[4 * q + 3])
                          : "memory");
         } else {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const int k = k0 + c0 + j;
-            if (k < prm.op.K) atomicAdd(rowp + (int64_t)k * prm.op.w_ks, v[j]);
+            const int k = kc0 + j;
+            if (k < Kc) atomicAdd(rowp + (int64_t)k * prm.op.w_ks, v[j]);
           }
         }
       }
@@ -246,6 +255,16 @@ static int wgrad_tc_launch(int B, int H, int W, int N, const accx_operand_t* op,
   prm.B = B; prm.H = H; prm.W = W; prm.N = N;
   prm.P = (int64_t)B * H * W;
   ACCX_REQUIRE(prm.P < (int64_t)1 << 31, "pw_wgrad_tc: too many pixels");
+  // narrow contiguous operands: two pixels per row (full 128-byte TMA rows, half the stages), see WgParams::fold
+  prm.fold = (knob(KNOB_TC_FOLD, 2) >= 2 && n_taps == 1 && taps_dy[0] == 0 && taps_dx[0] == 0 && !det_on() && prm.P % 2 == 0 &&
+              op->ld == op->K && ldy == N && op->K % 16 == 0 && N <= 64 && op->K <= 128 && (N <= 32 || op->K <= 32)) ? 1 : 0;
+  if (prm.fold) {
+    prm.op.K *= 2; prm.op.ld *= 2;
+    prm.N = N = 2 * N;
+    prm.P /= 2;
+    ldy *= 2;
+  }
+  op = &prm.op;
   prm.dw = dw;
   prm.n_taps = n_taps;
   prm.any_transform = op->act ? 1 : 0;

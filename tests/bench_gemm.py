@@ -207,9 +207,10 @@ if __name__ == "__main__":
         SHAPES[:] = [(802816, 32, 32, 2, 1), (802816, 32, 32, 0, 1), (802816, 96, 32, 2, 1), (802816, 32, 64, 0, 1),
                      (802816, 64, 32, 2, 1), (802816, 32, 96, 0, 1), (200704, 32, 64, 2, 1), (200704, 64, 32, 2, 1),
                      (200704, 64, 64, 2, 1)]
-        for f in (1, 2):
+        SHAPES += [(200704, 32, 96, 0, 1), (200704, 128, 64, 2, 1), (200704, 64, 128, 2, 1), (50176, 64, 64, 2, 1), (50176, 128, 128, 2, 1)]
+        for f in (1, 2, 3):
             _lib.call("accx_set_knob", 23, f)
-            print(f"---- pixel folding {'off' if f == 1 else 'on'}")
+            print(f"---- pixel folding {('off', 'on', 'on, wide tensors too')[f - 1]}")
             for i in range(len(SHAPES)):
                 run_graph(i)
         _lib.call("accx_set_knob", 23, 0)

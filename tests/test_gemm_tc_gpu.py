@@ -317,7 +317,8 @@ def test_tc_many_tiles_per_cta(ops_k, N, act, extra):
 @pytest.mark.parametrize("shape", [(3, 180, 188), (2, 12, 20), (1, 6, 6)])
 @pytest.mark.parametrize("ops_k,N,act,extra", [((32,), 32, 2, "res"), ((32,), 32, 1, "stats"), ((32, 32), 32, 2, "stats"),
                                                ((32,), 64, 0, "bias"), ((96,), 32, 2, "adds"), ((64,), 32, 2, "stats"),
-                                               ((16,), 48, 2, "stats"), ((32, 64), 64, 2, "adds"), ((8,), 16, 0, "res")])
+                                               ((16,), 48, 2, "stats"), ((32, 64), 64, 2, "adds"), ((8,), 16, 0, "res"),
+                                               ((32,), 96, 0, "stats"), ((32,), 128, 2, "bias")])
 def test_tc_pixel_folding(shape, ops_k, N, act, extra):
     """narrow contiguous contractions read two pixels per row ([P/2, 2C] views, block-diagonal weights; accx_pw_fwd_tc_res):
     outputs equal the unfolded launch (knob 23 = 1) bit for bit -- the extra products are exact zeros -- statistics agree up
@@ -373,6 +374,33 @@ def test_tc_pixel_folding(shape, ops_k, N, act, extra):
         close(st2, st1, 1e-4, 1e-3, "statistics, folded vs plain rows")
         close(st2[:N], y2.float().sum((0, 1, 2)), 2e-2, 2e-2, "stats sum")
         close(st2[N:], y2.float().square().sum((0, 1, 2)), 2e-2, 2e-2, "stats sumsq")
+
+
+@pytest.mark.parametrize("shape", [(6, 180, 187), (2, 12, 20), (1, 6, 6)])
+@pytest.mark.parametrize("K,N,act", [(32, 32, 2), (32, 64, 0), (96, 32, 2), (64, 32, 1), (16, 48, 2), (128, 32, 2), (32, 96, 2)])
+def test_tc_wgrad_pixel_folding(shape, K, N, act):
+    """weight gradients of narrow contiguous operands read two pixels per row and keep the two diagonal blocks of the
+    [2N, 2K] product: same result as plain rows (knob 23 = 1) up to the order of the fp32 sums, and both match the fp64
+    restatement; (32, 96) is not folded (N > 64)"""
+    from accx import _lib
+    e = E()
+    B, H, W = shape
+    L, a = mk_lazy((B, H, W, K), torch.bfloat16, act, 81)
+    dy = torch.randn(B, H, W, N, generator=torch.Generator().manual_seed(82)).to(DEV).to(torch.bfloat16)
+    w = torch.zeros(N, K, device=DEV)
+    ref = torch.einsum("bhwn,bhwk->nk", dy.double(), bf(a).double())
+    gw = torch.zeros(N, K, device=DEV)
+    e.wgrad(e.Op(L, K, e.WV(w, 0, K, 1)), dy, N, (B, H, W), gw)
+    torch.cuda.synchronize()
+    gw1 = torch.zeros(N, K, device=DEV)
+    _lib.call("accx_set_knob", 23, 1)
+    try:
+        e.wgrad(e.Op(L, K, e.WV(w, 0, K, 1)), dy, N, (B, H, W), gw1)
+        torch.cuda.synchronize()
+    finally:
+        _lib.call("accx_set_knob", 23, 0)
+    close(gw, ref, 1e-3, 1e-4, "folded weight gradient")
+    close(gw, gw1, 1e-4, 1e-5, "folded vs plain rows")
 
 
 def test_tc_wgrad_strided_weight_view_and_column_slices():
