@@ -32,12 +32,13 @@ enum {
   KNOB_SE_BWD_REDUCE_BLOCKS, KNOB_SE_BWD_REDUCE_U, KNOB_SE_BWD_APPLY_BLOCKS, KNOB_SE_BWD_APPLY_BN_BLOCKS,
   KNOB_SE_BWD_APPLY_U, KNOB_BN_REDUCE_BLOCKS, KNOB_EW_BLOCKS, KNOB_POOL_BLOCKS, KNOB_TC_SMEM_KB, KNOB_TC_MAX_STAGES, KNOB_WGRAD_MIN_STAGES, KNOB_WGRAD_SMEM_KB, KNOB_SE_BWD_VEC,
   KNOB_TC_CONV3,      // 18: dense-3x3 slab mode of pw_fwd_tc: 1 (default) on, 2 off (nine shifted operands)
-  KNOB_TC_DEBUG,      // 19: timing diagnostics of pw_fwd_tc (bit 0 no transform math, 1 no statistics pass, 2 no TMA store, 3 no TMEM drain)
+  KNOB_TC_DEBUG,      // 19: timing diagnostics of pw_fwd_tc (bit 0 no transform math, 1 no statistics pass, 2 no TMA store, 3 no TMEM drain, 4 no weight packing, 5 role timeline)
   KNOB_TC_F32_TERMS,  // 20: products of the tf32 split in fp32-storage contractions: 3 (default) or 4
   KNOB_TC_NACC,       // 21: TMEM accumulator ring of pw_fwd_tc: 2 (default) or 4 buffers (when 4 * BN <= 512 columns)
   KNOB_WGRAD_PX,      // 22: pixels per stage of the narrow weight-gradient contractions: 256 (default) or 128
   KNOB_TC_FOLD,       // 23: pixel folding of narrow contiguous contractions (pw_fwd_tc, pw_wgrad_tc; two pixels per row): 2 (default) on
                       //     when a side has <= 32 channels, 1 off, 3 on whenever legal
+  KNOB_UNPOOL_VEC,    // 24: channels per thread of hanc_unpool_bnred: 2 or 4 (default: 2 for 4x4 windows, 4 for 2x2 windows)
   KNOB_COUNT
 };
 extern int g_knobs[KNOB_COUNT];
@@ -107,10 +108,16 @@ template <typename T, int VEC>
 __device__ __forceinline__ void ldv(const T* __restrict__ p, float (&v)[VEC]) {
   if constexpr (VEC == 1) {
     v[0] = to_f(p[0]);
+  } else if constexpr (sizeof(T) == 4 && VEC == 2) {
+    float2 t = *reinterpret_cast<const float2*>(p);
+    v[0] = t.x; v[1] = t.y;
   } else if constexpr (sizeof(T) == 4) {
-    static_assert(VEC == 4, "fp32 vectors are 4 wide");
+    static_assert(VEC == 4, "fp32 vectors are 2 or 4 wide");
     float4 t = *reinterpret_cast<const float4*>(p);
     v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  } else if constexpr (VEC == 2) {      // quarter-width bf16 access (4 bytes)
+    const uint32_t t = *reinterpret_cast<const uint32_t*>(p);
+    v[0] = __uint_as_float(t << 16); v[1] = __uint_as_float(t & 0xffff0000u);
   } else if constexpr (VEC == 4) {      // half-width bf16 access (8 bytes), for register-heavy kernels
     uint2 t = *reinterpret_cast<const uint2*>(p);
     v[0] = __uint_as_float(t.x << 16); v[1] = __uint_as_float(t.x & 0xffff0000u);
@@ -131,8 +138,13 @@ template <typename T, int VEC>
 __device__ __forceinline__ void stv(T* __restrict__ p, const float (&v)[VEC]) {
   if constexpr (VEC == 1) {
     p[0] = from_f<T>(v[0]);
+  } else if constexpr (sizeof(T) == 4 && VEC == 2) {
+    *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]);
   } else if constexpr (sizeof(T) == 4) {
     *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  } else if constexpr (VEC == 2) {      // quarter-width bf16 access (4 bytes: a warp still covers a 128-byte line)
+    __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]);
+    *reinterpret_cast<uint32_t*>(p) = *reinterpret_cast<uint32_t*>(&h0);
   } else if constexpr (VEC == 4) {
     __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
     *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
@@ -161,6 +173,20 @@ template <> struct RawVec<float, 4> {
   __device__ __forceinline__ void load(const float* p) { r = *reinterpret_cast<const float4*>(p); }
   __device__ __forceinline__ void zero() { r = make_float4(0.f, 0.f, 0.f, 0.f); }
   __device__ __forceinline__ void unpack(float (&v)[4]) const { v[0] = r.x; v[1] = r.y; v[2] = r.z; v[3] = r.w; }
+};
+template <> struct RawVec<float, 2> {
+  float2 r;
+  __device__ __forceinline__ void load(const float* p) { r = *reinterpret_cast<const float2*>(p); }
+  __device__ __forceinline__ void zero() { r = make_float2(0.f, 0.f); }
+  __device__ __forceinline__ void unpack(float (&v)[2]) const { v[0] = r.x; v[1] = r.y; }
+};
+template <> struct RawVec<bf16, 2> {
+  uint32_t r;
+  __device__ __forceinline__ void load(const bf16* p) { r = *reinterpret_cast<const uint32_t*>(p); }
+  __device__ __forceinline__ void zero() { r = 0u; }
+  __device__ __forceinline__ void unpack(float (&v)[2]) const {
+    v[0] = __uint_as_float(r << 16); v[1] = __uint_as_float(r & 0xffff0000u);
+  }
 };
 template <> struct RawVec<bf16, 4> {
   uint2 r;
@@ -205,6 +231,9 @@ template <int VEC>
 __device__ __forceinline__ void ldf(const float* __restrict__ p, float (&v)[VEC]) {
   if constexpr (VEC == 1) {
     v[0] = p[0];
+  } else if constexpr (VEC == 2) {
+    float2 t = *reinterpret_cast<const float2*>(p);
+    v[0] = t.x; v[1] = t.y;
   } else {
 #pragma unroll
     for (int i = 0; i < VEC; i += 4) {

@@ -460,10 +460,9 @@ static int dw_launch_tw(DwParams& prm, const void* x, const void* dy, cudaStream
   const size_t g_bytes = BOX2 ? (size_t)TH * prm.TW * prm.CC * esz : 0;
   const size_t smem = 128 + 2 * (x_bytes + g_bytes) + 16 + DW_THREADS * sizeof(float);
   auto kern = dw3x3_tiled_kernel<T, TH, MODE, TW>;
-  static bool attr_set = false;       // one flag per template instantiation
-  if (!attr_set) {
+  static bool attr_set[ACCX_MAX_DEVICES] = {false};       // one flag per template instantiation
+  if (first_use_on_device(attr_set)) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    attr_set = true;
   }
   const int64_t total = prm.n_spatial * prm.n_chunks;
   int64_t grid = 2 * (int64_t)sm_count();

@@ -219,7 +219,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_fwd_tc_kernel(const __grid_c
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (prm.b_resident && warp < TC_WARP_TMA) {
+  // small weight matrices (<= 1536 16-byte chunks, e.g. 192 x 64) are packed by the eight epilogue warps alone -- idle until the
+  // first accumulator is full -- so the transform warps start on the first landed tiles at once (the packing, a chain of
+  // L2 loads -> convert -> st.shared -> fence -> barrier, costs 2-4 us per launch: profiles/r02_pw_fwd_tc_weight_pack_share.txt)
+  const int pack_warps = ((prm.any_transform || F32IN) && n_kb * bn * (F32IN ? 16 : 8) <= 1536) ? TC_WARP_XF0 : TC_WARP_TMA;
+  if (prm.b_resident && warp < pack_warps) {
     // Resident weights are packed straight into shared memory by the 512 epilogue + transform threads:
     // fp32 strided view -> bf16, K-major 128B-swizzled [bn rows][64] tiles, one per k-block (no pre-pack
     // launch, no workspace traffic).  Every CTA reads the (small, L2-resident) weight matrix once.
@@ -227,13 +231,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_fwd_tc_kernel(const __grid_c
     const int chunks_per_kb = bn * (F32IN ? 16 : 8);
     const int n_chunks_w = n_kb * chunks_per_kb;
     constexpr int WU = 4;                      // chunks in flight per thread: the loop is bound by L2 latency otherwise
-    for (int ch0 = tid; ch0 < n_chunks_w; ch0 += WU * TC_WARP_TMA * 32) {
+    const int pack_threads = pack_warps * 32;
+    for (int ch0 = tid; ch0 < ((prm.debug & 16) ? 0 : n_chunks_w); ch0 += WU * pack_threads) {
       float v[WU][8];
       uint32_t addr[WU];
       bool low[WU];                            // fp32 split: this chunk holds w_lo = bf16(w - w_hi)
 #pragma unroll
       for (int u = 0; u < WU; ++u) {
-        const int ch = ch0 + u * TC_WARP_TMA * 32;
+        const int ch = ch0 + u * pack_threads;
 #pragma unroll
         for (int e = 0; e < 8; ++e) v[u][e] = 0.f;
         addr[u] = 0;
@@ -297,7 +302,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_fwd_tc_kernel(const __grid_c
       }
     }
     fence_async_smem();
-    asm volatile("bar.sync 3, 512;" ::: "memory");
+    asm volatile("bar.sync 3, %0;" ::"r"(pack_threads) : "memory");
     if (tid == 0) mbar_arrive(bres_bar);
   }
 
@@ -1137,12 +1142,11 @@ int accx_pw_fwd_tc_res(int dtype, int out_dtype, int B, int H, int W, int N, con
     int rc = check_launch("tc_pack_weights");
     if (rc) return rc;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[ACCX_MAX_DEVICES] = {false};
+  if (first_use_on_device(attr_set)) {
     cudaFuncSetAttribute(pw_fwd_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX);
     cudaFuncSetAttribute(pw_fwd_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX);
     cudaFuncSetAttribute(pw_fwd_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX);
-    attr_set = true;
   }
   const int64_t total = (int64_t)prm.m_tiles * prm.n_tiles;
   int64_t grid = sm_count();

@@ -310,11 +310,10 @@ static int wgrad_tc_launch(int B, int H, int W, int N, const accx_operand_t* op,
   ACCX_REQUIRE(encode_2d_bf16(&prm.map_dy, dy, N, prm.P, ldy, WG_PX), "pw_wgrad_tc: tensor map (dY) failed");
   ACCX_REQUIRE(encode_2d_bf16(&prm.map_a, op->data, op->K, prm.P, op->ld, WG_PX), "pw_wgrad_tc: tensor map (A) failed");
   const size_t smem = 1024 + S * stage_bytes + 2 * (size_t)a_blocks * 64 * 4 + 24 * S + 64;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[ACCX_MAX_DEVICES] = {false};
+  if (first_use_on_device(attr_set)) {
     cudaFuncSetAttribute(pw_wgrad_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     cudaFuncSetAttribute(pw_wgrad_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    attr_set = true;
   }
   if (WG_PX == 256) launch_k(pw_wgrad_tc_kernel<256>, (unsigned)(pairs * splits), WG_THREADS, smem, (cudaStream_t)stream, prm);
   else launch_k(pw_wgrad_tc_kernel<128>, (unsigned)(pairs * splits), WG_THREADS, smem, (cudaStream_t)stream, prm);

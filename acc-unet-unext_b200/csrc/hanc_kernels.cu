@@ -158,7 +158,7 @@ __global__ void hanc_unpool_kernel(int B, int H, int W, int C, int log2s, const 
 // One thread owns a 2^LEVELS-square window of 4 channels: y and da are read ONCE (the per-level kernels read y
 // and read-modify-write da once per level, and the BN reduction reads both again), every load of the window is
 // in flight before the first compare.  bf16 storage.
-template <int LEVELS>
+template <int LEVELS, int VEC>
 __global__ void __launch_bounds__(128) hanc_unpool_bnred_kernel(int B, int H, int W, int C, const bf16* __restrict__ y,
                                                                 const float* scale, const float* shift, int act,
                                                                 const float* __restrict__ dp1,
@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(128) hanc_unpool_bnred_kernel(int B, int H, in
                                                                 const float* mean, const float* rstd, float* sums,
                                                                 Det det) {
   pdl_sync();
-  constexpr int S = 1 << LEVELS, NPX = S * S, VEC = 4;
+  constexpr int S = 1 << LEVELS, NPX = S * S;
   extern __shared__ float smem[];
   const int cv = blockIdx.y * blockDim.x + threadIdx.x;
   const bool active = cv * VEC < C;
@@ -324,24 +324,32 @@ int accx_hanc_unpool_bnred(int dtype, int B, int H, int W, int C, int levels, co
                "hanc_unpool_bnred: needs C %% 4 == 0 and aligned tensors");
   ACCX_REQUIRE(act == 0 || (scale && shift), "hanc_unpool_bnred: act %d needs scale/shift", act);
   const int64_t n_win = (int64_t)B * (H / S) * (W / S);
-  Lanes l;                                       // 128-thread blocks: the window state is register heavy
-  l.vec = 4;
-  l.cvn = C / 4;
+  // 128-thread blocks: the window state is register heavy.  4 x 4 windows (two levels) with 4 channels per thread hold 255
+  // registers (two blocks = 8 warps per SM, whose load / compute / store phases leave HBM idle half of the time); with 2
+  // channels per thread (4-byte accesses, a warp still covers whole 128-byte lines) 168 registers, three blocks, and
+  // 1.1-1.6x the rate: 16x56x56x4352 683 -> 437 us, 16x224x224x192 450 -> 333 us (profiles/r02_unpool_channels_per_thread.txt).
+  // 2 x 2 windows (one level, 118 registers) are faster with 4 channels per thread (71 vs 95 us at 16x28x28x1536).
+  Lanes l;
+  l.vec = knob(KNOB_UNPOOL_VEC, levels == 2 ? 2 : 4) == 2 ? 2 : 4;
+  l.cvn = C / l.vec;
   l.tx = l.cvn <= 128 ? l.cvn : 128;
   for (int d = 128; l.cvn > 128 && d >= 32; --d)
     if (l.cvn % d == 0) { l.tx = d; break; }
   l.ty = 128 / l.tx;
   l.gy = (l.cvn + l.tx - 1) / l.tx;
-  dim3 block(l.tx, l.ty), grid(grid_x_for(n_win, l.ty, 148 * 3), l.gy);
+  dim3 block(l.tx, l.ty), grid(grid_x_for(n_win, l.ty, 148 * (l.vec == 2 ? 6 : 3)), l.gy);
   const size_t sm = (size_t)l.tx * l.ty * l.vec * sizeof(float);
   Det det;
   if (!det_handle((int64_t)grid.x * grid.y * 2 * l.tx * l.vec, grid.y, (cudaStream_t)stream, det)) return ACCX_ERR_INVALID;
-  if (levels == 1)
-    launch_k(hanc_unpool_bnred_kernel<1>, grid, block, sm, (cudaStream_t)stream, B, H, W, C, (const bf16*)y, scale, shift, act,
-                                                                            dpool1, dpool2, (bf16*)da, mean, rstd, sums, det);
-  else
-    launch_k(hanc_unpool_bnred_kernel<2>, grid, block, sm, (cudaStream_t)stream, B, H, W, C, (const bf16*)y, scale, shift, act,
-                                                                            dpool1, dpool2, (bf16*)da, mean, rstd, sums, det);
+#define ACCX_UNPOOL_LAUNCH(LV, VC)                                                                                          \
+  launch_k(hanc_unpool_bnred_kernel<LV, VC>, grid, block, sm, (cudaStream_t)stream, B, H, W, C, (const bf16*)y, scale, shift, \
+           act, dpool1, dpool2, (bf16*)da, mean, rstd, sums, det)
+  if (levels == 1) {
+    if (l.vec == 2) ACCX_UNPOOL_LAUNCH(1, 2); else ACCX_UNPOOL_LAUNCH(1, 4);
+  } else {
+    if (l.vec == 2) ACCX_UNPOOL_LAUNCH(2, 2); else ACCX_UNPOOL_LAUNCH(2, 4);
+  }
+#undef ACCX_UNPOOL_LAUNCH
   return check_launch("hanc_unpool_bnred");
 }
 

@@ -446,6 +446,9 @@ __global__ void se_bwd_apply_kernel(int B, int HW, int C, int chunks, const T* _
     } else if ((lanes).vec == 4) {                                       \
       constexpr int VEC = 4;                                             \
       __VA_ARGS__                                                        \
+    } else if ((lanes).vec == 2) {                                       \
+      constexpr int VEC = 2;                                             \
+      __VA_ARGS__                                                        \
     } else {                                                             \
       constexpr int VEC = accx::DT<T>::VEC;                              \
       __VA_ARGS__                                                        \
@@ -539,7 +542,7 @@ int accx_se_bwd_reduce(int dtype, int B, int HW, int C, const void* x, const flo
   ACCX_REQUIRE(B > 0 && HW > 0 && C > 0 && x && gate && dout && G, "se_bwd_reduce: bad arguments");
   ACCX_REQUIRE(!dmix || (mix && residual), "se_bwd_reduce: dmix needs mix and residual");
   ACCX_DISPATCH_T(dtype, {
-    const int fv = knob(KNOB_SE_BWD_VEC, 4) == 4 ? 4 : DT<T>::VEC;
+    const int fv = knob(KNOB_SE_BWD_VEC, 4) == 4 ? 4 : (knob(KNOB_SE_BWD_VEC, 4) == 2 && sizeof(T) == 2 ? 2 : DT<T>::VEC);
     Lanes l = make_lanes(C, fv, aligned16(x) && aligned16(dout) && (!residual || aligned16(residual)));
     int chunks = se_chunks(B, HW, l.ty, 148 * knob(KNOB_SE_BWD_REDUCE_BLOCKS, 4));
     dim3 block(l.tx, l.ty), grid(B * chunks, l.gy);
@@ -588,7 +591,7 @@ int accx_se_bwd_apply(int dtype, int B, int HW, int C, const void* x, const floa
   ACCX_REQUIRE(B > 0 && HW > 0 && C > 0 && x && gate && dout && PQR && da, "se_bwd_apply: bad arguments");
   ACCX_REQUIRE(!bn_sums || (bn_mean && bn_rstd), "se_bwd_apply: bn_sums needs bn_mean and bn_rstd");
   ACCX_DISPATCH_T(dtype, {
-    const int fv = knob(KNOB_SE_BWD_VEC, 4) == 4 ? 4 : DT<T>::VEC;
+    const int fv = knob(KNOB_SE_BWD_VEC, 4) == 4 ? 4 : (knob(KNOB_SE_BWD_VEC, 4) == 2 && sizeof(T) == 2 ? 2 : DT<T>::VEC);
     Lanes l = make_lanes(C, fv, aligned16(x) && aligned16(dout) && aligned16(da));
     // reducing variant: few blocks (atomics)
     const int chunks = se_chunks(B, HW, l.ty, 148 * (bn_sums ? knob(KNOB_SE_BWD_APPLY_BN_BLOCKS, 4) : knob(KNOB_SE_BWD_APPLY_BLOCKS, 8)));

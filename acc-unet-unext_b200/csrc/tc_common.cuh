@@ -226,15 +226,32 @@ inline bool encode_2d_out(CUtensorMap* map, const void* data, int64_t cols, int6
                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// per-device caches (a process may drive several devices: cudaFuncSetAttribute and the SM count belong to the
+// CURRENT device, not to the process)
+constexpr int ACCX_MAX_DEVICES = 64;
+inline int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < ACCX_MAX_DEVICES) ? dev : 0;
+}
+
 inline int sm_count() {
-  static int n_sm = 0;
-  if (!n_sm) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    if (n_sm <= 0) n_sm = 148;
+  static int n_sm[ACCX_MAX_DEVICES] = {0};
+  const int dev = current_device();
+  if (!n_sm[dev]) {
+    int n = 0;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    n_sm[dev] = n > 0 ? n : 148;
   }
-  return n_sm;
+  return n_sm[dev];
+}
+
+// true the first time it is called for `flags` on the current device (opt-in shared-memory attributes are per device)
+inline bool first_use_on_device(bool (&flags)[ACCX_MAX_DEVICES]) {
+  const int dev = current_device();
+  if (flags[dev]) return false;
+  flags[dev] = true;
+  return true;
 }
 
 }  // namespace accx

@@ -202,6 +202,16 @@ if __name__ == "__main__":
         _lib.call("accx_set_knob", 19, 0)
         _lib.call("accx_set_knob", 14, 0)
         sys.exit(0)
+    if "pack" in args:           # share of the in-kernel weight packing (knob 19 bit 4 skips it; results are then wrong)
+        from accx import _lib
+        SHAPES[:] = SMALL + [(12544, 128, 384, 0, 1), (3136, 256, 256, 2, 1), (50176, 128, 256, 2, 1), (200704, 192, 64, 2, 1)]
+        for dbg, what in ((0, "full kernel"), (16, "weights not packed")):
+            _lib.call("accx_set_knob", 19, dbg)
+            print(f"---- {what}")
+            for i in range(len(SHAPES)):
+                run_graph(i)
+        _lib.call("accx_set_knob", 19, 0)
+        sys.exit(0)
     if "fold" in args:           # pixel folding of narrow contiguous contractions (knob 23: 1 = off, default on)
         from accx import _lib
         SHAPES[:] = [(802816, 32, 32, 2, 1), (802816, 32, 32, 0, 1), (802816, 96, 32, 2, 1), (802816, 32, 64, 0, 1),
