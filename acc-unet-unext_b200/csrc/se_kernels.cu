@@ -591,13 +591,18 @@ int accx_se_bwd_apply(int dtype, int B, int HW, int C, const void* x, const floa
   ACCX_REQUIRE(B > 0 && HW > 0 && C > 0 && x && gate && dout && PQR && da, "se_bwd_apply: bad arguments");
   ACCX_REQUIRE(!bn_sums || (bn_mean && bn_rstd), "se_bwd_apply: bn_sums needs bn_mean and bn_rstd");
   ACCX_DISPATCH_T(dtype, {
-    const int fv = knob(KNOB_SE_BWD_VEC, 4) == 4 ? 4 : (knob(KNOB_SE_BWD_VEC, 4) == 2 && sizeof(T) == 2 ? 2 : DT<T>::VEC);
+    // small maps (levels 3-5: <= 56 x 56 per image) in bf16: two channels per thread, four pixels in flight (72 registers,
+    // three blocks per SM) -- 24.9 -> 20.7 us at 16 x 3136 x 128, 22.9 -> 15.8 us at 16 x 784 x 256 with two blocks per SM;
+    // the large maps keep four channels (47 vs 57 us at 16 x 50176 x 32): profiles/r02_se_bwd_channels_per_thread.txt
+    const bool small_map = sizeof(T) == 2 && HW <= 3136 && g_knobs[KNOB_SE_BWD_VEC] == 0;
+    const int fv = small_map ? 2 : (knob(KNOB_SE_BWD_VEC, 4) == 4 ? 4 : (knob(KNOB_SE_BWD_VEC, 4) == 2 && sizeof(T) == 2 ? 2 : DT<T>::VEC));
     Lanes l = make_lanes(C, fv, aligned16(x) && aligned16(dout) && aligned16(da));
     // reducing variant: few blocks (atomics)
-    const int chunks = se_chunks(B, HW, l.ty, 148 * (bn_sums ? knob(KNOB_SE_BWD_APPLY_BN_BLOCKS, 4) : knob(KNOB_SE_BWD_APPLY_BLOCKS, 8)));
+    const int chunks = se_chunks(B, HW, l.ty, 148 * (bn_sums ? knob(KNOB_SE_BWD_APPLY_BN_BLOCKS, (small_map && HW <= 784) ? 2 : 4)
+                                                             : knob(KNOB_SE_BWD_APPLY_BLOCKS, 8)));
     dim3 block(l.tx, l.ty), grid(B * chunks, l.gy);
     const size_t sm = bn_sums ? (size_t)l.tx * l.ty * l.vec * sizeof(float) : 0;
-    const int u = knob(KNOB_SE_BWD_APPLY_U, 8);
+    const int u = knob(KNOB_SE_BWD_APPLY_U, small_map ? 4 : 8);
     Det det;
     if (!det_handle(bn_sums ? (int64_t)grid.x * grid.y * 2 * l.tx * l.vec : 0, grid.y, (cudaStream_t)stream, det)) return ACCX_ERR_INVALID;
     ACCX_DISPATCH_VEC_H(l, {
