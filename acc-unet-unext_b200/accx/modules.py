@@ -306,12 +306,20 @@ def _hanc_core_fwd(hnc, L2: Lazy, ar: Arena, training):
     if E.RECORD is not None:
         E.RECORD[("hanc", id(hnc))] = L2
     pools = E.hanc_pools(L2, k)
-    adds = []
-    for l in range(1, k):
+    # bf16 storage: coarsest level first; every level adds the (nearest-upsampled) sum of the coarser ones in its own
+    # epilogue, so the full-resolution contraction reads ONE addend whatever k is (addend loads are a chain of L2 round
+    # trips per chunk in the epilogue: K = N = 32 at 16x224x224 costs 32 us without addends and 100 us with three).
+    # fp32 storage (the parity mode) keeps one addend per level: the association of the fp32 sums stays what the
+    # reference-pinned tolerances were measured with.
+    chain = L2.y.dtype == torch.bfloat16
+    adds, r = [], None
+    for l in range(k - 1, 0, -1):
         Pl = Lazy(pools[l - 1])
         r = E.conv([Op(Pl, Ein, WV(wh, l, J * Ein, J), 0), Op(Pl, Ein, WV(wh, k - 1 + l, J * Ein, J), Ein)],
-                   C, (B, H >> l, W >> l), out_dtype=E.F32)
-        adds.append((r, l))
+                   C, (B, H >> l, W >> l), out_dtype=E.F32, adds=[(r, 1)] if (chain and r is not None) else ())
+        adds.insert(0, (r, l))
+    if chain:
+        adds = adds[:1]
     L3 = _pw_bn([Op(L2, Ein, WV(wh, 0, J * Ein, J))], C, (B, H, W), hnc.cnv, hnc.bn, 2, ar, training, adds)
     return L3, pools
 
@@ -713,11 +721,16 @@ class MLFC(_AccxModule):
                         arl = ars[l]
                         cb = getattr(self, f"cnv_blks{l + 1}")[i]
                         wb = _w(cb.conv1.weight)                                  # [C_l, tot], block order
-                        adds = []
-                        for s in range(l + 1, 4):                                 # coarser sources
+                        # coarser sources, coarsest first; bf16 storage: each adds the sum so far, so that the
+                        # contraction at this level reads one addend (see _hanc_core_fwd)
+                        chain = xs[0].dtype == torch.bfloat16
+                        adds, r = [], None
+                        for s in range(3, l, -1):
                             r = E.conv([Op(Lazy(xs[s]), filt[s], WV(wb, offs[s], tot, 1))], filt[l], dims[s],
-                                       out_dtype=E.F32)
-                            adds.append((r, s - l))
+                                       out_dtype=E.F32, adds=[(r, 1)] if (chain and r is not None) else ())
+                            adds.insert(0, (r, s - l))
+                        if chain:
+                            adds = adds[:1]
                         ops = [Op(Lazy(pooled[(s, l)] if s < l else xs[l]), filt[s], WV(wb, offs[s], tot, 1))
                                for s in range(l + 1)]
                         stt = arl.take(2 * filt[l]) if training else None

@@ -1,5 +1,7 @@
 """Aggregate an `ncu --metrics gpu__time_duration.sum --csv` launch list by kernel name.
-    python profiles/summarize_launches.py gpurun_out/launches.csv > profiles/<name>.md"""
+    python profiles/summarize_launches.py gpurun_out/launches.csv [--last-step] > profiles/<name>.md
+--last-step: only the launches of the last complete train step of the capture (everything after the second-to-last
+accx::adam_flat_kernel up to and including the last one)."""
 import csv
 import re
 import sys
@@ -16,6 +18,10 @@ for r in csv.DictReader(lines):
         name = re.sub(r"\(.*", "", r["Kernel Name"])
         name = re.sub(r"^void ", "", name)
         rows.append((name, ns))
+if "--last-step" in sys.argv:
+    ends = [i for i, (n, _) in enumerate(rows) if "adam_flat_kernel" in n]
+    if len(ends) >= 2:
+        rows = rows[ends[-2] + 1:ends[-1] + 1]
 agg = defaultdict(lambda: [0, 0.0])
 for n, ns in rows:
     agg[n][0] += 1

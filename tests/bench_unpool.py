@@ -45,6 +45,9 @@ def run(shape, vec, reps=5):
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "one":      # ncu target: the library's default geometry on one shape
+        run(tuple(int(v) for v in sys.argv[2:7]), 0, reps=2)
+        sys.exit(0)
     for shape in SHAPES:
         a, b = run(shape, 4), run(shape, 2)
         assert torch.equal(a[0], b[0]), "gradient differs between the variants"
