@@ -67,6 +67,11 @@ struct alignas(64) TcParams {
   // and the weights are block-diagonal: W'[n, k] = W[n % Nf, k % Kf] when n / Nf == k / Kf, else 0 (Nf = N/2, Kf = K/2);
   // scale / shift / bias / statistics / addend columns are taken modulo the real channel counts
   int fold;
+  // first addend staged through shared memory (narrow tiles, bn <= 64): every epilogue thread copies its own row's
+  // slice of the addend with cp.async at the top of the tile iteration, i.e. under the wait for the accumulator -- as
+  // direct loads the addend is a chain of L2 round trips per 16-column chunk inside the drain (K = N = 32 at
+  // 16x224x224: 32 us without an addend, 68 us with one).  addst_w = floats staged per row (0 = off).
+  int addst_w;
   int tap_op[3][3];
 };
 
@@ -190,6 +195,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_fwd_tc_kernel(const __grid_c
   const uint32_t tempty_bar = tfull_bar + 32;            // up to 4 x 8
   const uint32_t bres_bar = tempty_bar + 32;             // 8
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + bar_off + 24 * S + 72);
+  const uint32_t addst_off = (bar_off + 24 * S + 96 + 15u) & ~15u;      // float[2 groups][128 rows][addst_w + 4]
   const int nacc_log = prm.nacc_log, nacc_mask = (1 << nacc_log) - 1;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -725,9 +731,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_fwd_tc_kernel(const __grid_c
           }
         }
       }
+      const uint32_t addst_row = base + addst_off + (uint32_t)((grp * TC_BM + row) * (prm.addst_w + 4)) * 4u;
+      const bool staged = prm.addst_w != 0 && ap[0] != nullptr;
+      if (staged) {
+        const float* src = ap[0] + (prm.fold ? 0 : n0);
+        for (int j = 0; j < prm.addst_w; j += 4)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(addst_row + 4u * j), "l"(src + j) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      }
       mbar_wait(tfull_bar + 8 * acc, (tl >> nacc_log) & 1);
       if (gtid == 0) tc_trace(prm, 6, tl);
       tc_fence_after();
+      if (staged) asm volatile("cp.async.wait_group 0;" ::: "memory");
       // the staging boxes are free once the previous tile's TMA stores have read them and every thread has
       // finished its statistics pass
       if (gtid == 0) bulk_wait_read0();
@@ -756,9 +771,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_fwd_tc_kernel(const __grid_c
                   v[4 * q] += b4.x; v[4 * q + 1] += b4.y; v[4 * q + 2] += b4.z; v[4 * q + 3] += b4.w;
                 }
               }
+              if (staged) {
+                const uint32_t sa = addst_row + 4u * (prm.fold ? cb : c0);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  float4 a4;
+                  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(a4.x), "=f"(a4.y), "=f"(a4.z), "=f"(a4.w) : "r"(sa + 16u * q));
+                  v[4 * q] += a4.x; v[4 * q + 1] += a4.y; v[4 * q + 2] += a4.z; v[4 * q + 3] += a4.w;
+                }
+              }
 #pragma unroll
               for (int a = 0; a < ACCX_MAX_ADDENDS; ++a) {
-                if (a < n_add) {
+                if (a < n_add && !(a == 0 && staged)) {
                   const float4* a4p = reinterpret_cast<const float4*>(ap[a] + cb);
 #pragma unroll
                   for (int q = 0; q < 4; ++q) {
@@ -966,8 +990,13 @@ static size_t tc_geometry(int N, int64_t P, const accx_operand_t* ops, int n_ops
   prm.tmem_cols = cols;
   prm.out_boxes = (prm.bn + box_cols - 1) / box_cols;
   const size_t b_tile = (size_t)(prm.f32in ? 2 : 1) * prm.bn * 128;
+  // first addend through shared memory: narrow column tiles whose chunks are all full (see TcParams::addst_w)
+  prm.addst_w = 0;
+  if (prm.n_add >= 1 && prm.n_tiles == 1 && prm.bn <= 64 && N % 16 == 0 && !prm.conv3 && knob(KNOB_TC_ADD_STAGE, 2) == 2)
+    prm.addst_w = prm.fold ? N / 2 : N;
   fixed = 1024 + 2 * (size_t)prm.out_boxes * TC_BOX_BYTES + 4 * prm.bn * 4 + 512 +
-          ((prm.any_transform || prm.f32in) ? (size_t)kb * (bkc * 8 + 16) : 0) + (prm.conv3 ? 2 * TC_SLAB_ROWS * 2 : 0);
+          ((prm.any_transform || prm.f32in) ? (size_t)kb * (bkc * 8 + 16) : 0) + (prm.conv3 ? 2 * TC_SLAB_ROWS * 2 : 0) +
+          (prm.addst_w ? 2 * (size_t)TC_BM * (prm.addst_w + 4) * 4 + 16 : 0);
   prm.b_resident = (prm.n_tiles == 1 && fixed + (size_t)kb * b_tile + 3 * (size_t)(prm.f32in ? 2 : 1) * TC_A_BYTES <= (size_t)TC_SMEM_MAX) ? 1 : 0;
   if (prm.conv3) prm.b_resident = 1;   // nine tiles of <= 8 KB (checked by the caller)
   resident = prm.b_resident ? (size_t)kb * b_tile : 0;
@@ -1093,6 +1122,7 @@ int accx_pw_fwd_tc_res(int dtype, int out_dtype, int B, int H, int W, int N, con
     fold = fold && narrow && ksum <= 128;
   }
   size_t smem = 0;
+  prm.n_add = n_add;
   for (;;) {
     const int f = fold ? 2 : 1;
     prm.fold = fold ? 1 : 0;

@@ -376,6 +376,51 @@ def test_tc_pixel_folding(shape, ops_k, N, act, extra):
         close(st2[N:], y2.float().square().sum((0, 1, 2)), 2e-2, 2e-2, "stats sumsq")
 
 
+@pytest.mark.parametrize("shape", [(3, 180, 188), (2, 12, 20), (1, 4, 4)])
+@pytest.mark.parametrize("ops_k,N,act,levels", [((64,), 64, 2, (1,)), ((64,), 64, 2, (1, 2)), ((32,), 32, 2, (1,)), ((192,), 64, 1, (2, 1)),
+                                               ((96,), 32, 2, (1, 2)), ((64, 64), 48, 2, (1,)), ((128,), 16, 0, (2,))])
+def test_tc_first_addend_staged_through_shared_memory(shape, ops_k, N, act, levels):
+    """narrow column tiles (<= 64 channels, N % 16 == 0) copy the first nearest-upsampled addend into shared memory with
+    cp.async under the wait for the accumulator (knob 25); same outputs as direct loads bit for bit, with one and two
+    addends, folded and plain rows, and against the torch restatement"""
+    from accx import _lib
+    e = E()
+    B, H, W = shape
+    g = torch.Generator().manual_seed(91)
+    Ls, As = [], []
+    for i, K in enumerate(ops_k):
+        L, a = mk_lazy((B, H, W, K), torch.bfloat16, act, 92 + i)
+        Ls.append(L), As.append(a)
+    Kt = sum(ops_k)
+    w = (torch.randn(N, Kt, generator=g) / Kt ** 0.5).to(DEV)
+    adds = [(torch.randn(B, H >> l, W >> l, N, generator=g).to(DEV), l) for l in levels]
+    ops, k0 = [], 0
+    for L, K in zip(Ls, ops_k):
+        ops.append(e.Op(L, K, e.WV(w, k0, Kt, 1)))
+        k0 += K
+
+    def run():
+        stats = torch.zeros(2 * N, device=DEV)
+        return e.conv(ops, N, (B, H, W), adds=adds, stats=stats), stats
+
+    y2, st2 = run()
+    _lib.call("accx_set_knob", 25, 1)
+    try:
+        y1, st1 = run()
+    finally:
+        _lib.call("accx_set_knob", 25, 0)
+    assert torch.equal(y1, y2), "staging the addend changed the outputs"
+    ref = torch.zeros(B, H, W, N, device=DEV)
+    k0 = 0
+    for a, K in zip(As, ops_k):
+        ref = ref + bf(a) @ bf(w[:, k0:k0 + K]).t()
+        k0 += K
+    for t, l in adds:
+        ref = ref + t.repeat_interleave(1 << l, 1).repeat_interleave(1 << l, 2)
+    close(y2.float(), ref, RT, AT, "staged addend")
+    close(st2, st1, 1e-4, 1e-3, "statistics, staged vs direct addend")
+
+
 @pytest.mark.parametrize("shape", [(6, 180, 187), (2, 12, 20), (1, 6, 6)])
 @pytest.mark.parametrize("K,N,act", [(32, 32, 2), (32, 64, 0), (96, 32, 2), (64, 32, 1), (16, 48, 2), (128, 32, 2), (32, 96, 2)])
 def test_tc_wgrad_pixel_folding(shape, K, N, act):
