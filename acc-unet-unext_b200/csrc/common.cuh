@@ -38,7 +38,8 @@ enum {
   KNOB_WGRAD_PX,      // 22: pixels per stage of the narrow weight-gradient contractions: 256 (default) or 128
   KNOB_TC_FOLD,       // 23: pixel folding of narrow contiguous contractions (pw_fwd_tc, pw_wgrad_tc; two pixels per row): 2 (default) on
                       //     when a side has <= 32 channels, 1 off, 3 on whenever legal
-  KNOB_UNPOOL_VEC,    // 24: channels per thread of hanc_unpool_bnred: 2 or 4 (default: 2 for 4x4 windows, 4 for 2x2 windows)
+  KNOB_UNPOOL_VEC,    // 24: channels per thread of hanc_unpool_bnred: 4, 2, or 3 = two channels held to 128 registers
+                      //     (default: 3 for 4x4 windows, 4 for 2x2 windows)
   KNOB_TC_ADD_STAGE,  // 25: first addend of narrow pw_fwd_tc tiles staged through shared memory with cp.async: 2 (default) on, 1 off
   KNOB_COUNT
 };

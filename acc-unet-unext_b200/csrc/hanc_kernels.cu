@@ -158,8 +158,8 @@ __global__ void hanc_unpool_kernel(int B, int H, int W, int C, int log2s, const 
 // One thread owns a 2^LEVELS-square window of 4 channels: y and da are read ONCE (the per-level kernels read y
 // and read-modify-write da once per level, and the BN reduction reads both again), every load of the window is
 // in flight before the first compare.  bf16 storage.
-template <int LEVELS, int VEC>
-__global__ void __launch_bounds__(128) hanc_unpool_bnred_kernel(int B, int H, int W, int C, const bf16* __restrict__ y,
+template <int LEVELS, int VEC, int OCC = 1>
+__global__ void __launch_bounds__(128, OCC) hanc_unpool_bnred_kernel(int B, int H, int W, int C, const bf16* __restrict__ y,
                                                                 const float* scale, const float* shift, int act,
                                                                 const float* __restrict__ dp1,
                                                                 const float* __restrict__ dp2, bf16* __restrict__ da,
@@ -326,18 +326,20 @@ int accx_hanc_unpool_bnred(int dtype, int B, int H, int W, int C, int levels, co
   const int64_t n_win = (int64_t)B * (H / S) * (W / S);
   // 128-thread blocks: the window state is register heavy.  4 x 4 windows (two levels) with 4 channels per thread hold 255
   // registers (two blocks = 8 warps per SM, whose load / compute / store phases leave HBM idle half of the time); with 2
-  // channels per thread (4-byte accesses, a warp still covers whole 128-byte lines) 168 registers, three blocks, and
-  // 1.1-1.6x the rate: 16x56x56x4352 683 -> 437 us, 16x224x224x192 450 -> 333 us (profiles/r02_unpool_channels_per_thread.txt).
+  // channels per thread (4-byte accesses, a warp still covers whole 128-byte lines) 168 registers and three blocks, or --
+  // the default -- held to 128 registers (24 bytes of spills) and four blocks: 16x56x56x4352 683 -> 437 -> 396 us,
+  // 16x224x224x192 450 -> 333 -> 310 us (profiles/r02_unpool_channels_per_thread.txt).
   // 2 x 2 windows (one level, 118 registers) are faster with 4 channels per thread (71 vs 95 us at 16x28x28x1536).
   Lanes l;
-  l.vec = knob(KNOB_UNPOOL_VEC, levels == 2 ? 2 : 4) == 2 ? 2 : 4;
+  const int vk = knob(KNOB_UNPOOL_VEC, levels == 2 ? 3 : 4);      // 3 = two channels held to 128 registers (four blocks per SM)
+  l.vec = (vk == 2 || vk == 3) ? 2 : 4;
   l.cvn = C / l.vec;
   l.tx = l.cvn <= 128 ? l.cvn : 128;
   for (int d = 128; l.cvn > 128 && d >= 32; --d)
     if (l.cvn % d == 0) { l.tx = d; break; }
   l.ty = 128 / l.tx;
   l.gy = (l.cvn + l.tx - 1) / l.tx;
-  dim3 block(l.tx, l.ty), grid(grid_x_for(n_win, l.ty, 148 * (l.vec == 2 ? 6 : 3)), l.gy);
+  dim3 block(l.tx, l.ty), grid(grid_x_for(n_win, l.ty, 148 * (vk == 3 ? 8 : (l.vec == 2 ? 6 : 3))), l.gy);
   const size_t sm = (size_t)l.tx * l.ty * l.vec * sizeof(float);
   Det det;
   if (!det_handle((int64_t)grid.x * grid.y * 2 * l.tx * l.vec, grid.y, (cudaStream_t)stream, det)) return ACCX_ERR_INVALID;
@@ -346,6 +348,9 @@ int accx_hanc_unpool_bnred(int dtype, int B, int H, int W, int C, int levels, co
            act, dpool1, dpool2, (bf16*)da, mean, rstd, sums, det)
   if (levels == 1) {
     if (l.vec == 2) ACCX_UNPOOL_LAUNCH(1, 2); else ACCX_UNPOOL_LAUNCH(1, 4);
+  } else if (vk == 3) {
+    launch_k(hanc_unpool_bnred_kernel<2, 2, 4>, grid, block, sm, (cudaStream_t)stream, B, H, W, C, (const bf16*)y, scale, shift,
+             act, dpool1, dpool2, (bf16*)da, mean, rstd, sums, det);
   } else {
     if (l.vec == 2) ACCX_UNPOOL_LAUNCH(2, 2); else ACCX_UNPOOL_LAUNCH(2, 4);
   }
