@@ -261,7 +261,10 @@ class TrainStep:
     `graph_warmup` eager steps; inputs are then copied into static buffers each step."""
 
     def __init__(self, model: torch.nn.Module, lr: float = 1e-3, graph: bool = False, graph_warmup: int = 3,
-                 betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0, metrics: bool = False):
+                 betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0, metrics: bool = False,
+                 distributed: bool = True):
+        """distributed=False: a rank-local step inside an initialised process group (no start-up broadcast, no gradient
+        exchange) -- e.g. an instrumented step that only rank 0 runs; every collective needs ALL ranks"""
         self.model = model
         self.params = [p for p in model.parameters() if p.requires_grad]
         E.require_cuda(self.params[0])
@@ -269,6 +272,8 @@ class TrainStep:
         self.flat = FlatState(self.params)
         self.flat.step_state[1] = lr               # the Adam kernel reads the learning rate from the device
         self.avg = GradAverager(self.params, flat=self.flat)
+        if not distributed:
+            self.avg.world = 1
         # metrics=True: IoU / Dice of every step's predictions are computed on the device inside the step (and the
         # step's CUDA graph) and left in `last_metrics` -- no per-step device-to-host sync (Train_one_epoch.py:134-135)
         self.metrics = metrics

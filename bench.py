@@ -280,8 +280,9 @@ def main():
     roof = None
     if rank == 0 and not args.no_kernel_table:
         hbm, tflops, which = peaks()
-        eager = TrainStep(model, lr=1e-3, graph=False)
-        eager.avg.world = 1              # rank-0-only instrumentation: no collective (the other ranks are not in it)
+        # rank-0-only instrumentation: no collective at all, neither the start-up broadcast nor the gradient exchange
+        # (the other ranks are not in it: a broadcast here deadlocks against their final barrier)
+        eager = TrainStep(model, lr=1e-3, graph=False, distributed=False)
         # per-kernel timing needs kernels that run alone: no side stream, no parallel lanes in this step
         side_mode, lanes_mode = E.SIDE_MODE, E.LANES
         E.SIDE_MODE, E.LANES = 0, 0

@@ -282,3 +282,25 @@ def test_early_ranges_plus_final_reduction_equal_one_all_reduce(tmp_path):
     mp.spawn(_worker_ranges, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     r0, r1 = (torch.load(os.path.join(tmp_path, f"r{r}.pt")) for r in range(2))
     assert torch.allclose(r0["got"], r0["ref"], rtol=0, atol=1e-6) and torch.equal(r0["got"], r1["got"])
+
+
+def test_rank_local_legs_of_the_bench_never_enter_a_collective():
+    """bench.py under torchrun: after the timed region only rank 0 runs the instrumented per-kernel step, the other
+    ranks wait in the final barrier -- a TrainStep built there must be rank-local (distributed=False: no start-up
+    broadcast, no gradient exchange), and the fp32 / CPU legs run at N = 1 only.  (A plain TrainStep(...) in that leg
+    deadlocked every N > 1 run against the barrier until the collective timeout.)"""
+    import inspect
+    import re
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    rank0 = src[src.index("if rank == 0 and not args.no_kernel_table:"):src.index("# ---- secondary result")]
+    made = re.findall(r"TrainStep\(([^)]*)\)", rank0)
+    assert made and all("distributed=False" in a for a in made), made
+    assert "if world == 1 and args.dtype == \"bf16\" and not args.no_fp32:" in src
+    for p in (ROOT, os.path.join(ROOT, "acc-unet-unext_b200")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    from accx.train import TrainStep
+    sig = inspect.signature(TrainStep.__init__)
+    assert sig.parameters["distributed"].default is True
+    body = inspect.getsource(TrainStep.__init__)
+    assert body.index("if not distributed:") < body.index("dist.broadcast(self.flat.param"), "world must be 1 before the broadcast"
