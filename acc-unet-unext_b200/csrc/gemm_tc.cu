@@ -1007,6 +1007,17 @@ static size_t tc_geometry(int N, int64_t P, const accx_operand_t* ops, int n_ops
   // 227 KB 38.29 ms, 160 KB 37.82 ms, 112 KB 38.44 ms) leaves room for kernels of the other stream lanes on the SM
   size_t cap = (size_t)knob(KNOB_TC_SMEM_KB, 160) * 1024;
   if (cap > (size_t)TC_SMEM_MAX) cap = TC_SMEM_MAX;
+  // the addend staging rows must not cost pipeline stages (K = 192 -> N = 64 with an addend fell from six stages to two,
+  // 158 -> 183 us) and must not lift the footprint over the cap either (raising the cap by the staging bytes gave the
+  // step back what the staging had won: 32.26 vs 32.24 ms): where fewer than four stages would be left, the addend is
+  // loaded directly
+  if (prm.addst_w) {
+    const size_t st_bytes = 2 * (size_t)TC_BM * (prm.addst_w + 4) * 4 + 16;
+    if (fixed + resident + 4 * stage > cap) {
+      prm.addst_w = 0;
+      fixed -= st_bytes;
+    }
+  }
   if (cap < fixed + resident + 2 * stage) cap = fixed + resident + 2 * stage;
   if (cap > (size_t)TC_SMEM_MAX) cap = TC_SMEM_MAX;
   int S = (int)((cap - fixed - resident) / stage);
