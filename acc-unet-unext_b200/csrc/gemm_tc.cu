@@ -1033,6 +1033,74 @@ static size_t tc_geometry(int N, int64_t P, const accx_operand_t* ops, int n_ops
   return fixed + resident + (size_t)S * stage;
 }
 
+// Everything the launcher decides before it touches the device: the dense-3x3 slab mode, pixel folding (with the fall-back
+// when the folded weights would not stay resident), the operands as the kernel sees them, tile geometry, pipeline depth.
+// Returns the dynamic shared memory of the launch.  Shared by accx_pw_fwd_tc_res and accx_pw_fwd_tc_plan (CPU-testable).
+static size_t tc_plan(bool in_f32, bool out_f32, int B, int H, int W, int N, const accx_operand_t* ops, int n_ops, int n_add,
+                      const int* add_log2s, bool has_res, int64_t ld_res, int64_t ldy, bool has_stats, TcParams& prm) {
+  const int64_t P = (int64_t)B * H * W;
+  prm.n_ops = n_ops;
+  prm.any_transform = 0;
+  prm.any_shift = 0;
+  // dense 3x3 convolution (the nine taps of ONE tensor, <= 64 channels in and out): halo-slab mode, see TcParams
+  prm.conv3 = 0;
+  prm.f32in = in_f32 ? (knob(KNOB_TC_F32_TERMS, 3) == 4 ? 2 : 1) : 0;
+  for (int a = 0; a < 3; ++a)
+    for (int b = 0; b < 3; ++b) prm.tap_op[a][b] = -1;
+  if (!in_f32 && n_ops == 9 && N <= 64 && ops[0].K <= 64 && W >= 2 && knob(KNOB_TC_CONV3, 1) == 1) {
+    bool ok = true;
+    for (int i = 0; i < 9 && ok; ++i) {
+      const accx_operand_t& o = ops[i];
+      ok = o.data == ops[0].data && o.ld == ops[0].ld && o.K == ops[0].K && o.act == ops[0].act &&
+           o.scale == ops[0].scale && o.shift == ops[0].shift && o.dy >= -1 && o.dy <= 1 && o.dx >= -1 && o.dx <= 1 &&
+           prm.tap_op[o.dy + 1][o.dx + 1] < 0;
+      if (ok) prm.tap_op[o.dy + 1][o.dx + 1] = i;
+    }
+    prm.conv3 = ok ? 1 : 0;
+  }
+  for (int i = 0; i < n_ops; ++i) {
+    if (ops[i].dy || ops[i].dx || ops[i].act) prm.any_transform = 1;
+    if (ops[i].dy || ops[i].dx) prm.any_shift = 1;
+  }
+  // Pixel folding: a contiguous [P, C] tensor with C <= 32 has rows of <= 64 bytes, and the SM's TMA unit moves a
+  // 128-row box in ~255 ns whatever the row length (profiles/r02_tma_box_rate.txt) -- one load and one store box per
+  // 128-pixel tile, so such contractions run at the BOX rate (~2 TB/s), not at the HBM rate.  When every operand, the
+  // output and the residual are contiguous and unshifted, the same memory is read as [P/2, 2C] (two pixels per row) and
+  // contracted with block-diagonal weights diag(W, W): full 128-byte rows, 256 pixels per tile and per role hand-off,
+  // the same bytes.  The MMAs do twice the arithmetic (the zero blocks), which a narrow contraction has to spare.
+  // Not in the deterministic mode (a statistic would receive four contributions per CTA), not with addends of
+  // upsampling factor 1 (the two pixels of a row would need different addend rows).
+  const int fold_knob = knob(KNOB_TC_FOLD, 2);      // 1 off, 2 on (default), 3 on also when no side is narrower than 64 channels
+  bool fold = fold_knob >= 2 && !in_f32 && !out_f32 && !prm.conv3 && !prm.any_shift && !(det_on() && has_stats) &&
+              P % 2 == 0 && N % 16 == 0 && N <= 128 && ldy == N && (!has_res || ld_res == N) && (n_add == 0 || W % 2 == 0);
+  if (fold) {
+    int ksum = 0;
+    bool narrow = N <= 32 || fold_knob == 3;
+    for (int i = 0; i < n_ops; ++i) {
+      fold = fold && ops[i].ld == ops[i].K;
+      narrow = narrow || ops[i].K <= 32;
+      ksum += ops[i].K;
+    }
+    for (int i = 0; i < n_add; ++i) fold = fold && add_log2s[i] >= 1;
+    fold = fold && narrow && ksum <= 128;
+  }
+  size_t smem = 0;
+  prm.n_add = n_add;
+  for (;;) {
+    const int f = fold ? 2 : 1;
+    prm.fold = fold ? 1 : 0;
+    for (int i = 0; i < n_ops; ++i) {
+      prm.op[i] = ops[i];
+      prm.op[i].K = ops[i].K * f;
+      prm.op[i].ld = ops[i].ld * f;
+    }
+    smem = tc_geometry(N * f, P / f, prm.op, n_ops, out_f32, prm);
+    if (!fold || prm.b_resident) break;
+    fold = false;                             // folded weights are packed in shared memory only: back to plain rows
+  }
+  return smem;
+}
+
 }  // namespace accx
 
 using namespace accx;
@@ -1044,6 +1112,32 @@ int accx_debug_tc_trace(unsigned long long* dst, int n) {
   ACCX_REQUIRE(dst && n > 0 && n <= 640, "debug_tc_trace: bad arguments");
   cudaDeviceSynchronize();
   return cudaMemcpyFromSymbol(dst, g_tc_trace, (size_t)n * 8) == cudaSuccess ? ACCX_OK : ACCX_ERR_CUDA;
+}
+
+// the launch plan of accx_pw_fwd_tc_res for these arguments, without touching the device (host logic only: no pointer is
+// dereferenced except `ops`): plan[0..11] = {fold, conv3, bn, n_tiles, m_tiles, stages, shared-memory bytes, weights resident,
+// floats of the first addend staged per row, TMEM columns, k-blocks, grid}
+int accx_pw_fwd_tc_plan(int dtype, int out_dtype, int B, int H, int W, int N, const accx_operand_t* ops, int n_ops, int n_add,
+                        const int* add_log2s, int has_residual, int64_t ld_res, int64_t ldy, int has_stats, int* plan,
+                        int n_plan) {
+  ACCX_REQUIRE(B > 0 && H > 0 && W > 0 && N > 0 && ops && plan && n_plan >= 12, "pw_fwd_tc_plan: bad arguments");
+  ACCX_REQUIRE(n_ops >= 1 && n_ops <= ACCX_MAX_OPERANDS, "pw_fwd_tc_plan: n_ops %d out of range", n_ops);
+  ACCX_REQUIRE(n_add >= 0 && n_add <= ACCX_MAX_ADDENDS && (n_add == 0 || add_log2s), "pw_fwd_tc_plan: n_add %d out of range", n_add);
+  ACCX_REQUIRE(dtype == ACCX_BF16 || (dtype == ACCX_F32 && out_dtype == ACCX_F32), "pw_fwd_tc_plan: unsupported dtypes");
+  ACCX_REQUIRE((int64_t)B * H * W < (int64_t)1 << 31, "pw_fwd_tc_plan: too many pixels");
+  for (int i = 0; i < n_ops; ++i)
+    ACCX_REQUIRE(ops[i].K > 0 && ops[i].K % 8 == 0 && ops[i].ld % 8 == 0, "pw_fwd_tc_plan: operand %d needs K, ld multiples of 8", i);
+  TcParams prm;
+  const size_t smem = tc_plan(dtype == ACCX_F32, out_dtype == ACCX_F32, B, H, W, N, ops, n_ops, n_add, add_log2s,
+                              has_residual != 0, ld_res, ldy, has_stats != 0, prm);
+  const int64_t total = (int64_t)prm.m_tiles * prm.n_tiles;
+  int64_t grid = sm_count();
+  if (grid > total) grid = total;
+  if (det_on() && has_stats) grid = 1;
+  const int out[12] = {prm.fold, prm.conv3, prm.bn, prm.n_tiles, prm.m_tiles, prm.stages, (int)smem, prm.b_resident,
+                       prm.addst_w, prm.tmem_cols, prm.n_kb, (int)grid};
+  for (int i = 0; i < 12; ++i) plan[i] = out[i];
+  return ACCX_OK;
 }
 
 int64_t accx_pw_tc_workspace_bytes(int N, const accx_operand_t* ops, int n_ops) {
@@ -1079,30 +1173,12 @@ int accx_pw_fwd_tc_res(int dtype, int out_dtype, int B, int H, int W, int N, con
   prm.any_shift = 0;
   const int64_t P = (int64_t)B * H * W;
   ACCX_REQUIRE(P < (int64_t)1 << 31, "pw_fwd_tc: too many pixels");
-  // dense 3x3 convolution (the nine taps of ONE tensor, <= 64 channels in and out): halo-slab mode, see TcParams
-  prm.conv3 = 0;
-  prm.f32in = in_f32 ? (knob(KNOB_TC_F32_TERMS, 3) == 4 ? 2 : 1) : 0;
-  for (int a = 0; a < 3; ++a)
-    for (int b = 0; b < 3; ++b) prm.tap_op[a][b] = -1;
-  if (!in_f32 && n_ops == 9 && N <= 64 && ops[0].K <= 64 && W >= 2 && knob(KNOB_TC_CONV3, 1) == 1) {
-    bool ok = true;
-    for (int i = 0; i < 9 && ok; ++i) {
-      const accx_operand_t& o = ops[i];
-      ok = o.data == ops[0].data && o.ld == ops[0].ld && o.K == ops[0].K && o.act == ops[0].act &&
-           o.scale == ops[0].scale && o.shift == ops[0].shift && o.dy >= -1 && o.dy <= 1 && o.dx >= -1 && o.dx <= 1 &&
-           prm.tap_op[o.dy + 1][o.dx + 1] < 0;
-      if (ok) prm.tap_op[o.dy + 1][o.dx + 1] = i;
-    }
-    prm.conv3 = ok ? 1 : 0;
-  }
   for (int i = 0; i < n_ops; ++i) {
     ACCX_REQUIRE(ops[i].data && ops[i].w && ops[i].K > 0, "pw_fwd_tc: operand %d malformed", i);
     ACCX_REQUIRE(ops[i].K % 8 == 0 && ops[i].ld % 8 == 0 && aligned16(ops[i].data),
                  "pw_fwd_tc: operand %d needs K, ld multiples of 8 and a 16-byte aligned base (use accx_pw_fwd)", i);
     ACCX_REQUIRE(ops[i].act == 0 || (ops[i].scale && ops[i].shift && aligned16(ops[i].scale) && aligned16(ops[i].shift)),
                  "pw_fwd_tc: operand %d scale/shift missing or misaligned", i);
-    if (ops[i].dy || ops[i].dx || ops[i].act) prm.any_transform = 1;
-    if (ops[i].dy || ops[i].dx) prm.any_shift = 1;
   }
   ACCX_REQUIRE(!residual || (aligned16(residual) && (ld_res * esz) % 16 == 0 && ld_res >= N && N % 8 == 0),
                "pw_fwd_tc: residual needs a 16-byte aligned base and row pitch, ld_res >= N, N %% 8 == 0");
@@ -1110,51 +1186,22 @@ int accx_pw_fwd_tc_res(int dtype, int out_dtype, int B, int H, int W, int N, con
     ACCX_REQUIRE(add && add_log2s && add[i] && add_log2s[i] >= 0 && (H >> add_log2s[i]) << add_log2s[i] == H &&
                      (W >> add_log2s[i]) << add_log2s[i] == W,
                  "pw_fwd_tc: addend %d does not tile %dx%d", i, H, W);
-  // Pixel folding: a contiguous [P, C] tensor with C <= 32 has rows of <= 64 bytes, and the SM's TMA unit moves a
-  // 128-row box in ~255 ns whatever the row length (profiles/r02_tma_box_rate.txt) -- one load and one store box per
-  // 128-pixel tile, so such contractions run at the BOX rate (~2 TB/s), not at the HBM rate.  When every operand, the
-  // output and the residual are contiguous and unshifted, the same memory is read as [P/2, 2C] (two pixels per row) and
-  // contracted with block-diagonal weights diag(W, W): full 128-byte rows, 256 pixels per tile and per role hand-off,
-  // the same bytes.  The MMAs do twice the arithmetic (the zero blocks), which a narrow contraction has to spare.
-  // Not in the deterministic mode (a statistic would receive four contributions per CTA), not with addends of
-  // upsampling factor 1 (the two pixels of a row would need different addend rows).
-  const int fold_knob = knob(KNOB_TC_FOLD, 2);      // 1 off, 2 on (default), 3 on also when no side is narrower than 64 channels
-  bool fold = fold_knob >= 2 && !in_f32 && !out_f32 && !prm.conv3 && !prm.any_shift && !(det_on() && stats) &&
-              P % 2 == 0 && N % 16 == 0 && N <= 128 && ldy == N && (!residual || ld_res == N) && (n_add == 0 || W % 2 == 0);
-  if (fold) {
-    int ksum = 0;
-    bool narrow = N <= 32 || fold_knob == 3;
-    for (int i = 0; i < n_ops; ++i) {
-      fold = fold && ops[i].ld == ops[i].K;
-      narrow = narrow || ops[i].K <= 32;
-      ksum += ops[i].K;
-    }
-    for (int i = 0; i < n_add; ++i) fold = fold && add_log2s[i] >= 1;
-    fold = fold && narrow && ksum <= 128;
+  // everything decided on the host (3x3 slab mode, pixel folding, tile geometry, pipeline depth): tc_plan
+  const size_t smem = tc_plan(in_f32, out_f32, B, H, W, N, ops, n_ops, n_add, add_log2s, residual != nullptr, ld_res, ldy,
+                              stats != nullptr, prm);
+  const bool fold = prm.fold != 0;
+  const int f = fold ? 2 : 1;
+  for (int i = 0; i < n_ops; ++i) {
+    if (prm.conv3 && i > 0) continue;       // one map: the slab box of the shared tensor
+    if (in_f32)       // 128 x 32 fp32 boxes (128-byte rows, the same swizzle): one k-block of the split mode
+      ACCX_REQUIRE(encode_2d_out(&prm.tmap[i], ops[i].data, ops[i].K, P, ops[i].ld, 4, TC_BM),
+                   "pw_fwd_tc: cuTensorMapEncodeTiled failed for operand %d", i);
+    else
+      ACCX_REQUIRE(encode_2d_bf16(&prm.tmap[i], ops[i].data, prm.op[i].K, P / f, prm.op[i].ld, prm.conv3 ? TC_SLAB_ROWS : TC_BM),
+                   "pw_fwd_tc: cuTensorMapEncodeTiled failed for operand %d", i);
   }
-  size_t smem = 0;
-  prm.n_add = n_add;
-  for (;;) {
-    const int f = fold ? 2 : 1;
-    prm.fold = fold ? 1 : 0;
-    for (int i = 0; i < n_ops; ++i) {
-      prm.op[i] = ops[i];
-      prm.op[i].K = ops[i].K * f;
-      prm.op[i].ld = ops[i].ld * f;
-      if (prm.conv3 && i > 0) continue;       // one map: the slab box of the shared tensor
-      if (in_f32)       // 128 x 32 fp32 boxes (128-byte rows, the same swizzle): one k-block of the split mode
-        ACCX_REQUIRE(encode_2d_out(&prm.tmap[i], ops[i].data, ops[i].K, P, ops[i].ld, 4, TC_BM),
-                     "pw_fwd_tc: cuTensorMapEncodeTiled failed for operand %d", i);
-      else
-        ACCX_REQUIRE(encode_2d_bf16(&prm.tmap[i], ops[i].data, prm.op[i].K, P / f, prm.op[i].ld, prm.conv3 ? TC_SLAB_ROWS : TC_BM),
-                     "pw_fwd_tc: cuTensorMapEncodeTiled failed for operand %d", i);
-    }
-    ACCX_REQUIRE(encode_2d_out(&prm.tmap_y, y, (int64_t)N * f, P / f, ldy * f, esz, TC_BM),
-                 "pw_fwd_tc: cuTensorMapEncodeTiled failed for the output");
-    smem = tc_geometry(N * f, P / f, prm.op, n_ops, out_f32, prm);
-    if (!fold || prm.b_resident) break;
-    fold = false;                             // folded weights are packed in shared memory only: back to plain rows
-  }
+  ACCX_REQUIRE(encode_2d_out(&prm.tmap_y, y, (int64_t)N * f, P / f, ldy * f, esz, TC_BM),
+               "pw_fwd_tc: cuTensorMapEncodeTiled failed for the output");
   const int n_tiles = prm.n_tiles;
   const int64_t need = (int64_t)n_tiles * prm.n_kb * (in_f32 ? 2 : 1) * prm.bn * TC_BK * 2;
   ACCX_REQUIRE(prm.b_resident || (workspace_bytes >= need && aligned16(workspace)),

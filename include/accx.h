@@ -101,6 +101,14 @@ int accx_pw_fwd_tc(int dtype, int out_dtype, int B, int H, int W, int N,
 /* Diagnostics: with knob 19 (KNOB_TC_DEBUG) bit 5 set, CTA 0 of accx_pw_fwd_tc stamps %globaltimer at the role hand-offs
  * of its first 64 tiles; this copies the 10 x 64 nanosecond stamps out (event * 64 + tile; events in csrc/gemm_tc.cu). */
 int accx_debug_tc_trace(unsigned long long* dst, int n);
+/* The launch plan accx_pw_fwd_tc_res makes for these arguments, without touching the device (host logic only; of the
+ * pointers only `ops` and `add_log2s` are read, the operands' data / weight pointers are not dereferenced):
+ * plan[0..11] = {pixel folding (two pixels per row) 0/1, dense-3x3 slab mode 0/1, column tile BN, column tiles, pixel
+ * tiles, pipeline stages, dynamic shared-memory bytes, weights resident in shared memory 0/1, floats of the first addend
+ * staged per row (0 = direct loads), TMEM columns, k-blocks, grid}.  n_plan >= 12.  Nothing in the reference. */
+int accx_pw_fwd_tc_plan(int dtype, int out_dtype, int B, int H, int W, int N, const accx_operand_t* ops, int n_ops,
+                        int n_add, const int* add_log2s, int has_residual, int64_t ld_res, int64_t ldy, int has_stats,
+                        int* plan, int n_plan);
 /* accx_pw_fwd_tc with a residual: Y = contraction (+ bias + addends) + R, R a [P, ld_res] matrix in the OUTPUT dtype
  * (16-byte aligned base and row pitch).  R may be Y itself (in-place accumulation: every tile is read before it is
  * written).  Fuses the `x + inp` / gradient-accumulation passes that follow an input-gradient contraction

@@ -139,3 +139,100 @@ def test_product_never_imports_the_oracle():
         for f in fs:
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 assert "oracle" not in open(os.path.join(dp, f)).read().lower(), f
+
+
+# ---- host-side launch planning of the tensor-core contraction (no device needed) -----------------------------------
+PLAN = ("fold", "conv3", "bn", "n_tiles", "m_tiles", "stages", "smem", "resident", "addst_w", "tmem_cols", "n_kb", "grid")
+
+
+def _plan(B, H, W, N, ops, adds=(), res_ld=None, ldy=None, stats=True, dtype=1, out_dtype=1):
+    """ops: [(K, ld, dy, dx, act)]; -> dict of accx_pw_fwd_tc_plan (dtype 1 = bf16, 0 = fp32, include/accx.h)"""
+    from accx import _lib
+    lib = _lib.load()
+    arr = (_lib.Operand * len(ops))()
+    for o, (K, ld, dy, dx, act) in zip(arr, ops):
+        o.K, o.ld, o.dy, o.dx, o.act = K, ld, dy, dx, act
+    al = (ctypes.c_int * max(1, len(adds)))(*adds)
+    out = (ctypes.c_int * 12)()
+    rc = lib.accx_pw_fwd_tc_plan(dtype, out_dtype, B, H, W, N, arr, len(ops), len(adds), al, int(res_ld is not None),
+                                 res_ld or 0, N if ldy is None else ldy, int(stats), out, 12)
+    assert rc == 0, lib.accx_last_error().decode()
+    return dict(zip(PLAN, out))
+
+
+def test_plan_pixel_folding_rules():
+    """two pixels per row only for narrow, contiguous, unshifted bf16 contractions"""
+    from accx import _lib
+    lib = _lib.load()
+    F32 = 0                                   # ACCX_F32 (include/accx.h); the default of _plan is ACCX_BF16 = 1
+    base = dict(B=16, H=224, W=224, N=32, ops=[(32, 32, 0, 0, 2)])
+    p = _plan(**base)
+    assert p["fold"] == 1 and p["bn"] == 64 and p["n_kb"] == 1 and p["m_tiles"] == 16 * 224 * 224 // 256
+    assert p["resident"] == 1 and p["smem"] <= 227 * 1024 and p["stages"] >= 3 and p["grid"] == 148
+    assert _plan(**{**base, "N": 96})["fold"] == 1 and _plan(**{**base, "N": 96})["bn"] == 192
+    assert _plan(**{**base, "ops": [(96, 96, 0, 0, 2)]})["fold"] == 1                      # narrow output
+    assert _plan(**{**base, "ops": [(32, 32, 0, 0, 2), (32, 32, 0, 0, 0)]})["fold"] == 1      # several operands
+    assert _plan(**base, res_ld=32)["fold"] == 1
+    assert _plan(**base, adds=(1, 2))["fold"] == 1
+    # ... and not otherwise
+    assert _plan(**{**base, "N": 64, "ops": [(64, 64, 0, 0, 2)]})["fold"] == 0               # no side <= 32 channels
+    assert _plan(**{**base, "ops": [(32, 64, 0, 0, 2)]})["fold"] == 0                        # column slice of a wider tensor
+    assert _plan(**{**base, "ops": [(32, 32, 0, 1, 2)]})["fold"] == 0                        # shifted tap
+    assert _plan(**base, ldy=64)["fold"] == 0                                                # sliced output
+    assert _plan(**base, res_ld=64)["fold"] == 0
+    assert _plan(**base, adds=(0,))["fold"] == 0                                             # addend at full resolution
+    assert _plan(B=1, H=3, W=5, N=32, ops=[(32, 32, 0, 0, 2)])["fold"] == 0                  # odd pixel count
+    assert _plan(B=2, H=3, W=5, N=32, ops=[(32, 32, 0, 0, 2)], adds=())["fold"] == 1
+    assert _plan(**{**base, "N": 40})["fold"] == 0                                           # N % 16 != 0
+    assert _plan(**{**base, "ops": [(160, 160, 0, 0, 2)]})["fold"] == 0                      # sum K > 128
+    assert _plan(**base, dtype=F32, out_dtype=F32)["fold"] == 0                              # fp32 storage
+    assert _plan(**base, out_dtype=F32, stats=False)["fold"] == 0                            # fp32 output
+    assert lib.accx_set_knob(23, 1) == 0
+    try:
+        assert _plan(**base)["fold"] == 0                                                    # knob 23 = 1: off
+    finally:
+        lib.accx_set_knob(23, 0)
+
+
+def test_plan_slab_mode_and_addend_staging():
+    taps = [(32, 32, dy, dx, 2) for dy in (-1, 0, 1) for dx in (-1, 0, 1)]
+    p = _plan(16, 224, 224, 32, taps)
+    assert p["conv3"] == 1 and p["fold"] == 0 and p["resident"] == 1 and p["tmem_cols"] >= 2 * 3 * p["bn"]
+    assert _plan(16, 56, 56, 128, [(128, 128, dy, dx, 2) for dy in (-1, 0, 1) for dx in (-1, 0, 1)])["conv3"] == 0   # > 64 channels
+    # first addend through shared memory: narrow single column tile with all chunks full, four stages left under the cap
+    p = _plan(16, 224, 224, 32, [(32, 32, 0, 0, 2)], adds=(1,))
+    assert p["fold"] == 1 and p["addst_w"] == 32 and p["stages"] >= 4
+    p = _plan(16, 112, 112, 48, [(64, 64, 0, 0, 2)], adds=(1, 2))
+    assert p["fold"] == 0 and p["addst_w"] == 48 and p["stages"] >= 4 and p["smem"] <= 161 * 1024
+    p = _plan(16, 112, 112, 64, [(64, 64, 0, 0, 2)], adds=(1, 2))
+    assert p["fold"] == 0 and p["addst_w"] == 0 and p["stages"] >= 4    # 70 KB of staging rows would leave three stages
+    p = _plan(16, 224, 224, 64, [(192, 192, 0, 0, 2)], adds=(1,))
+    assert p["addst_w"] == 0 and p["stages"] >= 4                       # staging would leave two stages: direct loads
+    assert _plan(16, 56, 56, 128, [(384, 384, 0, 0, 2)], adds=(1,))["addst_w"] == 0          # 128-channel tile: not staged
+    assert _plan(16, 224, 224, 40, [(64, 64, 0, 0, 2)], adds=(1,))["addst_w"] == 0           # ragged last chunk
+
+
+def test_plan_always_fits_the_sm():
+    """every geometry the planner returns can be launched: shared memory <= 227 KB, TMEM <= 512 columns, >= 1 stage, and the
+    persistent grid never exceeds the tiles; swept over the model's shapes and some hostile ones"""
+    import itertools
+    Ks = (8, 16, 32, 64, 96, 128, 192, 256, 384, 512, 768, 1536, 4352)
+    Ns = (8, 16, 32, 48, 64, 96, 128, 192, 256, 384, 512, 768, 1536, 4352)
+    for (K, N), (B, H, W), n_add, res, f32out in itertools.product(
+            itertools.product(Ks, Ns), ((16, 224, 224), (16, 14, 14), (1, 7, 5), (2, 56, 56)), (0, 1, 3), (False, True), (False, True)):
+        if n_add and (H % 8 or W % 8):
+            continue
+        if res and N % 8:
+            continue
+        p = _plan(B, H, W, N, [(K, K, 0, 0, 2)], adds=tuple(range(1, n_add + 1)), res_ld=N if res else None,
+                  stats=not f32out, out_dtype=0 if f32out else 1)
+        what = (K, N, B, H, W, n_add, res, f32out, p)
+        assert 1 <= p["stages"] <= 8 and 0 < p["smem"] <= 227 * 1024, what
+        assert p["tmem_cols"] <= 512 and p["tmem_cols"] & (p["tmem_cols"] - 1) == 0, what
+        assert p["bn"] % 8 == 0 and p["bn"] * p["n_tiles"] >= N * (2 if p["fold"] else 1), what
+        assert 1 <= p["grid"] <= p["m_tiles"] * p["n_tiles"], what
+        assert not p["fold"] or p["resident"], what
+    # fp32 storage (3 x TF32): 32-channel k-blocks, two weight tiles each
+    for K, N in ((32, 32), (64, 192), (4352, 128), (128, 4352)):
+        p = _plan(16, 56, 56, N, [(K, K, 0, 0, 2)], dtype=0, out_dtype=0)
+        assert p["fold"] == 0 and p["n_kb"] == (K + 31) // 32 and p["smem"] <= 227 * 1024 and p["stages"] >= 1, (K, N, p)
