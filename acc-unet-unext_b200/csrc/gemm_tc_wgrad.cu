@@ -241,16 +241,18 @@ using namespace accx;
 
 extern "C" {
 
-static int wgrad_tc_launch(int B, int H, int W, int N, const accx_operand_t* op, int n_taps, const int* taps_dy,
-                           const int* taps_dx, const int64_t* taps_woff, float* dw, const void* dy, int64_t ldy,
-                           void* stream) {
-  ACCX_REQUIRE(B > 0 && H > 0 && W > 0 && N > 0 && op && op->data && dw && dy, "pw_wgrad_tc: bad arguments");
-  ACCX_REQUIRE(op->K % 8 == 0 && op->ld % 8 == 0 && aligned16(op->data) && ldy % 8 == 0 && aligned16(dy) && N % 8 == 0,
-               "pw_wgrad_tc: needs K, N, ld multiples of 8 and 16-byte aligned bases (use accx_pw_wgrad)");
-  ACCX_REQUIRE(op->act == 0 || (op->scale && op->shift && aligned16(op->scale) && aligned16(op->shift)),
-               "pw_wgrad_tc: scale/shift missing or misaligned");
+// Everything the launcher decides on the host: pixel folding, tile / split / pipeline geometry, shared memory.  Fills the
+// geometry fields of `prm` (operand, N, P as the kernel sees them) and returns the stage size, the shared memory and the
+// grid; N and ldy come back folded.  Shared by the launcher and accx_pw_wgrad_tc_plan (CPU-testable).
+struct WgPlan {
+  int wg_px;
+  size_t smem;
+  int64_t grid;
+};
+
+static int wg_plan(int B, int H, int W, int& N, const accx_operand_t* op, int n_taps, const int* taps_dy, const int* taps_dx,
+                   int64_t& ldy, WgParams& prm, WgPlan& pl) {
   ACCX_REQUIRE(n_taps >= 1 && n_taps <= 9, "pw_wgrad_tc: n_taps %d out of range", n_taps);
-  WgParams prm;
   prm.op = *op;
   prm.B = B; prm.H = H; prm.W = W; prm.N = N;
   prm.P = (int64_t)B * H * W;
@@ -265,12 +267,11 @@ static int wgrad_tc_launch(int B, int H, int W, int N, const accx_operand_t* op,
     ldy *= 2;
   }
   op = &prm.op;
-  prm.dw = dw;
   prm.n_taps = n_taps;
   prm.any_transform = op->act ? 1 : 0;
   for (int t = 0; t < 9; ++t) { prm.tap_dy[t] = 0; prm.tap_dx[t] = 0; prm.tap_woff[t] = 0; }
   for (int t = 0; t < n_taps; ++t) {
-    prm.tap_dy[t] = taps_dy[t]; prm.tap_dx[t] = taps_dx[t]; prm.tap_woff[t] = taps_woff[t];
+    prm.tap_dy[t] = taps_dy[t]; prm.tap_dx[t] = taps_dx[t];
     if (taps_dy[t] || taps_dx[t]) prm.any_transform = 1;
   }
   if (n_taps == 1) {
@@ -307,17 +308,54 @@ static int wgrad_tc_launch(int B, int H, int W, int N, const accx_operand_t* op,
   if (S > per) S = (int)per;
   ACCX_REQUIRE(S >= 1, "pw_wgrad_tc: one pipeline stage (%zu bytes) does not fit in shared memory", stage_bytes);
   prm.stages = S;
-  ACCX_REQUIRE(encode_2d_bf16(&prm.map_dy, dy, N, prm.P, ldy, WG_PX), "pw_wgrad_tc: tensor map (dY) failed");
-  ACCX_REQUIRE(encode_2d_bf16(&prm.map_a, op->data, op->K, prm.P, op->ld, WG_PX), "pw_wgrad_tc: tensor map (A) failed");
-  const size_t smem = 1024 + S * stage_bytes + 2 * (size_t)a_blocks * 64 * 4 + 24 * S + 64;
+  pl.wg_px = WG_PX;
+  pl.smem = 1024 + S * stage_bytes + 2 * (size_t)a_blocks * 64 * 4 + 24 * S + 64;
+  pl.grid = pairs * splits;
+  return ACCX_OK;
+}
+
+static int wgrad_tc_launch(int B, int H, int W, int N, const accx_operand_t* op, int n_taps, const int* taps_dy,
+                           const int* taps_dx, const int64_t* taps_woff, float* dw, const void* dy, int64_t ldy,
+                           void* stream) {
+  ACCX_REQUIRE(B > 0 && H > 0 && W > 0 && N > 0 && op && op->data && dw && dy, "pw_wgrad_tc: bad arguments");
+  ACCX_REQUIRE(op->K % 8 == 0 && op->ld % 8 == 0 && aligned16(op->data) && ldy % 8 == 0 && aligned16(dy) && N % 8 == 0,
+               "pw_wgrad_tc: needs K, N, ld multiples of 8 and 16-byte aligned bases (use accx_pw_wgrad)");
+  ACCX_REQUIRE(op->act == 0 || (op->scale && op->shift && aligned16(op->scale) && aligned16(op->shift)),
+               "pw_wgrad_tc: scale/shift missing or misaligned");
+  WgParams prm;
+  WgPlan pl;
+  const int rc = wg_plan(B, H, W, N, op, n_taps, taps_dy, taps_dx, ldy, prm, pl);      // (N, ldy: folded from here on)
+  if (rc != ACCX_OK) return rc;
+  prm.dw = dw;
+  for (int t = 0; t < n_taps; ++t) prm.tap_woff[t] = taps_woff[t];
+  ACCX_REQUIRE(encode_2d_bf16(&prm.map_dy, dy, N, prm.P, ldy, pl.wg_px), "pw_wgrad_tc: tensor map (dY) failed");
+  ACCX_REQUIRE(encode_2d_bf16(&prm.map_a, prm.op.data, prm.op.K, prm.P, prm.op.ld, pl.wg_px), "pw_wgrad_tc: tensor map (A) failed");
   static bool attr_set[ACCX_MAX_DEVICES] = {false};
   if (first_use_on_device(attr_set)) {
     cudaFuncSetAttribute(pw_wgrad_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     cudaFuncSetAttribute(pw_wgrad_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   }
-  if (WG_PX == 256) launch_k(pw_wgrad_tc_kernel<256>, (unsigned)(pairs * splits), WG_THREADS, smem, (cudaStream_t)stream, prm);
-  else launch_k(pw_wgrad_tc_kernel<128>, (unsigned)(pairs * splits), WG_THREADS, smem, (cudaStream_t)stream, prm);
+  if (pl.wg_px == 256) launch_k(pw_wgrad_tc_kernel<256>, (unsigned)pl.grid, WG_THREADS, pl.smem, (cudaStream_t)stream, prm);
+  else launch_k(pw_wgrad_tc_kernel<128>, (unsigned)pl.grid, WG_THREADS, pl.smem, (cudaStream_t)stream, prm);
   return check_launch("pw_wgrad_tc");
+}
+
+// the launch plan of accx_pw_wgrad_tc / accx_pw_wgrad_taps_tc for these arguments, without touching the device:
+// plan[0..10] = {fold, nb, dY-channel tiles, A-channel tiles, dY blocks per stage, pixels per stage, splits over pixels,
+// pipeline stages, shared-memory bytes, TMEM columns, grid}
+int accx_pw_wgrad_tc_plan(int B, int H, int W, int N, const accx_operand_t* op, int n_taps, const int* taps_dy,
+                          const int* taps_dx, int64_t ldy, int* plan, int n_plan) {
+  ACCX_REQUIRE(B > 0 && H > 0 && W > 0 && N > 0 && op && taps_dy && taps_dx && plan && n_plan >= 11, "pw_wgrad_tc_plan: bad arguments");
+  ACCX_REQUIRE(op->K > 0 && op->K % 8 == 0 && op->ld % 8 == 0 && ldy % 8 == 0 && N % 8 == 0,
+               "pw_wgrad_tc_plan: needs K, N, ld multiples of 8");
+  WgParams prm;
+  WgPlan pl;
+  const int rc = wg_plan(B, H, W, N, op, n_taps, taps_dy, taps_dx, ldy, prm, pl);
+  if (rc != ACCX_OK) return rc;
+  const int out[11] = {prm.fold, prm.nb, prm.n_tiles, prm.k_tiles, prm.dy_blocks, pl.wg_px, prm.splits, prm.stages, (int)pl.smem,
+                       prm.tmem_cols, (int)pl.grid};
+  for (int i = 0; i < 11; ++i) plan[i] = out[i];
+  return ACCX_OK;
 }
 
 int accx_pw_wgrad_tc(int B, int H, int W, int N, const accx_operand_t* op, float* dw, const void* dy, int64_t ldy,

@@ -136,6 +136,13 @@ int accx_pw_wgrad_tc(int B, int H, int W, int N, const accx_operand_t* op, float
 int accx_pw_wgrad_taps_tc(int B, int H, int W, int N, const accx_operand_t* op, int n_taps, const int* taps_dy,
                           const int* taps_dx, const int64_t* taps_woff, float* dw, const void* dy, int64_t ldy,
                           void* stream);
+/* The launch plan of accx_pw_wgrad_tc / accx_pw_wgrad_taps_tc for these arguments, without touching the device (host logic
+ * only; the operand's data / weight pointers are not dereferenced): plan[0..10] = {pixel folding 0/1, A-channel tile NB,
+ * dY-channel tiles, A-channel tiles, dY blocks per stage, pixels per pipeline stage, splits over pixels, pipeline stages,
+ * dynamic shared-memory bytes, TMEM columns, grid}.  n_plan >= 11.  Nothing in the reference. */
+int accx_pw_wgrad_tc_plan(int B, int H, int W, int N, const accx_operand_t* op, int n_taps, const int* taps_dy,
+                          const int* taps_dx, int64_t ldy, int* plan, int n_plan);
+
 
 /* BatchNorm2d statistics -> affine (torch.nn.BatchNorm2d as used at ACC_UNet.py:34,74,178,
  * 244-260,311-319,388-410).  training: mean/var from stats (biased var), running buffers

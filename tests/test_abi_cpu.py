@@ -236,3 +236,52 @@ def test_plan_always_fits_the_sm():
     for K, N in ((32, 32), (64, 192), (4352, 128), (128, 4352)):
         p = _plan(16, 56, 56, N, [(K, K, 0, 0, 2)], dtype=0, out_dtype=0)
         assert p["fold"] == 0 and p["n_kb"] == (K + 31) // 32 and p["smem"] <= 227 * 1024 and p["stages"] >= 1, (K, N, p)
+
+
+WPLAN = ("fold", "nb", "n_tiles", "k_tiles", "dy_blocks", "stage_px", "splits", "stages", "smem", "tmem_cols", "grid")
+
+
+def _wplan(B, H, W, N, K, ld=None, ldy=None, taps=((0, 0),), act=2, expect_rc=0):
+    from accx import _lib
+    lib = _lib.load()
+    o = _lib.Operand()
+    o.K, o.ld, o.act = K, K if ld is None else ld, act
+    tdy = (ctypes.c_int * len(taps))(*[t[0] for t in taps])
+    tdx = (ctypes.c_int * len(taps))(*[t[1] for t in taps])
+    out = (ctypes.c_int * 11)()
+    rc = lib.accx_pw_wgrad_tc_plan(B, H, W, N, ctypes.byref(o), len(taps), tdy, tdx, N if ldy is None else ldy, out, 11)
+    assert rc == expect_rc, lib.accx_last_error().decode()
+    return dict(zip(WPLAN, out))
+
+
+def test_wgrad_plan_folding_stages_and_launchability():
+    """host-side plan of the tensor-core weight gradient: two pixels per row for narrow contiguous single-tap operands,
+    256-pixel stages over >= 1e5 (folded) rows, and every plan fits an SM (227 KB, 512 TMEM columns, >= 1 stage)"""
+    p = _wplan(16, 224, 224, 32, 32)
+    assert p["fold"] == 1 and p["nb"] == 64 and p["stage_px"] == 256 and p["n_tiles"] == p["k_tiles"] == 1 and p["dy_blocks"] == 1
+    assert p["grid"] == p["splits"] and 1 <= p["grid"] <= 2 * 148
+    assert _wplan(16, 224, 224, 64, 32)["fold"] == 1 and _wplan(16, 224, 224, 32, 96)["fold"] == 1
+    assert _wplan(16, 224, 224, 64, 64)["fold"] == 0                      # no narrow side
+    assert _wplan(16, 224, 224, 96, 32)["fold"] == 0                      # N > 64
+    assert _wplan(16, 224, 224, 32, 32, ld=64)["fold"] == 0               # column slice
+    assert _wplan(16, 224, 224, 32, 32, ldy=96)["fold"] == 0
+    assert _wplan(16, 224, 224, 32, 32, taps=((0, 1),))["fold"] == 0      # shifted tap
+    assert _wplan(1, 15, 15, 32, 32)["fold"] == 0                         # odd pixel count
+    assert _wplan(16, 224, 224, 32, 24)["fold"] == 0                      # K % 16 != 0
+    assert _wplan(3, 181, 187, 32, 32)["stage_px"] == 256 and _wplan(2, 56, 56, 32, 32)["stage_px"] == 128
+    nine = tuple((dy, dx) for dy in (-1, 0, 1) for dx in (-1, 0, 1))
+    p = _wplan(16, 224, 224, 32, 32, taps=nine[:5])
+    assert p["fold"] == 0 and p["nb"] == 32 and p["tmem_cols"] == 256 and p["stage_px"] == 128
+    _wplan(16, 56, 56, 128, 128, taps=nine, expect_rc=-1)                 # 9 x 64 columns exceed TMEM: the engine sends <= 5 taps
+    for K in (8, 16, 32, 64, 96, 128, 192, 256, 384, 768, 1536, 4352):
+        for N in (8, 32, 64, 96, 128, 256, 768, 4352):
+            for B, H, W in ((16, 224, 224), (16, 14, 14), (1, 7, 5), (16, 56, 56)):
+                for taps in (((0, 0),), nine[:4], nine[4:]):
+                    if len(taps) > 1 and K > 256:
+                        continue
+                    p = _wplan(B, H, W, N, K, taps=taps)
+                    what = (K, N, B, H, W, len(taps), p)
+                    assert 1 <= p["stages"] <= 4 and 0 < p["smem"] <= 227 * 1024, what
+                    assert p["tmem_cols"] <= 512 and p["tmem_cols"] >= len(taps) * p["nb"], what
+                    assert p["grid"] == p["n_tiles"] * p["k_tiles"] * p["splits"] and p["grid"] >= 1, what
+                    assert p["nb"] % 16 == 0 and p["nb"] * p["k_tiles"] >= K * (2 if p["fold"] else 1), what
