@@ -98,18 +98,37 @@ def cpu_oracle_images_per_s(steps, warmup, threads):
     return CPU_SAMPLE_BATCH * steps / dt, dt / steps
 
 
+CLS_NAMES = {"base": "ACC_UNet", "w": "ACC_UNet_W", "lite": "ACC_UNet_Lite"}
+
+
+def workload_config(cls_name, B, hw, world, graph):
+    """the `config` object of the result line: the workload both arms are quoted on (BASELINE.json configs[1] by default)"""
+    return {"workload": f"{cls_name}(3,1,32) full train step (fwd + Dice/BCE + bwd + Adam), "
+                        f"{B}x3x{hw}x{hw} per GPU, GlaS-shaped synthetic",
+            "global_batch": B * world, "parallelism": f"dp{world}", "cuda_graph": bool(graph),
+            "l2_policy": "per-step working set (several GB of activations) >> 126 MB L2; no flush needed"}
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
     steps, warm = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
     ips, spstep = cpu_oracle_images_per_s(steps, warm, cores)
-    sample = f"{CPU_SAMPLE_BATCH}x3x{HW}x{HW} fp32 train step (fwd+Dice/BCE+bwd+Adam), {steps} timed steps after {warm} warm-up"
+    sample = (f"{CPU_SAMPLE_BATCH}x3x{HW}x{HW} fp32 train step (fwd+Dice/BCE+bwd+Adam) of ACC_UNet(3,1,32) through the CPU oracle "
+              f"port of the reference, {steps} timed steps after {warm} warm-up, normalised to images/s")
+    world = max(1, int(getattr(args, "gpus", 1)))
+    world_b = getattr(args, "batch", PER_GPU_BATCH)
+    if getattr(args, "global_batch", 0):
+        world_b = args.global_batch // world
     emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warm, "ms_per_step": spstep * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"ACC_UNet(3,1,32) train step, CPU oracle port of the reference, batch {CPU_SAMPLE_BATCH}"},
+        # the same workload / config as the accx arm is quoted on; what was actually timed (a bounded sample of it on the
+        # host cores, through the CPU port of the reference's formulas) is stated in cpu_baseline
+        "config": workload_config(CLS_NAMES[getattr(args, "variant", "base")], world_b, getattr(args, "hw", HW), world,
+                                  getattr(args, "graph", 1)),
         "cpu_baseline": {"value": ips, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
@@ -388,11 +407,7 @@ def main():
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong" if args.global_batch else "weak",
             "vs_baseline": None,
             "dtype": args.dtype if args.dtype == "bf16" else "f32", "data": "synthetic",
-            "config": {"workload": f"{cls.__name__}(3,1,32) full train step (fwd + Dice/BCE + bwd + Adam), "
-                                   f"{B}x3x{hw}x{hw} per GPU, GlaS-shaped synthetic",
-                       "global_batch": B * world, "parallelism": f"dp{world}",
-                       "cuda_graph": bool(args.graph),
-                       "l2_policy": "per-step working set (several GB of activations) >> 126 MB L2; no flush needed"},
+            "config": workload_config(cls.__name__, B, hw, world, args.graph),
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / K,
                     "h2d_bytes_per_step": x_host.numel() * 4 + m_host.numel() * 4, "d2h_bytes_per_step": 4},
             "gpu_launches": launches_per_step * K,

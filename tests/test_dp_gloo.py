@@ -216,6 +216,11 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["gpu_launches"] == 0
+    # the same config object as the accx arm's line for the same flags (the driver pairs the two lines by it)
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"] == bench.workload_config("ACC_UNet", bench.PER_GPU_BATCH, bench.HW, 1, 1)
+    assert "16x3x224x224 per GPU" in d["config"]["workload"] and "2x3x224x224" in d["cpu_baseline"]["sample"]
 
 
 # ---- backward-overlapped exchange: ranges of the flat buffer reduced early + the final reduction of the rest ----------
